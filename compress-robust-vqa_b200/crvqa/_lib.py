@@ -1,0 +1,61 @@
+"""Loader and prototypes for the C ABI declared in include/crvqa.h."""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_size_t, c_void_p
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcrvqa.so")
+
+
+class CrvqaError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise CrvqaError(
+            f"{LIB_PATH} not found: build it with compress-robust-vqa_b200/csrc/build.sh "
+            "(or __graft_entry__.build()); there is no CPU fallback for the masked kernels")
+    return ctypes.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_P = c_void_p
+_PROTOS = {
+    "crv_version": (c_int, []),
+    "crv_error_string": (c_char_p, [c_int]),
+    "crv_last_cuda_error": (c_int, []),
+    "crv_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
+    "crv_binarize": (c_int, [_P, _P, _P, _P, _P, c_int64, _P]),
+    "crv_apply_mask_bf16": (c_int, [_P, _P, _P, _P, c_int64, _P]),
+    "crv_masked_linear_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "crv_masked_linear_bwd_dx": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "crv_masked_linear_bwd_ds": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "crv_masked_linear_small_k_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "crv_masked_linear_small_k_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "crv_masked_embedding_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, _P]),
+    "crv_masked_embedding_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_longlong, _P]),
+    "crv_kth_value_workspace_bytes": (c_size_t, [c_int]),
+    "crv_kth_value_batched": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, c_size_t, _P]),
+    "crv_magnitude_init": (c_int, [_P, _P, c_float, c_float, _P, c_int64, _P]),
+    "crv_vqa_loss_workspace_bytes": (c_size_t, [c_int]),
+    "crv_vqa_loss_bce": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P]),
+    "crv_vqa_loss_lpf": (c_int, [_P, _P, _P, c_float, _P, _P, _P, c_int, c_int, _P, _P]),
+    "crv_vqa_loss_lmh": (c_int, [_P, _P, _P, _P, c_float, c_float, _P, _P, _P, c_int, c_int, _P, _P]),
+    "crv_sumsq": (c_int, [_P, c_int64, _P, _P]),
+    "crv_adamw_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float,
+                               c_float, _P, c_float, _P]),
+}
+EXPORTED = tuple(_PROTOS)
+for _name, (_res, _args) in _PROTOS.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(rc, what=""):
+    """Raise CrvqaError for a non-zero return code of a crv_* call."""
+    if rc != 0:
+        msg = lib.crv_error_string(int(rc))
+        msg = msg.decode() if msg else "?"
+        raise CrvqaError(f"{what or 'crvqa call'} failed: rc={rc} ({msg})")

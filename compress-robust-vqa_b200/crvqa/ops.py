@@ -1,0 +1,315 @@
+"""Torch-facing wrappers of the C ABI: raw ops on CUDA tensors + the autograd Functions that replace
+``_Binarizer1`` + ``weight * M_w`` + ``F.linear`` / ``F.embedding`` (masking/maskers.py:325-366) and the
+loss graphs of the trainers.  Every op runs on torch's current CUDA stream."""
+import ctypes
+import math
+
+import torch
+
+from ._lib import check, lib
+
+DT_F32, DT_BF16 = 0, 1
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("crvqa ops need CUDA tensors: the masked kernels have no CPU fallback")
+
+
+def to_bf16(x):
+    """fp32 -> bf16 (RNE) with the library's cast kernel; bf16 input is returned as is."""
+    if x.dtype == torch.bfloat16:
+        return x.contiguous()
+    _need_cuda(x)
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib.crv_cast_f32_to_bf16(_p(x), _p(out), x.numel(), _stream()), "crv_cast_f32_to_bf16")
+    return out
+
+
+def as_thr(thr, device):
+    """The reference keeps thresholds as 0-dim tensors (possibly on CPU); the kernels read a device float."""
+    if not torch.is_tensor(thr):
+        return torch.tensor(float(thr), dtype=torch.float32, device=device)
+    if thr.device != device or thr.dtype != torch.float32:
+        thr = thr.to(device=device, dtype=torch.float32)
+    return thr
+
+
+def binarize(scores, thr, want_count=False, as_bool=False):
+    """binarizer_fn1: 1.0 where scores > thr else 0.0 (masking/maskers.py:325-329)."""
+    _need_cuda(scores)
+    s = scores.detach().contiguous()
+    thr = as_thr(thr, s.device)
+    mf = None if as_bool else torch.empty_like(s)
+    mb = torch.empty(s.shape, dtype=torch.uint8, device=s.device) if as_bool else None
+    cnt = torch.zeros((), dtype=torch.int64, device=s.device) if want_count else None
+    check(lib.crv_binarize(_p(s), _p(thr), _p(mf), _p(mb), _p(cnt), s.numel(), _stream()), "crv_binarize")
+    out = mb.view(torch.bool) if as_bool else mf
+    return (out, cnt) if want_count else out
+
+
+def apply_mask_bf16(w_bf16, scores, thr):
+    _need_cuda(w_bf16, scores)
+    out = torch.empty_like(w_bf16)
+    thr = as_thr(thr, scores.device)
+    check(lib.crv_apply_mask_bf16(_p(w_bf16), _p(scores), _p(thr), _p(out), w_bf16.numel(), _stream()),
+          "crv_apply_mask_bf16")
+    return out
+
+
+def masked_linear_fwd(x_bf16, w_bf16, scores, thr, bias, out_dtype=torch.float32):
+    """Y[M,N] = X[M,K] . (W (.) (S > thr))^T + b; scores None => W taken as is."""
+    _need_cuda(x_bf16, w_bf16)
+    M, K = x_bf16.shape
+    N = w_bf16.shape[0]
+    y = torch.empty((M, N), dtype=out_dtype, device=x_bf16.device)
+    thr_t = as_thr(thr, x_bf16.device) if scores is not None else None
+    check(lib.crv_masked_linear_fwd(_p(x_bf16), _p(w_bf16), _p(scores), _p(thr_t), _p(bias), _p(y),
+                                    DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _stream()),
+          "crv_masked_linear_fwd")
+    return y
+
+
+def masked_linear_bwd_dx(dy_bf16, w_bf16, scores, thr, out_dtype=torch.float32):
+    _need_cuda(dy_bf16, w_bf16)
+    M, N = dy_bf16.shape
+    K = w_bf16.shape[1]
+    dx = torch.empty((M, K), dtype=out_dtype, device=dy_bf16.device)
+    thr_t = as_thr(thr, dy_bf16.device) if scores is not None else None
+    check(lib.crv_masked_linear_bwd_dx(_p(dy_bf16), _p(w_bf16), _p(scores), _p(thr_t), _p(dx),
+                                       DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _stream()),
+          "crv_masked_linear_bwd_dx")
+    return dx
+
+
+def masked_linear_bwd_ds(dy_bf16, x_bf16, w_bf16, out=None, accumulate=False):
+    _need_cuda(dy_bf16, x_bf16, w_bf16)
+    M, N = dy_bf16.shape
+    K = x_bf16.shape[1]
+    if out is None:
+        out = torch.empty((N, K), dtype=torch.float32, device=dy_bf16.device)
+        accumulate = False
+    check(lib.crv_masked_linear_bwd_ds(_p(dy_bf16), _p(x_bf16), _p(w_bf16), _p(out), int(bool(accumulate)),
+                                       M, N, K, _stream()), "crv_masked_linear_bwd_ds")
+    return out
+
+
+_kth_ws = {}
+
+
+def kth_value_batched(tensors, ks, use_abs=False):
+    """Exact k-th smallest (1-based) of each fp32 CUDA tensor; returns a float32 device vector."""
+    count = len(tensors)
+    if count == 0:
+        raise ValueError("no segments")
+    _need_cuda(*tensors)
+    dev = tensors[0].device
+    flat = [t.detach().reshape(-1) for t in tensors]
+    for t in flat:
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("kth_value_batched needs contiguous float32 tensors")
+    ptrs = (ctypes.c_void_p * count)(*[t.data_ptr() for t in flat])
+    ns = (ctypes.c_longlong * count)(*[t.numel() for t in flat])
+    kk = (ctypes.c_longlong * count)(*[int(k) for k in ks])
+    nbytes = lib.crv_kth_value_workspace_bytes(count)
+    key = (dev, count)
+    ws = _kth_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _kth_ws[key] = ws
+    out = torch.empty(count, dtype=torch.float32, device=dev)
+    check(lib.crv_kth_value_batched(ptrs, ns, kk, count, int(bool(use_abs)), _p(out), _p(ws), nbytes, _stream()),
+          "crv_kth_value_batched")
+    return out
+
+
+def magnitude_init(weight, w_thr, hi, lo):
+    _need_cuda(weight)
+    w = weight.detach().contiguous()
+    out = torch.empty_like(w)
+    check(lib.crv_magnitude_init(_p(w), _p(as_thr(w_thr, w.device)), float(hi), float(lo), _p(out), w.numel(),
+                                 _stream()), "crv_magnitude_init")
+    return out
+
+
+class MaskedLinearFn(torch.autograd.Function):
+    """y = F.linear(x, weight * binarize(scores, thr), bias) with the straight-through score gradient.
+
+    forward : bf16 tcgen05 GEMM with the mask applied in the TMA-fed prologue (fp32 accumulate)
+    backward: dX = dY . (W (.) M)   and   dS = (dY^T . X) (.) W   (no dW, no db: weights are frozen,
+              masking/maskers.py:564-569,594-596)
+    """
+
+    @staticmethod
+    def forward(ctx, x, scores, w_bf16, thr, bias):
+        shp = x.shape
+        x2 = to_bf16(x.reshape(-1, shp[-1]))
+        thr_t = as_thr(thr, x.device)
+        y = masked_linear_fwd(x2, w_bf16, scores.detach(), thr_t, bias, torch.float32)
+        ctx.save_for_backward(x2, scores, w_bf16, thr_t)
+        ctx.x_shape = shp
+        ctx.need_dx = x.requires_grad
+        return y.view(*shp[:-1], w_bf16.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, scores, w_bf16, thr_t = ctx.saved_tensors
+        dy2 = to_bf16(dy.reshape(-1, dy.shape[-1]))
+        dx = None
+        if ctx.need_dx:
+            dx = masked_linear_bwd_dx(dy2, w_bf16, scores.detach(), thr_t, torch.float32).view(ctx.x_shape)
+        ds = masked_linear_bwd_ds(dy2, x2, w_bf16) if ctx.needs_input_grad[1] else None
+        return dx, ds, None, None, None
+
+
+class MaskedLinearSmallKFn(torch.autograd.Function):
+    """Same contract for inner dimensions TMA cannot take (box_fc, K = 4): exact fp32 SIMT kernels."""
+
+    @staticmethod
+    def forward(ctx, x, scores, weight, thr, bias):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous().float()
+        thr_t = as_thr(thr, x.device)
+        N, K = weight.shape
+        y = torch.empty((x2.shape[0], N), dtype=torch.float32, device=x.device)
+        check(lib.crv_masked_linear_small_k_fwd(_p(x2), _p(weight), _p(scores.detach()), _p(thr_t), _p(bias), _p(y),
+                                                x2.shape[0], N, K, _stream()), "crv_masked_linear_small_k_fwd")
+        ctx.save_for_backward(x2, scores, weight, thr_t)
+        ctx.x_shape = shp
+        ctx.need_dx = x.requires_grad
+        return y.view(*shp[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, scores, weight, thr_t = ctx.saved_tensors
+        N, K = weight.shape
+        dy2 = dy.reshape(-1, N).contiguous().float()
+        dx = torch.empty_like(x2) if ctx.need_dx else None
+        ds = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+        check(lib.crv_masked_linear_small_k_bwd(_p(dy2), _p(x2), _p(weight), _p(scores.detach()), _p(thr_t), _p(dx),
+                                                _p(ds), 0, x2.shape[0], N, K, _stream()),
+              "crv_masked_linear_small_k_bwd")
+        return (dx.view(ctx.x_shape) if dx is not None else None), ds, None, None, None
+
+
+class MaskedEmbeddingFn(torch.autograd.Function):
+    """F.embedding(ids, weight * binarize(scores, thr), padding_idx) without masking the whole table."""
+
+    @staticmethod
+    def forward(ctx, ids, scores, weight, thr, padding_idx):
+        _need_cuda(ids, scores, weight)
+        ids_c = ids.contiguous()
+        thr_t = as_thr(thr, scores.device)
+        vocab, dim = weight.shape
+        out = torch.empty((*ids.shape, dim), dtype=torch.float32, device=weight.device)
+        check(lib.crv_masked_embedding_fwd(_p(ids_c), _p(weight), _p(scores.detach()), _p(thr_t), _p(out),
+                                           ids_c.numel(), vocab, dim, _stream()), "crv_masked_embedding_fwd")
+        ctx.save_for_backward(ids_c, weight)
+        ctx.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ids_c, weight = ctx.saved_tensors
+        vocab, dim = weight.shape
+        ds = torch.zeros((vocab, dim), dtype=torch.float32, device=weight.device)
+        d = dout.contiguous().float()
+        check(lib.crv_masked_embedding_bwd(_p(ids_c), _p(d), _p(weight), _p(ds), ids_c.numel(), vocab, dim,
+                                           ctx.padding_idx, _stream()), "crv_masked_embedding_bwd")
+        return None, ds, None, None, None
+
+
+# ----------------------------------------------------------------------------- losses
+def _loss_ws(B, device):
+    return torch.empty(3 * B, dtype=torch.float32, device=device)
+
+
+class _FusedLoss(torch.autograd.Function):
+    """Common shell: forward runs the fused fwd+bwd kernel and stashes the gradients."""
+
+    @staticmethod
+    def forward(ctx, kind, logits, *args):
+        _need_cuda(logits)
+        B, A = logits.shape
+        lg = logits.detach().contiguous().float()
+        out = torch.empty(2, dtype=torch.float32, device=lg.device)
+        dl = torch.empty_like(lg)
+        ws = _loss_ws(B, lg.device)
+        dfac = None
+        if kind == "bce":
+            (labels,) = args
+            check(lib.crv_vqa_loss_bce(_p(lg), _p(labels.contiguous()), _p(out), _p(dl), B, A, _p(ws), _stream()),
+                  "crv_vqa_loss_bce")
+        elif kind == "lpf":
+            bias, max_label, gamma, labels = args
+            check(lib.crv_vqa_loss_lpf(_p(lg), _p(bias.contiguous()), _p(max_label.contiguous()), float(gamma),
+                                       _p(out), _p(labels.contiguous() if labels is not None else None), _p(dl),
+                                       B, A, _p(ws), _stream()), "crv_vqa_loss_lpf")
+        elif kind == "lmh":
+            bias, labels, factor_pre, smooth, w = args
+            fp = factor_pre.detach().contiguous().float().view(-1)
+            dfac = torch.empty_like(fp)
+            check(lib.crv_vqa_loss_lmh(_p(lg), _p(bias.contiguous()), _p(labels.contiguous()), _p(fp), float(smooth),
+                                       float(w), _p(out), _p(dl), _p(dfac), B, A, _p(ws), _stream()),
+                  "crv_vqa_loss_lmh")
+            ctx.fshape = factor_pre.shape
+        else:
+            raise ValueError(kind)
+        ctx.kind = kind
+        ctx.nargs = len(args)
+        ctx.save_for_backward(dl, dfac) if dfac is not None else ctx.save_for_backward(dl)
+        ctx.mark_non_differentiable(out[1:])
+        loss = out[0]
+        score = out[1].detach()
+        return loss, score
+
+    @staticmethod
+    def backward(ctx, gloss, gscore):
+        saved = ctx.saved_tensors
+        dl = saved[0] * gloss
+        grads = [None, dl] + [None] * ctx.nargs
+        if ctx.kind == "lmh":
+            grads[2 + 2] = (saved[1] * gloss).view(ctx.fshape)  # factor_pre is the 3rd extra argument
+        return tuple(grads)
+
+
+def vqa_loss_bce(logits, labels):
+    """(loss, batch_score): instance_bce_with_logits (modeling_lxmert.py:248-253) + VQA score."""
+    return _FusedLoss.apply("bce", logits, labels)
+
+
+def vqa_loss_lpf(logits, bias, max_label, gamma, labels=None):
+    """LPF_loss (mask_trainer_VQA.py:111-129) + VQA score (needs labels)."""
+    return _FusedLoss.apply("lpf", logits, bias, max_label, gamma, labels)
+
+
+def vqa_loss_lmh(logits, bias, labels, factor_pre, smooth, w):
+    """LearnedMixin (vqa_debias_loss_functions.py:148-196); factor_pre = bias_lin(pooled), pre-softplus."""
+    return _FusedLoss.apply("lmh", logits, bias, labels, factor_pre, smooth, w)
+
+
+# ----------------------------------------------------------------------------- optimiser pieces
+def sumsq_into(x, acc):
+    check(lib.crv_sumsq(_p(x), x.numel(), _p(acc), _stream()), "crv_sumsq")
+
+
+def adamw_step_flat(p, g, m, v, s, lr, step, beta1, beta2, eps, weight_decay, total_sumsq=None, max_norm=1.0,
+                    correct_bias=True):
+    step_size = lr
+    if correct_bias:
+        step_size = lr * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
+    check(lib.crv_adamw_step(_p(p), _p(g), _p(m), _p(v), _p(s), p.numel(), float(lr), float(step_size),
+                             float(beta1), float(beta2), float(eps), float(weight_decay), _p(total_sumsq),
+                             float(max_norm), _stream()), "crv_adamw_step")

@@ -1,0 +1,415 @@
+// Streaming (HBM-bound) kernels: operand casts, binariser, mask application, magnitude init,
+// gradient-norm partial sums and the fused clip+AdamW update.  All are grid-stride loops over
+// 16-byte vectors, launched with a multiple of the SM count.
+#include "common.cuh"
+
+namespace crv {
+
+thread_local int g_last_cuda_error = 0;
+
+constexpr int kThreads = 256;
+
+static inline int stream_grid(int64_t nvec, int per_sm = 8) {
+  int64_t blocks = (nvec + kThreads - 1) / kThreads;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t n) {
+  const int64_t nvec = n >> 3;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    reinterpret_cast<uint4*>(dst)[i] =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const int64_t i = (nvec << 3) + threadIdx.x;
+    __nv_bfloat16 t = __float2bfloat16_rn(src[i]);
+    dst[i] = *reinterpret_cast<uint16_t*>(&t);
+  }
+}
+
+__global__ void binarize_kernel(const float* __restrict__ s, const float* __restrict__ thr_p,
+                                float* __restrict__ mf, uint8_t* __restrict__ mb, long long* __restrict__ kept,
+                                int64_t n) {
+  const float thr = __ldg(thr_p);
+  const int64_t nvec = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  long long local = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(s) + i);
+    const bool k0 = v.x > thr, k1 = v.y > thr, k2 = v.z > thr, k3 = v.w > thr;
+    if (mf) reinterpret_cast<float4*>(mf)[i] = make_float4(k0 ? 1.f : 0.f, k1 ? 1.f : 0.f, k2 ? 1.f : 0.f, k3 ? 1.f : 0.f);
+    if (mb) reinterpret_cast<uchar4*>(mb)[i] = make_uchar4(k0, k1, k2, k3);
+    local += int(k0) + int(k1) + int(k2) + int(k3);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (nvec << 2) + threadIdx.x;
+    const bool k = s[i] > thr;
+    if (mf) mf[i] = k ? 1.f : 0.f;
+    if (mb) mb[i] = k;
+    local += int(k);
+  }
+  if (kept) {
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    __shared__ long long wsum[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long t = 0;
+      for (int w = 0; w < kThreads / 32; ++w) t += wsum[w];
+      if (t) atomicAdd(reinterpret_cast<unsigned long long*>(kept), static_cast<unsigned long long>(t));
+    }
+  }
+}
+
+__global__ void apply_mask_kernel(const uint16_t* __restrict__ w, const float* __restrict__ s,
+                                  const float* __restrict__ thr_p, uint16_t* __restrict__ wm, int64_t n) {
+  const float thr = __ldg(thr_p);
+  const int64_t nvec = n >> 3;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(s) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(s) + 2 * i + 1);
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(w) + i);
+    v.x &= (a.x > thr ? 0x0000FFFFu : 0u) | (a.y > thr ? 0xFFFF0000u : 0u);
+    v.y &= (a.z > thr ? 0x0000FFFFu : 0u) | (a.w > thr ? 0xFFFF0000u : 0u);
+    v.z &= (b.x > thr ? 0x0000FFFFu : 0u) | (b.y > thr ? 0xFFFF0000u : 0u);
+    v.w &= (b.z > thr ? 0x0000FFFFu : 0u) | (b.w > thr ? 0xFFFF0000u : 0u);
+    reinterpret_cast<uint4*>(wm)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const int64_t i = (nvec << 3) + threadIdx.x;
+    wm[i] = s[i] > thr ? w[i] : uint16_t(0);
+  }
+}
+
+__global__ void magnitude_init_kernel(const float* __restrict__ w, const float* __restrict__ thr_p, float hi,
+                                      float lo, float* __restrict__ s, int64_t n) {
+  const float thr = __ldg(thr_p);
+  const int64_t nvec = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(w) + i);
+    reinterpret_cast<float4*>(s)[i] = make_float4(fabsf(v.x) > thr ? hi : lo, fabsf(v.y) > thr ? hi : lo,
+                                                  fabsf(v.z) > thr ? hi : lo, fabsf(v.w) > thr ? hi : lo);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (nvec << 2) + threadIdx.x;
+    s[i] = fabsf(w[i]) > thr ? hi : lo;
+  }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  const int64_t nvec = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float v = x[(nvec << 2) + threadIdx.x];
+    acc += v * v;
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float wsum[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) t += wsum[w];
+    atomicAdd(out, t);
+  }
+}
+
+struct AdamArgs {
+  float lr, step_size, beta1, beta2, eps, weight_decay, max_norm;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float* sum, const AdamArgs& a,
+                                         float clip) {
+  g *= clip;
+  if (sum) *sum += fabsf(g);
+  m = m * a.beta1 + (1.0f - a.beta1) * g;
+  v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+  const float denom = sqrtf(v) + a.eps;
+  p = p - a.step_size * (m / denom);
+  if (a.weight_decay > 0.f) p = p - a.lr * a.weight_decay * p;
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, float* __restrict__ sum, int64_t n, AdamArgs a,
+                             const float* __restrict__ total_sumsq) {
+  float clip = 1.0f;
+  if (total_sumsq) {
+    // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+    const float c = a.max_norm / (sqrtf(__ldg(total_sumsq)) + 1e-6f);
+    clip = c < 1.0f ? c : 1.0f;
+  }
+  const int64_t nvec = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float4 ss = sum ? reinterpret_cast<float4*>(sum)[i] : make_float4(0, 0, 0, 0);
+    adam_one(pp.x, gg.x, mm.x, vv.x, sum ? &ss.x : nullptr, a, clip);
+    adam_one(pp.y, gg.y, mm.y, vv.y, sum ? &ss.y : nullptr, a, clip);
+    adam_one(pp.z, gg.z, mm.z, vv.z, sum ? &ss.z : nullptr, a, clip);
+    adam_one(pp.w, gg.w, mm.w, vv.w, sum ? &ss.w : nullptr, a, clip);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (sum) reinterpret_cast<float4*>(sum)[i] = ss;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (nvec << 2) + threadIdx.x;
+    adam_one(p[i], g[i], m[i], v[i], sum ? sum + i : nullptr, a, clip);
+  }
+}
+
+// ------------------------------------------------------------------ tiny-K masked linear (box_fc, K = 4)
+__global__ void small_k_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                   const float* __restrict__ s, const float* __restrict__ thr_p,
+                                   const float* __restrict__ bias, float* __restrict__ y, int M, int N, int K) {
+  const float thr = s ? __ldg(thr_p) : 0.f;
+  const int64_t total = static_cast<int64_t>(M) * N;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(idx / N), n = static_cast<int>(idx % N);
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float wv = (!s || s[static_cast<int64_t>(n) * K + k] > thr) ? w[static_cast<int64_t>(n) * K + k] : 0.f;
+      acc = fmaf(x[static_cast<int64_t>(m) * K + k], wv, acc);
+    }
+    y[idx] = acc + (bias ? bias[n] : 0.f);
+  }
+}
+
+// dS[n,k] (+)= (sum_m dY[m,n] X[m,k]) * W[n,k]; one block per n, threads stride over m
+__global__ void small_k_bwd_ds_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                      const float* __restrict__ w, float* __restrict__ ds, int accumulate, int M,
+                                      int N, int K) {
+  extern __shared__ float red[];  // [blockDim.x / 32][K]
+  const int n = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int kc = min(8, K - k0);
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+      const float d = dy[static_cast<int64_t>(m) * N + n];
+      for (int k = 0; k < kc; ++k) acc[k] = fmaf(d, x[static_cast<int64_t>(m) * K + k0 + k], acc[k]);
+    }
+    for (int k = 0; k < kc; ++k) {
+      float v = acc[k];
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[wid * 8 + k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kc) {
+      float t = 0.f;
+      for (int i = 0; i < nw; ++i) t += red[i * 8 + threadIdx.x];
+      const int64_t o = static_cast<int64_t>(n) * K + k0 + threadIdx.x;
+      const float val = t * w[o];
+      ds[o] = accumulate ? ds[o] + val : val;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void small_k_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                      const float* __restrict__ s, const float* __restrict__ thr_p,
+                                      float* __restrict__ dx, int M, int N, int K) {
+  const float thr = s ? __ldg(thr_p) : 0.f;
+  const int64_t total = static_cast<int64_t>(M) * K;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(idx / K), k = static_cast<int>(idx % K);
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const int64_t o = static_cast<int64_t>(n) * K + k;
+      const float wv = (!s || s[o] > thr) ? w[o] : 0.f;
+      acc = fmaf(dy[static_cast<int64_t>(m) * N + n], wv, acc);
+    }
+    dx[idx] = acc;
+  }
+}
+
+// ------------------------------------------------------------------ masked embedding
+__global__ void embedding_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ w,
+                                     const float* __restrict__ s, const float* __restrict__ thr_p,
+                                     float* __restrict__ out, int64_t n_tokens, int64_t vocab, int dim) {
+  const float thr = __ldg(thr_p);
+  const int vec = dim >> 2;
+  for (int64_t t = blockIdx.x; t < n_tokens; t += gridDim.x) {
+    const long long id = ids[t];
+    const bool ok = id >= 0 && id < vocab;
+    const float4* wr = reinterpret_cast<const float4*>(w + (ok ? id : 0) * dim);
+    const float4* sr = reinterpret_cast<const float4*>(s + (ok ? id : 0) * dim);
+    float4* o = reinterpret_cast<float4*>(out + t * dim);
+    for (int i = threadIdx.x; i < vec; i += blockDim.x) {
+      float4 wv = __ldg(wr + i);
+      const float4 sv = __ldg(sr + i);
+      wv.x = (ok && sv.x > thr) ? wv.x : 0.f;
+      wv.y = (ok && sv.y > thr) ? wv.y : 0.f;
+      wv.z = (ok && sv.z > thr) ? wv.z : 0.f;
+      wv.w = (ok && sv.w > thr) ? wv.w : 0.f;
+      o[i] = wv;
+    }
+  }
+}
+
+__global__ void embedding_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dout,
+                                     const float* __restrict__ w, float* __restrict__ ds, int64_t n_tokens,
+                                     int64_t vocab, int dim, long long padding_idx) {
+  for (int64_t t = blockIdx.x; t < n_tokens; t += gridDim.x) {
+    const long long id = ids[t];
+    if (id < 0 || id >= vocab || id == padding_idx) continue;
+    const float* wr = w + id * dim;
+    const float* gr = dout + t * dim;
+    float* dr = ds + id * dim;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) atomicAdd(dr + i, gr[i] * wr[i]);
+  }
+}
+
+}  // namespace crv
+
+using namespace crv;
+
+extern "C" int crv_version(void) { return 1; }
+
+extern "C" const char* crv_error_string(int code) {
+  switch (code) {
+    case CRV_OK: return "ok";
+    case CRV_E_BADARG: return "bad argument (null pointer or non-positive size)";
+    case CRV_E_ALIGN: return "pointer or leading dimension not 16-byte aligned";
+    case CRV_E_SHAPE: return "shape not supported by this entry point";
+    case CRV_E_WORKSPACE: return "workspace too small";
+    case CRV_E_DRIVER: return "cuTensorMapEncodeTiled driver entry point unavailable";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown error";
+  }
+}
+
+extern "C" int crv_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" int crv_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream) {
+  if (!src || !dst || n < 0) return CRV_E_BADARG;
+  if (n == 0) return CRV_OK;
+  if (!aligned16(src) || !aligned16(dst)) return CRV_E_ALIGN;
+  cast_f32_bf16_kernel<<<stream_grid(n >> 3), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n);
+  return launch_status();
+}
+
+extern "C" int crv_binarize(const float* scores, const float* thr, float* mask_f32, uint8_t* mask_u8,
+                            long long* kept_count, int64_t n, void* stream) {
+  if (!scores || !thr || n < 0) return CRV_E_BADARG;
+  if (n == 0) return CRV_OK;
+  if (!aligned16(scores) || (mask_f32 && !aligned16(mask_f32)) || (mask_u8 && (reinterpret_cast<uintptr_t>(mask_u8) & 3)))
+    return CRV_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (kept_count) CRV_CUDA(cudaMemsetAsync(kept_count, 0, sizeof(long long), st));
+  binarize_kernel<<<stream_grid(n >> 2), kThreads, 0, st>>>(scores, thr, mask_f32, mask_u8, kept_count, n);
+  return launch_status();
+}
+
+extern "C" int crv_apply_mask_bf16(const uint16_t* w, const float* scores, const float* thr, uint16_t* wm,
+                                   int64_t n, void* stream) {
+  if (!w || !scores || !thr || !wm || n < 0) return CRV_E_BADARG;
+  if (n == 0) return CRV_OK;
+  if (!aligned16(w) || !aligned16(scores) || !aligned16(wm)) return CRV_E_ALIGN;
+  apply_mask_kernel<<<stream_grid(n >> 3), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(w, scores, thr, wm, n);
+  return launch_status();
+}
+
+extern "C" int crv_magnitude_init(const float* w, const float* w_thr, float hi, float lo, float* scores, int64_t n,
+                                  void* stream) {
+  if (!w || !w_thr || !scores || n < 0) return CRV_E_BADARG;
+  if (n == 0) return CRV_OK;
+  if (!aligned16(w) || !aligned16(scores)) return CRV_E_ALIGN;
+  magnitude_init_kernel<<<stream_grid(n >> 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(w, w_thr, hi, lo,
+                                                                                                  scores, n);
+  return launch_status();
+}
+
+extern "C" int crv_sumsq(const float* x, int64_t n, float* out, void* stream) {
+  if (!x || !out || n < 0) return CRV_E_BADARG;
+  if (n == 0) return CRV_OK;
+  if (!aligned16(x)) return CRV_E_ALIGN;
+  sumsq_kernel<<<stream_grid(n >> 2, 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out);
+  return launch_status();
+}
+
+extern "C" int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int64_t n, float lr,
+                              float step_size, float beta1, float beta2, float eps, float weight_decay,
+                              const float* total_sumsq, float max_norm, void* stream) {
+  if (!p || !g || !m || !v || n < 0) return CRV_E_BADARG;
+  if (n == 0) return CRV_OK;
+  if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (sum && !aligned16(sum))) return CRV_E_ALIGN;
+  AdamArgs a{lr, step_size, beta1, beta2, eps, weight_decay, max_norm};
+  adamw_kernel<<<stream_grid(n >> 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, sum, n, a,
+                                                                                         total_sumsq);
+  return launch_status();
+}
+
+extern "C" int crv_masked_linear_small_k_fwd(const float* x, const float* w, const float* scores, const float* thr,
+                                             const float* bias, float* y, int M, int N, int K, void* stream) {
+  if (!x || !w || !y || M <= 0 || N <= 0 || K <= 0) return CRV_E_BADARG;
+  if (scores && !thr) return CRV_E_BADARG;
+  if (K > 64) return CRV_E_SHAPE;
+  const int64_t total = static_cast<int64_t>(M) * N;
+  small_k_fwd_kernel<<<stream_grid(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, w, scores, thr, bias,
+                                                                                              y, M, N, K);
+  return launch_status();
+}
+
+extern "C" int crv_masked_linear_small_k_bwd(const float* dy, const float* x, const float* w, const float* scores,
+                                             const float* thr, float* dx, float* dscores, int accumulate, int M,
+                                             int N, int K, void* stream) {
+  if (!dy || !x || !w || !dscores || M <= 0 || N <= 0 || K <= 0) return CRV_E_BADARG;
+  if (scores && !thr) return CRV_E_BADARG;
+  if (K > 64) return CRV_E_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  small_k_bwd_ds_kernel<<<N, 256, (256 / 32) * 8 * sizeof(float), st>>>(dy, x, w, dscores, accumulate, M, N, K);
+  int rc = launch_status();
+  if (rc) return rc;
+  if (dx) {
+    const int64_t total = static_cast<int64_t>(M) * K;
+    small_k_bwd_dx_kernel<<<stream_grid(total), kThreads, 0, st>>>(dy, w, scores, thr, dx, M, N, K);
+    rc = launch_status();
+  }
+  return rc;
+}
+
+extern "C" int crv_masked_embedding_fwd(const long long* ids, const float* w, const float* scores, const float* thr,
+                                        float* out, int64_t n_tokens, int64_t vocab, int dim, void* stream) {
+  if (!ids || !w || !scores || !thr || !out || n_tokens < 0 || vocab <= 0 || dim <= 0) return CRV_E_BADARG;
+  if (n_tokens == 0) return CRV_OK;
+  if (dim % 4) return CRV_E_SHAPE;
+  if (!aligned16(w) || !aligned16(scores) || !aligned16(out)) return CRV_E_ALIGN;
+  const int grid = static_cast<int>(n_tokens < 16 * num_sms() ? n_tokens : 16 * num_sms());
+  embedding_fwd_kernel<<<grid, 192, 0, static_cast<cudaStream_t>(stream)>>>(ids, w, scores, thr, out, n_tokens, vocab,
+                                                                             dim);
+  return launch_status();
+}
+
+extern "C" int crv_masked_embedding_bwd(const long long* ids, const float* dout, const float* w, float* dscores,
+                                        int64_t n_tokens, int64_t vocab, int dim, long long padding_idx,
+                                        void* stream) {
+  if (!ids || !dout || !w || !dscores || n_tokens < 0 || vocab <= 0 || dim <= 0) return CRV_E_BADARG;
+  if (n_tokens == 0) return CRV_OK;
+  const int grid = static_cast<int>(n_tokens < 16 * num_sms() ? n_tokens : 16 * num_sms());
+  embedding_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, dout, w, dscores, n_tokens, vocab, dim,
+                                                                             padding_idx);
+  return launch_status();
+}

@@ -1,0 +1,301 @@
+"""LXMERT for VQA: the module tree whose Linear / Embedding call sites stage 2 masks.
+
+Reference: hg_transformers/modeling_lxmert.py (embeddings :729-767, attention :770-827, layers
+:830-1037, encoder :1041-1120, pooler :1123-1135, LxmertModel :1316-1448,
+LxmertForMultipleChoice :233-360).  Module and parameter names are kept identical so that
+``chain_module_names`` finds the same 168 modules, reference checkpoints load, and the same
+``torch.manual_seed`` reproduces the reference's random init (construction order and the two
+``init_weights`` passes are mirrored).  Everything between the masked GEMMs is plain PyTorch here
+("next" row f3 of SURVEY.md section 8); the Linear/Embedding modules are swapped for CUDA-backed
+``MaskedLinear1`` objects by ``masking.maskers*.Masker.patch_modules``.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .classifier import SimpleClassifier
+from .configuration_lxmert import LxmertConfig  # noqa: F401  (re-export)
+
+
+def _act(name):
+    if name == "gelu":
+        return F.gelu
+    if name == "relu":
+        return F.relu
+    raise KeyError(name)
+
+
+class LxmertEmbeddings(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(config.vocab_size, config.hidden_size, padding_idx=0)
+        self.position_embeddings = nn.Embedding(config.max_position_embeddings, config.hidden_size, padding_idx=0)
+        self.token_type_embeddings = nn.Embedding(config.type_vocab_size, config.hidden_size, padding_idx=0)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=1e-12)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+
+    def forward(self, input_ids, token_type_ids=None):
+        t = input_ids.size(1)
+        pos = torch.arange(t, dtype=torch.long, device=input_ids.device).unsqueeze(0).expand_as(input_ids)
+        if token_type_ids is None:
+            token_type_ids = torch.zeros_like(input_ids)
+        e = self.word_embeddings(input_ids) + self.position_embeddings(pos) + self.token_type_embeddings(token_type_ids)
+        return self.dropout(self.LayerNorm(e))
+
+
+class LxmertAttention(nn.Module):
+    def __init__(self, config, ctx_dim=None):
+        super().__init__()
+        h = config.hidden_size
+        if h % config.num_attention_heads:
+            raise ValueError("hidden size must be a multiple of the number of heads")
+        self.num_attention_heads = config.num_attention_heads
+        self.attention_head_size = h // config.num_attention_heads
+        self.head_size = h
+        ctx_dim = h if ctx_dim is None else ctx_dim
+        self.query = nn.Linear(h, h)
+        self.key = nn.Linear(ctx_dim, h)
+        self.value = nn.Linear(ctx_dim, h)
+        self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
+
+    def _heads(self, x):
+        b, s, _ = x.shape
+        return x.view(b, s, self.num_attention_heads, self.attention_head_size).permute(0, 2, 1, 3)
+
+    def forward(self, hidden_states, context, attention_mask=None):
+        q = self._heads(self.query(hidden_states))
+        k = self._heads(self.key(context))
+        v = self._heads(self.value(context))
+        scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(self.attention_head_size)
+        if attention_mask is not None:
+            scores = scores + attention_mask
+        probs = self.dropout(F.softmax(scores, dim=-1))
+        ctx = torch.matmul(probs, v).permute(0, 2, 1, 3).contiguous()
+        return ctx.view(ctx.size(0), ctx.size(1), self.head_size)
+
+
+class LxmertAttentionOutput(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=1e-12)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+
+    def forward(self, hidden_states, input_tensor):
+        return self.LayerNorm(self.dropout(self.dense(hidden_states)) + input_tensor)
+
+
+class LxmertCrossAttentionLayer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.att = LxmertAttention(config)
+        self.output = LxmertAttentionOutput(config)
+
+    def forward(self, input_tensor, ctx_tensor, ctx_att_mask=None):
+        return self.output(self.att(input_tensor, ctx_tensor, ctx_att_mask), input_tensor)
+
+
+class LxmertSelfAttentionLayer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.self = LxmertAttention(config)
+        self.output = LxmertAttentionOutput(config)
+
+    def forward(self, input_tensor, attention_mask=None):
+        return self.output(self.self(input_tensor, input_tensor, attention_mask), input_tensor)
+
+
+class LxmertIntermediate(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.intermediate_size)
+        self.intermediate_act_fn = _act(config.hidden_act)
+
+    def forward(self, hidden_states):
+        return self.intermediate_act_fn(self.dense(hidden_states))
+
+
+class LxmertOutput(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.intermediate_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=1e-12)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+
+    def forward(self, hidden_states, input_tensor):
+        return self.LayerNorm(self.dropout(self.dense(hidden_states)) + input_tensor)
+
+
+class LxmertLayer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.attention = LxmertSelfAttentionLayer(config)
+        self.intermediate = LxmertIntermediate(config)
+        self.output = LxmertOutput(config)
+
+    def forward(self, hidden_states, attention_mask=None):
+        a = self.attention(hidden_states, attention_mask)
+        return self.output(self.intermediate(a), a)
+
+
+class LxmertXLayer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.visual_attention = LxmertCrossAttentionLayer(config)
+        self.lang_self_att = LxmertSelfAttentionLayer(config)
+        self.visn_self_att = LxmertSelfAttentionLayer(config)
+        self.lang_inter = LxmertIntermediate(config)
+        self.lang_output = LxmertOutput(config)
+        self.visn_inter = LxmertIntermediate(config)
+        self.visn_output = LxmertOutput(config)
+
+    def forward(self, lang, lang_mask, visn, visn_mask):
+        # the SAME cross-attention module serves both directions (reference :947-958), so its four
+        # masked Linears are invoked twice per forward and their score gradients add.
+        lang_x = self.visual_attention(lang, visn, ctx_att_mask=visn_mask)
+        visn_x = self.visual_attention(visn, lang, ctx_att_mask=lang_mask)
+        lang_s = self.lang_self_att(lang_x, lang_mask)
+        visn_s = self.visn_self_att(visn_x, visn_mask)
+        lang_o = self.lang_output(self.lang_inter(lang_s), lang_s)
+        visn_o = self.visn_output(self.visn_inter(visn_s), visn_s)
+        return lang_o, visn_o
+
+
+class LxmertVisualFeatureEncoder(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.visn_fc = nn.Linear(config.visual_feat_dim, config.hidden_size)
+        self.visn_layer_norm = nn.LayerNorm(config.hidden_size, eps=1e-12)
+        self.box_fc = nn.Linear(config.visual_pos_dim, config.hidden_size)
+        self.box_layer_norm = nn.LayerNorm(config.hidden_size, eps=1e-12)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+
+    def forward(self, visual_feats, visual_pos):
+        x = self.visn_layer_norm(self.visn_fc(visual_feats))
+        y = self.box_layer_norm(self.box_fc(visual_pos))
+        return self.dropout((x + y) / 2)
+
+
+class LxmertEncoder(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.visn_fc = LxmertVisualFeatureEncoder(config)
+        self.config = config
+        self.num_l_layers, self.num_x_layers, self.num_r_layers = config.l_layers, config.x_layers, config.r_layers
+        self.layer = nn.ModuleList([LxmertLayer(config) for _ in range(config.l_layers)])
+        self.x_layers = nn.ModuleList([LxmertXLayer(config) for _ in range(config.x_layers)])
+        self.r_layers = nn.ModuleList([LxmertLayer(config) for _ in range(config.r_layers)])
+
+    def forward(self, lang, lang_mask, visual_feats, visual_pos, visn_mask=None):
+        visn = self.visn_fc(visual_feats, visual_pos)
+        for blk in self.layer:
+            lang = blk(lang, lang_mask)
+        for blk in self.r_layers:
+            visn = blk(visn, visn_mask)
+        for blk in self.x_layers:
+            lang, visn = blk(lang, lang_mask, visn, visn_mask)
+        return lang, visn
+
+
+class LxmertPooler(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.activation = nn.Tanh()
+
+    def forward(self, hidden_states):
+        return self.activation(self.dense(hidden_states[:, 0]))
+
+
+class LxmertPreTrainedModel(nn.Module):
+    config_class = LxmertConfig
+    base_model_prefix = "lxmert"
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+
+    def _init_weights(self, module):
+        # reference :205-219 -- N(0, initializer_range) weights, zero biases, zero padding row
+        if isinstance(module, nn.Linear):
+            module.weight.data.normal_(mean=0.0, std=self.config.initializer_range)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.Embedding):
+            module.weight.data.normal_(mean=0.0, std=self.config.initializer_range)
+            if module.padding_idx is not None:
+                module.weight.data[module.padding_idx].zero_()
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+
+    def init_weights(self):
+        self.apply(self._init_weights)
+
+    def resize_token_embeddings(self, new_num_tokens=None):
+        emb = getattr(self, self.base_model_prefix, self).embeddings.word_embeddings
+        if new_num_tokens is None or new_num_tokens == emb.num_embeddings:
+            return emb
+        raise NotImplementedError("vocabulary resizing is outside the stage-2 path")
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+
+class LxmertModel(LxmertPreTrainedModel):
+    def __init__(self, config):
+        super().__init__(config)
+        self.embeddings = LxmertEmbeddings(config)
+        self.encoder = LxmertEncoder(config)
+        self.pooler = LxmertPooler(config)
+        self.init_weights()
+
+    def forward(self, input_ids=None, visual_feats=None, visual_pos=None, attention_mask=None,
+                visual_attention_mask=None, token_type_ids=None, **unused):
+        if input_ids is None:
+            raise ValueError("You have to specify input_ids")
+        if visual_feats is None:
+            raise ValueError("`visual_feats` cannot be `None`")
+        if visual_pos is None:
+            raise ValueError("`visual_pos` cannot be `None`")
+        lang_mask = None
+        if attention_mask is not None:
+            lang_mask = (1.0 - attention_mask[:, None, None, :].to(visual_feats.dtype)) * -10000.0
+        visn_mask = None
+        if visual_attention_mask is not None:
+            visn_mask = (1.0 - visual_attention_mask[:, None, None, :].to(visual_feats.dtype)) * -10000.0
+        emb = self.embeddings(input_ids, token_type_ids)
+        lang, visn = self.encoder(emb, lang_mask, visual_feats, visual_pos, visn_mask)
+        return lang, visn, self.pooler(lang)
+
+
+class LxmertForMultipleChoice(LxmertPreTrainedModel):
+    """(loss, logits, pooled) = model(ids, feats, pos, labels=target)  -- reference :233-360."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.lxmert = LxmertModel(config)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self.classifier = SimpleClassifier(in_dim=config.hidden_size, hid_dim=2 * config.hidden_size,
+                                           out_dim=config.ans_num, dropout=0.5, norm="weight", act="ReLU")
+        self.init_weights()
+
+    @staticmethod
+    def instance_bce_with_logits(logits, labels, reduction="mean"):
+        assert logits.dim() == 2
+        loss = F.binary_cross_entropy_with_logits(logits, labels, reduction=reduction)
+        if reduction == "mean":
+            loss = loss * labels.size(1)
+        return loss
+
+    def forward(self, input_ids=None, visual_feats=None, visual_pos=None, attention_mask=None,
+                visual_attention_mask=None, token_type_ids=None, labels=None, **unused):
+        _, _, pooled = self.lxmert(input_ids=input_ids, visual_feats=visual_feats, visual_pos=visual_pos,
+                                   attention_mask=attention_mask, visual_attention_mask=visual_attention_mask,
+                                   token_type_ids=token_type_ids)
+        logits = self.classifier(pooled)
+        loss = self.instance_bce_with_logits(logits, labels) if labels is not None else None
+        return loss, logits, pooled

@@ -1,0 +1,160 @@
+/* crvqa.h -- C ABI of libcrvqa.so: the sm_100a kernels behind the stage-2 mask-training hot path of
+ * Compress-Robust-VQA.
+ *
+ * The reference (PhoebusSi/Compress-Robust-VQA) is pure Python on PyTorch and has NO FFI layer of its
+ * own; the boundary it offers is the Python object protocol of
+ * masking/maskers*.py and hg_transformers/mask_trainer_*VQA.py.  Each entry point below therefore
+ * cites the reference *call site* (file:line, relative to the reference root) whose PyTorch library
+ * calls it replaces.  The Python mirror of the reference interface lives in
+ * compress-robust-vqa_b200/{masking,hg_transformers}/ and binds these symbols with ctypes
+ * (compress-robust-vqa_b200/crvqa/_lib.py); INTEGRATION.md shows the stub a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *   - the library never allocates or frees caller memory; scratch comes from a caller workspace whose
+ *     size is returned by the matching *_workspace_bytes() query
+ *   - return value: 0 = success, < 0 = argument error (CRV_E_*), > 0 = cudaError_t / CUresult
+ *   - row-major tensors; "bf16" = __nv_bfloat16 bit pattern in uint16_t; thresholds are passed as a
+ *     device pointer to one float so that no host synchronisation is ever needed
+ */
+#ifndef CRVQA_H_
+#define CRVQA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRV_OK 0
+#define CRV_E_BADARG (-1)   /* null pointer / non-positive size */
+#define CRV_E_ALIGN (-2)    /* pointer or leading dimension violates the stated alignment */
+#define CRV_E_SHAPE (-3)    /* shape not supported by this entry point */
+#define CRV_E_WORKSPACE (-4) /* workspace too small */
+#define CRV_E_DRIVER (-5)   /* CUDA driver entry point (tensor-map encode) unavailable */
+
+#define CRV_DTYPE_F32 0
+#define CRV_DTYPE_BF16 1
+
+/* Library / device info -------------------------------------------------------------------- */
+int crv_version(void);                       /* ABI version, currently 1 */
+const char* crv_error_string(int code);      /* static string for CRV_E_* codes; "cuda error" otherwise */
+int crv_last_cuda_error(void);               /* last cudaError_t / CUresult seen by this thread */
+
+/* Elementwise helpers ------------------------------------------------------------------------ */
+/* fp32 -> bf16 (round-to-nearest-even) operand conversion in front of the bf16 MMAs. */
+int crv_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);
+
+/* binarizer_fn1 (masking/maskers.py:325-329): mask[i] = scores[i] > *thr ? 1 : 0 (strict >),
+ * written as fp32 0/1 (mask_f32) and/or bytes (mask_u8) -- either may be NULL.  Also the body of
+ * Trainer.save_model_mask / Trainer.binarizer_fn1 (hg_transformers/mask_trainer_VQA.py:930-968).
+ * If kept_count != NULL, *kept_count (device, int64) receives the number of ones. */
+int crv_binarize(const float* scores, const float* thr, float* mask_f32, uint8_t* mask_u8,
+                 long long* kept_count, int64_t n, void* stream);
+
+/* Materialised masked weight  Wm = W (.) (S > *thr)  in bf16 -- the `self.weight * M_w` of
+ * MaskedLinear1.forward (masking/maskers.py:363-366) for callers that reuse one mask across calls. */
+int crv_apply_mask_bf16(const uint16_t* w_bf16, const float* scores, const float* thr, uint16_t* wm_bf16,
+                        int64_t n, void* stream);
+
+/* Masked linear (tcgen05 GEMMs) --------------------------------------------------------------- */
+/* Forward of MaskedLinear1 (masking/maskers.py:359-366 = _Binarizer1 + `weight * M_w` + F.linear):
+ *     Y[M,N] = X[M,K] . (W[N,K] (.) (S[N,K] > *thr))^T + bias[N]
+ * X, W bf16; S fp32; accumulation fp32; Y fp32 or bf16 (y_dtype).  The mask is applied to the W tile
+ * in shared memory between the TMA load and the MMA; no masked weight is materialised in HBM.
+ * scores == NULL means "W is already masked / dense" (plain bf16 GEMM).  bias may be NULL.
+ * Requirements: K % 8 == 0 (use crv_masked_linear_small_k otherwise), X/W/S 16-byte aligned. */
+int crv_masked_linear_fwd(const uint16_t* x_bf16, const uint16_t* w_bf16, const float* scores,
+                          const float* thr, const float* bias, void* y, int y_dtype, int M, int N, int K,
+                          void* stream);
+
+/* dX of the above (autograd of masking/maskers.py:365-366 with frozen weights, :564-569):
+ *     dX[M,K] = dY[M,N] . (W (.) (S > *thr))
+ * dY bf16; dX fp32 or bf16.  Requirements: N % 8 == 0, K % 8 == 0. */
+int crv_masked_linear_bwd_dx(const uint16_t* dy_bf16, const uint16_t* w_bf16, const float* scores,
+                             const float* thr, void* dx, int dx_dtype, int M, int N, int K, void* stream);
+
+/* Straight-through score gradient (autograd of masking/maskers.py:337-339,365-366):
+ *     dS[N,K] (+)= (dY[M,N]^T . X[M,K]) (.) W[N,K]
+ * The (.)W happens in the GEMM epilogue; accumulate != 0 adds into dS (second invocation of the
+ * shared cross-attention modules, hg_transformers/modeling_lxmert.py:947-958), otherwise dS is
+ * overwritten.  The reduction over M may be split across CTAs (fp32 atomics).
+ * Requirements: N % 8 == 0, K % 8 == 0. */
+int crv_masked_linear_bwd_ds(const uint16_t* dy_bf16, const uint16_t* x_bf16, const uint16_t* w_bf16,
+                             float* dscores, int accumulate, int M, int N, int K, void* stream);
+
+/* Same three operations for inner dimensions the TMA path cannot take (box_fc has K = 4,
+ * hg_transformers/modeling_lxmert.py:1025): fp32 in / fp32 out SIMT kernels, exact fp32 math. */
+int crv_masked_linear_small_k_fwd(const float* x, const float* w, const float* scores, const float* thr,
+                                  const float* bias, float* y, int M, int N, int K, void* stream);
+int crv_masked_linear_small_k_bwd(const float* dy, const float* x, const float* w, const float* scores,
+                                  const float* thr, float* dx /* may be NULL */, float* dscores,
+                                  int accumulate, int M, int N, int K, void* stream);
+
+/* Masked embedding ---------------------------------------------------------------------------- */
+/* `F.embedding(x, self.weight * M_w, padding_idx)` branch of MaskedLinear1.forward
+ * (masking/maskers.py:362-363): out[t,:] = W[ids[t],:] (.) (S[ids[t],:] > *thr), fp32, without masking
+ * the whole table. */
+int crv_masked_embedding_fwd(const long long* ids, const float* w, const float* scores, const float* thr,
+                             float* out, int64_t n_tokens, int64_t vocab, int dim, void* stream);
+/* backward: dS[ids[t],:] += dOut[t,:] (.) W[ids[t],:] for ids[t] != padding_idx (pass -1 for none);
+ * rows never looked up stay untouched, so the caller zeroes dS (or accumulates). */
+int crv_masked_embedding_bwd(const long long* ids, const float* dout, const float* w, float* dscores,
+                             int64_t n_tokens, int64_t vocab, int dim, long long padding_idx, void* stream);
+
+/* Thresholds: exact k-th smallest value --------------------------------------------------------- */
+/* Trainer.reset_threshold (hg_transformers/mask_trainer_Robust_VQA.py:467-482,
+ * mask_trainer_VQA.py:470-477): for every segment i, thr_out[i] = k[i]-th smallest (1-based, as
+ * torch.kthvalue) of the n[i] floats at ptrs[i]; use_abs != 0 selects on |x| instead (magnitude
+ * init).  ptrs/n/k are HOST arrays of length count; thr_out is a device array of `count` floats.
+ * NaNs order above +inf (torch semantics). */
+size_t crv_kth_value_workspace_bytes(int count);
+int crv_kth_value_batched(const float* const* ptrs_host, const long long* n_host, const long long* k_host,
+                          int count, int use_abs, float* thr_out, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* MaskedLinearX.controlled_init._magnitude (masking/maskers.py:204-215):
+ *     S[i] = |W[i]| > *w_thr ? hi : lo      (hi = 2*threshold, lo = 0*threshold in the reference) */
+int crv_magnitude_init(const float* w, const float* w_thr, float hi, float lo, float* scores, int64_t n,
+                       void* stream);
+
+/* Losses over the answer head ------------------------------------------------------------------- */
+/* All three: logits/labels/bias are [B, A] fp32 row-major; outputs: loss_out[0] = scalar loss,
+ * loss_out[1] = batch VQA score sum_b labels[b, argmax_a logits[b,a]]
+ * (compute_score_with_logits, hg_transformers/data/metrics/__init__.py:90-104); dlogits[B, A] =
+ * d loss / d logits.  workspace: crv_vqa_loss_workspace_bytes(B). */
+size_t crv_vqa_loss_workspace_bytes(int B);
+/* instance_bce_with_logits (hg_transformers/modeling_lxmert.py:248-253): mean BCE * A. */
+int crv_vqa_loss_bce(const float* logits, const float* labels, float* loss_out, float* dlogits, int B, int A,
+                     void* workspace, void* stream);
+/* LPF_loss (hg_transformers/mask_trainer_VQA.py:111-129): mean_b (1-q[b,y])^gamma * -log p[b,y]. */
+int crv_vqa_loss_lpf(const float* logits, const float* bias, const long long* max_label, float gamma,
+                     float* loss_out, const float* labels /* for the score; may be NULL */, float* dlogits,
+                     int B, int A, void* workspace, void* stream);
+/* LearnedMixin.forward (hg_transformers/vqa_debias_loss_functions.py:148-196) with entropy weight w:
+ * factor_pre[B] = bias_lin(pooled) (pre-softplus), smooth = sigmoid(smooth_param) + constant_smooth.
+ * Outputs dlogits[B,A] and dfactor_pre[B] (gradient w.r.t. the pre-softplus factor). */
+int crv_vqa_loss_lmh(const float* logits, const float* bias, const float* labels, const float* factor_pre,
+                     float smooth, float w, float* loss_out, float* dlogits, float* dfactor_pre, int B, int A,
+                     void* workspace, void* stream);
+
+/* Optimiser ("next" row f1; hg_transformers/mask_trainer_VQA.py:646-659 + optimization.py:66-129) */
+/* sum of squares of n floats accumulated into *out (device, fp32; caller zeroes it) */
+int crv_sumsq(const float* x, int64_t n, float* out, void* stream);
+/* One AdamW step of the reference optimiser on a flat fp32 segment, with the clip coefficient of
+ * torch.nn.utils.clip_grad_norm_ folded in:  g' = g * min(1, max_norm / (sqrt(*total_sumsq) + 1e-6));
+ * sum += |g'|; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= step_size * m / (sqrt(v) + eps);
+ * p -= lr * weight_decay * p.  step_size = lr * sqrt(1-b2^t)/(1-b1^t) is computed by the caller.
+ * total_sumsq may be NULL (no clipping).  `sum` may be NULL.  If wm_bf16 != NULL the refreshed masked
+ * weight (W (.) (p_new > *thr)) is emitted in the same pass. */
+int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int64_t n, float lr,
+                   float step_size, float beta1, float beta2, float eps, float weight_decay,
+                   const float* total_sumsq, float max_norm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRVQA_H_ */

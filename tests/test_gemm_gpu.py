@@ -1,0 +1,72 @@
+"""Kernel-level parity of the three tcgen05 masked GEMMs against fp32 torch math on the SAME
+bf16-rounded operands (so the only difference is fp32 accumulation order; tolerance 2e-3 relative to
+the output scale, as BASELINE.json's north_star states)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(M, N, K, seed, rate=0.7):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) * 0.02
+    s = torch.rand(N, K, generator=g) * 0.02
+    s[torch.rand(N, K, generator=g) < 0.3] = 0.0          # ties at 0, like the magnitude init
+    thr = torch.tensor(0.02 * rate * 0.5)
+    b = torch.randn(N, generator=g)
+    dy = torch.randn(M, N, generator=g)
+    dev = torch.device("cuda")
+    return [t.to(dev) for t in (x, w, s, thr, b, dy)]
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+SHAPES = [(128, 128, 64), (256, 256, 128), (640, 768, 768), (1152, 3072, 768), (1152, 768, 3072),
+          (1152, 768, 2048), (32, 768, 768), (200, 136, 72), (5120, 768, 768)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("masked", [True, False])
+def test_fwd(M, N, K, masked):
+    from crvqa import ops
+    x, w, s, thr, b, _ = _mk(M, N, K, 1)
+    xb, wb = x.bfloat16(), w.bfloat16()
+    mask = (s > thr).float()
+    wm = wb.float() * mask if masked else wb.float()
+    ref = xb.float() @ wm.t() + b
+    y = ops.masked_linear_fwd(xb, wb, s if masked else None, thr, b)
+    torch.cuda.synchronize()
+    assert _rel(y, ref) < 2e-3, _rel(y, ref)
+    yb = ops.masked_linear_fwd(xb, wb, s if masked else None, thr, b, torch.bfloat16)
+    assert _rel(yb.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("masked", [True, False])
+def test_dx(M, N, K, masked):
+    from crvqa import ops
+    _, w, s, thr, _, dy = _mk(M, N, K, 2)
+    dyb, wb = dy.bfloat16(), w.bfloat16()
+    mask = (s > thr).float()
+    wm = wb.float() * mask if masked else wb.float()
+    ref = dyb.float() @ wm
+    dx = ops.masked_linear_bwd_dx(dyb, wb, s if masked else None, thr)
+    torch.cuda.synchronize()
+    assert _rel(dx, ref) < 2e-3, _rel(dx, ref)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_ds(M, N, K):
+    from crvqa import ops
+    x, w, _, _, _, dy = _mk(M, N, K, 3)
+    xb, wb, dyb = x.bfloat16(), w.bfloat16(), dy.bfloat16()
+    ref = (dyb.float().t() @ xb.float()) * wb.float()
+    ds = ops.masked_linear_bwd_ds(dyb, xb, wb)
+    torch.cuda.synchronize()
+    assert _rel(ds, ref) < 2e-3, _rel(ds, ref)
+    # accumulate: second invocation of a shared module adds
+    ds2 = ops.masked_linear_bwd_ds(dyb, xb, wb, out=ds.clone(), accumulate=True)
+    assert _rel(ds2, 2 * ref) < 2e-3
