@@ -25,6 +25,7 @@ _PROTOS = {
     "crv_version": (c_int, []),
     "crv_error_string": (c_char_p, [c_int]),
     "crv_last_cuda_error": (c_int, []),
+    "crv_launch_count": (ctypes.c_ulonglong, []),
     "crv_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
     "crv_binarize": (c_int, [_P, _P, _P, _P, _P, c_int64, _P]),
     "crv_apply_mask_bf16": (c_int, [_P, _P, _P, _P, c_int64, _P]),

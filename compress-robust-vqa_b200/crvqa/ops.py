@@ -25,6 +25,17 @@ def _need_cuda(*ts):
             raise RuntimeError("crvqa ops need CUDA tensors: the masked kernels have no CPU fallback")
 
 
+def _stage(t):
+    """Set-up-time ops (magnitude init, mask export, threshold refresh) accept CPU tensors when a GPU
+    exists -- the reference patches the model on the CPU and moves it afterwards -- by staging them on
+    the current CUDA device.  There is still no CPU implementation: without a GPU this raises."""
+    if t.is_cuda:
+        return t
+    if not torch.cuda.is_available():
+        raise RuntimeError("crvqa ops need a CUDA device: the masked kernels have no CPU fallback")
+    return t.cuda()
+
+
 def to_bf16(x):
     """fp32 -> bf16 (RNE) with the library's cast kernel; bf16 input is returned as is."""
     if x.dtype == torch.bfloat16:
@@ -49,14 +60,14 @@ def as_thr(thr, device):
 
 def binarize(scores, thr, want_count=False, as_bool=False):
     """binarizer_fn1: 1.0 where scores > thr else 0.0 (masking/maskers.py:325-329)."""
-    _need_cuda(scores)
-    s = scores.detach().contiguous()
+    home = scores.device
+    s = _stage(scores.detach()).contiguous().float()
     thr = as_thr(thr, s.device)
     mf = None if as_bool else torch.empty_like(s)
     mb = torch.empty(s.shape, dtype=torch.uint8, device=s.device) if as_bool else None
     cnt = torch.zeros((), dtype=torch.int64, device=s.device) if want_count else None
     check(lib.crv_binarize(_p(s), _p(thr), _p(mf), _p(mb), _p(cnt), s.numel(), _stream()), "crv_binarize")
-    out = mb.view(torch.bool) if as_bool else mf
+    out = (mb.view(torch.bool) if as_bool else mf).to(home)
     return (out, cnt) if want_count else out
 
 
@@ -114,9 +125,10 @@ def kth_value_batched(tensors, ks, use_abs=False):
     count = len(tensors)
     if count == 0:
         raise ValueError("no segments")
-    _need_cuda(*tensors)
+    home = tensors[0].device
+    tensors = [_stage(t.detach()) for t in tensors]
     dev = tensors[0].device
-    flat = [t.detach().reshape(-1) for t in tensors]
+    flat = [t.reshape(-1) for t in tensors]
     for t in flat:
         if t.dtype != torch.float32 or not t.is_contiguous():
             raise ValueError("kth_value_batched needs contiguous float32 tensors")
@@ -132,16 +144,28 @@ def kth_value_batched(tensors, ks, use_abs=False):
     out = torch.empty(count, dtype=torch.float32, device=dev)
     check(lib.crv_kth_value_batched(ptrs, ns, kk, count, int(bool(use_abs)), _p(out), _p(ws), nbytes, _stream()),
           "crv_kth_value_batched")
-    return out
+    return out.to(home)
 
 
 def magnitude_init(weight, w_thr, hi, lo):
-    _need_cuda(weight)
-    w = weight.detach().contiguous()
+    home = weight.device
+    w = _stage(weight.detach()).contiguous()
     out = torch.empty_like(w)
     check(lib.crv_magnitude_init(_p(w), _p(as_thr(w_thr, w.device)), float(hi), float(lo), _p(out), w.numel(),
                                  _stream()), "crv_magnitude_init")
-    return out
+    return out.to(home)
+
+
+def _sink_grad(sink):
+    """Arena gradient view of a masked module (hg_transformers._engine.ScoreArena), or None."""
+    return getattr(sink, "_arena_grad", None) if sink is not None else None
+
+
+def _sink_done(sink):
+    sink._grad_dirty = True
+    sync = getattr(sink, "_sync", None)
+    if sync is not None:
+        sync.module_backward_done(sink)
 
 
 class MaskedLinearFn(torch.autograd.Function):
@@ -150,10 +174,12 @@ class MaskedLinearFn(torch.autograd.Function):
     forward : bf16 tcgen05 GEMM with the mask applied in the TMA-fed prologue (fp32 accumulate)
     backward: dX = dY . (W (.) M)   and   dS = (dY^T . X) (.) W   (no dW, no db: weights are frozen,
               masking/maskers.py:564-569,594-596)
+    `sink` is the owning module when its score gradient lives in a ScoreArena: dS is then accumulated
+    in place by the GEMM epilogue and autograd receives no tensor for `scores`.
     """
 
     @staticmethod
-    def forward(ctx, x, scores, w_bf16, thr, bias):
+    def forward(ctx, x, scores, w_bf16, thr, bias, sink=None):
         shp = x.shape
         x2 = to_bf16(x.reshape(-1, shp[-1]))
         thr_t = as_thr(thr, x.device)
@@ -161,6 +187,7 @@ class MaskedLinearFn(torch.autograd.Function):
         ctx.save_for_backward(x2, scores, w_bf16, thr_t)
         ctx.x_shape = shp
         ctx.need_dx = x.requires_grad
+        ctx.sink = sink
         return y.view(*shp[:-1], w_bf16.shape[0])
 
     @staticmethod
@@ -170,15 +197,22 @@ class MaskedLinearFn(torch.autograd.Function):
         dx = None
         if ctx.need_dx:
             dx = masked_linear_bwd_dx(dy2, w_bf16, scores.detach(), thr_t, torch.float32).view(ctx.x_shape)
-        ds = masked_linear_bwd_ds(dy2, x2, w_bf16) if ctx.needs_input_grad[1] else None
-        return dx, ds, None, None, None
+        ds = None
+        if ctx.needs_input_grad[1]:
+            sink_grad = _sink_grad(ctx.sink)
+            if sink_grad is not None:
+                masked_linear_bwd_ds(dy2, x2, w_bf16, out=sink_grad, accumulate=ctx.sink._grad_dirty)
+                _sink_done(ctx.sink)
+            else:
+                ds = masked_linear_bwd_ds(dy2, x2, w_bf16)
+        return dx, ds, None, None, None, None
 
 
 class MaskedLinearSmallKFn(torch.autograd.Function):
     """Same contract for inner dimensions TMA cannot take (box_fc, K = 4): exact fp32 SIMT kernels."""
 
     @staticmethod
-    def forward(ctx, x, scores, weight, thr, bias):
+    def forward(ctx, x, scores, weight, thr, bias, sink=None):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1]).contiguous().float()
         thr_t = as_thr(thr, x.device)
@@ -189,6 +223,7 @@ class MaskedLinearSmallKFn(torch.autograd.Function):
         ctx.save_for_backward(x2, scores, weight, thr_t)
         ctx.x_shape = shp
         ctx.need_dx = x.requires_grad
+        ctx.sink = sink
         return y.view(*shp[:-1], N)
 
     @staticmethod
@@ -197,18 +232,26 @@ class MaskedLinearSmallKFn(torch.autograd.Function):
         N, K = weight.shape
         dy2 = dy.reshape(-1, N).contiguous().float()
         dx = torch.empty_like(x2) if ctx.need_dx else None
-        ds = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+        sink_grad = _sink_grad(ctx.sink)
+        acc = 0
+        if sink_grad is not None:
+            ds, acc = sink_grad, int(ctx.sink._grad_dirty)
+        else:
+            ds = torch.empty((N, K), dtype=torch.float32, device=dy.device)
         check(lib.crv_masked_linear_small_k_bwd(_p(dy2), _p(x2), _p(weight), _p(scores.detach()), _p(thr_t), _p(dx),
-                                                _p(ds), 0, x2.shape[0], N, K, _stream()),
+                                                _p(ds), acc, x2.shape[0], N, K, _stream()),
               "crv_masked_linear_small_k_bwd")
-        return (dx.view(ctx.x_shape) if dx is not None else None), ds, None, None, None
+        if sink_grad is not None:
+            _sink_done(ctx.sink)
+            ds = None
+        return (dx.view(ctx.x_shape) if dx is not None else None), ds, None, None, None, None
 
 
 class MaskedEmbeddingFn(torch.autograd.Function):
     """F.embedding(ids, weight * binarize(scores, thr), padding_idx) without masking the whole table."""
 
     @staticmethod
-    def forward(ctx, ids, scores, weight, thr, padding_idx):
+    def forward(ctx, ids, scores, weight, thr, padding_idx, sink=None):
         _need_cuda(ids, scores, weight)
         ids_c = ids.contiguous()
         thr_t = as_thr(thr, scores.device)
@@ -218,17 +261,27 @@ class MaskedEmbeddingFn(torch.autograd.Function):
                                            ids_c.numel(), vocab, dim, _stream()), "crv_masked_embedding_fwd")
         ctx.save_for_backward(ids_c, weight)
         ctx.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        ctx.sink = sink
         return out
 
     @staticmethod
     def backward(ctx, dout):
         ids_c, weight = ctx.saved_tensors
         vocab, dim = weight.shape
-        ds = torch.zeros((vocab, dim), dtype=torch.float32, device=weight.device)
+        sink_grad = _sink_grad(ctx.sink)
+        if sink_grad is not None:
+            ds = sink_grad
+            if not ctx.sink._grad_dirty:
+                ds.zero_()
+        else:
+            ds = torch.zeros((vocab, dim), dtype=torch.float32, device=weight.device)
         d = dout.contiguous().float()
         check(lib.crv_masked_embedding_bwd(_p(ids_c), _p(d), _p(weight), _p(ds), ids_c.numel(), vocab, dim,
                                            ctx.padding_idx, _stream()), "crv_masked_embedding_bwd")
-        return None, ds, None, None, None
+        if sink_grad is not None:
+            _sink_done(ctx.sink)
+            ds = None
+        return None, ds, None, None, None, None
 
 
 # ----------------------------------------------------------------------------- losses

@@ -10,6 +10,7 @@
 namespace crv {
 
 extern thread_local int g_last_cuda_error;
+extern unsigned long long g_launch_count;  // kernels launched by this library (all threads; racy by design)
 
 inline int record(cudaError_t e) {
   if (e != cudaSuccess) {
@@ -25,7 +26,10 @@ inline int record(cudaError_t e) {
     if (_rc != CRV_OK) return _rc;            \
   } while (0)
 
-inline int launch_status() { return record(cudaGetLastError()); }
+inline int launch_status(int kernels = 1) {
+  g_launch_count += static_cast<unsigned long long>(kernels);
+  return record(cudaGetLastError());
+}
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -6,6 +6,7 @@
 namespace crv {
 
 thread_local int g_last_cuda_error = 0;
+unsigned long long g_launch_count = 0;
 
 constexpr int kThreads = 256;
 
@@ -302,6 +303,8 @@ extern "C" const char* crv_error_string(int code) {
 }
 
 extern "C" int crv_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" unsigned long long crv_launch_count(void) { return g_launch_count; }
 
 extern "C" int crv_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream) {
   if (!src || !dst || n < 0) return CRV_E_BADARG;

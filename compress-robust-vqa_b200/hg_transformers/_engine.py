@@ -1,0 +1,215 @@
+"""B200 engine pieces under the stage-2 trainers: HBM layout of the trainable state and the
+data-parallel gradient exchange.  None of this exists in the reference (which wraps the model in
+nn.DataParallel / DDP, hg_transformers/mask_trainer_VQA.py:533-543); it is what makes the reference's
+loop cheap on one 8 x B200 box.
+
+ScoreArena
+    All score tensors (`weight_mask`, 207 M fp32 for LXMERT) live in ONE flat buffer, their gradients
+    in a second one, Adam's exp_avg / exp_avg_sq / sum in three more (5 x 829 MB of 180 GB HBM).
+    Module parameters are views, so the reference's per-tensor API keeps working, while
+      * the dS GEMM epilogue accumulates straight into the gradient buffer (no autograd copy),
+      * clip + AdamW is one streaming launch over the arena,
+      * the threshold refresh reads one pointer table,
+      * the gradient all-reduce runs on large contiguous slices with no flatten / unflatten copies.
+
+GradSync
+    Data parallel = all-reduce(mean) of the score gradients and the classifier gradients only (the
+    frozen weights have none).  The arena is cut into buckets in forward order; as soon as the
+    backward pass has produced every module of a bucket, its slice is all-reduced asynchronously (NCCL
+    over NVLink / NVSwitch) while the remaining dS / dX GEMMs run.
+"""
+import torch
+import torch.distributed as dist
+
+from crvqa import ops
+
+_ALIGN = 64  # floats: 256-byte alignment of every module slice (TMA needs 16 B; keep sector alignment)
+
+
+def masked_modules_of(model):
+    """(name, module) for every masked module, found the way the reference trainers find them: by the
+    presence of a `threshold` attribute (mask_trainer_VQA.py:473,935)."""
+    out = []
+    for name, module in model.named_modules():
+        if hasattr(module, "threshold") and hasattr(module, "weight_mask"):
+            out.append((name[7:] if name.startswith("module.") else name, module))
+    return out
+
+
+class ScoreArena:
+    def __init__(self, named_modules, device=None):
+        self.names = [n for n, _ in named_modules]
+        self.modules = [m for _, m in named_modules]
+        if not self.modules:
+            raise ValueError("no masked modules to place in the arena")
+        device = device or self.modules[0].weight_mask.device
+        self.offsets, off = [], 0
+        for m in self.modules:
+            self.offsets.append(off)
+            off += (m.weight_mask.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.total = off
+        self.scores = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=device)
+        self.exp_avg = self.exp_avg_sq = self.sum = None
+        self._index = {}
+        for i, m in enumerate(self.modules):
+            p = m.weight_mask
+            view = self._view(self.scores, i)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self._view(self.grads, i)
+            m._arena_grad = p.grad
+            m._grad_dirty = False
+            m._arena = self
+            self._index[id(p)] = i
+
+    def _view(self, flat, i):
+        p = self.modules[i].weight_mask
+        return flat[self.offsets[i]: self.offsets[i] + p.numel()].view(p.shape)
+
+    def owns(self, p):
+        return id(p) in self._index
+
+    def _ensure_state(self):
+        if self.exp_avg is None:
+            self.exp_avg = torch.zeros_like(self.scores)
+            self.exp_avg_sq = torch.zeros_like(self.scores)
+            self.sum = torch.zeros_like(self.scores)
+
+    def state_views(self, p):
+        i = self._index.get(id(p))
+        if i is None:
+            return None
+        self._ensure_state()
+        return {"sum": self._view(self.sum, i), "exp_avg": self._view(self.exp_avg, i),
+                "exp_avg_sq": self._view(self.exp_avg_sq, i)}
+
+    # -- per-step protocol ---------------------------------------------------------------------
+    def begin_step(self):
+        """Replaces zero_grad for the arena: nothing is memset; the first dS of a module overwrites."""
+        for m in self.modules:
+            m._grad_dirty = False
+            if m.weight_mask.grad is None:  # someone called zero_grad(set_to_none=True)
+                m.weight_mask.grad = m._arena_grad
+
+    def finalize_grads(self):
+        """Modules that received no gradient this step (e.g. the vision side of the last cross layer,
+        which nothing downstream reads) must contribute zeros."""
+        for m in self.modules:
+            if not m._grad_dirty:
+                m._arena_grad.zero_()
+                m._grad_dirty = True
+
+    def grad_sumsq_into(self, acc):
+        ops.sumsq_into(self.grads, acc)
+
+    def adamw_step(self, lr, step, beta1, beta2, eps, weight_decay, correct_bias, clip_sumsq, max_norm,
+                   with_sum=True):
+        self._ensure_state()
+        ops.adamw_step_flat(self.scores, self.grads, self.exp_avg, self.exp_avg_sq, self.sum if with_sum else None,
+                            lr, step, beta1, beta2, eps, weight_decay, clip_sumsq, max_norm, correct_bias)
+
+    def release(self):
+        """Give the parameters their own storage back (used when a trainer is torn down)."""
+        for m in self.modules:
+            p = m.weight_mask
+            p.data = p.data.clone()
+            p.grad = None
+            m._arena_grad = None
+            m._arena = None
+
+
+class GradSync:
+    """Bucketed asynchronous all-reduce(mean) of an arena's gradient buffer + a few loose tensors."""
+
+    def __init__(self, arena, bucket_bytes=64 << 20, group=None):
+        self.arena = arena
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.enabled = self.world > 1
+        # buckets = runs of consecutive modules (arena order == forward order)
+        self.bucket_of, self.bucket_ranges, self.bucket_members = [], [], []
+        start_mod, start_off, cur = 0, 0, 0
+        limit = bucket_bytes // 4
+        n = len(arena.modules)
+        for i in range(n):
+            end = arena.offsets[i + 1] if i + 1 < n else arena.total
+            cur = end - start_off
+            self.bucket_of.append(len(self.bucket_ranges))
+            if cur >= limit or i == n - 1:
+                self.bucket_ranges.append((start_off, end))
+                self.bucket_members.append(list(range(start_mod, i + 1)))
+                start_mod, start_off = i + 1, end
+        self._pending = None
+        self._handles = []
+        self._sent = None
+        self.defer = False  # gradient accumulation: exchange only after the last micro-batch
+        for i, m in enumerate(arena.modules):
+            m._sync = self
+            m._sync_index = i
+            m._calls_outstanding = 0
+
+    # called by MaskedLinear1.forward in training mode: one more backward invocation is owed
+    @staticmethod
+    def note_forward(module):
+        module._calls_outstanding = getattr(module, "_calls_outstanding", 0) + 1
+
+    def begin_step(self):
+        self._pending = [len(b) for b in self.bucket_members]
+        self._sent = [False] * len(self.bucket_ranges)
+        self._handles = []
+        for m in self.arena.modules:
+            m._calls_outstanding = 0
+
+    def _launch(self, b):
+        if self._sent[b]:
+            return
+        self._sent[b] = True
+        if not self.enabled:
+            return
+        lo, hi = self.bucket_ranges[b]
+        view = self.arena.grads[lo:hi]
+        if dist.get_backend(self.group) == "nccl":
+            self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        else:
+            h = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._handles.append((h, view))
+
+    def module_backward_done(self, module):
+        """One backward invocation of `module` finished writing its dS."""
+        if self._pending is None:
+            return
+        module._calls_outstanding -= 1
+        if module._calls_outstanding > 0:
+            return
+        b = self.bucket_of[module._sync_index]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and not self.defer:
+            self._launch(b)
+
+    def finish(self, loose=()):
+        """After backward: zero-fill untouched modules, send what is left, all-reduce the loose
+        (classifier) gradients as one flat message, and wait for everything."""
+        self.arena.finalize_grads()
+        if self._sent is None:
+            self.begin_step()
+        for b in range(len(self.bucket_ranges)):
+            self._launch(b)
+        if self.enabled:
+            loose = [g for g in loose if g is not None]
+            if loose:
+                flat = torch.cat([g.reshape(-1) for g in loose])
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                flat.div_(self.world)
+                off = 0
+                for g in loose:
+                    g.copy_(flat[off: off + g.numel()].view_as(g))
+                    off += g.numel()
+            for h in self._handles:
+                if isinstance(h, tuple):
+                    h[0].wait()
+                    h[1].div_(self.world)
+                else:
+                    h.wait()
+        self._handles = []
+        self._pending = None

@@ -1,0 +1,20 @@
+"""Drop-in for the reference's ``masking/maskers.py`` (LXMERT baseline masker: one global initial
+sparsity from the scheduler).  Same public names; bodies in ``masking._core`` -> libcrvqa.so."""
+from ._core import (  # noqa: F401
+    MaskedLinear0, MaskedLinear1, MaskedLinear2, MaskedLinear3, MaskedLinearX, MaskerBase,
+    _Binarizer1, _Binarizer2, _Binarizer3, _bert_roberta_names, _distilbert_names, _get_nnz_from,
+    _lxmert_names, _scheme_idx_to_fn, binarizer_fn1, binarizer_fn2, binarizer_fn3, chain_names_plain,
+    finish_magnitude_init, reshape_mask_for_sp,
+)
+
+
+def chain_module_names(which_ptl, layer_idices, abbres):
+    """Names of the modules to mask (reference masking/maskers.py:70-82 -- always the LXMERT table)."""
+    return chain_names_plain(_lxmert_names, which_ptl, layer_idices, abbres)
+
+
+class Masker(MaskerBase):
+    def __init__(self, masker_scheduler, logger, mask_biases, structured_masking_info, threshold, init_scale,
+                 which_ptl, controlled_init):
+        self._setup(masker_scheduler, logger, mask_biases, structured_masking_info, threshold, init_scale,
+                    which_ptl, controlled_init)

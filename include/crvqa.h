@@ -43,6 +43,7 @@ extern "C" {
 int crv_version(void);                       /* ABI version, currently 1 */
 const char* crv_error_string(int code);      /* static string for CRV_E_* codes; "cuda error" otherwise */
 int crv_last_cuda_error(void);               /* last cudaError_t / CUresult seen by this thread */
+unsigned long long crv_launch_count(void);   /* kernels this library has launched so far (process-wide) */
 
 /* Elementwise helpers ------------------------------------------------------------------------ */
 /* fp32 -> bf16 (round-to-nearest-even) operand conversion in front of the bf16 MMAs. */
@@ -148,8 +149,7 @@ int crv_sumsq(const float* x, int64_t n, float* out, void* stream);
  * torch.nn.utils.clip_grad_norm_ folded in:  g' = g * min(1, max_norm / (sqrt(*total_sumsq) + 1e-6));
  * sum += |g'|; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= step_size * m / (sqrt(v) + eps);
  * p -= lr * weight_decay * p.  step_size = lr * sqrt(1-b2^t)/(1-b1^t) is computed by the caller.
- * total_sumsq may be NULL (no clipping).  `sum` may be NULL.  If wm_bf16 != NULL the refreshed masked
- * weight (W (.) (p_new > *thr)) is emitted in the same pass. */
+ * total_sumsq may be NULL (no clipping).  `sum` may be NULL. */
 int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int64_t n, float lr,
                    float step_size, float beta1, float beta2, float eps, float weight_decay,
                    const float* total_sumsq, float max_norm, void* stream);
