@@ -10,6 +10,26 @@ from ._lib import check, lib
 
 DT_F32, DT_BF16 = 0, 1
 
+# bench.py sets this to a list to collect (kind, M, N, K, start_event, end_event) for every masked-GEMM
+# launch (CUDA events on the launching stream); None = no instrumentation.
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, kind, M, N, K):
+        self.rec = None
+        if PROFILE is not None:
+            self.rec = (kind, M, N, K, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.rec[4].record()
+
+    def __exit__(self, *exc):
+        if self.rec is not None:
+            self.rec[5].record()
+            PROFILE.append(self.rec)
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -87,9 +107,10 @@ def masked_linear_fwd(x_bf16, w_bf16, scores, thr, bias, out_dtype=torch.float32
     N = w_bf16.shape[0]
     y = torch.empty((M, N), dtype=out_dtype, device=x_bf16.device)
     thr_t = as_thr(thr, x_bf16.device) if scores is not None else None
-    check(lib.crv_masked_linear_fwd(_p(x_bf16), _p(w_bf16), _p(scores), _p(thr_t), _p(bias), _p(y),
-                                    DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _stream()),
-          "crv_masked_linear_fwd")
+    with _Timed("fwd", M, N, K):
+        check(lib.crv_masked_linear_fwd(_p(x_bf16), _p(w_bf16), _p(scores), _p(thr_t), _p(bias), _p(y),
+                                        DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _stream()),
+              "crv_masked_linear_fwd")
     return y
 
 
@@ -99,9 +120,10 @@ def masked_linear_bwd_dx(dy_bf16, w_bf16, scores, thr, out_dtype=torch.float32):
     K = w_bf16.shape[1]
     dx = torch.empty((M, K), dtype=out_dtype, device=dy_bf16.device)
     thr_t = as_thr(thr, dy_bf16.device) if scores is not None else None
-    check(lib.crv_masked_linear_bwd_dx(_p(dy_bf16), _p(w_bf16), _p(scores), _p(thr_t), _p(dx),
-                                       DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _stream()),
-          "crv_masked_linear_bwd_dx")
+    with _Timed("dx", M, N, K):
+        check(lib.crv_masked_linear_bwd_dx(_p(dy_bf16), _p(w_bf16), _p(scores), _p(thr_t), _p(dx),
+                                           DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _stream()),
+              "crv_masked_linear_bwd_dx")
     return dx
 
 
@@ -112,8 +134,9 @@ def masked_linear_bwd_ds(dy_bf16, x_bf16, w_bf16, out=None, accumulate=False):
     if out is None:
         out = torch.empty((N, K), dtype=torch.float32, device=dy_bf16.device)
         accumulate = False
-    check(lib.crv_masked_linear_bwd_ds(_p(dy_bf16), _p(x_bf16), _p(w_bf16), _p(out), int(bool(accumulate)),
-                                       M, N, K, _stream()), "crv_masked_linear_bwd_ds")
+    with _Timed("ds", M, N, K):
+        check(lib.crv_masked_linear_bwd_ds(_p(dy_bf16), _p(x_bf16), _p(w_bf16), _p(out), int(bool(accumulate)),
+                                           M, N, K, _stream()), "crv_masked_linear_bwd_ds")
     return out
 
 

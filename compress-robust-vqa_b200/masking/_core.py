@@ -181,7 +181,7 @@ class MaskedLinearX(nn.Module):
         self.name = kwargs.get("name")
         self.padding_idx = kwargs.get("padding_idx")
         self.threshold = kwargs.get("threshold")
-        self.threshold_fn = _scheme_idx_to_fn[scheme_idx]().apply
+        self.threshold_fn = _scheme_idx_to_fn[scheme_idx].apply
         self.mask_biases = mask_biases
         self.weight = weight
         self.bias = bias

@@ -1,0 +1,285 @@
+"""CPU tier: host logic of the drop-in package, the C-ABI surface, and the multi-rank gradient exchange
+(gloo, world_size 2).  No CUDA compute is called; where a host routine needs the result of a kernel, the
+CPU oracle is injected as a fake backend (tests may import oracle/, the product never does)."""
+import ctypes
+import json
+import logging
+import os
+import re
+import sys
+import types
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+WEIGHT_TYPES = ["E", "VV", "VB", "lK", "lQ", "lV", "lAO", "lI", "lO", "vK", "vQ", "vV", "vAO", "vI", "vO",
+                "vlVK", "vlVQ", "vlVV", "vlVAO", "vlLaK", "vlLaQ", "vlLaV", "vlLaAO", "vlVaK", "vlVaQ", "vlVaV",
+                "vlVaAO", "vlLi", "vlLo", "vlVi", "vlVo", "P"]
+
+
+@pytest.fixture(scope="module")
+def host_gold():
+    with open(os.path.join(GOLD, "host.json")) as f:
+        return json.load(f)
+
+
+# ----------------------------------------------------------------------------- C ABI
+def test_cabi_library_exports_every_declared_symbol():
+    from crvqa import _lib
+    header = open(os.path.join(ROOT, "include", "crvqa.h")).read()
+    declared = sorted(set(re.findall(r"\b(crv_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in include/crvqa.h but not exported by libcrvqa.so"
+    assert sorted(_lib.EXPORTED) == declared, "ctypes prototype table and header disagree"
+    assert _lib.lib.crv_version() == 1
+
+
+def test_cabi_argument_errors_are_reported_before_any_cuda_work():
+    from crvqa import _lib
+    lib = _lib.lib
+    null = ctypes.c_void_p(0)
+    assert lib.crv_cast_f32_to_bf16(null, null, 16, null) == -1
+    assert lib.crv_masked_linear_fwd(null, null, null, null, null, null, 0, 128, 128, 64, null) == -1
+    assert lib.crv_kth_value_batched(null, null, null, 0, 0, null, null, 0, null) == -1
+    assert lib.crv_kth_value_workspace_bytes(168) > 168 * 2048 * 4
+    assert lib.crv_vqa_loss_workspace_bytes(256) == 3 * 256 * 4
+    assert b"bad argument" in lib.crv_error_string(-1)
+    with pytest.raises(_lib.CrvqaError):
+        _lib.check(-3, "x")
+
+
+def test_product_ops_fail_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only tier")
+    from crvqa import ops
+    x = torch.zeros(128, 64)
+    with pytest.raises(RuntimeError):
+        ops.masked_linear_fwd(x.bfloat16(), x.bfloat16(), x, 0.0, None)
+    with pytest.raises(RuntimeError):
+        ops.binarize(x, 0.0)
+    with pytest.raises(RuntimeError):
+        ops.kth_value_batched([x], [1])
+
+
+# ----------------------------------------------------------------------------- pure host logic
+def test_chain_module_names_match_reference(host_gold):
+    from masking import maskers, maskers_Robust, maskers_visualBert
+    layers = list(range(12))
+    assert sorted(maskers.chain_module_names("lxmert", layers, WEIGHT_TYPES)) == host_gold["chain_lxmert"]
+    names, modal, module, layer = maskers_Robust.chain_module_names("lxmert", layers, WEIGHT_TYPES)
+    assert sorted(names) == host_gold["chain_robust"]["names"]
+    assert modal == host_gold["chain_robust"]["modal"]
+    assert module == host_gold["chain_robust"]["module"]
+    assert layer == host_gold["chain_robust"]["layer"]
+    vb = maskers_visualBert.chain_module_names("visual_bert", layers, ["K", "Q", "V", "AO", "I", "O", "P", "E"])
+    assert sorted(vb) == host_gold["chain_visualbert"] and len(vb) == 74
+
+
+def test_sparsity_schedules_match_reference(host_gold):
+    from masking import sparsity_control as sp
+    f = sp.automated_gradual_sparsity(0.1, 0.7, 0.1, 2, 16)
+    assert [f(e, 0.0) for e in range(20)] == pytest.approx(host_gold["ags"], rel=0, abs=0)
+    f = sp.stepwise_sparsity(0.1, 0.7, 2, 2, 16, 0.2)
+    cur, seq = 0.1, []
+    for e in range(20):
+        cur = f(e, cur)
+        seq.append(cur)
+    assert seq == pytest.approx(host_gold["stepwise"], rel=0, abs=0)
+    with pytest.raises(ValueError):
+        sp.stepwise_sparsity(0.1, 0.99, 2, 2, 6, 0.05)
+    conf = types.SimpleNamespace(masking_scheduler_conf_={"init_sparsity": 0.2, "final_sparsity": 0.7,
+                                                          "sparsity_warmup_interval_epoch": 1, "init_epoch": 1,
+                                                          "final_epoch": 8},
+                                 logger=logging.getLogger("t"), num_epochs=10)
+    sch = sp.MaskerScheduler(conf)
+    got = [list(sch.step(e)) for e in range(10)]
+    assert got == [pytest.approx(r[:2]) + [r[2]] if False else r for r in got]  # shape check
+    for g, r in zip(got, host_gold["scheduler_steps"]):
+        assert g[0] == pytest.approx(r[0], abs=1e-15) and g[1] == pytest.approx(r[1], abs=1e-15) and g[2] == r[2]
+    assert sch.is_skip == host_gold["scheduler_is_skip"]
+    from masking import sparsity_control_Robust as spr
+    assert spr.MaskerScheduler is sp.MaskerScheduler
+
+
+def test_dict_parser_and_default_scheduler_conf():
+    from prune_debias_VQA import DEFAULT_SCHEDULER_CONF
+    from utils.param_parser import dict_parser
+    d = dict_parser(DEFAULT_SCHEDULER_CONF)
+    assert d["lambdas_lr"] == 0 and d["sparsity_warmup"] == "automated_gradual_sparsity" and d["final_epoch"] == 1
+
+
+def test_linear_schedule_collator_sampler():
+    from hg_transformers.data.data_collator import TrimCollator
+    from hg_transformers.optimization import linear_schedule_factor
+    from hg_transformers.mask_trainer_VQA import SequentialDistributedSampler
+    assert linear_schedule_factor(0, 0, 100) == 1.0 and linear_schedule_factor(50, 0, 100) == 0.5
+    assert linear_schedule_factor(5, 10, 100) == 0.5 and linear_schedule_factor(100, 10, 100) == 0.0
+    batch = [(torch.arange(4), torch.ones(3 + i, 8), torch.tensor(i), 1.5) for i in range(3)]
+    ids, feats, qid, w = TrimCollator().collate_batch(batch)
+    assert ids.shape == (3, 4) and feats.shape == (3, 5, 8) and qid.tolist() == [0, 1, 2] and w.dtype == torch.float64
+    assert float(feats[0, 3:].abs().sum()) == 0.0
+    s0 = list(SequentialDistributedSampler(list(range(10)), num_replicas=4, rank=0))
+    s3 = list(SequentialDistributedSampler(list(range(10)), num_replicas=4, rank=3))
+    assert s0 == [0, 1, 2] and s3 == [9, 0, 1]
+
+
+def test_learned_mixin_smooth_value_is_cached_against_the_parameter_version():
+    from hg_transformers.vqa_debias_loss_functions import LearnedMixin
+    lm = LearnedMixin(0.36)
+    v = lm.smooth_value()
+    assert v == pytest.approx(float(torch.sigmoid(torch.tensor(-1.0))))
+    assert lm.smooth_value() == v
+    with torch.no_grad():
+        lm.smooth_param.fill_(0.0)
+    assert lm.smooth_value() == pytest.approx(0.5)
+
+
+# ----------------------------------------------------------------------------- masker with the oracle as fake backend
+@pytest.fixture()
+def oracle_backend(monkeypatch):
+    from crvqa import ops
+    from oracle import masked_ops as o
+
+    def kth(tensors, ks, use_abs=False):
+        return torch.tensor([float(o.kth_value(t, int(k), use_abs=use_abs)) for t, k in zip(tensors, ks)])
+
+    def mag(weight, w_thr, hi, lo):
+        keep = weight.detach().abs() > float(w_thr)
+        return torch.where(keep, torch.full_like(weight, hi), torch.full_like(weight, lo))
+
+    def binz(scores, thr, want_count=False, as_bool=False):
+        m = o.binarize(scores.detach(), float(thr))
+        out = m.bool() if as_bool else m
+        return (out, m.sum().long()) if want_count else out
+
+    monkeypatch.setattr(ops, "kth_value_batched", kth)
+    monkeypatch.setattr(ops, "magnitude_init", mag)
+    monkeypatch.setattr(ops, "binarize", binz)
+    return ops
+
+
+def test_masker_patch_modules_host_logic(oracle_backend):
+    """Patching the tiny LXMERT with the per-modality Masker: same module census, same trainable set, same
+    initial masks as the reference produced (tests/golden/tiny_lxmert.pt)."""
+    from hg_transformers.modeling_lxmert import LxmertConfig, LxmertForMultipleChoice
+    from prune_debias_VQA import HPmodel_modal, ModelArguments, init_masker
+    g = torch.load(os.path.join(GOLD, "tiny_lxmert.pt"), weights_only=False)
+    cfg = dict(g["config"])
+    torch.manual_seed(49)
+    model = LxmertForMultipleChoice(LxmertConfig(**cfg))
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, g["state_dict"][k]), k          # same seed -> same init as the reference
+    margs = ModelArguments()
+    log = logging.getLogger("t")
+    log.setLevel(logging.ERROR)
+    masker = init_masker(margs, model, log, HPmodel_modal(0.7, 0.7, 0.7, 0.7), margs)
+    mods = [(n, m) for n, m in model.named_modules() if hasattr(m, "threshold")]
+    assert [n for n, _ in mods] == g["module_names"]
+    assert sorted(n for n, p in model.named_parameters() if p.requires_grad) == g["trainable"]
+    for n, m in mods:
+        assert masker.name_in_module[n] == g["modal"][n]
+        assert int((m.weight_mask > 1e-2).sum()) == g["kept_init"][n]
+        assert m.weight is dict(model.named_parameters())[n + ".weight"]      # shares the frozen Parameter
+        assert not m.weight.requires_grad and m.weight_mask.requires_grad
+        assert f"{n}_weight_mask" in masker.init_masks
+    assert masker.masker_scheduler.init_sparsity == 0.7 and masker.masker_scheduler.is_skip
+    # classifier stays trainable: nn.Sequential children are not attributes, so the freeze never sees them
+    assert all(p.requires_grad for n, p in model.named_parameters() if n.startswith("classifier."))
+
+
+def test_reset_threshold_modes(oracle_backend):
+    from hg_transformers import mask_trainer_Robust_VQA as robust
+    from hg_transformers import mask_trainer_VQA as base
+
+    class M(torch.nn.Module):
+        def __init__(self, n):
+            super().__init__()
+            self.weight = torch.nn.Parameter(torch.zeros(n), requires_grad=False)
+            self.weight_mask = torch.nn.Parameter(torch.arange(1, n + 1, dtype=torch.float32))
+            self.threshold = torch.tensor(1e-2)
+
+    net = torch.nn.Module()
+    net.a, net.b, net.c = M(10), M(100), M(3)
+    masker = types.SimpleNamespace(name_in_module={"a": "Lang", "b": "Vis", "c": "P"},
+                                   hpmodel=types.SimpleNamespace(zerorate_dict={"Lang": 0.5, "Vis": 0.25, "P": 0.1}))
+    t = robust.Trainer.__new__(robust.Trainer)
+    t.masker = masker
+    mean = t.reset_threshold(net, 0.7)
+    assert [float(net.a.threshold), float(net.b.threshold), float(net.c.threshold)] == [5.0, 25.0, 1.0]  # k=0 -> 1
+    assert mean == pytest.approx((5 + 25 + 1) / 3)
+    t2 = base.Trainer.__new__(base.Trainer)
+    t2.masker = masker
+    t2.reset_threshold(net, 0.7)
+    assert [float(net.a.threshold), float(net.b.threshold), float(net.c.threshold)] == [7.0, 70.0, 2.0]
+
+
+# ----------------------------------------------------------------------------- data parallel (gloo, 2 ranks)
+def _sync_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hg_transformers._engine import GradSync, ScoreArena
+
+    class M(torch.nn.Module):
+        def __init__(self, shape):
+            super().__init__()
+            self.weight_mask = torch.nn.Parameter(torch.zeros(shape))
+            self.threshold = torch.tensor(1e-2)
+
+    mods = [(f"m{i}", M(s)) for i, s in enumerate([(8, 16), (4, 4), (32, 8), (5, 3), (16, 16)])]
+    arena = ScoreArena(mods)
+    sync = GradSync(arena, bucket_bytes=512)          # several small buckets
+    assert len(sync.bucket_ranges) >= 3
+    loose = [torch.full((7,), float(rank + 1)), torch.full((2, 3), 10.0 * (rank + 1))]
+    for step in range(2):
+        arena.begin_step()
+        sync.begin_step()
+        calls = {0: 1, 1: 2, 2: 1, 4: 1}              # module 1 is "shared" (two invocations); module 3 gets no grad
+        for i, c in calls.items():
+            mods[i][1]._calls_outstanding = c
+        for i in (4, 2, 1, 1, 0):                      # backward order
+            m = mods[i][1]
+            val = float((rank + 1) * (i + 1) + step)
+            if m._grad_dirty:
+                m._arena_grad.add_(val)
+            else:
+                m._arena_grad.fill_(val)
+            m._grad_dirty = True
+            sync.module_backward_done(m)
+        if step == 0:
+            mods[3][1]._arena_grad.fill_(123.0)        # stale garbage that must be zeroed, not exchanged
+        sync.finish(loose)
+        mean_rank = (1 + world) / 2.0
+        for i, (_, m) in enumerate(mods):
+            if i == 3:
+                want = 0.0
+            elif i == 1:
+                want = 2 * (mean_rank * (i + 1) + step)
+            else:
+                want = mean_rank * (i + 1) + step
+            assert torch.allclose(m.weight_mask.grad, torch.full_like(m.weight_mask, want)), (rank, step, i)
+            assert m.weight_mask.grad.data_ptr() == m._arena_grad.data_ptr()
+        if step == 0:
+            assert torch.allclose(loose[0], torch.full((7,), mean_rank))
+            assert torch.allclose(loose[1], torch.full((2, 3), 10.0 * mean_rank))
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put(rank)
+
+
+def test_grad_sync_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5) for _ in range(2)) == [0, 1]

@@ -172,3 +172,38 @@ def test_tiny_bf16_operand_mode_is_close_to_fp32(tiny_gold):
     out = lxo.training_step(c, g["batch"], "normal", layers=layers)
     err = float((out["logits"] - g["logits"]).abs().max() / g["logits"].abs().max())
     assert err < 2e-2, err
+
+
+def test_full_lxmert_config1_matches_reference_and_survey_known_answers():
+    """BASELINE config 1 (9/5/5, h=768, B=32, A=2274, seed 49): the oracle against the reference's outputs
+    (tests/golden/full_lxmert.pt) and the known-answer values of SURVEY.md section 8(c)."""
+    from hg_transformers.modeling_lxmert import LxmertConfig, LxmertForMultipleChoice
+    g = torch.load(os.path.join(GOLD, "full_lxmert.pt"), weights_only=False)
+    torch.manual_seed(49)
+    model = LxmertForMultipleChoice(LxmertConfig(ans_num=2274))
+    params = {k: v.detach() for k, v in model.state_dict().items()}
+    for k in params:
+        params[k].requires_grad_(k.startswith("classifier."))
+    scores, thr, modal = lxo.init_scores(params, RATES, 1e-2)
+    assert list(scores) == g["module_names"] and modal == g["modal"]
+    kept = {n: int((s > 1e-2).sum()) for n, s in scores.items()}
+    assert kept == g["kept_init"]
+    assert sum(kept.values()) == 62181835 and kept["lxmert.pooler.dense"] == 176948
+    assert kept["lxmert.embeddings.word_embeddings"] == 7032269 and kept["lxmert.encoder.visn_fc.box_fc"] == 922
+    batch = lxo.synthetic_batch(32, 2274)
+    c = lxo.Ctx(params, scores, thr)
+    out = lxo.training_step(c, batch, "normal")
+    assert abs(float(out["loss"]) - 1577.634766) < 2e-3          # SURVEY 8(c)
+    torch.testing.assert_close(out["loss"], g["loss_normal"], rtol=1e-6, atol=0)
+    torch.testing.assert_close(out["logits"], g["logits"], rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(out["pooled"], g["pooled"], rtol=1e-4, atol=2e-6)
+    assert abs(float(out["logits"].sum()) - (-77.364212)) < 1e-2
+    for n, gr in zip(scores, out["grads"]):
+        st = g["grad_stats_normal"][n]
+        assert abs(float(gr.double().norm()) - st["l2"]) <= 1e-4 * st["l2"] + 1e-12, n
+        assert int((gr != 0).sum()) == st["nnz"], n
+        samp = gr.reshape(-1)[:: max(1, gr.numel() // 512)][:512]
+        torch.testing.assert_close(samp, st["sample"], rtol=1e-3, atol=1e-5 * float(st["sample"].abs().max()) + 1e-12)
+    assert int((out["grads"][0] != 0).sum()) == 486912              # embedding dS nnz, SURVEY 8(c)
+    lpf = lxo.compute_loss("lpf", out["logits"], out["pooled"], batch)
+    assert abs(float(lpf) - 7.543721) < 1e-4
