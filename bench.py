@@ -175,11 +175,16 @@ def run_ours(args):
     dev_inputs = [t.to(dev) for t in host_inputs]
     h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in order if k)
 
-    def one_step(inputs):
-        loss, score = trainer._training_step(model, inputs, optimizer)
-        trainer.grad_sync.finish([p.grad for p in trainer._loose_params()])
-        trainer._clip_and_step(model, optimizer, scheduler)
-        trainer._zero_grad(optimizer)
+    graphed = None if args.eager else trainer._make_graphed_step(model, optimizer, scheduler)
+
+    def one_step(inputs, force_eager=False):
+        if graphed is not None and not force_eager:
+            loss, score = graphed.step(inputs)
+        elif graphed is not None:
+            loss, score = graphed._eager(inputs)
+        else:
+            loss, score = trainer._device_step(model, inputs, optimizer)
+            scheduler.step()
         trainer.global_step += 1
         if trainer.global_step % targs.logging_steps == 0:
             trainer.reset_threshold(model, masker.masker_scheduler.init_sparsity)
@@ -203,13 +208,21 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
-        if i == args.steps - 1:
+        if graphed is None and i == args.steps - 1:
             ops.PROFILE = []          # per-launch CUDA events on the masked GEMMs of the last timed step
         one_step(dev_inputs)
     ev1.record()
     barrier()
-    prof, ops.PROFILE = ops.PROFILE, None
     launches = lib.crv_launch_count() - launches0
+    if graphed is not None:
+        # graph replay launches no kernel from this process' Python: count the captured launches instead, and
+        # take the per-launch GEMM timings from one eager step of the same workload right after the timed region
+        ops.PROFILE = []
+        c0 = lib.crv_launch_count()
+        one_step(dev_inputs, force_eager=True)
+        torch.cuda.synchronize()
+        launches = (lib.crv_launch_count() - c0) * args.steps
+    prof, ops.PROFILE = ops.PROFILE, None
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -270,6 +283,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(B, A, args.loss), "global_batch": B * world,
                        "parallelism": f"dp{world}", "threshold_refresh_every": targs.logging_steps,
+                       "step_execution": "eager" if graphed is None else "cuda-graph replay of the whole step",
+                       "mask_mode": os.environ.get("CRVQA_MASK_MODE", "cached"),
                        "l2": "per-step working set (weights 0.4 GB + scores/grads/Adam 4 GB) far exceeds the 126 MB L2",
                        "gflop_per_sample_masked_gemm": GFLOP_PER_SAMPLE},
             "clocks": clock_info,
@@ -294,6 +309,7 @@ def main():
     ap.add_argument("--ans-num", type=int, default=3129)
     ap.add_argument("--loss", default="lpf", choices=["normal", "lpf", "lmh"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="do not replay the step as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -29,6 +29,7 @@ _PROTOS = {
     "crv_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
     "crv_binarize": (c_int, [_P, _P, _P, _P, _P, c_int64, _P]),
     "crv_apply_mask_bf16": (c_int, [_P, _P, _P, _P, c_int64, _P]),
+    "crv_apply_mask_segmented": (c_int, [_P, _P, _P, _P, c_int, _P, _P]),
     "crv_masked_linear_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "crv_masked_linear_bwd_dx": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "crv_masked_linear_bwd_ds": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
@@ -45,7 +46,7 @@ _PROTOS = {
     "crv_vqa_loss_lmh": (c_int, [_P, _P, _P, _P, c_float, c_float, _P, _P, _P, c_int, c_int, _P, _P]),
     "crv_sumsq": (c_int, [_P, c_int64, _P, _P]),
     "crv_adamw_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float,
-                               c_float, _P, c_float, _P]),
+                               c_float, _P, c_float, _P, _P]),
 }
 EXPORTED = tuple(_PROTOS)
 for _name, (_res, _args) in _PROTOS.items():

@@ -100,6 +100,13 @@ def apply_mask_bf16(w_bf16, scores, thr):
     return out
 
 
+def apply_mask_segmented(w_flat, s_flat, thr_vec, chunks, wm_flat):
+    """Refresh a whole mask cache: wm = w (.) (s > thr_vec[segment]) in one launch (chunks: int32 [n,4])."""
+    _need_cuda(w_flat, s_flat, thr_vec, chunks, wm_flat)
+    check(lib.crv_apply_mask_segmented(_p(w_flat), _p(s_flat), _p(thr_vec), _p(chunks), chunks.shape[0],
+                                       _p(wm_flat), _stream()), "crv_apply_mask_segmented")
+
+
 def masked_linear_fwd(x_bf16, w_bf16, scores, thr, bias, out_dtype=torch.float32):
     """Y[M,N] = X[M,K] . (W (.) (S > thr))^T + b; scores None => W taken as is."""
     _need_cuda(x_bf16, w_bf16)
@@ -202,12 +209,16 @@ class MaskedLinearFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, scores, w_bf16, thr, bias, sink=None):
+    def forward(ctx, x, scores, w_bf16, thr, bias, sink=None, wm_bf16=None):
         shp = x.shape
         x2 = to_bf16(x.reshape(-1, shp[-1]))
         thr_t = as_thr(thr, x.device)
-        y = masked_linear_fwd(x2, w_bf16, scores.detach(), thr_t, bias, torch.float32)
+        if wm_bf16 is not None:   # mask cache: W (.) M was materialised for this (scores, threshold) state
+            y = masked_linear_fwd(x2, wm_bf16, None, None, bias, torch.float32)
+        else:
+            y = masked_linear_fwd(x2, w_bf16, scores.detach(), thr_t, bias, torch.float32)
         ctx.save_for_backward(x2, scores, w_bf16, thr_t)
+        ctx.wm = wm_bf16
         ctx.x_shape = shp
         ctx.need_dx = x.requires_grad
         ctx.sink = sink
@@ -219,7 +230,10 @@ class MaskedLinearFn(torch.autograd.Function):
         dy2 = to_bf16(dy.reshape(-1, dy.shape[-1]))
         dx = None
         if ctx.need_dx:
-            dx = masked_linear_bwd_dx(dy2, w_bf16, scores.detach(), thr_t, torch.float32).view(ctx.x_shape)
+            if ctx.wm is not None:
+                dx = masked_linear_bwd_dx(dy2, ctx.wm, None, None, torch.float32).view(ctx.x_shape)
+            else:
+                dx = masked_linear_bwd_dx(dy2, w_bf16, scores.detach(), thr_t, torch.float32).view(ctx.x_shape)
         ds = None
         if ctx.needs_input_grad[1]:
             sink_grad = _sink_grad(ctx.sink)
@@ -228,7 +242,7 @@ class MaskedLinearFn(torch.autograd.Function):
                 _sink_done(ctx.sink)
             else:
                 ds = masked_linear_bwd_ds(dy2, x2, w_bf16)
-        return dx, ds, None, None, None, None
+        return dx, ds, None, None, None, None, None
 
 
 class MaskedLinearSmallKFn(torch.autograd.Function):
@@ -381,11 +395,16 @@ def sumsq_into(x, acc):
     check(lib.crv_sumsq(_p(x), x.numel(), _p(acc), _stream()), "crv_sumsq")
 
 
+def adam_step_size(lr, step, beta1, beta2, correct_bias=True):
+    if not correct_bias:
+        return lr
+    return lr * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
+
+
 def adamw_step_flat(p, g, m, v, s, lr, step, beta1, beta2, eps, weight_decay, total_sumsq=None, max_norm=1.0,
-                    correct_bias=True):
-    step_size = lr
-    if correct_bias:
-        step_size = lr * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
+                    correct_bias=True, hyper=None):
+    """hyper: optional device tensor {lr, step_size}; when given it overrides lr / step (CUDA-graph replay)."""
+    step_size = adam_step_size(lr, step, beta1, beta2, correct_bias)
     check(lib.crv_adamw_step(_p(p), _p(g), _p(m), _p(v), _p(s), p.numel(), float(lr), float(step_size),
                              float(beta1), float(beta2), float(eps), float(weight_decay), _p(total_sumsq),
-                             float(max_norm), _stream()), "crv_adamw_step")
+                             float(max_norm), _p(hyper), _stream()), "crv_adamw_step")

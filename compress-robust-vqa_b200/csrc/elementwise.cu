@@ -94,6 +94,32 @@ __global__ void apply_mask_kernel(const uint16_t* __restrict__ w, const float* _
   }
 }
 
+// Wm = W (.) (S > thr[seg]) over a whole score arena in one launch.  `chunks` holds (start, len, seg)
+// triples (element units, start % 8 == 0, no chunk straddles a module) built once by the host.
+__global__ void apply_mask_segmented_kernel(const uint16_t* __restrict__ w, const float* __restrict__ s,
+                                            const float* __restrict__ thr_vec, const int4* __restrict__ chunks,
+                                            int nchunks, uint16_t* __restrict__ wm) {
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int4 ch = __ldg(chunks + c);
+    const float thr = __ldg(thr_vec + ch.z);
+    const int64_t base = static_cast<int64_t>(ch.x) * 8;  // start is stored in units of 8 elements
+    const int nvec = ch.y >> 3;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const int64_t e = base + static_cast<int64_t>(i) * 8;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(s + e));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(s + e) + 1);
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(w + e));
+      v.x &= (a.x > thr ? 0x0000FFFFu : 0u) | (a.y > thr ? 0xFFFF0000u : 0u);
+      v.y &= (a.z > thr ? 0x0000FFFFu : 0u) | (a.w > thr ? 0xFFFF0000u : 0u);
+      v.z &= (b.x > thr ? 0x0000FFFFu : 0u) | (b.y > thr ? 0xFFFF0000u : 0u);
+      v.w &= (b.z > thr ? 0x0000FFFFu : 0u) | (b.w > thr ? 0xFFFF0000u : 0u);
+      *reinterpret_cast<uint4*>(wm + e) = v;
+    }
+    for (int i = (nvec << 3) + threadIdx.x; i < ch.y; i += blockDim.x)
+      wm[base + i] = s[base + i] > thr ? w[base + i] : uint16_t(0);
+  }
+}
+
 __global__ void magnitude_init_kernel(const float* __restrict__ w, const float* __restrict__ thr_p, float hi,
                                       float lo, float* __restrict__ s, int64_t n) {
   const float thr = __ldg(thr_p);
@@ -150,7 +176,11 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, float* __restrict__ sum, int64_t n, AdamArgs a,
-                             const float* __restrict__ total_sumsq) {
+                             const float* __restrict__ total_sumsq, const float* __restrict__ hyper) {
+  if (hyper) {  // {lr, step_size} live in device memory so a captured CUDA graph follows the LR schedule
+    a.lr = __ldg(hyper);
+    a.step_size = __ldg(hyper + 1);
+  }
   float clip = 1.0f;
   if (total_sumsq) {
     // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
@@ -335,6 +365,17 @@ extern "C" int crv_apply_mask_bf16(const uint16_t* w, const float* scores, const
   return launch_status();
 }
 
+extern "C" int crv_apply_mask_segmented(const uint16_t* w, const float* scores, const float* thr_vec,
+                                        const int* chunks, int nchunks, uint16_t* wm, void* stream) {
+  if (!w || !scores || !thr_vec || !chunks || !wm || nchunks < 0) return CRV_E_BADARG;
+  if (nchunks == 0) return CRV_OK;
+  if (!aligned16(w) || !aligned16(scores) || !aligned16(wm) || !aligned16(chunks)) return CRV_E_ALIGN;
+  const int grid = nchunks < num_sms() * 8 ? nchunks : num_sms() * 8;
+  apply_mask_segmented_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, scores, thr_vec, reinterpret_cast<const int4*>(chunks), nchunks, wm);
+  return launch_status();
+}
+
 extern "C" int crv_magnitude_init(const float* w, const float* w_thr, float hi, float lo, float* scores, int64_t n,
                                   void* stream) {
   if (!w || !w_thr || !scores || n < 0) return CRV_E_BADARG;
@@ -355,13 +396,13 @@ extern "C" int crv_sumsq(const float* x, int64_t n, float* out, void* stream) {
 
 extern "C" int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int64_t n, float lr,
                               float step_size, float beta1, float beta2, float eps, float weight_decay,
-                              const float* total_sumsq, float max_norm, void* stream) {
+                              const float* total_sumsq, float max_norm, const float* hyper_dev, void* stream) {
   if (!p || !g || !m || !v || n < 0) return CRV_E_BADARG;
   if (n == 0) return CRV_OK;
   if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (sum && !aligned16(sum))) return CRV_E_ALIGN;
   AdamArgs a{lr, step_size, beta1, beta2, eps, weight_decay, max_norm};
   adamw_kernel<<<stream_grid(n >> 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, sum, n, a,
-                                                                                         total_sumsq);
+                                                                                         total_sumsq, hyper_dev);
   return launch_status();
 }
 

@@ -1,6 +1,6 @@
 // Masked GEMM family for sm_100a: TMA -> (mask transform in shared memory) -> tcgen05.mma -> TMEM
-// -> epilogue.  One kernel template covers the three GEMMs of a masked linear layer
-// (reference: masking/maskers.py:359-366 and its autograd):
+// -> epilogue -> TMA store.  One persistent, warp-specialised kernel template covers the three GEMMs
+// of a masked linear layer (reference: masking/maskers.py:359-366 and its autograd):
 //
 //   FWD : Y [M,N]  = X [M,K]  . (W (.) (S > thr))^T + b      A = X  K-major,  B = W  K-major  (+S)
 //   DX  : dX[M,K]  = dY[M,N]  . (W (.) (S > thr))            A = dY K-major,  B = W  MN-major (+S)
@@ -8,16 +8,20 @@
 //
 // Generic view used below:  D[MM,NN] = sum_kk A(mm,kk) * B(nn,kk).
 //
-// CTA = 128 x BN output tile, BK = 64 bf16 (one 128-byte swizzle row) per pipeline stage.
-// Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-5 = epilogue
-// (TMEM -> registers -> global), warps6-9 = mask transform (only when XFORM).
-// Shared-memory operand tiles are in the canonical 128B-swizzled UMMA layouts written by TMA:
+// Grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n fastest).  Tile =
+// 128 x BN outputs, BK = 64 bf16 (one 128-byte swizzle row) per pipeline stage.  Warp roles:
+//   warp 0      TMA producer (runs ahead across tile boundaries through the smem ring)
+//   warp 1      MMA issuer, one thread; accumulators double-buffered in TMEM (2 x BN columns) so the
+//               next tile's mainloop overlaps this tile's epilogue
+//   warps 2-5   epilogue: tcgen05.ld -> registers -> (+bias | (.)W) -> 128B-swizzled smem staging ->
+//               TMA store (or TMA reduce-add for split / accumulating dS); TMA clips partial tiles
+//   warps 6-9   mask transform (XFORM only): AND the bf16 lanes of the W tile with (S > thr) in place
+// Shared-memory operand tiles are the canonical 128B-swizzled UMMA layouts written by TMA:
 //   K-major  tile [R rows][64 k]   : R x 128 B, 8-row swizzle atoms, SBO = 1024 B
 //   MN-major tile [64 kk][R mn]    : R/64 boxes of (64 kk rows x 128 B), LBO = 8192 B, SBO = 1024 B
-// The score tile (fp32) is loaded by TMA as boxes of 32 floats (128 B) per row with the same
-// swizzle, so a transform thread reads one 16-byte chunk of W (8 bf16) plus the two matching
-// 16-byte chunks of S without bank conflicts, zeroes the masked-out bf16 lanes in place, then
-// fences the generic-proxy writes towards the async proxy before the MMA warp is released.
+// The score tile (fp32) arrives as boxes of 32 floats (128 B) per row with the same swizzle, so a
+// transform thread reads one 16-byte chunk of W (8 bf16) plus the two matching 16-byte chunks of S
+// without bank conflicts, then fences its generic-proxy writes towards the async proxy.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -25,18 +29,18 @@ namespace crv {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiStoreF32 = 0;
-constexpr int kEpiStoreBF16 = 1;
-constexpr int kEpiScoreGrad = 2;
+constexpr int kEpiStore = 0;      // D (+ bias) -> out
+constexpr int kEpiScoreGrad = 2;  // D (.) W -> out (store or reduce-add)
 
 struct GemmParams {
   int MM, NN, KK;          // generic problem extents
-  int kb_per_split;        // k-blocks handled by one blockIdx.z
+  int kb_per_split;        // k-blocks handled by one split
+  int splits;              // reduction splits (score-grad only)
+  int num_m, num_n;        // tile counts
   const float* thr;        // device scalar (XFORM)
-  const float* bias;       // [NN] or null (store epilogues)
-  void* out;               // D, row-major [MM, NN]
+  const float* bias;       // [NN] or null (store epilogue)
   const __nv_bfloat16* w;  // [MM, NN] bf16 multiplier (score-grad epilogue)
-  int atomic_out;          // score-grad: 1 = red.add into out, 0 = plain store
+  int reduce_out;          // score-grad: 1 = TMA reduce-add into out, 0 = plain TMA store
 };
 
 template <int BN, bool XFORM>
@@ -46,54 +50,90 @@ struct SmemLayout {
   static constexpr int kS = XFORM ? BN * BK * 4 : 0;     // 32 KB
   static constexpr int kStage = kA + kB + kS;
   static constexpr int kStages = XFORM ? 3 : (BN == 256 ? 4 : 6);
-  static constexpr int kBarBytes = 1024;
-  static constexpr int kTotal = kStages * kStage + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kEpi = 4 * 2 * 4096;              // 4 warps x 2 staging buffers x (32 rows x 128 B)
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kStages * kStage + kEpi + kBarBytes + 1024;  // + alignment slack
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <bool A_MN, bool B_MN, int BN, bool XFORM, int EPI>
+struct TileCoord {
+  int m0, n0, kb_begin, num_kb;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile, int bn) {
+  const int per_z = p.num_m * p.num_n;
+  const int z = tile / per_z;
+  const int r = tile - z * per_z;
+  const int mt = r / p.num_n;
+  const int nt = r - mt * p.num_n;
+  const int total_kb = (p.KK + BK - 1) / BK;
+  TileCoord t;
+  t.m0 = mt * BM;
+  t.n0 = nt * bn;
+  t.kb_begin = z * p.kb_per_split;
+  int e = t.kb_begin + p.kb_per_split;
+  if (e > total_kb) e = total_kb;
+  t.num_kb = e - t.kb_begin;  // host guarantees >= 1
+  return t;
+}
+
+template <bool A_MN, bool B_MN, int BN, bool XFORM, int EPI, bool OUT_BF16>
 __global__ void __launch_bounds__(XFORM ? 320 : 192, 1)
 masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmS, const GemmParams p) {
+                   const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmOut,
+                   const GemmParams p) {
   using L = SmemLayout<BN, XFORM>;
   constexpr int STAGES = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bar_base = smem + STAGES * L::kStage;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint8_t* epi_base = smem + STAGES * L::kStage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_base + L::kEpi);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* xform_bar = empty_bar + STAGES;
-  uint64_t* tmem_full_bar = xform_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = xform_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
-  const int num_kb_total = (p.KK + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(kb_begin + p.kb_per_split, num_kb_total);
-  const int num_kb = kb_end - kb_begin;
-  if (num_kb <= 0) return;  // uniform per CTA: an empty split contributes nothing
+  const int num_tiles = p.num_m * p.num_n * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
     if (XFORM) tma_prefetch_desc(&tmS);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
-      mbar_init(&xform_bar[s], 128);
+      mbar_init(&xform_bar[s], 4);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, 2 * BN);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -104,33 +144,38 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int it = 0; it < num_kb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], L::kStage);
-        uint8_t* sA = smem + s * L::kStage;
-        uint8_t* sB = sA + L::kA;
-        uint8_t* sS = sB + L::kB;
-        const int kk0 = (kb_begin + it) * BK;
-        if (!A_MN) {
-          tma_load_2d(sA, &tmA, &full_bar[s], kk0, m0);
-        } else {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(p, tile, BN);
+        for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], L::kStage);
+          uint8_t* sA = smem + s * L::kStage;
+          uint8_t* sB = sA + L::kA;
+          uint8_t* sS = sB + L::kB;
+          const int kk0 = (tc.kb_begin + kb) * BK;
+          if (!A_MN) {
+            tma_load_2d(sA, &tmA, &full_bar[s], kk0, tc.m0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * 8192, &tmA, &full_bar[s], m0 + 64 * j, kk0);
-        }
-        if (!B_MN) {
-          tma_load_2d(sB, &tmB, &full_bar[s], kk0, n0);
-          if (XFORM) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) tma_load_2d(sS + h * (BN * 128), &tmS, &full_bar[s], kk0 + 32 * h, n0);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * 8192, &tmA, &full_bar[s], tc.m0 + 64 * j, kk0);
           }
-        } else {
+          if (!B_MN) {
+            tma_load_2d(sB, &tmB, &full_bar[s], kk0, tc.n0);
+            if (XFORM) {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * 8192, &tmB, &full_bar[s], n0 + 64 * j, kk0);
-          if (XFORM) {
+              for (int h = 0; h < 2; ++h)
+                tma_load_2d(sS + h * (BN * 128), &tmS, &full_bar[s], kk0 + 32 * h, tc.n0);
+            }
+          } else {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j) tma_load_2d(sS + j * 8192, &tmS, &full_bar[s], n0 + 32 * j, kk0);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * 8192, &tmB, &full_bar[s], tc.n0 + 64 * j, kk0);
+            if (XFORM) {
+#pragma unroll
+              for (int j = 0; j < BN / 32; ++j) tma_load_2d(sS + j * 8192, &tmS, &full_bar[s], tc.n0 + 32 * j, kk0);
+            }
           }
         }
       }
@@ -138,159 +183,177 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-    for (int it = 0; it < num_kb; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      mbar_wait(&full_bar[s], ph);
-      if (XFORM) mbar_wait(&xform_bar[s], ph);
+    int it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const TileCoord tc = tile_coord(p, tile, BN);
+      const int acc = tcount & 1;
+      mbar_wait(&tmem_empty_bar[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t aBase = smem_u32(smem + s * L::kStage);
-        const uint32_t bBase = aBase + L::kA;
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        if (XFORM) mbar_wait(&xform_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t aBase = smem_u32(smem + s * L::kStage);
+          const uint32_t bBase = aBase + L::kA;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = A_MN ? make_sw128_desc(aBase + k * 2048, 8192, 1024)
-                                   : make_sw128_desc(aBase + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? make_sw128_desc(bBase + k * 2048, 8192, 1024)
-                                   : make_sw128_desc(bBase + k * 32, 16, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? make_sw128_desc(aBase + k * 2048, 8192, 1024)
+                                     : make_sw128_desc(aBase + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_sw128_desc(bBase + k * 2048, 8192, 1024)
+                                     : make_sw128_desc(bBase + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);                                // frees the smem slot when these MMAs retire
+          if (kb == tc.num_kb - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
         }
-        umma_commit(&empty_bar[s]);                       // frees the smem slot when these MMAs retire
-        if (it == num_kb - 1) umma_commit(tmem_full_bar);  // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp < 6) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    uint8_t* stage_buf = epi_base + (warp - 2) * 8192;
+    constexpr int COLS = OUT_BF16 ? 64 : 32;  // columns per 128-byte staging row
+    int tcount = 0, chunk_no = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const TileCoord tc = tile_coord(p, tile, BN);
+      const int acc = tcount & 1;
+      const int row0 = tc.m0 + q * 32;
+      const int m = row0 + lane;
+      mbar_wait(&tmem_full_bar[acc], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
-      tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (m < p.MM && nb < p.NN) {
-        const bool full = (nb + 32 <= p.NN) && ((p.NN & 3) == 0);
-        if (EPI == kEpiStoreF32) {
-          float* o = static_cast<float*>(p.out) + static_cast<size_t>(m) * p.NN + nb;
-          if (full) {
+      for (int c = 0; c < BN / COLS; ++c, ++chunk_no) {
+        const int nb = tc.n0 + c * COLS;
+        uint32_t r[32];
+        uint32_t pk[32];  // staging row as 32 words (fp32) or 32 packed bf16 pairs
+        tmem_ld_32x32(t_addr + c * COLS, r);
+        tmem_ld_wait();
+        if (OUT_BF16) {
+          uint32_t r2[32];
+          tmem_ld_32x32(t_addr + c * COLS + 32, r2);
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v;
-              v.x = __uint_as_float(r[j]);
-              v.y = __uint_as_float(r[j + 1]);
-              v.z = __uint_as_float(r[j + 2]);
-              v.w = __uint_as_float(r[j + 3]);
-              if (p.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              }
-              *reinterpret_cast<float4*>(o + j) = v;
+          for (int j = 0; j < 16; ++j) {
+            float a0 = __uint_as_float(r[2 * j]), a1 = __uint_as_float(r[2 * j + 1]);
+            float b0 = __uint_as_float(r2[2 * j]), b1 = __uint_as_float(r2[2 * j + 1]);
+            if (p.bias) {
+              if (nb + 2 * j + 1 < p.NN) { a0 += __ldg(p.bias + nb + 2 * j); a1 += __ldg(p.bias + nb + 2 * j + 1); }
+              if (nb + 32 + 2 * j + 1 < p.NN) { b0 += __ldg(p.bias + nb + 32 + 2 * j); b1 += __ldg(p.bias + nb + 33 + 2 * j); }
             }
-          } else {
-            for (int j = 0; j < 32 && nb + j < p.NN; ++j)
-              o[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[nb + j] : 0.f);
+            __nv_bfloat162 ta = __floats2bfloat162_rn(a0, a1);
+            __nv_bfloat162 tb = __floats2bfloat162_rn(b0, b1);
+            pk[j] = *reinterpret_cast<uint32_t*>(&ta);
+            pk[16 + j] = *reinterpret_cast<uint32_t*>(&tb);
           }
-        } else if (EPI == kEpiStoreBF16) {
-          __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.NN + nb;
-          if (full && (p.NN & 7) == 0) {
+        } else if (EPI == kEpiStore) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float lo = __uint_as_float(r[j + 2 * e]);
-                float hi = __uint_as_float(r[j + 2 * e + 1]);
-                if (p.bias) { lo += __ldg(p.bias + nb + j + 2 * e); hi += __ldg(p.bias + nb + j + 2 * e + 1); }
-                __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-                pk[e] = *reinterpret_cast<uint32_t*>(&t);
-              }
-              *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-          } else {
-            for (int j = 0; j < 32 && nb + j < p.NN; ++j)
-              o[j] = __float2bfloat16_rn(__uint_as_float(r[j]) + (p.bias ? p.bias[nb + j] : 0.f));
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]);
+            if (p.bias && nb + j < p.NN) v += __ldg(p.bias + nb + j);
+            pk[j] = __float_as_uint(v);
           }
-        } else {  // kEpiScoreGrad: (.) W then accumulate / store
-          float* o = static_cast<float*>(p.out) + static_cast<size_t>(m) * p.NN + nb;
-          const __nv_bfloat16* wrow = p.w + static_cast<size_t>(m) * p.NN + nb;
-          if (full && (p.NN & 7) == 0) {
+        } else {  // score gradient: (.) W
+          const bool row_ok = m < p.MM;
+          const __nv_bfloat16* wrow = p.w + static_cast<size_t>(row_ok ? m : 0) * p.NN + nb;
+          if (row_ok && nb + 32 <= p.NN && (p.NN & 7) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wrow + j));
               const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-              float v[8];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                v[2 * e] = __uint_as_float(r[j + 2 * e]) * __uint_as_float(ww[e] << 16);
-                v[2 * e + 1] = __uint_as_float(r[j + 2 * e + 1]) * __uint_as_float(ww[e] & 0xFFFF0000u);
-              }
-              if (p.atomic_out) {
-                red_add_v4(o + j, v[0], v[1], v[2], v[3]);
-                red_add_v4(o + j + 4, v[4], v[5], v[6], v[7]);
-              } else {
-                *reinterpret_cast<float4*>(o + j) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(o + j + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                pk[j + 2 * e] = __float_as_uint(__uint_as_float(r[j + 2 * e]) * __uint_as_float(ww[e] << 16));
+                pk[j + 2 * e + 1] =
+                    __float_as_uint(__uint_as_float(r[j + 2 * e + 1]) * __uint_as_float(ww[e] & 0xFFFF0000u));
               }
             }
           } else {
-            for (int j = 0; j < 32 && nb + j < p.NN; ++j) {
-              const float v = __uint_as_float(r[j]) * __bfloat162float(wrow[j]);
-              if (p.atomic_out) atomicAdd(o + j, v); else o[j] = v;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float wv = (row_ok && nb + j < p.NN) ? __bfloat162float(wrow[j]) : 0.f;
+              pk[j] = __float_as_uint(__uint_as_float(r[j]) * wv);
             }
           }
         }
+        // staging buffer (double-buffered per warp): wait until the TMA store issued two chunks ago has read it
+        uint8_t* buf = stage_buf + (chunk_no & 1) * 4096;
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        const int sw = lane & 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ sw) << 4)) =
+              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && nb < p.NN && row0 < p.MM) {
+          if (EPI == kEpiScoreGrad && p.reduce_out) tma_reduce_add_2d(&tmOut, buf, nb, row0);
+          else tma_store_2d(&tmOut, buf, nb, row0);
+        }
+        if (lane == 0) bulk_commit();
       }
+      // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if (lane == 0) bulk_wait_all();
   } else if (XFORM) {
     // ------------------------------------------------------------------ mask transform (128 threads)
     const int tid = threadIdx.x - 192;
     const float thr = __ldg(p.thr);
-    for (int it = 0; it < num_kb; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      uint8_t* sB = smem + s * L::kStage + L::kA;
-      uint8_t* sS = sB + L::kB;
-      mbar_wait(&full_bar[s], ph);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord tc = tile_coord(p, tile, BN);
+      for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        uint8_t* sB = smem + s * L::kStage + L::kA;
+        uint8_t* sS = sB + L::kB;
+        mbar_wait(&full_bar[s], ph);
 #pragma unroll
-      for (int i = 0; i < BN * 8 / 128; ++i) {
-        const int qd = i * 128 + tid;
-        const int c = qd & 7;     // 16-byte chunk of the 128-byte W row (8 bf16)
-        const int rr = qd >> 3;   // row over the whole tile
-        int r, wbox_off, sbox_off;
-        if (!B_MN) {              // W: one box of BN rows; S: two boxes (k halves) of BN rows
-          r = rr;
-          wbox_off = 0;
-          sbox_off = (c >> 2) * (BN * 128);
-        } else {                  // W: BN/64 boxes of 64 rows; S: BN/32 boxes of 64 rows
-          r = rr & 63;
-          wbox_off = (rr >> 6) * 8192;
-          sbox_off = ((rr >> 6) * 2 + (c >> 2)) * 8192;
+        for (int i = 0; i < BN * 8 / 128; ++i) {
+          const int qd = i * 128 + tid;
+          const int c = qd & 7;     // 16-byte chunk of the 128-byte W row (8 bf16)
+          const int rr = qd >> 3;   // row over the whole tile
+          int r, wbox_off, sbox_off;
+          if (!B_MN) {              // W: one box of BN rows; S: two boxes (k halves) of BN rows
+            r = rr;
+            wbox_off = 0;
+            sbox_off = (c >> 2) * (BN * 128);
+          } else {                  // W: BN/64 boxes of 64 rows; S: BN/32 boxes of 64 rows
+            r = rr & 63;
+            wbox_off = (rr >> 6) * 8192;
+            sbox_off = ((rr >> 6) * 2 + (c >> 2)) * 8192;
+          }
+          const int sw = r & 7;
+          uint4* wp = reinterpret_cast<uint4*>(sB + wbox_off + r * 128 + ((c ^ sw) << 4));
+          const int j0 = (c & 3) * 2;
+          // lanes with c >= 4 fetch the odd chunk first so a quarter-warp touches 8 distinct banksets
+          const int first = j0 + (c >> 2);
+          const int second = j0 + 1 - (c >> 2);
+          const uint8_t* srow = sS + sbox_off + r * 128;
+          const float4 f1 = *reinterpret_cast<const float4*>(srow + ((first ^ sw) << 4));
+          const float4 f2 = *reinterpret_cast<const float4*>(srow + ((second ^ sw) << 4));
+          const float4 lo = (c >> 2) ? f2 : f1;  // scores of elements 0..3
+          const float4 hi = (c >> 2) ? f1 : f2;  // scores of elements 4..7
+          uint4 w = *wp;
+          w.x &= (lo.x > thr ? 0x0000FFFFu : 0u) | (lo.y > thr ? 0xFFFF0000u : 0u);
+          w.y &= (lo.z > thr ? 0x0000FFFFu : 0u) | (lo.w > thr ? 0xFFFF0000u : 0u);
+          w.z &= (hi.x > thr ? 0x0000FFFFu : 0u) | (hi.y > thr ? 0xFFFF0000u : 0u);
+          w.w &= (hi.z > thr ? 0x0000FFFFu : 0u) | (hi.w > thr ? 0xFFFF0000u : 0u);
+          *wp = w;
         }
-        const int sw = r & 7;
-        uint4* wp = reinterpret_cast<uint4*>(sB + wbox_off + r * 128 + ((c ^ sw) << 4));
-        const int j0 = (c & 3) * 2;
-        // lanes with c >= 4 fetch the odd chunk first so a quarter-warp touches 8 distinct banksets
-        const int first = j0 + (c >> 2);
-        const int second = j0 + 1 - (c >> 2);
-        const uint8_t* srow = sS + sbox_off + r * 128;
-        const float4 f1 = *reinterpret_cast<const float4*>(srow + ((first ^ sw) << 4));
-        const float4 f2 = *reinterpret_cast<const float4*>(srow + ((second ^ sw) << 4));
-        const float4 lo = (c >> 2) ? f2 : f1;  // scores of elements 0..3
-        const float4 hi = (c >> 2) ? f1 : f2;  // scores of elements 4..7
-        uint4 w = *wp;
-        w.x &= (lo.x > thr ? 0x0000FFFFu : 0u) | (lo.y > thr ? 0xFFFF0000u : 0u);
-        w.y &= (lo.z > thr ? 0x0000FFFFu : 0u) | (lo.w > thr ? 0xFFFF0000u : 0u);
-        w.z &= (hi.x > thr ? 0x0000FFFFu : 0u) | (hi.y > thr ? 0xFFFF0000u : 0u);
-        w.w &= (hi.z > thr ? 0x0000FFFFu : 0u) | (hi.w > thr ? 0xFFFF0000u : 0u);
-        *wp = w;
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xform_bar[s]);
       }
-      fence_proxy_async_smem();
-      mbar_arrive(&xform_bar[s]);
     }
   }
 
@@ -298,7 +361,7 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -324,7 +387,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D row-major tensor [rows][cols] of elem_bytes elements; box = [box_rows][box_cols], 128B swizzle.
-static int make_map(CUtensorMap* map, const void* base, int elem_bytes, int64_t rows, int64_t cols,
+static int make_map(CUtensorMap* map, const void* base, int elem_bytes, bool is_float, int64_t rows, int64_t cols,
                     int box_rows, int box_cols) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return CRV_E_DRIVER;
@@ -332,10 +395,9 @@ static int make_map(CUtensorMap* map, const void* base, int elem_bytes, int64_t 
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * elem_bytes};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = is_float ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     g_last_cuda_error = static_cast<int>(r);
     return static_cast<int>(r);
@@ -343,25 +405,37 @@ static int make_map(CUtensorMap* map, const void* base, int elem_bytes, int64_t 
   return CRV_OK;
 }
 
-template <bool A_MN, bool B_MN, int BN, bool XFORM, int EPI>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmS, const GemmParams& p,
-                  int splits, cudaStream_t stream) {
+static int make_out_map(CUtensorMap* map, void* out, bool bf16, int64_t rows, int64_t cols) {
+  return bf16 ? make_map(map, out, 2, false, rows, cols, 32, 64) : make_map(map, out, 4, true, rows, cols, 32, 32);
+}
+
+template <bool A_MN, bool B_MN, int BN, bool XFORM, int EPI, bool OUT_BF16>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmS, const CUtensorMap& tmOut,
+                  GemmParams p, cudaStream_t stream) {
   using L = SmemLayout<BN, XFORM>;
-  auto kern = masked_gemm_kernel<A_MN, B_MN, BN, XFORM, EPI>;
+  auto kern = masked_gemm_kernel<A_MN, B_MN, BN, XFORM, EPI, OUT_BF16>;
   static bool configured = false;
   if (!configured) {
     CRV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  dim3 grid((p.NN + BN - 1) / BN, (p.MM + BM - 1) / BM, splits);
-  kern<<<grid, XFORM ? 320 : 192, L::kTotal, stream>>>(tmA, tmB, tmS, p);
+  p.num_m = (p.MM + BM - 1) / BM;
+  p.num_n = (p.NN + BN - 1) / BN;
+  const int tiles = p.num_m * p.num_n * p.splits;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, XFORM ? 320 : 192, L::kTotal, stream>>>(tmA, tmB, tmS, tmOut, p);
   return launch_status();
 }
 
 static int pick_bn(int MM, int NN) {
-  // 256-wide tiles halve the A re-reads; use them when the grid still fills the machine
-  const int tiles256 = ((NN + 255) / 256) * ((MM + BM - 1) / BM);
-  return (NN % 256 == 0 && tiles256 >= num_sms()) ? 256 : 128;
+  // wave quantisation on a persistent grid: cost ~ ceil(tiles / SMs) * BN; 256-wide tiles halve the A
+  // re-reads and win ties
+  if (NN % 256) return 128;
+  const int sms = num_sms();
+  const int mt = (MM + BM - 1) / BM;
+  const int t256 = mt * (NN / 256), t128 = mt * ((NN + 127) / 128);
+  const int c256 = ((t256 + sms - 1) / sms) * 256, c128 = ((t128 + sms - 1) / sms) * 128;
+  return c256 <= c128 ? 256 : 128;
 }
 
 }  // namespace crv
@@ -372,31 +446,34 @@ extern "C" int crv_masked_linear_fwd(const uint16_t* x, const uint16_t* w, const
                                      const float* bias, void* y, int y_dtype, int M, int N, int K, void* stream) {
   if (!x || !w || !y || M <= 0 || N <= 0 || K <= 0) return CRV_E_BADARG;
   if (scores && !thr) return CRV_E_BADARG;
-  if (K % 8) return CRV_E_SHAPE;
-  if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (scores && !aligned16(scores))) return CRV_E_ALIGN;
   if (y_dtype != CRV_DTYPE_F32 && y_dtype != CRV_DTYPE_BF16) return CRV_E_BADARG;
+  const bool obf = y_dtype == CRV_DTYPE_BF16;
+  if ((K % 8) || (N % (obf ? 8 : 4))) return CRV_E_SHAPE;
+  if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (scores && !aligned16(scores))) return CRV_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GemmParams p{};
   p.MM = M; p.NN = N; p.KK = K;
   p.kb_per_split = (K + BK - 1) / BK;
-  p.thr = thr; p.bias = bias; p.out = y;
-  CUtensorMap tmA, tmB, tmS;
+  p.splits = 1;
+  p.thr = thr; p.bias = bias;
+  CUtensorMap tmA, tmB, tmS, tmO;
   int rc;
-  if ((rc = make_map(&tmA, x, 2, M, K, BM, BK))) return rc;
+  if ((rc = make_map(&tmA, x, 2, false, M, K, BM, BK))) return rc;
+  if ((rc = make_out_map(&tmO, y, obf, M, N))) return rc;
   if (scores) {
-    if ((rc = make_map(&tmB, w, 2, N, K, 128, BK))) return rc;
-    if ((rc = make_map(&tmS, scores, 4, N, K, 128, 32))) return rc;
-    return y_dtype == CRV_DTYPE_F32 ? launch<false, false, 128, true, kEpiStoreF32>(tmA, tmB, tmS, p, 1, st)
-                                    : launch<false, false, 128, true, kEpiStoreBF16>(tmA, tmB, tmS, p, 1, st);
+    if ((rc = make_map(&tmB, w, 2, false, N, K, 128, BK))) return rc;
+    if ((rc = make_map(&tmS, scores, 4, true, N, K, 128, 32))) return rc;
+    return obf ? launch<false, false, 128, true, kEpiStore, true>(tmA, tmB, tmS, tmO, p, st)
+               : launch<false, false, 128, true, kEpiStore, false>(tmA, tmB, tmS, tmO, p, st);
   }
   const int bn = pick_bn(M, N);
-  if ((rc = make_map(&tmB, w, 2, N, K, bn, BK))) return rc;
+  if ((rc = make_map(&tmB, w, 2, false, N, K, bn, BK))) return rc;
   tmS = tmB;
   if (bn == 256)
-    return y_dtype == CRV_DTYPE_F32 ? launch<false, false, 256, false, kEpiStoreF32>(tmA, tmB, tmS, p, 1, st)
-                                    : launch<false, false, 256, false, kEpiStoreBF16>(tmA, tmB, tmS, p, 1, st);
-  return y_dtype == CRV_DTYPE_F32 ? launch<false, false, 128, false, kEpiStoreF32>(tmA, tmB, tmS, p, 1, st)
-                                  : launch<false, false, 128, false, kEpiStoreBF16>(tmA, tmB, tmS, p, 1, st);
+    return obf ? launch<false, false, 256, false, kEpiStore, true>(tmA, tmB, tmS, tmO, p, st)
+               : launch<false, false, 256, false, kEpiStore, false>(tmA, tmB, tmS, tmO, p, st);
+  return obf ? launch<false, false, 128, false, kEpiStore, true>(tmA, tmB, tmS, tmO, p, st)
+             : launch<false, false, 128, false, kEpiStore, false>(tmA, tmB, tmS, tmO, p, st);
 }
 
 extern "C" int crv_masked_linear_bwd_dx(const uint16_t* dy, const uint16_t* w, const float* scores,
@@ -407,27 +484,30 @@ extern "C" int crv_masked_linear_bwd_dx(const uint16_t* dy, const uint16_t* w, c
   if ((N % 8) || (K % 8)) return CRV_E_SHAPE;
   if (!aligned16(dy) || !aligned16(w) || !aligned16(dx) || (scores && !aligned16(scores))) return CRV_E_ALIGN;
   if (dx_dtype != CRV_DTYPE_F32 && dx_dtype != CRV_DTYPE_BF16) return CRV_E_BADARG;
+  const bool obf = dx_dtype == CRV_DTYPE_BF16;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // generic: MM = M, NN = K, KK = N;  A = dY [M][N] K-major;  B = W [N][K] = [KK][NN] MN-major
   GemmParams p{};
   p.MM = M; p.NN = K; p.KK = N;
   p.kb_per_split = (N + BK - 1) / BK;
-  p.thr = thr; p.bias = nullptr; p.out = dx;
-  CUtensorMap tmA, tmB, tmS;
+  p.splits = 1;
+  p.thr = thr;
+  CUtensorMap tmA, tmB, tmS, tmO;
   int rc;
-  if ((rc = make_map(&tmA, dy, 2, M, N, BM, BK))) return rc;
-  if ((rc = make_map(&tmB, w, 2, N, K, 64, 64))) return rc;
+  if ((rc = make_map(&tmA, dy, 2, false, M, N, BM, BK))) return rc;
+  if ((rc = make_map(&tmB, w, 2, false, N, K, 64, 64))) return rc;
+  if ((rc = make_out_map(&tmO, dx, obf, M, K))) return rc;
   if (scores) {
-    if ((rc = make_map(&tmS, scores, 4, N, K, 64, 32))) return rc;
-    return dx_dtype == CRV_DTYPE_F32 ? launch<false, true, 128, true, kEpiStoreF32>(tmA, tmB, tmS, p, 1, st)
-                                     : launch<false, true, 128, true, kEpiStoreBF16>(tmA, tmB, tmS, p, 1, st);
+    if ((rc = make_map(&tmS, scores, 4, true, N, K, 64, 32))) return rc;
+    return obf ? launch<false, true, 128, true, kEpiStore, true>(tmA, tmB, tmS, tmO, p, st)
+               : launch<false, true, 128, true, kEpiStore, false>(tmA, tmB, tmS, tmO, p, st);
   }
   tmS = tmB;
   if (pick_bn(M, K) == 256)
-    return dx_dtype == CRV_DTYPE_F32 ? launch<false, true, 256, false, kEpiStoreF32>(tmA, tmB, tmS, p, 1, st)
-                                     : launch<false, true, 256, false, kEpiStoreBF16>(tmA, tmB, tmS, p, 1, st);
-  return dx_dtype == CRV_DTYPE_F32 ? launch<false, true, 128, false, kEpiStoreF32>(tmA, tmB, tmS, p, 1, st)
-                                   : launch<false, true, 128, false, kEpiStoreBF16>(tmA, tmB, tmS, p, 1, st);
+    return obf ? launch<false, true, 256, false, kEpiStore, true>(tmA, tmB, tmS, tmO, p, st)
+               : launch<false, true, 256, false, kEpiStore, false>(tmA, tmB, tmS, tmO, p, st);
+  return obf ? launch<false, true, 128, false, kEpiStore, true>(tmA, tmB, tmS, tmO, p, st)
+             : launch<false, true, 128, false, kEpiStore, false>(tmA, tmB, tmS, tmO, p, st);
 }
 
 extern "C" int crv_masked_linear_bwd_ds(const uint16_t* dy, const uint16_t* x, const uint16_t* w, float* dscores,
@@ -438,23 +518,25 @@ extern "C" int crv_masked_linear_bwd_ds(const uint16_t* dy, const uint16_t* x, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // generic: MM = N, NN = K, KK = M;  A = dY [M][N] = [KK][MM] MN-major;  B = X [M][K] = [KK][NN] MN-major
   const int num_kb = (M + BK - 1) / BK;
-  const int tiles = ((N + BM - 1) / BM) * ((K + 127) / 128);
-  int splits = num_sms() / tiles;  // one wave of CTAs; every extra split costs one more fp32 red pass
-  if (splits < 1) splits = 1;
-  const int max_splits = (num_kb + 7) / 8;  // keep >= 8 k-blocks per split so the atomics stay a minor cost
+  const int bn = pick_bn(N, K);
+  const int tiles = ((N + BM - 1) / BM) * ((K + bn - 1) / bn);
+  int splits = num_sms() / tiles;  // one wave of CTAs; every extra split costs one more fp32 reduce pass
+  const int max_splits = (num_kb + 7) / 8;  // keep >= 8 k-blocks per split
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   GemmParams p{};
   p.MM = N; p.NN = K; p.KK = M;
   p.kb_per_split = (num_kb + splits - 1) / splits;
-  splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
-  p.out = dscores; p.w = reinterpret_cast<const __nv_bfloat16*>(w);
-  p.atomic_out = (splits > 1 || accumulate) ? 1 : 0;
-  if (splits > 1 && !accumulate)
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.w = reinterpret_cast<const __nv_bfloat16*>(w);
+  p.reduce_out = (p.splits > 1 || accumulate) ? 1 : 0;
+  if (p.splits > 1 && !accumulate)
     CRV_CUDA(cudaMemsetAsync(dscores, 0, static_cast<size_t>(N) * K * sizeof(float), st));
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
   int rc;
-  if ((rc = make_map(&tmA, dy, 2, M, N, 64, 64))) return rc;
-  if ((rc = make_map(&tmB, x, 2, M, K, 64, 64))) return rc;
-  return launch<true, true, 128, false, kEpiScoreGrad>(tmA, tmB, tmB, p, splits, st);
+  if ((rc = make_map(&tmA, dy, 2, false, M, N, 64, 64))) return rc;
+  if ((rc = make_map(&tmB, x, 2, false, M, K, 64, 64))) return rc;
+  if ((rc = make_out_map(&tmO, dscores, false, N, K))) return rc;
+  if (bn == 256) return launch<true, true, 256, false, kEpiScoreGrad, false>(tmA, tmB, tmB, tmO, p, st);
+  return launch<true, true, 128, false, kEpiScoreGrad, false>(tmA, tmB, tmB, tmO, p, st);
 }

@@ -62,6 +62,14 @@ class ScoreArena:
             m._grad_dirty = False
             m._arena = self
             self._index[id(p)] = i
+        # thresholds of all modules in one device vector; module.threshold stays a 0-dim tensor (a view)
+        self.thr_vec = torch.tensor([float(m.threshold) for m in self.modules], dtype=torch.float32, device=device)
+        for i, m in enumerate(self.modules):
+            m.threshold = self.thr_vec[i]
+        # mask cache (enable_mask_cache): bf16 weights and W (.) M, same element offsets as the scores
+        self.cache_on = False
+        self.epoch = 0
+        self.w16 = self.wm = self.chunks = None
 
     def _view(self, flat, i):
         p = self.modules[i].weight_mask
@@ -84,6 +92,57 @@ class ScoreArena:
         return {"sum": self._view(self.sum, i), "exp_avg": self._view(self.exp_avg, i),
                 "exp_avg_sq": self._view(self.exp_avg_sq, i)}
 
+    # -- mask cache ------------------------------------------------------------------------------
+    def set_thresholds(self, thr):
+        """New thresholds (device vector, arena order) from reset_threshold; invalidates the mask cache."""
+        self.thr_vec.copy_(thr)
+        for i, m in enumerate(self.modules):
+            m.threshold = self.thr_vec[i]
+        self.epoch += 1
+
+    def _gemm_module(self, m):
+        return "embedding" not in m.name and m.weight.dim() == 2 and m.weight.shape[1] % 8 == 0
+
+    def enable_mask_cache(self):
+        """Scores change only at the optimiser step and thresholds only at reset_threshold, so the masked
+        bf16 weight of every module is materialised once per step (ONE launch over the arena) and the
+        forward / dX GEMMs read it as a plain operand instead of re-deriving the mask per call."""
+        if self.cache_on:
+            return
+        dev = self.scores.device
+        self.w16 = torch.zeros(self.total, dtype=torch.bfloat16, device=dev)
+        self.wm = torch.zeros(self.total, dtype=torch.bfloat16, device=dev)
+        rows = []
+        for i, m in enumerate(self.modules):
+            if not self._gemm_module(m):
+                continue
+            n, off = m.weight_mask.numel(), self.offsets[i]
+            self.w16[off: off + n].view(m.weight.shape).copy_(ops.to_bf16(m.weight.detach()))
+            m._w16 = self.w16[off: off + n].view(m.weight.shape)
+            m._w16_key = (m.weight.data_ptr(), m.weight._version, m.weight.device)
+            m._wm = self.wm[off: off + n].view(m.weight.shape)
+            for c0 in range(0, n, 8192):
+                rows.append(((off + c0) // 8, min(8192, n - c0), i, 0))
+        self.chunks = torch.tensor(rows, dtype=torch.int32, device=dev).contiguous()
+        self.cache_on = True
+        self.refresh_masked()
+
+    def refresh_masked(self):
+        if not self.cache_on:
+            return
+        ops.apply_mask_segmented(self.w16, self.scores, self.thr_vec, self.chunks, self.wm)
+        for m in self.modules:
+            m._wm_epoch = self.epoch
+            m._wm_sver = m.weight_mask._version
+            m._wm_thr_ptr = m.threshold.data_ptr()
+
+    def cached_masked_weight(self, m):
+        """The module's W (.) M if it is valid for the current scores and threshold, else None."""
+        if (self.cache_on and getattr(m, "_wm_epoch", -1) == self.epoch and m.weight_mask._version == m._wm_sver
+                and torch.is_tensor(m.threshold) and m.threshold.data_ptr() == m._wm_thr_ptr):
+            return m._wm
+        return None
+
     # -- per-step protocol ---------------------------------------------------------------------
     def begin_step(self):
         """Replaces zero_grad for the arena: nothing is memset; the first dS of a module overwrites."""
@@ -104,10 +163,12 @@ class ScoreArena:
         ops.sumsq_into(self.grads, acc)
 
     def adamw_step(self, lr, step, beta1, beta2, eps, weight_decay, correct_bias, clip_sumsq, max_norm,
-                   with_sum=True):
+                   with_sum=True, hyper=None):
         self._ensure_state()
         ops.adamw_step_flat(self.scores, self.grads, self.exp_avg, self.exp_avg_sq, self.sum if with_sum else None,
-                            lr, step, beta1, beta2, eps, weight_decay, clip_sumsq, max_norm, correct_bias)
+                            lr, step, beta1, beta2, eps, weight_decay, clip_sumsq, max_norm, correct_bias, hyper)
+        self.epoch += 1            # scores moved: the mask cache is stale until refresh_masked()
+        self.refresh_masked()
 
     def release(self):
         """Give the parameters their own storage back (used when a trainer is torn down)."""
@@ -213,3 +274,90 @@ class GradSync:
                     h.wait()
         self._handles = []
         self._pending = None
+
+
+class GraphedStep:
+    """One whole optimisation step -- forward (188 masked-module calls), loss, backward, gradient exchange,
+    clip + AdamW, mask-cache refresh -- captured as ONE CUDA graph and replayed per batch.
+
+    The reference's loop is ~3000 small kernels issued from Python per step; once the kernels are fast
+    the host cannot keep up (measured: 52 ms of Python per step against 43 ms of GPU work at batch 256).
+    Replay needs (a) static input buffers, (b) the learning rate and Adam's bias-corrected step size in
+    device memory (`optimizer.use_device_hyper`), because kernel arguments are frozen at capture, and
+    (c) the host-side bookkeeping (scheduler, step counters) done outside the graph.
+    """
+
+    TENSOR_SLOTS = (0, 1, 2, 3, 6, 7)  # ids, feats, pos, target, bias, max_label of the 8-tuple batch
+
+    def __init__(self, trainer, model, optimizer, scheduler, warmup_steps=3):
+        self.trainer, self.model, self.optimizer, self.scheduler = trainer, model, optimizer, scheduler
+        self.warmup_steps = warmup_steps
+        self.seen = 0
+        self.graph = None
+        self.static_inputs = None
+        self.static_out = None
+        dev = trainer.args.device
+        self.hyper = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.hyper_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.shapes = None
+        # warm-up steps and the capture share one side stream, so the AccumulateGrad nodes of the loose
+        # (classifier) parameters live on the capture stream, as torch.cuda.graph requires
+        self.stream = torch.cuda.Stream(device=dev)
+
+    def _next_step_index(self):
+        p0 = self.optimizer.param_groups[0]["params"][0]
+        return self.optimizer.state[p0]["step"] + 1
+
+    def _upload_hyper(self):
+        lr, step_size = self.optimizer.hyper_values(self._next_step_index())
+        self.hyper_host[0], self.hyper_host[1] = lr, step_size
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+
+    def _shape_key(self, inputs):
+        return tuple((tuple(inputs[i].shape), inputs[i].dtype) for i in self.TENSOR_SLOTS)
+
+    def step(self, inputs):
+        """Returns (loss, score) as 0-dim device tensors, like Trainer._training_step."""
+        t = self.trainer
+        if self.graph is not None and self._shape_key(inputs) != self.shapes:
+            return self._eager(inputs)  # odd-sized last batch of an epoch
+        if self.graph is None and self.seen < self.warmup_steps:
+            self.seen += 1
+            cur = torch.cuda.current_stream()
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                out = self._eager(inputs)
+            cur.wait_stream(self.stream)
+            return out
+        dev = t.args.device
+        if self.graph is None:
+            self.shapes = self._shape_key(inputs)
+            self.static_inputs = list(inputs)
+            for i in self.TENSOR_SLOTS:
+                self.static_inputs[i] = inputs[i].to(dev, copy=True)
+            self.optimizer.use_device_hyper(self.hyper)
+            self._upload_hyper()
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            steps_before = self._next_step_index()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                loss, score = t._device_step(self.model, self.static_inputs, self.optimizer)
+                self.static_out = (loss, score)
+            # capture ran the Python side of optimizer.step() once without executing any kernel
+            self.optimizer.advance_steps(steps_before - self._next_step_index())
+        else:
+            for i in self.TENSOR_SLOTS:
+                self.static_inputs[i].copy_(inputs[i], non_blocking=True)
+        self._upload_hyper()
+        self.graph.replay()
+        self.optimizer.advance_steps(1)
+        self.scheduler.step()
+        return self.static_out
+
+    def _eager(self, inputs):
+        self.optimizer.use_device_hyper(None)
+        out = self.trainer._device_step(self.model, inputs, self.optimizer)
+        self.scheduler.step()
+        if self.graph is not None:
+            self.optimizer.use_device_hyper(self.hyper)
+        return out

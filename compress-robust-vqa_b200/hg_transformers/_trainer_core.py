@@ -32,7 +32,7 @@ from torch.utils.data.sampler import Sampler
 
 from crvqa import ops
 
-from ._engine import GradSync, ScoreArena, masked_modules_of
+from ._engine import GradSync, GraphedStep, ScoreArena, masked_modules_of
 from .data.data_collator import DataCollator, DefaultDataCollator, TrimCollator  # noqa: F401
 from .optimization import AdamW, get_constant_schedule, get_linear_schedule_with_warmup  # noqa: F401
 from .trainer_utils import PREFIX_CHECKPOINT_DIR, EvalPrediction, PredictionOutput, TrainOutput
@@ -220,8 +220,13 @@ class TrainerCore:
             k = int(module.weight.nelement() * self._sparsity_of(name, init_sparsity))
             ks.append(1 if k == 0 else k)
         thr = ops.kth_value_batched([m.weight_mask.data for _, m in mods], ks)
-        for i, (_, module) in enumerate(mods):
-            module.threshold = thr[i]
+        arena = getattr(self, "arena", None)
+        if arena is not None and [m for _, m in mods] == arena.modules:
+            arena.set_thresholds(thr)          # one device vector; module.threshold = 0-dim views of it
+            arena.refresh_masked()
+        else:
+            for i, (_, module) in enumerate(mods):
+                module.threshold = thr[i]
         return float(thr.mean())
 
     def binarizer_fn1(self, inputs, threshold):
@@ -278,10 +283,21 @@ class TrainerCore:
         if not mods:
             return
         self.arena = ScoreArena(mods)
+        if os.environ.get("CRVQA_MASK_MODE", "cached") == "cached":
+            self.arena.enable_mask_cache()
         if hasattr(optimizer, "attach_arena"):
             optimizer.attach_arena(self.arena)
         self.grad_sync = GradSync(self.arena)
         self.grad_sync.defer = self.args.gradient_accumulation_steps > 1
+
+    def _make_graphed_step(self, model, optimizer, scheduler):
+        """CUDA-graph replay of the whole step when it is safe: arena engine, our AdamW, no accumulation.
+        CRVQA_CUDA_GRAPH=0 keeps the eager loop; multi-rank runs capture the NCCL all-reduces too."""
+        if os.environ.get("CRVQA_CUDA_GRAPH", "1") == "0" or self.arena is None or not torch.cuda.is_available():
+            return None
+        if self.args.gradient_accumulation_steps != 1 or not hasattr(optimizer, "use_device_hyper"):
+            return None
+        return GraphedStep(self, model, optimizer, scheduler)
 
     def _loose_params(self):
         return [p for p in self.model.parameters() if p.requires_grad and not (self.arena and self.arena.owns(p))]
@@ -294,8 +310,8 @@ class TrainerCore:
         else:
             optimizer.zero_grad()
 
-    def _clip_and_step(self, model, optimizer, scheduler):
-        """clip_grad_norm_(max_grad_norm) + optimizer.step() + scheduler.step() (reference :646-656)."""
+    def _clip_and_optimizer_step(self, model, optimizer):
+        """clip_grad_norm_(max_grad_norm) + optimizer.step() (reference :646-653): device work only."""
         max_norm = self.args.max_grad_norm
         if self.arena is not None and hasattr(optimizer, "set_clip"):
             sumsq = torch.zeros((), dtype=torch.float32, device=self.args.device)
@@ -307,7 +323,21 @@ class TrainerCore:
         else:
             torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
         optimizer.step()
+
+    def _clip_and_step(self, model, optimizer, scheduler):
+        self._clip_and_optimizer_step(model, optimizer)
         scheduler.step()
+
+    def _device_step(self, model, inputs, optimizer):
+        """Everything of one optimisation step that runs on the GPU (gradient_accumulation_steps == 1):
+        forward, loss, backward, gradient exchange, clip + AdamW (+ mask-cache refresh), zero_grad.
+        This is the unit hg_transformers._engine.GraphedStep captures as one CUDA graph."""
+        loss, score = self._training_step(model, inputs, optimizer)
+        if self.grad_sync is not None:
+            self.grad_sync.finish([p.grad for p in self._loose_params()])
+        self._clip_and_optimizer_step(model, optimizer)
+        self._zero_grad(optimizer)
+        return loss, score
 
     # ------------------------------------------------------------------ the loop
     def train(self, model_path: Optional[str] = None):
@@ -352,20 +382,25 @@ class TrainerCore:
             print(result_start)
             print("\n\n\n!!!!PLZ check the results of the models loaded checkpoint+mask+clf!\n\n\n\n")
 
+        graphed = self._make_graphed_step(model, optimizer, scheduler)
         stop = False
         for epoch in range(int(np.ceil(num_train_epochs))):
             if isinstance(train_dataloader.sampler, DistributedSampler):
                 train_dataloader.sampler.set_epoch(epoch)
             n_batches = len(train_dataloader)
             for step, inputs in enumerate(train_dataloader):
-                loss_batch, score_batch = self._training_step(model, inputs, optimizer)
+                if graphed is not None:
+                    loss_batch, score_batch = graphed.step(inputs)
+                else:
+                    loss_batch, score_batch = self._training_step(model, inputs, optimizer)
                 tr_loss += loss_batch
                 tr_score += score_batch
                 if (step + 1) % accum == 0 or (n_batches <= accum and (step + 1) == n_batches):
-                    if self.grad_sync is not None:
-                        self.grad_sync.finish([p.grad for p in self._loose_params()])
-                    self._clip_and_step(model, optimizer, scheduler)
-                    self._zero_grad(optimizer)
+                    if graphed is None:
+                        if self.grad_sync is not None:
+                            self.grad_sync.finish([p.grad for p in self._loose_params()])
+                        self._clip_and_step(model, optimizer, scheduler)
+                        self._zero_grad(optimizer)
                     self.global_step += 1
                     self.epoch = epoch + (step + 1) / n_batches
 

@@ -389,7 +389,9 @@ class MaskedLinear1(MaskedLinearX):
             return ops.MaskedEmbeddingFn.apply(x, self.weight_mask, self.weight, thr, self.padding_idx, sink)
         if self.weight.shape[1] % 8 != 0:
             return ops.MaskedLinearSmallKFn.apply(x, self.weight_mask, self.weight, thr, self.bias, sink)
-        return ops.MaskedLinearFn.apply(x, self.weight_mask, self._weight_bf16(), thr, self.bias, sink)
+        arena = getattr(self, "_arena", None)
+        wm = arena.cached_masked_weight(self) if arena is not None else None
+        return ops.MaskedLinearFn.apply(x, self.weight_mask, self._weight_bf16(), thr, self.bias, sink, wm)
 
 
 class MaskedLinear2(MaskedLinearX):

@@ -31,6 +31,7 @@ class AdamW(Optimizer):
         self.initial_accumulator_value = initial_accumulator_value
         self._clip = None      # (device sum-of-squares tensor, max_norm) set by the trainer for one step
         self._arena = None     # ScoreArena whose flat buffers cover a contiguous run of parameters
+        self._hyper = None     # device tensor {lr, step_size}: set while a CUDA graph of the step is in use
         for group in self.param_groups:
             for p in group["params"]:
                 state = self.state[p]
@@ -47,6 +48,20 @@ class AdamW(Optimizer):
     def set_clip(self, total_sumsq, max_norm):
         """Fold clip_grad_norm_(max_norm) into the next step: total_sumsq is a device scalar."""
         self._clip = (total_sumsq, float(max_norm))
+
+    def use_device_hyper(self, hyper):
+        """All parameter groups share one lr schedule; {lr, step_size} are read from `hyper` on the device."""
+        self._hyper = hyper
+
+    def advance_steps(self, n=1):
+        """Bookkeeping for steps executed by CUDA-graph replay (no Python optimiser code runs there)."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                self.state[p]["step"] += n
+
+    def hyper_values(self, next_step):
+        g = self.param_groups[0]
+        return g["lr"], ops.adam_step_size(g["lr"], next_step, g["betas"][0], g["betas"][1], g["correct_bias"])
 
     def attach_arena(self, arena):
         """Parameters that are views of `arena` are updated by one flat launch; their state tensors
@@ -91,7 +106,8 @@ class AdamW(Optimizer):
                         self._arena.adamw_step(lr=group["lr"], step=state["step"], beta1=beta1, beta2=beta2,
                                                eps=group["eps"], weight_decay=group["weight_decay"],
                                                correct_bias=group["correct_bias"], clip_sumsq=clip_sumsq,
-                                               max_norm=max_norm, with_sum=self.grad_mask is None)
+                                               max_norm=max_norm, with_sum=self.grad_mask is None,
+                                               hyper=self._hyper)
                         arena_done = True
                     continue
                 if not p.is_cuda:
@@ -102,5 +118,5 @@ class AdamW(Optimizer):
                 ops.adamw_step_flat(p.data, g, state["exp_avg"], state["exp_avg_sq"],
                                     state["sum"] if self.grad_mask is None else None, group["lr"], state["step"],
                                     beta1, beta2, group["eps"], group["weight_decay"], clip_sumsq, max_norm,
-                                    group["correct_bias"])
+                                    group["correct_bias"], self._hyper)
         return loss

@@ -61,6 +61,14 @@ int crv_binarize(const float* scores, const float* thr, float* mask_f32, uint8_t
 int crv_apply_mask_bf16(const uint16_t* w_bf16, const float* scores, const float* thr, uint16_t* wm_bf16,
                         int64_t n, void* stream);
 
+/* The same over a whole score arena in ONE launch (mask cache of the training engine: scores only change
+ * at the optimiser step, thresholds only at reset_threshold, so W (.) M can be refreshed once per step
+ * instead of once per module call).  w / scores / wm are flat buffers with identical element offsets;
+ * chunks = nchunks x int4 {start / 8, length, segment index, 0} (device), no chunk straddling a module;
+ * thr_vec[segment] is that module's threshold. */
+int crv_apply_mask_segmented(const uint16_t* w_bf16, const float* scores, const float* thr_vec,
+                             const int* chunks, int nchunks, uint16_t* wm_bf16, void* stream);
+
 /* Masked linear (tcgen05 GEMMs) --------------------------------------------------------------- */
 /* Forward of MaskedLinear1 (masking/maskers.py:359-366 = _Binarizer1 + `weight * M_w` + F.linear):
  *     Y[M,N] = X[M,K] . (W[N,K] (.) (S[N,K] > *thr))^T + bias[N]
@@ -149,10 +157,12 @@ int crv_sumsq(const float* x, int64_t n, float* out, void* stream);
  * torch.nn.utils.clip_grad_norm_ folded in:  g' = g * min(1, max_norm / (sqrt(*total_sumsq) + 1e-6));
  * sum += |g'|; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= step_size * m / (sqrt(v) + eps);
  * p -= lr * weight_decay * p.  step_size = lr * sqrt(1-b2^t)/(1-b1^t) is computed by the caller.
- * total_sumsq may be NULL (no clipping).  `sum` may be NULL. */
+ * total_sumsq may be NULL (no clipping).  `sum` may be NULL.  If hyper_dev != NULL, {lr, step_size} are
+ * read from that device array instead of the by-value arguments (so a captured CUDA graph of the step
+ * follows the learning-rate schedule). */
 int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int64_t n, float lr,
                    float step_size, float beta1, float beta2, float eps, float weight_decay,
-                   const float* total_sumsq, float max_norm, void* stream);
+                   const float* total_sumsq, float max_norm, const float* hyper_dev, void* stream);
 
 #ifdef __cplusplus
 }
