@@ -1,0 +1,284 @@
+"""Engine-side fused transformer-layer ops (SURVEY.md section 8 "next" row f3).
+
+When the masked modules of a layer live in a ScoreArena with a valid mask cache (the training engine of
+hg_transformers._trainer_core), the layer is evaluated as
+
+    bf16 activations --> [grouped masked GEMM: Q|K|V in one launch] --> SDPA --> [masked GEMM] -->
+    [dropout + residual + LayerNorm, one kernel, fp32 residual + bf16 operand copy] -->
+    [masked GEMM] --> [GELU bf16] --> [masked GEMM] --> [dropout + residual + LayerNorm]
+
+instead of the reference's fp32 op-by-op chain (hg_transformers/modeling_lxmert.py:770-903).  The math is
+the same; every GEMM operand is bf16 as before; the residual stream stays fp32.  Modules outside an arena
+(plain drop-in use) keep the generic per-module path of masking._core.MaskedLinear1.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from ._lib import check, lib
+
+_p, _stream = ops._p, ops._stream
+
+
+# ----------------------------------------------------------------------------- dropout RNG state
+class RngState:
+    """(seed, step counter) in device memory: kernels hash (seed, counter, site, element) -> keep bit, so a
+    captured CUDA graph draws new masks on every replay once `advance()` is part of the graph."""
+    _per_device = {}
+    _next_site = [1]
+
+    def __init__(self, device, seed):
+        self.state = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+
+    @classmethod
+    def get(cls, device):
+        key = (device.type, device.index)
+        st = cls._per_device.get(key)
+        if st is None:
+            st = cls._per_device[key] = RngState(device, int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF)
+        return st
+
+    @classmethod
+    def new_site(cls):
+        cls._next_site[0] += 1
+        return cls._next_site[0]
+
+    def advance(self):
+        check(lib.crv_rng_advance(_p(self.state), _stream()), "crv_rng_advance")
+
+
+# ----------------------------------------------------------------------------- grouped masked linear
+class ProjectionGroup:
+    """Adjacent arena modules sharing one input (query|key|value, or key|value): their masked bf16 weights,
+    bf16 weights and score gradients are contiguous [sum N, K] slabs of the arena, so one GEMM serves all."""
+
+    def __init__(self, modules):
+        self.modules = list(modules)
+        arena = self.modules[0]._arena
+        idx = [arena._index[id(m.weight_mask)] for m in self.modules]
+        off0 = arena.offsets[idx[0]]
+        off = off0
+        for i, m in zip(idx, self.modules):
+            if arena.offsets[i] != off or m.weight.shape[1] != self.modules[0].weight.shape[1]:
+                raise ValueError("modules are not adjacent in the arena")
+            off += m.weight_mask.numel()
+        self.arena = arena
+        self.K = self.modules[0].weight.shape[1]
+        self.N = sum(m.weight.shape[0] for m in self.modules)
+        n = self.N * self.K
+        self.wm = arena.wm[off0: off0 + n].view(self.N, self.K)
+        self.w16 = arena.w16[off0: off0 + n].view(self.N, self.K)
+        self.grad = arena.grads[off0: off0 + n].view(self.N, self.K)
+        biases = [m.bias for m in self.modules]
+        self.bias = None if any(b is None for b in biases) else torch.cat([b.detach().float() for b in biases]).contiguous()
+        self.anchor = self.modules[0].weight_mask  # keeps the autograd node alive even if x needs no gradient
+
+    def valid(self):
+        a = self.arena
+        return all(a.cached_masked_weight(m) is not None for m in self.modules)
+
+    def note_forward(self):
+        if torch.is_grad_enabled():
+            for m in self.modules:
+                if getattr(m, "_sync", None) is not None:
+                    m._calls_outstanding = getattr(m, "_calls_outstanding", 0) + 1
+
+
+class GroupLinearFn(torch.autograd.Function):
+    """bf16 in -> (bf16 | fp32) out masked linear over a ProjectionGroup, reading the cached W (.) M."""
+
+    @staticmethod
+    def forward(ctx, x16, anchor, group, out_dtype):
+        shp = x16.shape
+        x2 = x16.reshape(-1, shp[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        y = ops.masked_linear_fwd(x2, group.wm, None, None, group.bias, out_dtype)
+        ctx.save_for_backward(x2)
+        ctx.group, ctx.x_shape, ctx.need_dx = group, shp, x16.requires_grad
+        return y.view(*shp[:-1], group.N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x2,) = ctx.saved_tensors
+        g = ctx.group
+        dy2 = dy.reshape(-1, g.N)
+        dy2 = ops.to_bf16(dy2) if dy2.dtype != torch.bfloat16 else (dy2 if dy2.is_contiguous() else dy2.contiguous())
+        dx = None
+        if ctx.need_dx:
+            dx = ops.masked_linear_bwd_dx(dy2, g.wm, None, None, torch.bfloat16).view(ctx.x_shape)
+        dirty = g.modules[0]._grad_dirty
+        ops.masked_linear_bwd_ds(dy2, x2, g.w16, out=g.grad, accumulate=dirty)
+        for m in g.modules:
+            ops._sink_done(m)
+        return dx, None, None, None
+
+
+def group_linear(group, x16, out_dtype=torch.bfloat16):
+    group.note_forward()
+    return GroupLinearFn.apply(x16, group.anchor, group, out_dtype)
+
+
+# ----------------------------------------------------------------------------- dropout + residual + LayerNorm
+class DropAddLayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, res32, gamma, beta, eps, p, site, rng):
+        H = g.shape[-1]
+        g2 = g.reshape(-1, H)
+        g2 = g2 if g2.is_contiguous() else g2.contiguous()
+        M = g2.shape[0]
+        r2 = None
+        if res32 is not None:
+            r2 = res32.reshape(-1, H)
+            r2 = r2 if r2.is_contiguous() else r2.contiguous()
+        dev = g.device
+        y32 = torch.empty((M, H), dtype=torch.float32, device=dev)
+        y16 = torch.empty((M, H), dtype=torch.bfloat16, device=dev)
+        mean = torch.empty(M, dtype=torch.float32, device=dev)
+        rstd = torch.empty(M, dtype=torch.float32, device=dev)
+        state = rng.state if (rng is not None and p > 0) else None
+        check(lib.crv_ln_fwd(_p(g2), ops.DT_BF16 if g2.dtype == torch.bfloat16 else ops.DT_F32, _p(r2), _p(gamma),
+                             _p(beta), float(eps), float(p), _p(state), int(site), _p(y32), _p(y16), _p(mean),
+                             _p(rstd), M, H, _stream()), "crv_ln_fwd")
+        ctx.save_for_backward(g2, r2, gamma, mean, rstd)
+        ctx.p, ctx.site, ctx.state, ctx.shape = float(p), int(site), state, g.shape
+        ctx.need_res = res32 is not None and res32.requires_grad
+        return y32.view(g.shape), y16.view(g.shape)
+
+    @staticmethod
+    def backward(ctx, dy32, dy16):
+        g2, r2, gamma, mean, rstd = ctx.saved_tensors
+        M, H = g2.shape
+        d32 = dy32.reshape(M, H).contiguous() if dy32 is not None else None
+        d16 = dy16.reshape(M, H).contiguous() if dy16 is not None else None
+        dg = torch.empty((M, H), dtype=torch.bfloat16, device=g2.device)
+        dres = torch.empty((M, H), dtype=torch.float32, device=g2.device) if ctx.need_res else None
+        check(lib.crv_ln_bwd(_p(d32), _p(d16), _p(g2), ops.DT_BF16 if g2.dtype == torch.bfloat16 else ops.DT_F32,
+                             _p(r2), _p(gamma), _p(mean), _p(rstd), ctx.p, _p(ctx.state), ctx.site, _p(dg),
+                             ops.DT_BF16, _p(dres), M, H, _stream()), "crv_ln_bwd")
+        return (dg.view(ctx.shape), dres.view(ctx.shape) if dres is not None else None, None, None, None, None, None,
+                None)
+
+
+def drop_add_layernorm(g, res32, ln, p, site, training):
+    """(y fp32, y bf16) = LayerNorm(dropout(g) + res32): LxmertAttentionOutput / LxmertOutput tail."""
+    p = float(p) if training else 0.0
+    rng = RngState.get(g.device) if p > 0 else None
+    return DropAddLayerNormFn.apply(g, res32, ln.weight, ln.bias, ln.eps, p, site, rng)
+
+
+class GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u):
+        u = u if u.is_contiguous() else u.contiguous()
+        y = torch.empty_like(u)
+        check(lib.crv_gelu_fwd(_p(u), _p(y), u.numel(), _stream()), "crv_gelu_fwd")
+        ctx.save_for_backward(u)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (u,) = ctx.saved_tensors
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        du = torch.empty_like(u)
+        check(lib.crv_gelu_bwd(_p(u), _p(dy), _p(du), u.numel(), _stream()), "crv_gelu_bwd")
+        return du
+
+
+def gelu_bf16(u):
+    return GeluFn.apply(u)
+
+
+# ----------------------------------------------------------------------------- layer plans
+def _arena_ready(*mods):
+    for m in mods:
+        a = getattr(m, "_arena", None)
+        if a is None or not a.cache_on or a.cached_masked_weight(m) is None or not m.weight_mask.is_cuda:
+            return False
+    return True
+
+
+class AttentionPlan:
+    """Fast path of LxmertSelfAttentionLayer / LxmertCrossAttentionLayer (att = .self or .att, out = .output)."""
+
+    def __init__(self, att, out):
+        self.att, self.out = att, out
+        self.mods = (att.query, att.key, att.value, out.dense)
+        self.qkv = self.q = self.kv = self.ao = None
+        self.site = RngState.new_site()
+
+    def ready(self):
+        if not _arena_ready(*self.mods):
+            return False
+        if self.ao is None:
+            a = self.att
+            try:
+                self.qkv = ProjectionGroup([a.query, a.key, a.value])
+            except ValueError:
+                self.qkv = None
+            self.q = ProjectionGroup([a.query])
+            try:
+                self.kv = ProjectionGroup([a.key, a.value])
+            except ValueError:
+                self.kv = None
+            self.k1, self.v1 = ProjectionGroup([a.key]), ProjectionGroup([a.value])
+            self.ao = ProjectionGroup([self.out.dense])
+        return True
+
+    def _sdpa(self, q, k, v, mask, training):
+        a = self.att
+        B, Sq, _ = q.shape
+        h, d = a.num_attention_heads, a.attention_head_size
+        q = q.view(B, Sq, h, d).transpose(1, 2)
+        k = k.view(B, k.shape[1], h, d).transpose(1, 2)
+        v = v.view(B, v.shape[1], h, d).transpose(1, 2)
+        if mask is not None:
+            mask = mask.to(q.dtype)
+        p = a.dropout.p if training else 0.0
+        ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=p)
+        return ctx.transpose(1, 2).reshape(B, Sq, h * d)
+
+    def self_attention(self, x32, x16, mask, training):
+        H = x16.shape[-1]
+        if self.qkv is not None:
+            q, k, v = group_linear(self.qkv, x16).split(H, dim=-1)
+        else:
+            q, k, v = group_linear(self.q, x16), group_linear(self.k1, x16), group_linear(self.v1, x16)
+        ctx = self._sdpa(q, k, v, mask, training)
+        ao = group_linear(self.ao, ctx)
+        return drop_add_layernorm(ao, x32, self.out.LayerNorm, self.out.dropout.p, self.site, training)
+
+    def cross_attention(self, x32, x16, c16, ctx_mask, training, site):
+        H = x16.shape[-1]
+        q = group_linear(self.q, x16)
+        if self.kv is not None:
+            k, v = group_linear(self.kv, c16).split(H, dim=-1)
+        else:
+            k, v = group_linear(self.k1, c16), group_linear(self.v1, c16)
+        ctx = self._sdpa(q, k, v, ctx_mask, training)
+        ao = group_linear(self.ao, ctx)
+        return drop_add_layernorm(ao, x32, self.out.LayerNorm, self.out.dropout.p, site, training)
+
+
+class FfnPlan:
+    """Fast path of LxmertIntermediate + LxmertOutput."""
+
+    def __init__(self, inter, out):
+        self.inter, self.out = inter, out
+        self.gi = self.go = None
+        self.site = RngState.new_site()
+
+    def ready(self):
+        if not _arena_ready(self.inter.dense, self.out.dense):
+            return False
+        if self.gi is None:
+            self.gi = ProjectionGroup([self.inter.dense])
+            self.go = ProjectionGroup([self.out.dense])
+        return True
+
+    def __call__(self, x32, x16, training):
+        a = gelu_bf16(group_linear(self.gi, x16))
+        o = group_linear(self.go, a)
+        return drop_add_layernorm(o, x32, self.out.LayerNorm, self.out.dropout.p, self.site, training)

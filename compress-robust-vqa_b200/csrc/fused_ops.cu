@@ -1,0 +1,288 @@
+// Fused elementwise kernels between the masked GEMMs of a transformer layer ("next" row f3 of SURVEY.md
+// section 8: hg_transformers/modeling_lxmert.py:830-903).  They exist so that the activations flowing
+// from one tcgen05 GEMM to the next are produced directly as bf16 operands, the residual stream stays
+// fp32, and one pass over HBM replaces PyTorch's bias-add / dropout / add / LayerNorm / cast chain:
+//
+//   ln_fwd : z = dropout(g) + res ; y = LayerNorm(z) -> y (fp32) and y (bf16), per-row mean / rstd
+//   ln_bwd : dz = LayerNorm'(dy32 + dy16) ; d_res = dz (fp32) ; d_g = dropout'(dz) (bf16)
+//            (gamma / beta are frozen in stage 2, masking/maskers.py:564-569: no parameter gradients)
+//   gelu   : y = gelu(u) (erf form, bf16 in / bf16 out) and du = dy * gelu'(u)
+//
+// Dropout is counter based: keep(i) = hash(seed, step counter, call-site id, element index) >= p * 2^32,
+// with (seed, counter) read from device memory so a captured CUDA graph draws a fresh mask every replay
+// and the backward pass regenerates the forward mask instead of storing it.
+// One warp per row (H <= 1024, H % 128 == 0), 16-byte accesses, fp32 math.
+#include "common.cuh"
+
+namespace crv {
+
+constexpr int kRowsPerBlock = 8;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  // splitmix64 finaliser
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+
+struct Rng {
+  uint64_t key;
+  uint32_t thresh;  // per 16-bit lane: drop when lane < thresh (p quantised to 1/65536)
+  float scale;
+  // one 64-bit hash decides the four elements of a float4 (element index e, e % 4 == 0)
+  __device__ __forceinline__ void drop4(float4& v, int64_t e) const {
+    const uint64_t h = mix64(key + static_cast<uint64_t>(e >> 2) * 0x9E3779B97F4A7C15ull);
+    v.x = ((h)&0xFFFFu) >= thresh ? v.x * scale : 0.f;
+    v.y = ((h >> 16) & 0xFFFFu) >= thresh ? v.y * scale : 0.f;
+    v.z = ((h >> 32) & 0xFFFFu) >= thresh ? v.z * scale : 0.f;
+    v.w = ((h >> 48) & 0xFFFFu) >= thresh ? v.w * scale : 0.f;
+  }
+};
+
+__device__ __forceinline__ Rng make_rng(const unsigned long long* state, int site, float p) {
+  Rng r;
+  r.thresh = 0;
+  r.scale = 1.f;
+  r.key = 0;
+  if (state != nullptr && p > 0.f) {
+    const uint64_t seed = state[0], ctr = state[1];
+    r.key = (seed * 0xD1342543DE82EF95ull) ^ (ctr * 0xA24BAED4963EE407ull) ^ (static_cast<uint64_t>(site) << 40);
+    r.thresh = static_cast<uint32_t>(fminf(p, 0.9999f) * 65536.0f);
+    if (r.thresh == 0) r.thresh = 1;
+    r.scale = 1.f / (1.f - p);
+  }
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float4 load4(const void* base, bool is_bf16, int64_t e) {
+  if (is_bf16) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(base) + e));
+    return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xFFFF0000u),
+                       __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xFFFF0000u));
+  }
+  return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(base) + e));
+}
+__device__ __forceinline__ uint2 pack4(float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
+template <int VEC>  // VEC = H / 128 float4 chunks per lane
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+ln_fwd_kernel(const void* __restrict__ g, int g_bf16, const float* __restrict__ res, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float eps, float p, const unsigned long long* __restrict__ rng_state,
+              int site, float* __restrict__ y32, uint16_t* __restrict__ y16, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out, int M, int H) {
+  const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const Rng rng = make_rng(rng_state, site, p);
+  float4 z[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const int64_t e = static_cast<int64_t>(row) * H + col;
+    float4 gv = load4(g, g_bf16, e);
+    if (rng.thresh) rng.drop4(gv, e);
+    if (res) {
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(res + e));
+      gv.x += rv.x; gv.y += rv.y; gv.z += rv.z; gv.w += rv.w;
+    }
+    z[i] = gv;
+    s += gv.x + gv.y + gv.z + gv.w;
+  }
+  const float mean = warp_sum(s) / H;
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float a = z[i].x - mean, b = z[i].y - mean, c = z[i].z - mean, d = z[i].w - mean;
+    v += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(v) / H + eps);
+  if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const int64_t e = static_cast<int64_t>(row) * H + col;
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + col));
+    float4 o;
+    o.x = (z[i].x - mean) * rstd * ga.x + be.x;
+    o.y = (z[i].y - mean) * rstd * ga.y + be.y;
+    o.z = (z[i].z - mean) * rstd * ga.z + be.z;
+    o.w = (z[i].w - mean) * rstd * ga.w + be.w;
+    if (y32) *reinterpret_cast<float4*>(y32 + e) = o;
+    if (y16) *reinterpret_cast<uint2*>(y16 + e) = pack4(o);
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+ln_bwd_kernel(const float* __restrict__ dy32, const uint16_t* __restrict__ dy16, const void* __restrict__ g, int g_bf16,
+              const float* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ mean_in,
+              const float* __restrict__ rstd_in, float p, const unsigned long long* __restrict__ rng_state, int site,
+              void* __restrict__ dg, int dg_bf16, float* __restrict__ dres, int M, int H) {
+  const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const Rng rng = make_rng(rng_state, site, p);
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  float4 xh[VEC], dyg[VEC];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const int64_t e = static_cast<int64_t>(row) * H + col;
+    float4 gv = load4(g, g_bf16, e);
+    if (rng.thresh) rng.drop4(gv, e);
+    if (res) {
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(res + e));
+      gv.x += rv.x; gv.y += rv.y; gv.z += rv.z; gv.w += rv.w;
+    }
+    xh[i] = make_float4((gv.x - mean) * rstd, (gv.y - mean) * rstd, (gv.z - mean) * rstd, (gv.w - mean) * rstd);
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dy32) d = __ldg(reinterpret_cast<const float4*>(dy32 + e));
+    if (dy16) {
+      const float4 d2 = load4(dy16, 1, e);
+      d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+    }
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    d.x *= ga.x; d.y *= ga.y; d.z *= ga.z; d.w *= ga.w;
+    dyg[i] = d;
+    s1 += d.x + d.y + d.z + d.w;
+    s2 += d.x * xh[i].x + d.y * xh[i].y + d.z * xh[i].z + d.w * xh[i].w;
+  }
+  const float m1 = warp_sum(s1) / H, m2 = warp_sum(s2) / H;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const int64_t e = static_cast<int64_t>(row) * H + col;
+    float4 dz;
+    dz.x = rstd * (dyg[i].x - m1 - xh[i].x * m2);
+    dz.y = rstd * (dyg[i].y - m1 - xh[i].y * m2);
+    dz.z = rstd * (dyg[i].z - m1 - xh[i].z * m2);
+    dz.w = rstd * (dyg[i].w - m1 - xh[i].w * m2);
+    if (dres) *reinterpret_cast<float4*>(dres + e) = dz;
+    if (dg) {
+      if (rng.thresh) rng.drop4(dz, e);
+      if (dg_bf16) *reinterpret_cast<uint2*>(static_cast<uint16_t*>(dg) + e) = pack4(dz);
+      else *reinterpret_cast<float4*>(static_cast<float*>(dg) + e) = dz;
+    }
+  }
+}
+
+__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float u) {
+  return 0.5f * (1.f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * expf(-0.5f * u * u);
+}
+
+__global__ void gelu_fwd_kernel(const uint16_t* __restrict__ u, uint16_t* __restrict__ y, int64_t n) {
+  const int64_t nvec = n >> 3;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    const float4 a = load4(u, 1, i * 8), b = load4(u, 1, i * 8 + 4);
+    const uint2 p0 = pack4(make_float4(gelu_f(a.x), gelu_f(a.y), gelu_f(a.z), gelu_f(a.w)));
+    const uint2 p1 = pack4(make_float4(gelu_f(b.x), gelu_f(b.y), gelu_f(b.z), gelu_f(b.w)));
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(p0.x, p0.y, p1.x, p1.y);
+  }
+}
+
+__global__ void gelu_bwd_kernel(const uint16_t* __restrict__ u, const uint16_t* __restrict__ dy,
+                                uint16_t* __restrict__ du, int64_t n) {
+  const int64_t nvec = n >> 3;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    const float4 a = load4(u, 1, i * 8), b = load4(u, 1, i * 8 + 4);
+    const float4 c = load4(dy, 1, i * 8), d = load4(dy, 1, i * 8 + 4);
+    const uint2 p0 = pack4(make_float4(c.x * gelu_grad_f(a.x), c.y * gelu_grad_f(a.y), c.z * gelu_grad_f(a.z),
+                                       c.w * gelu_grad_f(a.w)));
+    const uint2 p1 = pack4(make_float4(d.x * gelu_grad_f(b.x), d.y * gelu_grad_f(b.y), d.z * gelu_grad_f(b.z),
+                                       d.w * gelu_grad_f(b.w)));
+    reinterpret_cast<uint4*>(du)[i] = make_uint4(p0.x, p0.y, p1.x, p1.y);
+  }
+}
+
+__global__ void counter_inc_kernel(unsigned long long* state) { state[1] += 1ull; }
+
+template <typename F>
+static int dispatch_vec(int H, F&& f) {
+  switch (H / 128) {
+    case 1: return f(std::integral_constant<int, 1>{});
+    case 2: return f(std::integral_constant<int, 2>{});
+    case 4: return f(std::integral_constant<int, 4>{});
+    case 6: return f(std::integral_constant<int, 6>{});
+    case 8: return f(std::integral_constant<int, 8>{});
+    default: return CRV_E_SHAPE;
+  }
+}
+
+}  // namespace crv
+
+using namespace crv;
+
+extern "C" int crv_ln_fwd(const void* g, int g_dtype, const float* res, const float* gamma, const float* beta,
+                          float eps, float p_drop, const unsigned long long* rng_state, int site, float* y_f32,
+                          uint16_t* y_bf16, float* mean, float* rstd, int M, int H, void* stream) {
+  if (!g || !gamma || !beta || !mean || !rstd || M <= 0 || H <= 0) return CRV_E_BADARG;
+  if (H % 128 || H > 1024) return CRV_E_SHAPE;
+  if (!aligned16(g) || (res && !aligned16(res)) || (y_f32 && !aligned16(y_f32)) || (y_bf16 && !aligned16(y_bf16)))
+    return CRV_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (M + kRowsPerBlock - 1) / kRowsPerBlock;
+  return dispatch_vec(H, [&](auto v) {
+    constexpr int VEC = decltype(v)::value;
+    ln_fwd_kernel<VEC><<<grid, kRowsPerBlock * 32, 0, st>>>(g, g_dtype == CRV_DTYPE_BF16, res, gamma, beta, eps, p_drop,
+                                                            rng_state, site, y_f32, y_bf16, mean, rstd, M, H);
+    return launch_status();
+  });
+}
+
+extern "C" int crv_ln_bwd(const float* dy_f32, const uint16_t* dy_bf16, const void* g, int g_dtype, const float* res,
+                          const float* gamma, const float* mean, const float* rstd, float p_drop,
+                          const unsigned long long* rng_state, int site, void* dg, int dg_dtype, float* dres, int M,
+                          int H, void* stream) {
+  if ((!dy_f32 && !dy_bf16) || !g || !gamma || !mean || !rstd || M <= 0 || H <= 0) return CRV_E_BADARG;
+  if (H % 128 || H > 1024) return CRV_E_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (M + kRowsPerBlock - 1) / kRowsPerBlock;
+  return dispatch_vec(H, [&](auto v) {
+    constexpr int VEC = decltype(v)::value;
+    ln_bwd_kernel<VEC><<<grid, kRowsPerBlock * 32, 0, st>>>(dy_f32, dy_bf16, g, g_dtype == CRV_DTYPE_BF16, res, gamma,
+                                                            mean, rstd, p_drop, rng_state, site, dg,
+                                                            dg_dtype == CRV_DTYPE_BF16, dres, M, H);
+    return launch_status();
+  });
+}
+
+extern "C" int crv_gelu_fwd(const uint16_t* u, uint16_t* y, int64_t n, void* stream) {
+  if (!u || !y || n < 0) return CRV_E_BADARG;
+  if (n % 8) return CRV_E_SHAPE;
+  if (n == 0) return CRV_OK;
+  int64_t blocks = ((n >> 3) + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  gelu_fwd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(u, y, n);
+  return launch_status();
+}
+
+extern "C" int crv_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du, int64_t n, void* stream) {
+  if (!u || !dy || !du || n < 0) return CRV_E_BADARG;
+  if (n % 8) return CRV_E_SHAPE;
+  if (n == 0) return CRV_OK;
+  int64_t blocks = ((n >> 3) + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  gelu_bwd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(u, dy, du, n);
+  return launch_status();
+}
+
+extern "C" int crv_rng_advance(unsigned long long* rng_state, void* stream) {
+  if (!rng_state) return CRV_E_BADARG;
+  counter_inc_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(rng_state);
+  return launch_status();
+}

@@ -22,6 +22,8 @@
 // The score tile (fp32) arrives as boxes of 32 floats (128 B) per row with the same swizzle, so a
 // transform thread reads one 16-byte chunk of W (8 bf16) plus the two matching 16-byte chunks of S
 // without bank conflicts, then fences its generic-proxy writes towards the async proxy.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -431,6 +433,8 @@ static int pick_bn(int MM, int NN) {
   // wave quantisation on a persistent grid: cost ~ ceil(tiles / SMs) * BN; 256-wide tiles halve the A
   // re-reads and win ties
   if (NN % 256) return 128;
+  static const int forced = [] { const char* e = getenv("CRVQA_BN"); return e ? atoi(e) : 0; }();
+  if (forced == 128 || forced == 256) return forced;
   const int sms = num_sms();
   const int mt = (MM + BM - 1) / BM;
   const int t256 = mt * (NN / 256), t128 = mt * ((NN + 127) / 128);

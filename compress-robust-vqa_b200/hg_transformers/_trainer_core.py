@@ -332,6 +332,9 @@ class TrainerCore:
         """Everything of one optimisation step that runs on the GPU (gradient_accumulation_steps == 1):
         forward, loss, backward, gradient exchange, clip + AdamW (+ mask-cache refresh), zero_grad.
         This is the unit hg_transformers._engine.GraphedStep captures as one CUDA graph."""
+        if torch.cuda.is_available():
+            from crvqa.fused import RngState
+            RngState.get(self.args.device).advance()   # fresh dropout masks for the fused kernels, graph-safe
         loss, score = self._training_step(model, inputs, optimizer)
         if self.grad_sync is not None:
             self.grad_sync.finish([p.grad for p in self._loose_params()])

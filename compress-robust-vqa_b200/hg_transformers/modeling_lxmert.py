@@ -190,6 +190,9 @@ class LxmertEncoder(nn.Module):
 
     def forward(self, lang, lang_mask, visual_feats, visual_pos, visn_mask=None):
         visn = self.visn_fc(visual_feats, visual_pos)
+        fast = self._fast_plans() if lang.is_cuda else None
+        if fast is not None:
+            return self._forward_fast(fast, lang, lang_mask, visn, visn_mask)
         for blk in self.layer:
             lang = blk(lang, lang_mask)
         for blk in self.r_layers:
@@ -197,6 +200,59 @@ class LxmertEncoder(nn.Module):
         for blk in self.x_layers:
             lang, visn = blk(lang, lang_mask, visn, visn_mask)
         return lang, visn
+
+    # -- engine fast path (crvqa.fused): same math, bf16 operands produced by fused kernels ------------
+    def _fast_plans(self):
+        """Layer plans when every masked module of the encoder stack sits in a ScoreArena with a valid mask
+        cache (i.e. under the stage-2 training engine); None selects the generic per-module path."""
+        import os
+        if os.environ.get("CRVQA_FUSED", "1") == "0":
+            return None
+        from crvqa import fused
+        plans = getattr(self, "_plans", None)
+        if plans is None:
+            def layer_plan(blk):
+                return (fused.AttentionPlan(blk.attention.self, blk.attention.output),
+                        fused.FfnPlan(blk.intermediate, blk.output))
+            plans = {
+                "lang": [layer_plan(b) for b in self.layer],
+                "visn": [layer_plan(b) for b in self.r_layers],
+                "cross": [(fused.AttentionPlan(b.visual_attention.att, b.visual_attention.output),
+                           fused.RngState.new_site(), fused.RngState.new_site(),
+                           fused.AttentionPlan(b.lang_self_att.self, b.lang_self_att.output),
+                           fused.AttentionPlan(b.visn_self_att.self, b.visn_self_att.output),
+                           fused.FfnPlan(b.lang_inter, b.lang_output), fused.FfnPlan(b.visn_inter, b.visn_output))
+                          for b in self.x_layers],
+            }
+            self._plans = plans
+        try:
+            for att, ffn in plans["lang"] + plans["visn"]:
+                if not (att.ready() and ffn.ready()):
+                    return None
+            for cross, _, _, ls, vs, lf, vf in plans["cross"]:
+                if not all(x.ready() for x in (cross, ls, vs, lf, vf)):
+                    return None
+        except AttributeError:  # modules are not MaskedLinear1 (model not patched)
+            return None
+        return plans
+
+    def _forward_fast(self, plans, lang32, lang_mask, visn32, visn_mask):
+        tr = self.training
+        lang16, visn16 = lang32.to(torch.bfloat16), visn32.to(torch.bfloat16)
+        for att, ffn in plans["lang"]:
+            a32, a16 = att.self_attention(lang32, lang16, lang_mask, tr)
+            lang32, lang16 = ffn(a32, a16, tr)
+        for att, ffn in plans["visn"]:
+            a32, a16 = att.self_attention(visn32, visn16, visn_mask, tr)
+            visn32, visn16 = ffn(a32, a16, tr)
+        for cross, site_l, site_v, ls, vs, lf, vf in plans["cross"]:
+            lx32, lx16 = cross.cross_attention(lang32, lang16, visn16, visn_mask, tr, site_l)
+            vx32, vx16 = cross.cross_attention(visn32, visn16, lang16, lang_mask, tr, site_v)
+            ls32, ls16 = ls.self_attention(lx32, lx16, lang_mask, tr)
+            vs32, vs16 = vs.self_attention(vx32, vx16, visn_mask, tr)
+            lang32, lang16 = lf(ls32, ls16, tr)
+            visn32, visn16 = vf(vs32, vs16, tr)
+        return lang32, visn32
 
 
 class LxmertPooler(nn.Module):

@@ -150,6 +150,28 @@ int crv_vqa_loss_lmh(const float* logits, const float* bias, const float* labels
                      float smooth, float w, float* loss_out, float* dlogits, float* dfactor_pre, int B, int A,
                      void* workspace, void* stream);
 
+/* Fused elementwise ops between the GEMMs ("next" row f3; hg_transformers/modeling_lxmert.py:830-903) -- */
+/* LxmertAttentionOutput / LxmertOutput tail: z = dropout(g) + res; y = LayerNorm(z).  g is the GEMM output
+ * (bias already added) in fp32 or bf16; res fp32 or NULL; y is written as fp32 and/or bf16 (either may be
+ * NULL); mean / rstd [M] are saved for the backward.  Dropout is counter based on (rng_state[0] = seed,
+ * rng_state[1] = step counter, site, element index); rng_state == NULL or p_drop == 0 disables it.
+ * H % 128 == 0, H <= 1024. */
+int crv_ln_fwd(const void* g, int g_dtype, const float* res, const float* gamma, const float* beta, float eps,
+               float p_drop, const unsigned long long* rng_state, int site, float* y_f32, uint16_t* y_bf16,
+               float* mean, float* rstd, int M, int H, void* stream);
+/* backward: dz = LayerNorm'(dy_f32 + dy_bf16) (either may be NULL); d_res = dz (fp32, may be NULL);
+ * d_g = dropout'(dz) in fp32 or bf16 (may be NULL).  gamma / beta are frozen in stage 2: no parameter
+ * gradients.  The forward mask is regenerated from the same (rng_state, site). */
+int crv_ln_bwd(const float* dy_f32, const uint16_t* dy_bf16, const void* g, int g_dtype, const float* res,
+               const float* gamma, const float* mean, const float* rstd, float p_drop,
+               const unsigned long long* rng_state, int site, void* dg, int dg_dtype, float* dres, int M, int H,
+               void* stream);
+/* erf GELU on bf16 (LxmertIntermediate): y = gelu(u);  du = dy * gelu'(u).  n % 8 == 0. */
+int crv_gelu_fwd(const uint16_t* u, uint16_t* y, int64_t n, void* stream);
+int crv_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du, int64_t n, void* stream);
+/* rng_state[1] += 1 on the device (once per training step, inside the captured graph). */
+int crv_rng_advance(unsigned long long* rng_state, void* stream);
+
 /* Optimiser ("next" row f1; hg_transformers/mask_trainer_VQA.py:646-659 + optimization.py:66-129) */
 /* sum of squares of n floats accumulated into *out (device, fp32; caller zeroes it) */
 int crv_sumsq(const float* x, int64_t n, float* out, void* stream);

@@ -1,0 +1,126 @@
+"""Fused layer kernels (dropout + residual + LayerNorm, GELU) and the engine fast path vs plain torch math."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("H,gdt", [(768, torch.bfloat16), (768, torch.float32), (256, torch.bfloat16), (1024, torch.float32)])
+def test_drop_add_layernorm_no_dropout(H, gdt):
+    from crvqa import fused
+    torch.manual_seed(0)
+    M = 1000
+    g = torch.randn(M, H, device="cuda").to(gdt).requires_grad_(True)
+    res = torch.randn(M, H, device="cuda", requires_grad=True)
+    ln = torch.nn.LayerNorm(H, eps=1e-12).cuda()
+    ln.weight.data.uniform_(0.5, 1.5)
+    ln.bias.data.uniform_(-0.5, 0.5)
+    ln.weight.requires_grad_(False)
+    ln.bias.requires_grad_(False)
+    y32, y16 = fused.drop_add_layernorm(g, res, ln, 0.1, 7, training=False)
+    ref = F.layer_norm(g.float() + res, (H,), ln.weight, ln.bias, 1e-12)
+    torch.testing.assert_close(y32, ref, rtol=1e-5, atol=1e-5)
+    assert torch.equal(y16, y32.bfloat16())
+    d32 = torch.randn(M, H, device="cuda")
+    d16 = torch.randn(M, H, device="cuda").bfloat16()
+    torch.autograd.backward([y32, y16], [d32, d16])
+    g_ref = g.detach().float().requires_grad_(True)
+    r_ref = res.detach().clone().requires_grad_(True)
+    F.layer_norm(g_ref + r_ref, (H,), ln.weight, ln.bias, 1e-12).backward(d32 + d16.float())
+    torch.testing.assert_close(res.grad, r_ref.grad, rtol=1e-4, atol=1e-4)
+    assert g.grad.dtype == gdt
+    torch.testing.assert_close(g.grad.float(), g_ref.grad.bfloat16().float(), rtol=2e-2, atol=2e-2)
+
+
+def test_drop_add_layernorm_dropout_statistics_and_backward_consistency():
+    from crvqa import fused
+    M, H, p = 2048, 768, 0.1
+    g = torch.ones(M, H, device="cuda", requires_grad=True)
+    ln = torch.nn.LayerNorm(H, eps=1e-12).cuda()
+    ln.weight.requires_grad_(False)
+    ln.bias.requires_grad_(False)
+    rng = fused.RngState.get(g.device)
+    rng.advance()
+    # z = dropout(1): entries are 0 or 1/(1-p); recover the mask from y (normalised z keeps the two levels apart)
+    y32, _ = fused.drop_add_layernorm(g, None, ln, p, 11, training=True)
+    keep = y32 > 0
+    rate = 1.0 - float(keep.float().mean())
+    assert abs(rate - p) < 5e-3, rate
+    y_again, _ = fused.drop_add_layernorm(g, None, ln, p, 11, training=True)
+    assert torch.equal(y_again, y32)                       # same (seed, counter, site) -> same mask
+    y_site, _ = fused.drop_add_layernorm(g, None, ln, p, 12, training=True)
+    assert not torch.equal(y_site > 0, keep)               # another call site -> another mask
+    rng.advance()
+    y_next, _ = fused.drop_add_layernorm(g, None, ln, p, 11, training=True)
+    assert not torch.equal(y_next > 0, keep)               # next step -> another mask
+    # backward regenerates the forward mask: dropped positions get zero gradient
+    rng2 = fused.RngState.get(g.device)
+    x = torch.randn(M, H, device="cuda", requires_grad=True)
+    y, _ = fused.drop_add_layernorm(x, None, ln, p, 21, training=True)
+    z_keep = None
+    y.backward(torch.randn_like(y))
+    # positions whose gradient is exactly zero are the dropped ones; their share must be ~p
+    zero_share = float((x.grad == 0).float().mean())
+    assert abs(zero_share - p) < 5e-3, zero_share
+
+
+def test_gelu_bf16():
+    from crvqa import fused
+    u = (torch.randn(4096, 3072, device="cuda") * 2).bfloat16().requires_grad_(True)
+    y = fused.gelu_bf16(u)
+    ref = F.gelu(u.detach().float())
+    assert torch.equal(y, ref.bfloat16())
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    u_ref = u.detach().float().requires_grad_(True)
+    F.gelu(u_ref).backward(dy.float())
+    torch.testing.assert_close(u.grad.float(), u_ref.grad.bfloat16().float(), rtol=1e-2, atol=1e-3)
+
+
+def test_engine_fast_path_matches_generic_path():
+    """Same model, same scores: fused fast path (arena + mask cache) vs generic per-module path, dropout off."""
+    import os
+    from crvqa import ops
+    from hg_transformers._engine import ScoreArena, masked_modules_of
+    from oracle import lxmert_oracle as lxo
+    from prune_debias_VQA import build_stage2
+    cfg = dict(vocab_size=1000, hidden_size=256, num_attention_heads=4, intermediate_size=512, l_layers=2,
+               x_layers=2, r_layers=1, visual_feat_dim=128, max_position_embeddings=32)
+    model, masker, _ = build_stage2(96, device=torch.device("cuda"), seed=5, config_kwargs=cfg)
+    model.eval()
+    batch = {k: v.cuda() for k, v in lxo.synthetic_batch(16, 96, seed=5, T=10, R=8, feat=128, vocab=1000).items()}
+
+    def run(zero=True):
+        if zero:
+            model.zero_grad()
+        _, logits, _ = model(batch["ids"], batch["feats"], batch["pos"], labels=batch["target"])
+        loss, _ = ops.vqa_loss_bce(logits, batch["target"])
+        loss.backward()
+        return logits.detach().clone(), float(loss.detach())
+
+    lg0, l0 = run()
+    mods = masked_modules_of(model)
+    plain = {n: (m.weight_mask.grad.clone() if m.weight_mask.grad is not None else None) for n, m in mods}
+    arena = ScoreArena(mods)
+    arena.enable_mask_cache()
+    assert model.lxmert.encoder._fast_plans() is not None
+    arena.begin_step()
+    lg1, l1 = run(zero=False)
+    arena.finalize_grads()
+    err = float((lg1 - lg0).abs().max() / lg0.abs().max())
+    assert err < 2e-2, err                                  # bf16 intermediates (QKV, GELU, AO outputs) vs fp32 ones
+    assert abs(l1 - l0) <= 1e-3 * abs(l0)
+    worst = 0.0
+    for n, m in mods:
+        if plain[n] is None:
+            assert float(m.weight_mask.grad.abs().max()) == 0.0
+            continue
+        rel = float((m.weight_mask.grad - plain[n]).double().norm() / (plain[n].double().norm() + 1e-30))
+        worst = max(worst, rel)
+    assert worst < 8e-2, worst
+    os.environ["CRVQA_FUSED"] = "0"
+    try:
+        assert model.lxmert.encoder._fast_plans() is None
+    finally:
+        os.environ.pop("CRVQA_FUSED")
