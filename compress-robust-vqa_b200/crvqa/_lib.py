@@ -46,6 +46,11 @@ _PROTOS = {
     "crv_vqa_loss_lmh": (c_int, [_P, _P, _P, _P, c_float, c_float, _P, _P, _P, c_int, c_int, _P, _P]),
     "crv_ln_fwd": (c_int, [_P, c_int, _P, _P, _P, c_float, c_float, _P, c_int, _P, _P, _P, _P, c_int, c_int, _P]),
     "crv_ln_bwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P, c_float, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
+    "crv_attention_fwd": (c_int, [_P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P,
+                                  _P, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),
+    "crv_attention_bwd": (c_int, [_P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P,
+                                  _P, _P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P, c_longlong, c_longlong,
+                                  c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),
     "crv_gelu_fwd": (c_int, [_P, _P, c_int64, _P]),
     "crv_gelu_bwd": (c_int, [_P, _P, _P, c_int64, _P]),
     "crv_rng_advance": (c_int, [_P, _P]),

@@ -12,6 +12,7 @@ the same; every GEMM operand is bf16 as before; the residual stream stays fp32. 
 (plain drop-in use) keep the generic per-module path of masking._core.MaskedLinear1.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -44,6 +45,13 @@ class RngState:
     def new_site(cls):
         cls._next_site[0] += 1
         return cls._next_site[0]
+
+    @classmethod
+    def new_sites(cls, n):
+        """First of n consecutive call-site ids."""
+        first = cls._next_site[0] + 1
+        cls._next_site[0] += n
+        return first
 
     def advance(self):
         check(lib.crv_rng_advance(_p(self.state), _stream()), "crv_rng_advance")
@@ -191,6 +199,72 @@ def gelu_bf16(u):
     return GeluFn.apply(u)
 
 
+# ----------------------------------------------------------------------------- small-sequence attention
+def _off(t, elems):
+    return ctypes.c_void_p(t.data_ptr() + 2 * elems)
+
+
+class SmallAttentionFn(torch.autograd.Function):
+    """softmax(Q K^T / sqrt(d) + mask) V with dropout for S <= 64, d = 64 (crv_attention_fwd / _bwd).
+    kind 0: srcs = (qkv [B,S,3H],)   kind 1: srcs = (q [B,Sq,H], kv [B,Sk,2H])   kind 2: srcs = (q, k, v)."""
+
+    @staticmethod
+    def _views(kind, srcs):
+        if kind == 0:
+            (qkv,) = srcs
+            H = qkv.shape[-1] // 3
+            return H, [(qkv, 0), (qkv, H), (qkv, 2 * H)]
+        if kind == 1:
+            q, kv = srcs
+            H = q.shape[-1]
+            return H, [(q, 0), (kv, 0), (kv, H)]
+        q, k, v = srcs
+        return q.shape[-1], [(q, 0), (k, 0), (v, 0)]
+
+    @staticmethod
+    def forward(ctx, kind, heads, mask, p, site, rng, *srcs):
+        srcs = tuple(s if s.is_contiguous() else s.contiguous() for s in srcs)
+        H, views = SmallAttentionFn._views(kind, srcs)
+        (qt, qo), (kt, ko), (vt, vo) = views
+        B, Sq, Sk = qt.shape[0], qt.shape[1], kt.shape[1]
+        out = torch.empty((B, Sq, H), dtype=torch.bfloat16, device=qt.device)
+        scale = 1.0 / (H // heads) ** 0.5
+        state = rng.state if (rng is not None and p > 0) else None
+        m2 = None
+        if mask is not None:
+            m2 = mask.reshape(B, Sk).float().contiguous()
+        check(lib.crv_attention_fwd(_off(qt, qo), qt.stride(0), qt.stride(1), _off(kt, ko), kt.stride(0), kt.stride(1),
+                                    _off(vt, vo), vt.stride(0), vt.stride(1), _p(m2), _p(out), B, heads, Sq, Sk,
+                                    scale, float(p), _p(state), int(site), _stream()), "crv_attention_fwd")
+        ctx.save_for_backward(*srcs)
+        ctx.cfg = (kind, heads, m2, float(p), int(site), state, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        kind, heads, m2, p, site, state, scale = ctx.cfg
+        srcs = ctx.saved_tensors
+        H, views = SmallAttentionFn._views(kind, srcs)
+        grads = tuple(torch.empty_like(s) for s in srcs)
+        _, gviews = SmallAttentionFn._views(kind, grads)
+        (qt, qo), (kt, ko), (vt, vo) = views
+        (dq, dqo), (dk, dko), (dv, dvo) = gviews
+        B, Sq, Sk = qt.shape[0], qt.shape[1], kt.shape[1]
+        dout = dout if dout.is_contiguous() else dout.contiguous()
+        check(lib.crv_attention_bwd(_off(qt, qo), qt.stride(0), qt.stride(1), _off(kt, ko), kt.stride(0), kt.stride(1),
+                                    _off(vt, vo), vt.stride(0), vt.stride(1), _p(m2), _p(dout),
+                                    _off(dq, dqo), dq.stride(0), dq.stride(1), _off(dk, dko), dk.stride(0), dk.stride(1),
+                                    _off(dv, dvo), dv.stride(0), dv.stride(1), B, heads, Sq, Sk, scale, p, _p(state),
+                                    site, _stream()), "crv_attention_bwd")
+        return (None, None, None, None, None, None) + grads
+
+
+def small_attention(kind, heads, mask, p, site, training, *srcs):
+    p = float(p) if training else 0.0
+    rng = RngState.get(srcs[0].device) if p > 0 else None
+    return SmallAttentionFn.apply(kind, heads, mask, p, site, rng, *srcs)
+
+
 # ----------------------------------------------------------------------------- layer plans
 def _arena_ready(*mods):
     for m in mods:
@@ -208,6 +282,7 @@ class AttentionPlan:
         self.mods = (att.query, att.key, att.value, out.dense)
         self.qkv = self.q = self.kv = self.ao = None
         self.site = RngState.new_site()
+        self.site_att = RngState.new_site()
 
     def ready(self):
         if not _arena_ready(*self.mods):
@@ -240,24 +315,46 @@ class AttentionPlan:
         ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=p)
         return ctx.transpose(1, 2).reshape(B, Sq, h * d)
 
-    def self_attention(self, x32, x16, mask, training):
-        H = x16.shape[-1]
-        if self.qkv is not None:
-            q, k, v = group_linear(self.qkv, x16).split(H, dim=-1)
+    def _small(self, Sq, Sk):
+        # crv_attention_* (one warp per head, WMMA) is exact but measured slower than cuDNN's flash SDPA at
+        # B=256 (94 / 248 us vs 65 / 137 us per call, profiles/), so it is opt-in until it is register-resident
+        a = self.att
+        return (os.environ.get("CRVQA_ATTN", "sdpa") == "small" and a.attention_head_size == 64
+                and Sq <= 64 and Sk <= 64)
+
+    def _attend(self, kind, mask, training, site, Sq, Sk, *srcs):
+        a = self.att
+        if self._small(Sq, Sk):
+            m = None if mask is None else mask.reshape(mask.shape[0], -1)
+            return small_attention(kind, a.num_attention_heads, m, a.dropout.p, site, training, *srcs)
+        H = a.head_size
+        if kind == 0:
+            q, k, v = srcs[0].split(H, dim=-1)
+        elif kind == 1:
+            q = srcs[0]
+            k, v = srcs[1].split(H, dim=-1)
         else:
-            q, k, v = group_linear(self.q, x16), group_linear(self.k1, x16), group_linear(self.v1, x16)
-        ctx = self._sdpa(q, k, v, mask, training)
+            q, k, v = srcs
+        return self._sdpa(q, k, v, mask, training)
+
+    def self_attention(self, x32, x16, mask, training):
+        S = x16.shape[1]
+        if self.qkv is not None:
+            ctx = self._attend(0, mask, training, self.site_att, S, S, group_linear(self.qkv, x16))
+        else:
+            ctx = self._attend(2, mask, training, self.site_att, S, S, group_linear(self.q, x16),
+                               group_linear(self.k1, x16), group_linear(self.v1, x16))
         ao = group_linear(self.ao, ctx)
         return drop_add_layernorm(ao, x32, self.out.LayerNorm, self.out.dropout.p, self.site, training)
 
     def cross_attention(self, x32, x16, c16, ctx_mask, training, site):
-        H = x16.shape[-1]
+        Sq, Sk = x16.shape[1], c16.shape[1]
         q = group_linear(self.q, x16)
         if self.kv is not None:
-            k, v = group_linear(self.kv, c16).split(H, dim=-1)
+            ctx = self._attend(1, ctx_mask, training, site + 1, Sq, Sk, q, group_linear(self.kv, c16))
         else:
-            k, v = group_linear(self.k1, c16), group_linear(self.v1, c16)
-        ctx = self._sdpa(q, k, v, ctx_mask, training)
+            ctx = self._attend(2, ctx_mask, training, site + 1, Sq, Sk, q, group_linear(self.k1, c16),
+                               group_linear(self.v1, c16))
         ao = group_linear(self.ao, ctx)
         return drop_add_layernorm(ao, x32, self.out.LayerNorm, self.out.dropout.p, site, training)
 

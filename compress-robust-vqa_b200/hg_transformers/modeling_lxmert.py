@@ -218,7 +218,7 @@ class LxmertEncoder(nn.Module):
                 "lang": [layer_plan(b) for b in self.layer],
                 "visn": [layer_plan(b) for b in self.r_layers],
                 "cross": [(fused.AttentionPlan(b.visual_attention.att, b.visual_attention.output),
-                           fused.RngState.new_site(), fused.RngState.new_site(),
+                           fused.RngState.new_sites(2), fused.RngState.new_sites(2),
                            fused.AttentionPlan(b.lang_self_att.self, b.lang_self_att.output),
                            fused.AttentionPlan(b.visn_self_att.self, b.visn_self_att.output),
                            fused.FfnPlan(b.lang_inter, b.lang_output), fused.FfnPlan(b.visn_inter, b.visn_output))

@@ -166,6 +166,23 @@ int crv_ln_bwd(const float* dy_f32, const uint16_t* dy_bf16, const void* g, int 
                const float* gamma, const float* mean, const float* rstd, float p_drop,
                const unsigned long long* rng_state, int site, void* dg, int dg_dtype, float* dres, int M, int H,
                void* stream);
+/* Small-sequence multi-head attention, head dim 64, Sq, Sk <= 64 (LxmertAttention.forward,
+ * hg_transformers/modeling_lxmert.py:798-827): out = dropout(softmax(Q K^T * scale + mask)) V.
+ * q / k / v are bf16 and addressed as base + b * bs + s * ss + head * 64 + d (element strides), so they can
+ * be slices of a fused QKV projection; mask is additive fp32 [B, Sk] or NULL; out is [B, Sq, heads * 64].
+ * One warp per (batch, head); warp-level tensor-core MMAs; the backward recomputes the probabilities and
+ * regenerates the dropout mask from (rng_state, site). */
+int crv_attention_fwd(const uint16_t* q, long long q_bs, long long q_ss, const uint16_t* k, long long k_bs,
+                      long long k_ss, const uint16_t* v, long long v_bs, long long v_ss, const float* mask,
+                      uint16_t* out, int B, int heads, int Sq, int Sk, float scale, float p_drop,
+                      const unsigned long long* rng_state, int site, void* stream);
+int crv_attention_bwd(const uint16_t* q, long long q_bs, long long q_ss, const uint16_t* k, long long k_bs,
+                      long long k_ss, const uint16_t* v, long long v_bs, long long v_ss, const float* mask,
+                      const uint16_t* dout, uint16_t* dq, long long dq_bs, long long dq_ss, uint16_t* dk,
+                      long long dk_bs, long long dk_ss, uint16_t* dv, long long dv_bs, long long dv_ss, int B,
+                      int heads, int Sq, int Sk, float scale, float p_drop, const unsigned long long* rng_state,
+                      int site, void* stream);
+
 /* erf GELU on bf16 (LxmertIntermediate): y = gelu(u);  du = dy * gelu'(u).  n % 8 == 0. */
 int crv_gelu_fwd(const uint16_t* u, uint16_t* y, int64_t n, void* stream);
 int crv_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du, int64_t n, void* stream);

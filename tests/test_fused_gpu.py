@@ -124,3 +124,76 @@ def test_engine_fast_path_matches_generic_path():
         assert model.lxmert.encoder._fast_plans() is None
     finally:
         os.environ.pop("CRVQA_FUSED")
+
+
+def _ref_attention(q, k, v, heads, mask):
+    B, Sq, H = q.shape
+    d = H // heads
+    qh = q.float().view(B, Sq, heads, d).transpose(1, 2)
+    kh = k.float().view(B, -1, heads, d).transpose(1, 2)
+    vh = v.float().view(B, -1, heads, d).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) / d ** 0.5
+    if mask is not None:
+        s = s + mask[:, None, None, :]
+    return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Sq, H)
+
+
+@pytest.mark.parametrize("Sq,Sk,kind,use_mask", [(20, 20, 0, False), (36, 36, 0, True), (20, 36, 1, False),
+                                                 (36, 20, 1, True), (56, 56, 0, False), (7, 64, 2, True)])
+def test_small_attention_vs_torch(Sq, Sk, kind, use_mask):
+    from crvqa import fused
+    torch.manual_seed(Sq * 100 + Sk)
+    B, heads, H = 5, 12, 768
+    mask = None
+    if use_mask:
+        mask = torch.zeros(B, Sk, device="cuda")
+        mask[:, Sk - 3:] = -10000.0
+    if kind == 0:
+        qkv = (torch.randn(B, Sq, 3 * H, device="cuda") * 0.7).bfloat16().requires_grad_(True)
+        srcs = (qkv,)
+        q, k, v = qkv.detach().split(H, -1)
+    elif kind == 1:
+        qt = (torch.randn(B, Sq, H, device="cuda") * 0.7).bfloat16().requires_grad_(True)
+        kv = (torch.randn(B, Sk, 2 * H, device="cuda") * 0.7).bfloat16().requires_grad_(True)
+        srcs = (qt, kv)
+        q, (k, v) = qt.detach(), kv.detach().split(H, -1)
+    else:
+        srcs = tuple((torch.randn(B, s, H, device="cuda") * 0.7).bfloat16().requires_grad_(True) for s in (Sq, Sk, Sk))
+        q, k, v = (t.detach() for t in srcs)
+    out = fused.small_attention(kind, heads, mask, 0.1, 3, False, *srcs)
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref = _ref_attention(qr, kr, vr, heads, mask)
+    err = float((out.float() - ref).abs().max() / ref.abs().max())
+    assert err < 2e-2, err                                      # bf16 probabilities / bf16 output
+    do = torch.randn_like(out)
+    out.backward(do)
+    ref.backward(do.float())
+    if kind == 0:
+        got = srcs[0].grad.float().split(H, -1)
+    elif kind == 1:
+        got = (srcs[0].grad.float(),) + tuple(srcs[1].grad.float().split(H, -1))
+    else:
+        got = tuple(t.grad.float() for t in srcs)
+    for g, r in zip(got, (qr.grad, kr.grad, vr.grad)):
+        rel = float((g - r).norm() / r.norm())
+        assert rel < 2e-2, rel
+
+
+def test_small_attention_dropout_is_unbiased_and_replayable():
+    from crvqa import fused
+    B, S, heads, H = 64, 36, 12, 768
+    qkv = (torch.randn(B, S, 3 * H, device="cuda") * 0.5).bfloat16()
+    base = fused.small_attention(0, heads, None, 0.1, 5, False, qkv).float()
+    rng = fused.RngState.get(qkv.device)
+    rng.advance()
+    a = fused.small_attention(0, heads, None, 0.1, 5, True, qkv).float()
+    b = fused.small_attention(0, heads, None, 0.1, 5, True, qkv).float()
+    assert torch.equal(a, b)                                    # same step, same site -> same mask
+    assert not torch.equal(a, base)
+    acc = torch.zeros_like(base)
+    n = 24
+    for _ in range(n):
+        rng.advance()
+        acc += fused.small_attention(0, heads, None, 0.1, 5, True, qkv).float()
+    rel = float((acc / n - base).norm() / base.norm())
+    assert rel < 0.1, rel                                       # E[dropout(P)] = P
