@@ -244,9 +244,18 @@ def run_ours(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms2)
 
-    if rank != 0:
+    def finish():
+        """Multi-rank teardown: NCCL communicators referenced by a live CUDA graph can block in
+        destroy_process_group, so flush and leave without tearing NCCL down."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     peaks = measured_peaks()
@@ -295,8 +304,7 @@ def run_ours(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():
