@@ -31,6 +31,7 @@ _PROTOS = {
     "crv_apply_mask_bf16": (c_int, [_P, _P, _P, _P, c_int64, _P]),
     "crv_apply_mask_segmented": (c_int, [_P, _P, _P, _P, c_int, _P, _P]),
     "crv_masked_linear_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "crv_gemm_debug_timestamps": (c_int, [_P]),
     "crv_masked_linear_bwd_dx": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "crv_masked_linear_bwd_ds": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "crv_masked_linear_small_k_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),

@@ -316,10 +316,9 @@ class AttentionPlan:
         return ctx.transpose(1, 2).reshape(B, Sq, h * d)
 
     def _small(self, Sq, Sk):
-        # crv_attention_* (one warp per head, WMMA) is exact but measured slower than cuDNN's flash SDPA at
-        # B=256 (94 / 248 us vs 65 / 137 us per call, profiles/), so it is opt-in until it is register-resident
+        # crv_attention_*: one warp per (batch, head), register-resident; CRVQA_ATTN=sdpa selects the library
         a = self.att
-        return (os.environ.get("CRVQA_ATTN", "sdpa") == "small" and a.attention_head_size == 64
+        return (os.environ.get("CRVQA_ATTN", "small") == "small" and a.attention_head_size == 64
                 and Sq <= 64 and Sk <= 64)
 
     def _attend(self, kind, mask, training, site, Sq, Sk, *srcs):

@@ -13,6 +13,9 @@ DT_F32, DT_BF16 = 0, 1
 # bench.py sets this to a list to collect (kind, M, N, K, start_event, end_event) for every masked-GEMM
 # launch (CUDA events on the launching stream); None = no instrumentation.
 PROFILE = None
+# bench.py sets this to a list to collect re-issuable (kind, M, N, K, thunk) records of every masked-GEMM
+# launch of a step, so the GEMM family can be replayed back to back (as one CUDA graph) and timed alone.
+RECORD = None
 
 
 class _Timed:
@@ -114,6 +117,8 @@ def masked_linear_fwd(x_bf16, w_bf16, scores, thr, bias, out_dtype=torch.float32
     N = w_bf16.shape[0]
     y = torch.empty((M, N), dtype=out_dtype, device=x_bf16.device)
     thr_t = as_thr(thr, x_bf16.device) if scores is not None else None
+    if RECORD is not None:
+        RECORD.append(("fwd", M, N, K, lambda: masked_linear_fwd(x_bf16, w_bf16, scores, thr, bias, out_dtype)))
     with _Timed("fwd", M, N, K):
         check(lib.crv_masked_linear_fwd(_p(x_bf16), _p(w_bf16), _p(scores), _p(thr_t), _p(bias), _p(y),
                                         DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _stream()),
@@ -127,6 +132,8 @@ def masked_linear_bwd_dx(dy_bf16, w_bf16, scores, thr, out_dtype=torch.float32):
     K = w_bf16.shape[1]
     dx = torch.empty((M, K), dtype=out_dtype, device=dy_bf16.device)
     thr_t = as_thr(thr, dy_bf16.device) if scores is not None else None
+    if RECORD is not None:
+        RECORD.append(("dx", M, N, K, lambda: masked_linear_bwd_dx(dy_bf16, w_bf16, scores, thr, out_dtype)))
     with _Timed("dx", M, N, K):
         check(lib.crv_masked_linear_bwd_dx(_p(dy_bf16), _p(w_bf16), _p(scores), _p(thr_t), _p(dx),
                                            DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _stream()),
@@ -141,6 +148,10 @@ def masked_linear_bwd_ds(dy_bf16, x_bf16, w_bf16, out=None, accumulate=False):
     if out is None:
         out = torch.empty((N, K), dtype=torch.float32, device=dy_bf16.device)
         accumulate = False
+    if RECORD is not None:
+        scratch = torch.empty_like(out)
+        RECORD.append(("ds", M, N, K, lambda: masked_linear_bwd_ds(dy_bf16, x_bf16, w_bf16, out=scratch,
+                                                                     accumulate=accumulate)))
     with _Timed("ds", M, N, K):
         check(lib.crv_masked_linear_bwd_ds(_p(dy_bf16), _p(x_bf16), _p(w_bf16), _p(out), int(bool(accumulate)),
                                            M, N, K, _stream()), "crv_masked_linear_bwd_ds")

@@ -3,10 +3,10 @@
 // section 8; hg_transformers/modeling_lxmert.py:798-827).
 //
 // Library flash kernels tile 128 x 128 and spend > 90 % of their work on padding at these lengths (cuDNN
-// SDPA measured 7.8 ms per training step, 28 % of it).  Here ONE WARP owns one (batch, head) pair: Q, K, V
-// (and dO) sit in that warp's shared-memory slab, the four small matmuls run on the tensor cores through
-// warp-level 16x16x16 bf16 MMAs with fp32 accumulation, softmax / dropout are fp32 in shared memory, and
-// the backward recomputes P instead of storing it.  No block-level barrier is needed (only __syncwarp).
+// SDPA measured 7.8 ms per training step, 28 % of it).  Here ONE WARP owns one (batch, head) pair: the
+// small matmuls run on the tensor cores (mma.sync m16n8k16, bf16 in / fp32 accumulate), scores and
+// probabilities stay in registers, softmax / dropout are fp32, and the backward recomputes P (both in
+// row and in transposed orientation) instead of storing it.  No block-level barrier (only __syncwarp).
 // Inputs are read in place from the fused QKV projection ([B, S, 3H] row stride) and gradients are written
 // straight into the fused dQKV tensor, so no split / concat copies exist.
 #include <mma.h>
@@ -44,15 +44,58 @@ struct AttnParams {
   int site;
 };
 
-template <int SP>
+// ---------------------------------------------------------------------------------------------------
+// Register-resident formulation (flash-attention-2 style, specialised for S <= 64):
+// one warp per (batch, head); scores / probabilities never leave registers; K, V (and Q, dO in the
+// backward) are staged once per warp in shared memory with 16-byte loads and read back as MMA fragments
+// with ldmatrix; mma.sync.m16n8k16 (bf16 x bf16 -> fp32).  Lane = 4 g + t:
+//   A (16x16): a0 (row g, k 2t..2t+1)  a1 (row g+8, same k)  a2 (row g, k+8)  a3 (row g+8, k+8)
+//   B (16x8) : b0 (k 2t..2t+1, n g)    b1 (k 2t+8.., n g)
+//   C (16x8) : c0 c1 (row g, n 2t, 2t+1)   c2 c3 (row g+8, n 2t, 2t+1)
+// so the C fragments of two adjacent 8-wide score tiles ARE the A fragment of the next GEMM (P . V).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t sptr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// A fragment of rows [r0, r0+16), k [k0, k0+16) of a row-major [row][k] tile (pitch kLdH)
+__device__ __forceinline__ void ld_a(uint32_t (&a)[4], const __nv_bfloat16* tile, int r0, int k0, int lane) {
+  const __nv_bfloat16* p = tile + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kLdH + k0 + (lane >> 4) * 8;
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(sptr(p)));
+}
+// B fragment (k [k0,k0+16), n [n0,n0+8)) from a tile stored [n][k]  (B[k][n] = tile[n][k])
+__device__ __forceinline__ void ld_b_nk(uint32_t (&b)[2], const __nv_bfloat16* tile, int n0, int k0, int lane) {
+  const __nv_bfloat16* p = tile + (n0 + (lane & 7)) * kLdH + k0 + ((lane >> 3) & 1) * 8;
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(b[0]), "=r"(b[1]) : "r"(sptr(p)));
+}
+// B fragment from a tile stored [k][n]  (B[k][n] = tile[k][n]) -- transposing load
+__device__ __forceinline__ void ld_b_kn(uint32_t (&b)[2], const __nv_bfloat16* tile, int n0, int k0, int lane) {
+  const __nv_bfloat16* p = tile + (k0 + (lane & 15)) * kLdH + n0;
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(b[0]), "=r"(b[1]) : "r"(sptr(p)));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+template <int KT2>  // padded length SP = 16 * KT2 covers max(Sq, Sk)
 struct AttnSmem {
-  static constexpr int kLdS = SP + 4;   // fp32 pitch of score tiles
-  static constexpr int kLdP = SP + 8;   // bf16 pitch of probability tiles
-  static constexpr int kTile = SP * kLdH * 2;                 // one bf16 operand tile
-  static constexpr int kF32 = SP * ((SP > 64 ? SP : 64) + 4) * 4;  // fp32 scratch: scores or a [SP][64] output
-  static constexpr int kP = SP * kLdP * 2;
-  static constexpr int kFwd = 3 * kTile + kF32 + kP;
-  static constexpr int kBwd = 4 * kTile + 2 * kF32 + kP;
+  static constexpr int SP = 16 * KT2;
+  static constexpr int kTile = SP * kLdH * 2;
+  static constexpr int kFwd = 2 * kTile;                  // K, V
+  static constexpr int kBwd = 4 * kTile + 3 * SP * 4;     // Q, K, V, dO + row max / row sum / D
 };
 
 // rows [0, S) of a [S][64] bf16 global tile -> smem [SP][72]; rows >= S zero-filled
@@ -65,43 +108,6 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat1
     if (r < S) v = __ldg(reinterpret_cast<const uint4*>(src + r * row_stride) + c);
     *reinterpret_cast<uint4*>(dst + r * kLdH + c * 8) = v;
   }
-}
-
-// fp32 smem [rows][ld] (first 64 columns) -> bf16 global rows
-__device__ __forceinline__ void store_tile(__nv_bfloat16* dst, long long row_stride, const float* src, int ld, int S,
-                                           int lane) {
-  for (int i = lane; i < S * 8; i += 32) {
-    const int r = i >> 3, c = i & 7;
-    const float* s = src + r * ld + c * 8;
-    __nv_bfloat162 a = __floats2bfloat162_rn(s[0], s[1]), b = __floats2bfloat162_rn(s[2], s[3]);
-    __nv_bfloat162 e = __floats2bfloat162_rn(s[4], s[5]), f = __floats2bfloat162_rn(s[6], s[7]);
-    uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
-                         *reinterpret_cast<uint32_t*>(&e), *reinterpret_cast<uint32_t*>(&f));
-    *reinterpret_cast<uint4*>(dst + r * row_stride + c * 8) = v;
-  }
-}
-
-// C[MT*16 x NT*16] (fp32, ldc) = A . B with KT k-steps of 16; A / B majors chosen by the caller
-template <typename ALayout, typename BLayout>
-__device__ __forceinline__ void warp_gemm(float* C, int ldc, const __nv_bfloat16* A, int lda, const __nv_bfloat16* Bm,
-                                          int ldb, int MT, int NT, int KT) {
-  for (int mt = 0; mt < MT; ++mt)
-    for (int nt = 0; nt < NT; ++nt) {
-      wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
-      wmma::fill_fragment(acc, 0.f);
-      for (int kt = 0; kt < KT; ++kt) {
-        wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, ALayout> a;
-        wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, BLayout> b;
-        const __nv_bfloat16* ap = std::is_same<ALayout, wmma::row_major>::value ? A + mt * 16 * lda + kt * 16
-                                                                                 : A + kt * 16 * lda + mt * 16;
-        const __nv_bfloat16* bp = std::is_same<BLayout, wmma::row_major>::value ? Bm + kt * 16 * ldb + nt * 16
-                                                                                 : Bm + nt * 16 * ldb + kt * 16;
-        wmma::load_matrix_sync(a, ap, lda);
-        wmma::load_matrix_sync(b, bp, ldb);
-        wmma::mma_sync(acc, a, b, acc);
-      }
-      wmma::store_matrix_sync(C + mt * 16 * ldc + nt * 16, acc, ldc, wmma::mem_row_major);
-    }
 }
 
 struct DropKey {
@@ -123,148 +129,295 @@ __device__ __forceinline__ DropKey make_key(const unsigned long long* state, int
   return r;
 }
 
-// softmax over the first Sk columns of rows < Sq of S (fp32, in place -> P); also writes dropout(P) as bf16
-template <int SP>
-__device__ __forceinline__ void softmax_rows(float* S, __nv_bfloat16* Pd, const AttnParams& p, int b, int pair,
-                                             const DropKey& dk, int lane) {
-  using L = AttnSmem<SP>;
-  for (int r = lane; r < SP; r += 32) {
-    float* row = S + r * L::kLdS;
-    __nv_bfloat16* prow = Pd + r * L::kLdP;
-    if (r >= p.Sq) {
-      for (int j = 0; j < SP; ++j) prow[j] = __float2bfloat16(0.f);
-      continue;
+// scores of one 16-row block against all keys: acc[nt] = A(16 x 64) . tile[nt*8 .. +8][64]^T
+template <int KT2>
+__device__ __forceinline__ void scores_16(float (&acc)[2 * KT2][4], const uint32_t (&a)[4][4], const __nv_bfloat16* sB,
+                                          int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 2 * KT2; ++nt) {
+    acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      uint32_t b[2];
+      ld_b_nk(b, sB, nt * 8, kt * 16, lane);
+      mma16816(acc[nt], a[kt], b);
     }
-    float mx = -3.0e38f;
-    for (int j = 0; j < p.Sk; ++j) {
-      float x = row[j] * p.scale;
-      if (p.mask) x += p.mask[static_cast<long long>(b) * p.Sk + j];
-      row[j] = x;
-      mx = fmaxf(mx, x);
-    }
-    float sum = 0.f;
-    for (int j = 0; j < p.Sk; ++j) {
-      const float e = __expf(row[j] - mx);
-      row[j] = e;
-      sum += e;
-    }
-    const float inv = 1.f / sum;
-    const uint64_t base = (static_cast<uint64_t>(pair) * p.Sq + r) * p.Sk;
-    for (int j = 0; j < p.Sk; ++j) {
-      const float pr = row[j] * inv;
-      row[j] = pr;
-      prow[j] = __float2bfloat16(dk.keep(base + j) ? pr * dk.scale : 0.f);
-    }
-    for (int j = p.Sk; j < SP; ++j) { row[j] = 0.f; prow[j] = __float2bfloat16(0.f); }
   }
 }
 
-template <int SP, int WARPS>
+template <int KT2, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_fwd_kernel(const AttnParams p) {
-  using L = AttnSmem<SP>;
+  using L = AttnSmem<KT2>;
+  constexpr int SP = L::SP, NT = 2 * KT2;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * WARPS + warp;
   if (pair >= p.B * p.heads) return;
   const int b = pair / p.heads, h = pair % p.heads;
-  uint8_t* base = smem + warp * L::kFwd;
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(base);
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(base + L::kTile);
-  __nv_bfloat16* sV = reinterpret_cast<__nv_bfloat16*>(base + 2 * L::kTile);
-  float* sS = reinterpret_cast<float*>(base + 3 * L::kTile);
-  __nv_bfloat16* sP = reinterpret_cast<__nv_bfloat16*>(base + 3 * L::kTile + L::kF32);
-  load_tile<SP>(sQ, p.q + b * p.q_bs + h * kHeadDim, p.q_ss, p.Sq, lane);
+  const int g = lane >> 2, t = lane & 3;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem + warp * L::kFwd);
+  __nv_bfloat16* sV = sK + SP * kLdH;
   load_tile<SP>(sK, p.k + b * p.k_bs + h * kHeadDim, p.k_ss, p.Sk, lane);
   load_tile<SP>(sV, p.v + b * p.v_bs + h * kHeadDim, p.v_ss, p.Sk, lane);
   __syncwarp();
-  const int MT = (p.Sq + 15) / 16, NT = (p.Sk + 15) / 16;
-  warp_gemm<wmma::row_major, wmma::col_major>(sS, L::kLdS, sQ, kLdH, sK, kLdH, MT, NT, kHeadDim / 16);
-  __syncwarp();
   const DropKey dk = make_key(p.rng_state, p.site, p.p_drop);
-  softmax_rows<SP>(sS, sP, p, b, pair, dk, lane);
-  __syncwarp();
-  float* sO = sS;  // scores are dead; reuse as [SP][68] output staging
-  warp_gemm<wmma::row_major, wmma::row_major>(sO, 68, sP, L::kLdP, sV, kLdH, MT, kHeadDim / 16, NT);
-  __syncwarp();
-  store_tile(p.out + (static_cast<long long>(b) * p.Sq) * (p.heads * kHeadDim) + h * kHeadDim, p.heads * kHeadDim, sO,
-             68, p.Sq, lane);
+  const __nv_bfloat16* qb = p.q + b * p.q_bs + h * kHeadDim;
+  const float* mrow = p.mask ? p.mask + static_cast<long long>(b) * p.Sk : nullptr;
+  const long long HD = static_cast<long long>(p.heads) * kHeadDim;
+  const int MT = (p.Sq + 15) >> 4;
+  for (int mt = 0; mt < MT; ++mt) {
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    uint32_t a[4][4];
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const int c = kt * 16 + 2 * t;
+      a[kt][0] = r0 < p.Sq ? __ldg(reinterpret_cast<const uint32_t*>(qb + r0 * p.q_ss + c)) : 0u;
+      a[kt][1] = r1 < p.Sq ? __ldg(reinterpret_cast<const uint32_t*>(qb + r1 * p.q_ss + c)) : 0u;
+      a[kt][2] = r0 < p.Sq ? __ldg(reinterpret_cast<const uint32_t*>(qb + r0 * p.q_ss + c + 8)) : 0u;
+      a[kt][3] = r1 < p.Sq ? __ldg(reinterpret_cast<const uint32_t*>(qb + r1 * p.q_ss + c + 8)) : 0u;
+    }
+    float s[NT][4];
+    scores_16<KT2>(s, a, sK, lane);
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = nt * 8 + 2 * t + e;
+        const float add = j < p.Sk ? (mrow ? mrow[j] : 0.f) : -INFINITY;
+        s[nt][e] = s[nt][e] * p.scale + add;
+        s[nt][2 + e] = s[nt][2 + e] * p.scale + add;
+        m0 = fmaxf(m0, s[nt][e]);
+        m1 = fmaxf(m1, s[nt][2 + e]);
+      }
+    }
+    m0 = quad_max(m0);
+    m1 = quad_max(m1);
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[nt][e] = __expf(s[nt][e] - m0);
+        s[nt][2 + e] = __expf(s[nt][2 + e] - m1);
+        l0 += s[nt][e];
+        l1 += s[nt][2 + e];
+      }
+    }
+    const float i0 = 1.f / quad_sum(l0), i1 = 1.f / quad_sum(l1);
+    uint32_t pa[KT2][4];
+    const uint64_t ib0 = (static_cast<uint64_t>(pair) * p.Sq + r0) * p.Sk, ib1 = ib0 + 8ull * p.Sk;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = nt * 8 + 2 * t + e;
+        v[e] = dk.keep(ib0 + j) ? s[nt][e] * i0 * dk.scale : 0.f;
+        v[2 + e] = dk.keep(ib1 + j) ? s[nt][2 + e] * i1 * dk.scale : 0.f;
+      }
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(v[0], v[1]);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(v[2], v[3]);
+    }
+    __nv_bfloat16* ob = p.out + (static_cast<long long>(b) * p.Sq) * HD + h * kHeadDim;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kt = 0; kt < KT2; ++kt) {
+        uint32_t bv[2];
+        ld_b_kn(bv, sV, dt * 8, kt * 16, lane);
+        mma16816(o, pa[kt], bv);
+      }
+      const int c = dt * 8 + 2 * t;
+      if (r0 < p.Sq) *reinterpret_cast<uint32_t*>(ob + r0 * HD + c) = pack_bf16x2(o[0], o[1]);
+      if (r1 < p.Sq) *reinterpret_cast<uint32_t*>(ob + r1 * HD + c) = pack_bf16x2(o[2], o[3]);
+    }
+  }
 }
 
-template <int SP, int WARPS>
+template <int KT2, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_bwd_kernel(const AttnParams p) {
-  using L = AttnSmem<SP>;
+  using L = AttnSmem<KT2>;
+  constexpr int SP = L::SP, NT = 2 * KT2;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * WARPS + warp;
   if (pair >= p.B * p.heads) return;
   const int b = pair / p.heads, h = pair % p.heads;
+  const int g = lane >> 2, t = lane & 3;
   uint8_t* base = smem + warp * L::kBwd;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(base);
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(base + L::kTile);
-  __nv_bfloat16* sV = reinterpret_cast<__nv_bfloat16*>(base + 2 * L::kTile);
-  __nv_bfloat16* sdO = reinterpret_cast<__nv_bfloat16*>(base + 3 * L::kTile);
-  float* sS = reinterpret_cast<float*>(base + 4 * L::kTile);
-  float* sT = reinterpret_cast<float*>(base + 4 * L::kTile + L::kF32);
-  __nv_bfloat16* sP = reinterpret_cast<__nv_bfloat16*>(base + 4 * L::kTile + 2 * L::kF32);
+  __nv_bfloat16* sK = sQ + SP * kLdH;
+  __nv_bfloat16* sV = sK + SP * kLdH;
+  __nv_bfloat16* sdO = sV + SP * kLdH;
+  float* sM = reinterpret_cast<float*>(base + 4 * L::kTile);
+  float* sL = sM + SP;
+  float* sD = sL + SP;
   const long long HD = static_cast<long long>(p.heads) * kHeadDim;
   load_tile<SP>(sQ, p.q + b * p.q_bs + h * kHeadDim, p.q_ss, p.Sq, lane);
   load_tile<SP>(sK, p.k + b * p.k_bs + h * kHeadDim, p.k_ss, p.Sk, lane);
   load_tile<SP>(sV, p.v + b * p.v_bs + h * kHeadDim, p.v_ss, p.Sk, lane);
   load_tile<SP>(sdO, p.dout + static_cast<long long>(b) * p.Sq * HD + h * kHeadDim, HD, p.Sq, lane);
   __syncwarp();
-  const int MT = (p.Sq + 15) / 16, NT = (p.Sk + 15) / 16, DT = kHeadDim / 16;
-  // 1-2. P = softmax(Q K^T * scale + mask) (fp32 in sS), Pd = dropout(P) (bf16 in sP)
-  warp_gemm<wmma::row_major, wmma::col_major>(sS, L::kLdS, sQ, kLdH, sK, kLdH, MT, NT, DT);
-  __syncwarp();
   const DropKey dk = make_key(p.rng_state, p.site, p.p_drop);
-  softmax_rows<SP>(sS, sP, p, b, pair, dk, lane);
-  __syncwarp();
-  // 3. dV = Pd^T . dO
-  warp_gemm<wmma::col_major, wmma::row_major>(sT, 68, sP, L::kLdP, sdO, kLdH, NT, DT, MT);
-  __syncwarp();
-  store_tile(p.dv + b * p.dv_bs + h * kHeadDim, p.dv_ss, sT, 68, p.Sk, lane);
-  __syncwarp();
-  // 4. dPd = dO . V^T
-  warp_gemm<wmma::row_major, wmma::col_major>(sT, L::kLdS, sdO, kLdH, sV, kLdH, MT, NT, DT);
-  __syncwarp();
-  // 5. dS = P (.) (dP - sum_j dP_j P_j) * scale, dP = dropout'(dPd)   -> bf16 in sP
-  for (int r = lane; r < SP; r += 32) {
-    __nv_bfloat16* prow = sP + r * L::kLdP;
-    if (r >= p.Sq) {
-      for (int j = 0; j < SP; ++j) prow[j] = __float2bfloat16(0.f);
-      continue;
+  const float* mrow = p.mask ? p.mask + static_cast<long long>(b) * p.Sk : nullptr;
+  const int MT = (p.Sq + 15) >> 4, JT = (p.Sk + 15) >> 4;
+
+  // ---- pass A: query-row blocks.  P, dP, D_i = sum_j dP_ij P_ij, dS -> dQ; row statistics to smem
+  for (int mt = 0; mt < MT; ++mt) {
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    uint32_t a[4][4];
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) ld_a(a[kt], sQ, mt * 16, kt * 16, lane);
+    float s[NT][4];
+    scores_16<KT2>(s, a, sK, lane);
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = nt * 8 + 2 * t + e;
+        const float add = j < p.Sk ? (mrow ? mrow[j] : 0.f) : -INFINITY;
+        s[nt][e] = s[nt][e] * p.scale + add;
+        s[nt][2 + e] = s[nt][2 + e] * p.scale + add;
+        m0 = fmaxf(m0, s[nt][e]);
+        m1 = fmaxf(m1, s[nt][2 + e]);
+      }
     }
-    const float* P = sS + r * L::kLdS;
-    float* dP = sT + r * L::kLdS;
-    const uint64_t ib = (static_cast<uint64_t>(pair) * p.Sq + r) * p.Sk;
-    float t = 0.f;
-    for (int j = 0; j < p.Sk; ++j) {
-      const float d = dk.keep(ib + j) ? dP[j] * dk.scale : 0.f;
-      dP[j] = d;
-      t += d * P[j];
+    m0 = quad_max(m0);
+    m1 = quad_max(m1);
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[nt][e] = __expf(s[nt][e] - m0);
+        s[nt][2 + e] = __expf(s[nt][2 + e] - m1);
+        l0 += s[nt][e];
+        l1 += s[nt][2 + e];
+      }
     }
-    for (int j = 0; j < p.Sk; ++j) prow[j] = __float2bfloat16(P[j] * (dP[j] - t) * p.scale);
-    for (int j = p.Sk; j < SP; ++j) prow[j] = __float2bfloat16(0.f);
+    l0 = quad_sum(l0);
+    l1 = quad_sum(l1);
+    if (t == 0) { sM[r0] = m0; sL[r0] = l0; sM[r1] = m1; sL[r1] = l1; }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    // dPd = dO . V^T
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) ld_a(a[kt], sdO, mt * 16, kt * 16, lane);
+    float dp[NT][4];
+    scores_16<KT2>(dp, a, sV, lane);
+    const uint64_t ib0 = (static_cast<uint64_t>(pair) * p.Sq + r0) * p.Sk, ib1 = ib0 + 8ull * p.Sk;
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = nt * 8 + 2 * t + e;
+        s[nt][e] *= i0;            // P
+        s[nt][2 + e] *= i1;
+        dp[nt][e] = (j < p.Sk && dk.keep(ib0 + j)) ? dp[nt][e] * dk.scale : 0.f;
+        dp[nt][2 + e] = (j < p.Sk && dk.keep(ib1 + j)) ? dp[nt][2 + e] * dk.scale : 0.f;
+        d0 += dp[nt][e] * s[nt][e];
+        d1 += dp[nt][2 + e] * s[nt][2 + e];
+      }
+    }
+    d0 = quad_sum(d0);
+    d1 = quad_sum(d1);
+    if (t == 0) { sD[r0] = d0; sD[r1] = d1; }
+    uint32_t da[KT2][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      da[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(s[nt][0] * (dp[nt][0] - d0) * p.scale, s[nt][1] * (dp[nt][1] - d0) * p.scale);
+      da[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(s[nt][2] * (dp[nt][2] - d1) * p.scale, s[nt][3] * (dp[nt][3] - d1) * p.scale);
+    }
+    __nv_bfloat16* qo = p.dq + b * p.dq_bs + h * kHeadDim;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kt = 0; kt < KT2; ++kt) {
+        uint32_t bk[2];
+        ld_b_kn(bk, sK, dt * 8, kt * 16, lane);   // B[k = j][n = d] = K[j][d]
+        mma16816(o, da[kt], bk);
+      }
+      const int c = dt * 8 + 2 * t;
+      if (r0 < p.Sq) *reinterpret_cast<uint32_t*>(qo + r0 * p.dq_ss + c) = pack_bf16x2(o[0], o[1]);
+      if (r1 < p.Sq) *reinterpret_cast<uint32_t*>(qo + r1 * p.dq_ss + c) = pack_bf16x2(o[2], o[3]);
+    }
   }
   __syncwarp();
-  // 6. dQ = dS . K
-  warp_gemm<wmma::row_major, wmma::row_major>(sT, 68, sP, L::kLdP, sK, kLdH, MT, DT, NT);
-  __syncwarp();
-  store_tile(p.dq + b * p.dq_bs + h * kHeadDim, p.dq_ss, sT, 68, p.Sq, lane);
-  __syncwarp();
-  // 7. dK = dS^T . Q
-  warp_gemm<wmma::col_major, wmma::row_major>(sT, 68, sP, L::kLdP, sQ, kLdH, NT, DT, MT);
-  __syncwarp();
-  store_tile(p.dk + b * p.dk_bs + h * kHeadDim, p.dk_ss, sT, 68, p.Sk, lane);
+
+  // ---- pass B: key-row blocks on the transposed problem.  P^T, dP^T -> dV = Pd^T dO, dK = dS^T Q
+  for (int jt = 0; jt < JT; ++jt) {
+    const int j0 = jt * 16 + g, j1 = j0 + 8;
+    uint32_t a[4][4];
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) ld_a(a[kt], sK, jt * 16, kt * 16, lane);
+    float s[NT][4];
+    scores_16<KT2>(s, a, sQ, lane);               // S^T[j][i] = K[j] . Q[i]
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) ld_a(a[kt], sV, jt * 16, kt * 16, lane);
+    float dp[NT][4];
+    scores_16<KT2>(dp, a, sdO, lane);             // dPd^T[j][i] = V[j] . dO[i]
+    const float add0 = j0 < p.Sk ? (mrow ? mrow[j0] : 0.f) : 0.f, add1 = j1 < p.Sk ? (mrow ? mrow[j1] : 0.f) : 0.f;
+    uint32_t pa[KT2][4], da[KT2][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float pv[4], dv[4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = nt * 8 + 2 * t + e;
+        const bool iv = i < p.Sq;
+        const float mi = iv ? sM[i] : 0.f, li = iv ? 1.f / sL[i] : 0.f, Di = iv ? sD[i] : 0.f;
+        const uint64_t ib = (static_cast<uint64_t>(pair) * p.Sq + i) * p.Sk;
+        const float p0 = (iv && j0 < p.Sk) ? __expf(s[nt][e] * p.scale + add0 - mi) * li : 0.f;
+        const float p1 = (iv && j1 < p.Sk) ? __expf(s[nt][2 + e] * p.scale + add1 - mi) * li : 0.f;
+        const bool k0 = iv && j0 < p.Sk && dk.keep(ib + j0), k1 = iv && j1 < p.Sk && dk.keep(ib + j1);
+        pv[e] = k0 ? p0 * dk.scale : 0.f;
+        pv[2 + e] = k1 ? p1 * dk.scale : 0.f;
+        const float dp0 = k0 ? dp[nt][e] * dk.scale : 0.f, dp1 = k1 ? dp[nt][2 + e] * dk.scale : 0.f;
+        dv[e] = p0 * (dp0 - Di) * p.scale;
+        dv[2 + e] = p1 * (dp1 - Di) * p.scale;
+      }
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(pv[0], pv[1]);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
+      da[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(dv[0], dv[1]);
+      da[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(dv[2], dv[3]);
+    }
+    __nv_bfloat16* vo = p.dv + b * p.dv_bs + h * kHeadDim;
+    __nv_bfloat16* ko = p.dk + b * p.dk_bs + h * kHeadDim;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      float ov[4] = {0.f, 0.f, 0.f, 0.f}, ok[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kt = 0; kt < KT2; ++kt) {
+        uint32_t bo[2], bq[2];
+        ld_b_kn(bo, sdO, dt * 8, kt * 16, lane);   // B[k = i][n = d] = dO[i][d]
+        ld_b_kn(bq, sQ, dt * 8, kt * 16, lane);    // B[k = i][n = d] = Q[i][d]
+        mma16816(ov, pa[kt], bo);
+        mma16816(ok, da[kt], bq);
+      }
+      const int c = dt * 8 + 2 * t;
+      if (j0 < p.Sk) {
+        *reinterpret_cast<uint32_t*>(vo + j0 * p.dv_ss + c) = pack_bf16x2(ov[0], ov[1]);
+        *reinterpret_cast<uint32_t*>(ko + j0 * p.dk_ss + c) = pack_bf16x2(ok[0], ok[1]);
+      }
+      if (j1 < p.Sk) {
+        *reinterpret_cast<uint32_t*>(vo + j1 * p.dv_ss + c) = pack_bf16x2(ov[2], ov[3]);
+        *reinterpret_cast<uint32_t*>(ko + j1 * p.dk_ss + c) = pack_bf16x2(ok[2], ok[3]);
+      }
+    }
+  }
 }
 
-template <int SP, int WARPS, bool BWD>
+template <int KT2, int WARPS, bool BWD>
 static int launch_attn(const AttnParams& p, cudaStream_t st) {
-  using L = AttnSmem<SP>;
+  using L = AttnSmem<KT2>;
   constexpr int smem = WARPS * (BWD ? L::kBwd : L::kFwd);
-  auto kern = BWD ? attn_bwd_kernel<SP, WARPS> : attn_fwd_kernel<SP, WARPS>;
+  auto kern = BWD ? attn_bwd_kernel<KT2, WARPS> : attn_fwd_kernel<KT2, WARPS>;
   static bool configured = false;
   if (!configured) {
     CRV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -302,9 +455,9 @@ extern "C" int crv_attention_fwd(const uint16_t* q, long long q_bs, long long q_
   if (!out || !aligned16(out)) return CRV_E_BADARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int S = Sq > Sk ? Sq : Sk;
-  if (S <= 32) return launch_attn<32, 4, false>(p, st);
-  if (S <= 48) return launch_attn<48, 4, false>(p, st);
-  return launch_attn<64, 4, false>(p, st);
+  if (S <= 32) return launch_attn<2, 8, false>(p, st);
+  if (S <= 48) return launch_attn<3, 8, false>(p, st);
+  return launch_attn<4, 8, false>(p, st);
 }
 
 extern "C" int crv_attention_bwd(const uint16_t* q, long long q_bs, long long q_ss, const uint16_t* k, long long k_bs,
@@ -328,7 +481,7 @@ extern "C" int crv_attention_bwd(const uint16_t* q, long long q_bs, long long q_
   if ((dq_ss | dk_ss | dv_ss | dq_bs | dk_bs | dv_bs) & 7) return CRV_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int S = Sq > Sk ? Sq : Sk;
-  if (S <= 32) return launch_attn<32, 3, true>(p, st);
-  if (S <= 48) return launch_attn<48, 3, true>(p, st);
-  return launch_attn<64, 2, true>(p, st);
+  if (S <= 32) return launch_attn<2, 4, true>(p, st);
+  if (S <= 48) return launch_attn<3, 4, true>(p, st);
+  return launch_attn<4, 4, true>(p, st);
 }

@@ -43,6 +43,7 @@ struct GemmParams {
   const float* bias;       // [NN] or null (store epilogue)
   const __nv_bfloat16* w;  // [MM, NN] bf16 multiplier (score-grad epilogue)
   int reduce_out;          // score-grad: 1 = TMA reduce-add into out, 0 = plain TMA store
+  long long* dbg;          // optional per-CTA timestamps (crv_gemm_debug_timestamps), else null
 };
 
 template <int BN, bool XFORM>
@@ -75,6 +76,12 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 struct TileCoord {
   int m0, n0, kb_begin, num_kb;
@@ -117,6 +124,7 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m * p.num_n * p.splits;
+  if (p.dbg && threadIdx.x == 0) p.dbg[static_cast<size_t>(blockIdx.x) * 8 + 7] = gtime();  // kernel entry
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -142,6 +150,8 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = gtime();  // setup done
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -158,6 +168,7 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint8_t* sB = sA + L::kA;
           uint8_t* sS = sB + L::kB;
           const int kk0 = (tc.kb_begin + kb) * BK;
+          if (dbg && it == 0) dbg[1] = gtime();  // first TMA issue
           if (!A_MN) {
             tma_load_2d(sA, &tmA, &full_bar[s], kk0, tc.m0);
           } else {
@@ -198,6 +209,7 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(&full_bar[s], ph);
         if (XFORM) mbar_wait(&xform_bar[s], ph);
         tc_fence_after();
+        if (dbg && it == 0 && lane == 0) dbg[2] = gtime();  // first stage landed
         if (lane == 0) {
           const uint32_t aBase = smem_u32(smem + s * L::kStage);
           const uint32_t bBase = aBase + L::kA;
@@ -228,39 +240,43 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int m = row0 + lane;
       mbar_wait(&tmem_full_bar[acc], (tcount >> 1) & 1);
       tc_fence_after();
+      if (dbg && tcount == 0 && warp == 2 && lane == 0) dbg[3] = gtime();  // first accumulator ready
       const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < BN / COLS; ++c, ++chunk_no) {
         const int nb = tc.n0 + c * COLS;
         uint32_t r[32];
         uint32_t pk[32];  // staging row as 32 words (fp32) or 32 packed bf16 pairs
+        // bias of this chunk: lane l fetches columns nb + l (and nb + 32 + l); broadcast by shuffle below.
+        // Issued before the TMEM wait so the two latencies overlap.
+        float bias_lo = 0.f, bias_hi = 0.f;
+        if (EPI == kEpiStore && p.bias != nullptr) {
+          if (nb + lane < p.NN) bias_lo = __ldg(p.bias + nb + lane);
+          if (OUT_BF16 && nb + 32 + lane < p.NN) bias_hi = __ldg(p.bias + nb + 32 + lane);
+        }
         tmem_ld_32x32(t_addr + c * COLS, r);
-        tmem_ld_wait();
         if (OUT_BF16) {
           uint32_t r2[32];
           tmem_ld_32x32(t_addr + c * COLS + 32, r2);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float a0 = __uint_as_float(r[2 * j]), a1 = __uint_as_float(r[2 * j + 1]);
-            float b0 = __uint_as_float(r2[2 * j]), b1 = __uint_as_float(r2[2 * j + 1]);
-            if (p.bias) {
-              if (nb + 2 * j + 1 < p.NN) { a0 += __ldg(p.bias + nb + 2 * j); a1 += __ldg(p.bias + nb + 2 * j + 1); }
-              if (nb + 32 + 2 * j + 1 < p.NN) { b0 += __ldg(p.bias + nb + 32 + 2 * j); b1 += __ldg(p.bias + nb + 33 + 2 * j); }
-            }
+            const float a0 = __uint_as_float(r[2 * j]) + __shfl_sync(0xffffffffu, bias_lo, 2 * j);
+            const float a1 = __uint_as_float(r[2 * j + 1]) + __shfl_sync(0xffffffffu, bias_lo, 2 * j + 1);
+            const float b0 = __uint_as_float(r2[2 * j]) + __shfl_sync(0xffffffffu, bias_hi, 2 * j);
+            const float b1 = __uint_as_float(r2[2 * j + 1]) + __shfl_sync(0xffffffffu, bias_hi, 2 * j + 1);
             __nv_bfloat162 ta = __floats2bfloat162_rn(a0, a1);
             __nv_bfloat162 tb = __floats2bfloat162_rn(b0, b1);
             pk[j] = *reinterpret_cast<uint32_t*>(&ta);
             pk[16 + j] = *reinterpret_cast<uint32_t*>(&tb);
           }
         } else if (EPI == kEpiStore) {
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = __uint_as_float(r[j]);
-            if (p.bias && nb + j < p.NN) v += __ldg(p.bias + nb + j);
-            pk[j] = __float_as_uint(v);
-          }
+          for (int j = 0; j < 32; ++j)
+            pk[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lo, j));
         } else {  // score gradient: (.) W
+          tmem_ld_wait();
           const bool row_ok = m < p.MM;
           const __nv_bfloat16* wrow = p.w + static_cast<size_t>(row_ok ? m : 0) * p.NN + nb;
           if (row_ok && nb + 32 <= p.NN && (p.NN & 7) == 0) {
@@ -304,8 +320,10 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (dbg && tcount == 0 && warp == 2 && lane == 0) dbg[4] = gtime();  // first epilogue drained TMEM
     }
     if (lane == 0) bulk_wait_all();
+    if (dbg && warp == 2 && lane == 0) { dbg[5] = gtime(); dbg[6] = tcount; }  // all stores done
   } else if (XFORM) {
     // ------------------------------------------------------------------ mask transform (128 threads)
     const int tid = threadIdx.x - 192;
@@ -368,6 +386,286 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.  Each CTA
+// stages its own 128 rows of A and HALF of B (128 of the 256 columns) per k-block -- 32 KB instead of
+// 48 KB per 512 MMA cycles, which is what the L2 -> SM path sustains (measured ~62 B/cycle/SM: the
+// 1-CTA 128 x 256 kernel above needs 94 and runs its mainloop at 67 %).  The leader CTA's single thread
+// issues tcgen05.mma.cta_group::2 (M = 256); each CTA's TMEM holds its own 128 accumulator rows and its
+// own four epilogue warps drain them.  Barriers: both producers signal the LEADER's full barrier (2SM TMA
+// with the peer bit cleared); the MMA commit multicasts to both CTAs' empty / tmem-full barriers; both
+// CTAs' epilogue warps arrive remotely on the leader's tmem-empty barrier.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                   "r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+
+struct Smem2 {
+  static constexpr int kA = BM * BK * 2;        // 16 KB: this CTA's 128 rows of A
+  static constexpr int kB = 128 * BK * 2;       // 16 KB: this CTA's half of the 256 B columns
+  static constexpr int kStage = kA + kB;
+  static constexpr int kStages = 6;
+  static constexpr int kEpi = 4 * 2 * 4096;
+  static constexpr int kTotal = kStages * kStage + kEpi + 256 + 1024;
+};
+
+template <bool A_MN, bool B_MN, int EPI, bool OUT_BF16>
+__global__ void __launch_bounds__(192, 1)
+masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmOut, const GemmParams p) {
+  using L = Smem2;
+  constexpr int STAGES = L::kStages;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_base = smem + STAGES * L::kStage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_base + L::kEpi);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_tiles = p.num_m * p.num_n * p.splits;   // num_m counts 256-row pair tiles here
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        TileCoord tc = tile_coord(p, tile, BN);
+        const int m0 = tc.m0 * 2 + rank * BM;   // tile_coord used BM = 128 per m index; pair tiles are 256 rows
+        const int nh = tc.n0 + rank * 128;      // this CTA's half of the B columns
+        for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * L::kStage);
+          else mbar_arrive_remote(&full_bar[s], 0);
+          uint8_t* sA = smem + s * L::kStage;
+          uint8_t* sB = sA + L::kA;
+          const int kk0 = (tc.kb_begin + kb) * BK;
+          if (!A_MN) {
+            tma_load_2d_2sm(sA, &tmA, &full_bar[s], kk0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sA + j * 8192, &tmA, &full_bar[s], m0 + 64 * j, kk0);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(sB, &tmB, &full_bar[s], kk0, nh);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sB + j * 8192, &tmB, &full_bar[s], nh + 64 * j, kk0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int it = 0, tcount = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tcount) {
+        const TileCoord tc = tile_coord(p, tile, BN);
+        const int acc = tcount & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t aBase = smem_u32(smem + s * L::kStage);
+            const uint32_t bBase = aBase + L::kA;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = A_MN ? make_sw128_desc(aBase + k * 2048, 8192, 1024)
+                                       : make_sw128_desc(aBase + k * 32, 16, 1024);
+              const uint64_t db = B_MN ? make_sw128_desc(bBase + k * 2048, 8192, 1024)
+                                       : make_sw128_desc(bBase + k * 32, 16, 1024);
+              umma_bf16_2sm(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[s]);
+            if (kb == tc.num_kb - 1) umma_commit_2sm(&tmem_full_bar[acc]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    uint8_t* stage_buf = epi_base + (warp - 2) * 8192;
+    constexpr int COLS = OUT_BF16 ? 64 : 32;
+    int tcount = 0, chunk_no = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tcount) {
+      const TileCoord tc = tile_coord(p, tile, BN);
+      const int acc = tcount & 1;
+      const int row0 = tc.m0 * 2 + rank * BM + q * 32;
+      const int m = row0 + lane;
+      mbar_wait(&tmem_full_bar[acc], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / COLS; ++c, ++chunk_no) {
+        const int nb = tc.n0 + c * COLS;
+        uint32_t r[32];
+        uint32_t pk[32];
+        float bias_lo = 0.f, bias_hi = 0.f;
+        if (EPI == kEpiStore && p.bias != nullptr) {
+          if (nb + lane < p.NN) bias_lo = __ldg(p.bias + nb + lane);
+          if (OUT_BF16 && nb + 32 + lane < p.NN) bias_hi = __ldg(p.bias + nb + 32 + lane);
+        }
+        tmem_ld_32x32(t_addr + c * COLS, r);
+        if (OUT_BF16) {
+          uint32_t r2[32];
+          tmem_ld_32x32(t_addr + c * COLS + 32, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a0 = __uint_as_float(r[2 * j]) + __shfl_sync(0xffffffffu, bias_lo, 2 * j);
+            const float a1 = __uint_as_float(r[2 * j + 1]) + __shfl_sync(0xffffffffu, bias_lo, 2 * j + 1);
+            const float b0 = __uint_as_float(r2[2 * j]) + __shfl_sync(0xffffffffu, bias_hi, 2 * j);
+            const float b1 = __uint_as_float(r2[2 * j + 1]) + __shfl_sync(0xffffffffu, bias_hi, 2 * j + 1);
+            __nv_bfloat162 ta = __floats2bfloat162_rn(a0, a1);
+            __nv_bfloat162 tb = __floats2bfloat162_rn(b0, b1);
+            pk[j] = *reinterpret_cast<uint32_t*>(&ta);
+            pk[16 + j] = *reinterpret_cast<uint32_t*>(&tb);
+          }
+        } else if (EPI == kEpiStore) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            pk[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lo, j));
+        } else {
+          tmem_ld_wait();
+          const bool row_ok = m < p.MM;
+          const __nv_bfloat16* wrow = p.w + static_cast<size_t>(row_ok ? m : 0) * p.NN + nb;
+          if (row_ok && nb + 32 <= p.NN && (p.NN & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wrow + j));
+              const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                pk[j + 2 * e] = __float_as_uint(__uint_as_float(r[j + 2 * e]) * __uint_as_float(ww[e] << 16));
+                pk[j + 2 * e + 1] =
+                    __float_as_uint(__uint_as_float(r[j + 2 * e + 1]) * __uint_as_float(ww[e] & 0xFFFF0000u));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float wv = (row_ok && nb + j < p.NN) ? __bfloat162float(wrow[j]) : 0.f;
+              pk[j] = __float_as_uint(__uint_as_float(r[j]) * wv);
+            }
+          }
+        }
+        uint8_t* buf = stage_buf + (chunk_no & 1) * 4096;
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        const int sw = lane & 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ sw) << 4)) =
+              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && nb < p.NN && row0 < p.MM) {
+          if (EPI == kEpiScoreGrad && p.reduce_out) tma_reduce_add_2d(&tmOut, buf, nb, row0);
+          else tma_store_2d(&tmOut, buf, nb, row0);
+        }
+        if (lane == 0) bulk_commit();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();   // the peer may still be signalling this CTA's barriers / reading its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -411,6 +709,8 @@ static int make_out_map(CUtensorMap* map, void* out, bool bf16, int64_t rows, in
   return bf16 ? make_map(map, out, 2, false, rows, cols, 32, 64) : make_map(map, out, 4, true, rows, cols, 32, 32);
 }
 
+static long long* g_dbg = nullptr;
+
 template <bool A_MN, bool B_MN, int BN, bool XFORM, int EPI, bool OUT_BF16>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmS, const CUtensorMap& tmOut,
                   GemmParams p, cudaStream_t stream) {
@@ -423,10 +723,48 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   }
   p.num_m = (p.MM + BM - 1) / BM;
   p.num_n = (p.NN + BN - 1) / BN;
+  p.dbg = g_dbg;
   const int tiles = p.num_m * p.num_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, XFORM ? 320 : 192, L::kTotal, stream>>>(tmA, tmB, tmS, tmOut, p);
   return launch_status();
+}
+
+
+template <bool A_MN, bool B_MN, int EPI, bool OUT_BF16>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, GemmParams p,
+                   cudaStream_t stream) {
+  auto kern = masked_gemm2_kernel<A_MN, B_MN, EPI, OUT_BF16>;
+  static bool configured = false;
+  if (!configured) {
+    CRV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::kTotal));
+    configured = true;
+  }
+  p.num_m = (p.MM + 255) / 256;
+  p.num_n = (p.NN + 255) / 256;
+  p.dbg = nullptr;
+  const int tiles = p.num_m * p.num_n * p.splits;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Smem2::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CRV_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, p));
+  return launch_status();
+}
+
+static bool use_2cta(int MM, int NN) {
+  static const int mode = [] { const char* e = getenv("CRVQA_2CTA"); return e ? atoi(e) : 1; }();
+  return mode != 0 && NN % 256 == 0 && MM >= 256;
 }
 
 static int pick_bn(int MM, int NN) {
@@ -445,6 +783,13 @@ static int pick_bn(int MM, int NN) {
 }  // namespace crv
 
 using namespace crv;
+
+// Debug aid: when set, every GEMM CTA writes 8 x int64 globaltimer stamps {setup, first TMA, first stage
+// landed, first accumulator ready, first epilogue drained, all stores done, tiles, -} at buf[8 * blockIdx.x].
+extern "C" int crv_gemm_debug_timestamps(long long* buf) {
+  g_dbg = buf;
+  return CRV_OK;
+}
 
 extern "C" int crv_masked_linear_fwd(const uint16_t* x, const uint16_t* w, const float* scores, const float* thr,
                                      const float* bias, void* y, int y_dtype, int M, int N, int K, void* stream) {
@@ -469,6 +814,11 @@ extern "C" int crv_masked_linear_fwd(const uint16_t* x, const uint16_t* w, const
     if ((rc = make_map(&tmS, scores, 4, true, N, K, 128, 32))) return rc;
     return obf ? launch<false, false, 128, true, kEpiStore, true>(tmA, tmB, tmS, tmO, p, st)
                : launch<false, false, 128, true, kEpiStore, false>(tmA, tmB, tmS, tmO, p, st);
+  }
+  if (use_2cta(M, N)) {
+    if ((rc = make_map(&tmB, w, 2, false, N, K, 128, BK))) return rc;
+    return obf ? launch2<false, false, kEpiStore, true>(tmA, tmB, tmO, p, st)
+               : launch2<false, false, kEpiStore, false>(tmA, tmB, tmO, p, st);
   }
   const int bn = pick_bn(M, N);
   if ((rc = make_map(&tmB, w, 2, false, N, K, bn, BK))) return rc;
@@ -507,6 +857,9 @@ extern "C" int crv_masked_linear_bwd_dx(const uint16_t* dy, const uint16_t* w, c
                : launch<false, true, 128, true, kEpiStore, false>(tmA, tmB, tmS, tmO, p, st);
   }
   tmS = tmB;
+  if (use_2cta(M, K))
+    return obf ? launch2<false, true, kEpiStore, true>(tmA, tmB, tmO, p, st)
+               : launch2<false, true, kEpiStore, false>(tmA, tmB, tmO, p, st);
   if (pick_bn(M, K) == 256)
     return obf ? launch<false, true, 256, false, kEpiStore, true>(tmA, tmB, tmS, tmO, p, st)
                : launch<false, true, 256, false, kEpiStore, false>(tmA, tmB, tmS, tmO, p, st);
@@ -522,9 +875,12 @@ extern "C" int crv_masked_linear_bwd_ds(const uint16_t* dy, const uint16_t* x, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // generic: MM = N, NN = K, KK = M;  A = dY [M][N] = [KK][MM] MN-major;  B = X [M][K] = [KK][NN] MN-major
   const int num_kb = (M + BK - 1) / BK;
-  const int bn = pick_bn(N, K);
-  const int tiles = ((N + BM - 1) / BM) * ((K + bn - 1) / bn);
-  int splits = num_sms() / tiles;  // one wave of CTAs; every extra split costs one more fp32 reduce pass
+  // 256-wide tiles need 62 instead of 94 operand bytes per MMA cycle from L2; the reduction over M (144 k-blocks at
+  // batch 256) is split across blockIdx.z so that one wave of CTAs covers the machine even for 768 x 768 modules
+  const bool two = use_2cta(N, K);
+  const int bn = (K % 256 == 0) ? 256 : 128;
+  const int tiles = two ? ((N + 255) / 256) * (K / 256) : ((N + BM - 1) / BM) * ((K + bn - 1) / bn);
+  int splits = (two ? num_sms() / 2 : num_sms()) / tiles;
   const int max_splits = (num_kb + 7) / 8;  // keep >= 8 k-blocks per split
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -541,6 +897,7 @@ extern "C" int crv_masked_linear_bwd_ds(const uint16_t* dy, const uint16_t* x, c
   if ((rc = make_map(&tmA, dy, 2, false, M, N, 64, 64))) return rc;
   if ((rc = make_map(&tmB, x, 2, false, M, K, 64, 64))) return rc;
   if ((rc = make_out_map(&tmO, dscores, false, N, K))) return rc;
+  if (two) return launch2<true, true, kEpiScoreGrad, false>(tmA, tmB, tmO, p, st);
   if (bn == 256) return launch<true, true, 256, false, kEpiScoreGrad, false>(tmA, tmB, tmB, tmO, p, st);
   return launch<true, true, 128, false, kEpiScoreGrad, false>(tmA, tmB, tmB, tmO, p, st);
 }

@@ -80,6 +80,10 @@ int crv_masked_linear_fwd(const uint16_t* x_bf16, const uint16_t* w_bf16, const 
                           const float* thr, const float* bias, void* y, int y_dtype, int M, int N, int K,
                           void* stream);
 
+/* Debug aid (not part of the drop-in path): when buf != NULL every masked-GEMM CTA writes 8 int64
+ * globaltimer stamps at buf[8 * blockIdx.x]; pass NULL to switch it off. */
+int crv_gemm_debug_timestamps(long long* buf);
+
 /* dX of the above (autograd of masking/maskers.py:365-366 with frozen weights, :564-569):
  *     dX[M,K] = dY[M,N] . (W (.) (S > *thr))
  * dY bf16; dX fp32 or bf16.  Requirements: N % 8 == 0, K % 8 == 0. */

@@ -35,3 +35,16 @@ tot = sum(v[1] for v in agg.values())
 print('total kernel us', tot)
 for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:40]:
     print(f'{t:9.1f} us {100*t/tot:5.1f}% n={c:4d} avg={t/c:7.1f} {k}')
+
+# per-shape masked-GEMM timings (CUDA events around each launch, eager)
+from crvqa import ops
+ops.PROFILE = []
+tr._device_step(model, inputs, opt); sch.step()
+torch.cuda.synchronize()
+shape = collections.defaultdict(lambda: [0, 0.0])
+for kind, M, N, K, s, e in ops.PROFILE:
+    d = shape[(kind, M, N, K)]; d[0] += 1; d[1] += s.elapsed_time(e)
+ops.PROFILE = None
+print('kind M N K : launches total_ms avg_us TFLOP/s')
+for (kind, M, N, K), (c, t) in sorted(shape.items(), key=lambda x: -x[1][1]):
+    print(f'{kind:3s} {M:5d} {N:5d} {K:5d} : {c:3d} {t:7.3f} {1e3*t/c:7.1f} {2.0*M*N*K*c/(t*1e-3)/1e12:7.0f}')
