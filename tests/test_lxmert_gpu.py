@@ -227,3 +227,92 @@ def test_arena_gradients_equal_autograd_gradients():
             assert float(got.abs().max()) == 0.0
         else:
             torch.testing.assert_close(got, plain[n], rtol=1e-4, atol=1e-9)
+
+
+def _tiny_trainer(tmp_path, steps, graph, seed=49, dropout=0.0, loss="lpf"):
+    import os
+    from hg_transformers.data.data_collator import TrimCollator
+    from hg_transformers.data.metrics import vqa_compute_metrics
+    from hg_transformers.mask_trainer_Robust_VQA import Trainer
+    from hg_transformers.training_args import TrainingArguments
+    from prune_debias_VQA import SyntheticVQADataset, build_stage2, init_optimizer
+    os.environ["CRVQA_CUDA_GRAPH"] = "1" if graph else "0"
+    cfg = dict(vocab_size=1000, hidden_size=256, num_attention_heads=4, intermediate_size=512, l_layers=2,
+               x_layers=2, r_layers=1, visual_feat_dim=128, max_position_embeddings=32,
+               hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout)
+    targs = TrainingArguments(output_dir=str(tmp_path), per_gpu_train_batch_size=16, max_steps=steps,
+                              logging_steps=1000, seed=seed, Masker_type=loss, training_type="Masker", save_steps=0,
+                              dataloader_num_workers=0)
+    model, masker, margs = build_stage2(120, device=targs.device, seed=seed, config_kwargs=cfg)
+    model.classifier.main[2].p = dropout  # classifier dropout (0.5 in the reference) off for determinism
+    data = SyntheticVQADataset(16 * steps, 120, seed=seed, tokens=10, regions=8, feat_dim=128, vocab=1000)
+    trainer = Trainer(model=model, args=targs, model_args=margs, data_collator=TrimCollator(), train_dataset=data,
+                      compute_metrics=vqa_compute_metrics, optimizers=init_optimizer(model, targs, len(data)),
+                      masker=masker)
+    out = trainer.train()
+    os.environ.pop("CRVQA_CUDA_GRAPH")
+    scores = {n: m.weight_mask.detach().clone() for n, m in model.named_modules() if hasattr(m, "threshold")}
+    return out, scores, model
+
+
+def test_cuda_graph_replay_matches_eager_training(tmp_path):
+    """8 optimisation steps with dropout off: the whole-step CUDA graph (3 eager warm-up steps + 5 replays, LR and
+    Adam step size read from device memory) must land on the same scores as the eager loop."""
+    out_e, s_e, _ = _tiny_trainer(tmp_path / "e", 8, graph=False)
+    out_g, s_g, _ = _tiny_trainer(tmp_path / "g", 8, graph=True)
+    assert out_e[0].global_step == out_g[0].global_step == 8
+    assert abs(out_e[0].training_loss - out_g[0].training_loss) <= 2e-3 * abs(out_e[0].training_loss)
+    moved = 0
+    for n in s_e:
+        # Adam's first steps are sign-like (lr-sized moves), so scores agree to a fraction of one lr step
+        assert float((s_e[n] - s_g[n]).abs().max()) <= 1.0e-4, n
+        moved += int(float((s_e[n] - s_e[n].round(decimals=2)).abs().max()) > 0)
+    assert moved > len(s_e) // 2
+
+
+def test_visualbert_stage2_trainer_runs(tmp_path):
+    """BASELINE config 3 in miniature: VisualBERT, uniform zero rate 0.7, baseline masker + visualBERT trainer."""
+    import logging
+    import types
+    from hg_transformers.data.data_collator import TrimCollator
+    from hg_transformers.data.metrics import vqa_compute_metrics
+    from hg_transformers.mask_trainer_visualBERT_VQA import Trainer
+    from hg_transformers.modeling_visualbert import VisualBertForMultipleChoice, visualBERTConfig
+    from hg_transformers.training_args import TrainingArguments
+    from masking import maskers_visualBert as mk
+    from masking import sparsity_control as spc
+    from oracle import masked_ops as o
+    from prune_debias_VQA import SyntheticVQADataset, init_optimizer
+    torch.manual_seed(49)
+    cfg = visualBERTConfig(vocab_size=1000, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                           intermediate_size=512, visual_embedding_dim=128, ans_num=64, max_position_embeddings=64)
+    targs = TrainingArguments(output_dir=str(tmp_path), per_gpu_train_batch_size=8, max_steps=3, logging_steps=3,
+                              seed=49, Masker_type="normal", training_type="Masker", save_steps=0,
+                              learning_rate=5e-5, dataloader_num_workers=0)
+    model = VisualBertForMultipleChoice(cfg).to(targs.device)
+    conf = types.SimpleNamespace(masking_scheduler_conf_={"final_sparsity": 0.7, "sparsity_warmup_interval_epoch": 0.1,
+                                                          "lambdas_lr": 0.0, "init_epoch": 0, "final_epoch": 1},
+                                 logger=logging.getLogger("vb"), num_epochs=1)
+    log = logging.getLogger("vb")
+    log.setLevel(logging.ERROR)
+    masker = mk.Masker(masker_scheduler=spc.MaskerScheduler(conf), logger=log, mask_biases=False,
+                       structured_masking_info={"structured_masking": None, "structured_masking_types": None,
+                                                "force_masking": "bert"},
+                       threshold=1e-2, init_scale=2e-2, which_ptl="visual_bert", controlled_init="magnitude")
+    names = mk.chain_module_names("visual_bert", list(range(12)), ["K", "Q", "V", "AO", "I", "O", "P", "E"])
+    masker.patch_modules(model, names, "MaskedLinear1")
+    mods = [(n, m) for n, m in model.named_modules() if hasattr(m, "threshold")]
+    assert len(mods) == 2 * 6 + 2                                   # K,Q,V,AO,I,O per layer + pooler + embeddings
+    assert not hasattr(model.visual_bert.embeddings.visual_projection, "threshold")   # stays dense and frozen
+    for n, m in mods:
+        k = int(m.weight.numel() * 0.7)
+        assert int((m.weight_mask > 1e-2).sum()) == m.weight.numel() - k, n
+    data = SyntheticVQADataset(24, 64, seed=49, tokens=12, regions=9, feat_dim=128, vocab=1000)
+    trainer = Trainer(model=model, args=targs, model_args=types.SimpleNamespace(structured=False),
+                      data_collator=TrimCollator(), train_dataset=data, compute_metrics=vqa_compute_metrics,
+                      optimizers=init_optimizer(model, targs, len(data)), masker=masker)
+    out = trainer.train()
+    assert out[0].global_step == 3 and out[0].training_loss > 0
+    for n, m in mods:                                               # thresholds refreshed at step 3 (logging_steps)
+        k = max(1, int(m.weight.nelement() * 0.7))
+        assert float(m.threshold) == float(o.kth_value(m.weight_mask.detach().cpu(), k)), n
