@@ -361,3 +361,51 @@ class GraphedStep:
         if self.graph is not None:
             self.optimizer.use_device_hyper(self.hyper)
         return out
+
+
+class InputPrefetcher:
+    """Host -> device copy of the NEXT batch on a side stream while the current step runs.
+
+    `stage(batch)` starts the copies from (pinned) host memory into a device staging set and returns a
+    handle; `take(handle)` makes the compute stream wait for them and hands the device tensors to the step
+    (GraphedStep then copies them device-to-device into its static buffers, ~25 us for an 82 MB batch).
+    Two staging sets alternate so a batch is never overwritten while a step still reads it."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [None, None]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.done = [None, None]
+        self.turn = 0
+
+    def stage(self, batch):
+        i = self.turn
+        self.turn ^= 1
+        if self.done[i] is not None:
+            self.stream.wait_event(self.done[i])      # the step that consumed this slot has finished
+        with torch.cuda.stream(self.stream):
+            out = []
+            for j, t in enumerate(batch):
+                if not torch.is_tensor(t):
+                    out.append(t)
+                    continue
+                slot = self.slots[i][j] if self.slots[i] is not None and j < len(self.slots[i]) else None
+                if slot is None or slot.shape != t.shape or slot.dtype != t.dtype:
+                    slot = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+                slot.copy_(t, non_blocking=True)
+                out.append(slot)
+            self.slots[i] = out
+            self.events[i].record(self.stream)
+        return i
+
+    def take(self, handle):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.events[handle])
+        return self.slots[handle]
+
+    def release(self, handle):
+        """Call after the step that used `handle` has been enqueued."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.done[handle] = ev

@@ -32,7 +32,7 @@ from torch.utils.data.sampler import Sampler
 
 from crvqa import ops
 
-from ._engine import GradSync, GraphedStep, ScoreArena, masked_modules_of
+from ._engine import GradSync, GraphedStep, InputPrefetcher, ScoreArena, masked_modules_of
 from .data.data_collator import DataCollator, DefaultDataCollator, TrimCollator  # noqa: F401
 from .optimization import AdamW, get_constant_schedule, get_linear_schedule_with_warmup  # noqa: F401
 from .trainer_utils import PREFIX_CHECKPOINT_DIR, EvalPrediction, PredictionOutput, TrainOutput
@@ -290,6 +290,27 @@ class TrainerCore:
         self.grad_sync = GradSync(self.arena)
         self.grad_sync.defer = self.args.gradient_accumulation_steps > 1
 
+    def _prefetched(self, dataloader):
+        """Yield batches whose host -> device copy was started one step ahead on a side stream."""
+        if not torch.cuda.is_available() or self.args.device.type != "cuda":
+            yield from dataloader
+            return
+        pre = InputPrefetcher(self.args.device)
+        it = iter(dataloader)
+        try:
+            handle = pre.stage(next(it))
+        except StopIteration:
+            return
+        while handle is not None:
+            batch = pre.take(handle)
+            cur = handle
+            try:
+                handle = pre.stage(next(it))
+            except StopIteration:
+                handle = None
+            yield batch
+            pre.release(cur)
+
     def _make_graphed_step(self, model, optimizer, scheduler):
         """CUDA-graph replay of the whole step when it is safe: arena engine, our AdamW, no accumulation.
         CRVQA_CUDA_GRAPH=0 keeps the eager loop; multi-rank runs capture the NCCL all-reduces too."""
@@ -391,7 +412,7 @@ class TrainerCore:
             if isinstance(train_dataloader.sampler, DistributedSampler):
                 train_dataloader.sampler.set_epoch(epoch)
             n_batches = len(train_dataloader)
-            for step, inputs in enumerate(train_dataloader):
+            for step, inputs in enumerate(self._prefetched(train_dataloader)):
                 if graphed is not None:
                     loss_batch, score_batch = graphed.step(inputs)
                 else:
