@@ -161,31 +161,43 @@ def masked_linear_bwd_ds(dy_bf16, x_bf16, w_bf16, out=None, accumulate=False):
 _kth_ws = {}
 
 
+class KthPlan:
+    """The fixed half of a batched select -- segment pointers, sizes and the workspace -- built once for a set of
+    tensors whose storage does not move (the score arena), so a reset_threshold call only marshals the ranks."""
+
+    def __init__(self, tensors):
+        self.count = len(tensors)
+        if self.count == 0:
+            raise ValueError("no segments")
+        self.home = tensors[0].device
+        staged = [_stage(t.detach()) for t in tensors]
+        self.dev = staged[0].device
+        self.flat = [t.reshape(-1) for t in staged]   # keeps the storages alive
+        for t in self.flat:
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("kth_value_batched needs contiguous float32 tensors")
+        self.sizes = [t.numel() for t in self.flat]
+        self.ptrs = (ctypes.c_void_p * self.count)(*[t.data_ptr() for t in self.flat])
+        self.ns = (ctypes.c_longlong * self.count)(*self.sizes)
+        self.nbytes = lib.crv_kth_value_workspace_bytes_for(self.ns, self.count)
+        key = (self.dev, self.count)
+        ws = _kth_ws.get(key)
+        if ws is None or ws.numel() < self.nbytes:
+            ws = torch.empty(self.nbytes, dtype=torch.uint8, device=self.dev)
+            _kth_ws[key] = ws
+        self.ws = ws
+
+    def __call__(self, ks, use_abs=False):
+        kk = (ctypes.c_longlong * self.count)(*ks)
+        out = torch.empty(self.count, dtype=torch.float32, device=self.dev)
+        check(lib.crv_kth_value_batched(self.ptrs, self.ns, kk, self.count, int(bool(use_abs)), _p(out), _p(self.ws),
+                                        self.nbytes, _stream()), "crv_kth_value_batched")
+        return out if self.home == self.dev else out.to(self.home)
+
+
 def kth_value_batched(tensors, ks, use_abs=False):
     """Exact k-th smallest (1-based) of each fp32 CUDA tensor; returns a float32 device vector."""
-    count = len(tensors)
-    if count == 0:
-        raise ValueError("no segments")
-    home = tensors[0].device
-    tensors = [_stage(t.detach()) for t in tensors]
-    dev = tensors[0].device
-    flat = [t.reshape(-1) for t in tensors]
-    for t in flat:
-        if t.dtype != torch.float32 or not t.is_contiguous():
-            raise ValueError("kth_value_batched needs contiguous float32 tensors")
-    ptrs = (ctypes.c_void_p * count)(*[t.data_ptr() for t in flat])
-    ns = (ctypes.c_longlong * count)(*[t.numel() for t in flat])
-    kk = (ctypes.c_longlong * count)(*[int(k) for k in ks])
-    nbytes = lib.crv_kth_value_workspace_bytes(count)
-    key = (dev, count)
-    ws = _kth_ws.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _kth_ws[key] = ws
-    out = torch.empty(count, dtype=torch.float32, device=dev)
-    check(lib.crv_kth_value_batched(ptrs, ns, kk, count, int(bool(use_abs)), _p(out), _p(ws), nbytes, _stream()),
-          "crv_kth_value_batched")
-    return out.to(home)
+    return KthPlan(tensors)([int(k) for k in ks], use_abs)
 
 
 def magnitude_init(weight, w_thr, hi, lo):

@@ -219,7 +219,13 @@ class TrainerCore:
         for name, module in mods:
             k = int(module.weight.nelement() * self._sparsity_of(name, init_sparsity))
             ks.append(1 if k == 0 else k)
-        thr = ops.kth_value_batched([m.weight_mask.data for _, m in mods], ks)
+        tensors = [m.weight_mask.data for _, m in mods]
+        sig = tuple(t.data_ptr() for t in tensors)
+        plan = getattr(self, "_kth_plan", None)
+        if plan is None or plan[0] != sig:       # scores live in the arena: same storage every call
+            plan = (sig, ops.KthPlan(tensors))
+            self._kth_plan = plan
+        thr = plan[1](ks)
         arena = getattr(self, "arena", None)
         if arena is not None and [m for _, m in mods] == arena.modules:
             arena.set_thresholds(thr)          # one device vector; module.threshold = 0-dim views of it

@@ -123,8 +123,14 @@ int crv_masked_embedding_bwd(const long long* ids, const float* dout, const floa
  * mask_trainer_VQA.py:470-477): for every segment i, thr_out[i] = k[i]-th smallest (1-based, as
  * torch.kthvalue) of the n[i] floats at ptrs[i]; use_abs != 0 selects on |x| instead (magnitude
  * init).  ptrs/n/k are HOST arrays of length count; thr_out is a device array of `count` floats.
- * NaNs order above +inf (torch semantics). */
+ * NaNs order above +inf (torch semantics).
+ * Segments larger than 65536 elements take a sample -> filter -> select path that reads the data ONCE
+ * (pivots from a 16384-element stratified sample, one streaming pass that counts against the pivots and
+ * compacts the ~2.5 % of keys between them, exact radix select of the survivors); it needs candidate space,
+ * so size the workspace with crv_kth_value_workspace_bytes_for(n_host, count).  With the smaller
+ * crv_kth_value_workspace_bytes(count) every segment takes the 3-pass radix core.  Both are exact. */
 size_t crv_kth_value_workspace_bytes(int count);
+size_t crv_kth_value_workspace_bytes_for(const long long* n_host, int count);
 int crv_kth_value_batched(const float* const* ptrs_host, const long long* n_host, const long long* k_host,
                           int count, int use_abs, float* thr_out, void* workspace, size_t workspace_bytes,
                           void* stream);

@@ -1,0 +1,79 @@
+"""HBM-bound kernels of the path at BASELINE sizes: achieved GB/s (algorithmic bytes / CUDA-event time)."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'compress-robust-vqa_b200')); sys.path.insert(0, ROOT)
+import torch
+from crvqa import ops, fused
+from oracle import lxmert_oracle as lxo
+dev = torch.device('cuda')
+peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+def timeit(fn, iters=5, flush_l2=True):
+    fn(); fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush_l2: flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+out = {}
+def rec(name, ms, nbytes, note=''):
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    out[name] = {'ms': ms, 'algorithmic_MB': nbytes / 1e6, 'GBps': gbs, 'frac_of_measured_hbm': gbs / peak, 'note': note}
+    print(f'{name:28s} {ms*1e3:9.1f} us  {nbytes/1e6:9.1f} MB  {gbs:8.0f} GB/s  {100*gbs/peak:5.1f}% of {peak:.0f}  {note}')
+# --- select over the 168 LXMERT score tensors (207,272,448 floats), trained-like score distribution
+shapes = []
+for name, modal in lxo.module_names():
+    if name.endswith('word_embeddings'): shapes.append((30522, 768))
+    elif name.endswith('visn_fc.visn_fc'): shapes.append((768, 2048))
+    elif name.endswith('box_fc'): shapes.append((768, 4))
+    elif 'intermediate.dense' in name or '_inter.dense' in name: shapes.append((3072, 768))
+    elif (name.endswith('output.dense') and 'attention' not in name and '_att' not in name): shapes.append((768, 3072))
+    else: shapes.append((768, 768))
+g = torch.Generator(device='cuda').manual_seed(1)
+scores = [torch.where(torch.rand(s, device=dev, generator=g) < 0.7, 0.0, 0.02) + torch.randn(s, device=dev, generator=g) * 3e-3 for s in shapes]
+n_total = sum(s.numel() for s in scores)
+ks = [max(1, int(s.numel() * 0.7)) for s in scores]
+rec('kth_value_batched (168 seg)', timeit(lambda: ops.kth_value_batched(scores, ks)), 4 * n_total, f'{n_total} floats, exact radix select, 3 passes')
+init = [torch.where(torch.rand(s, device=dev, generator=g) < 0.7, 0.0, 0.02) for s in shapes]
+rec('kth_value_batched (ties)', timeit(lambda: ops.kth_value_batched(init, ks)), 4 * n_total, 'scores exactly {0, 0.02} (state before the first optimiser step)')
+big = torch.cat([s.reshape(-1) for s in scores])
+rec('kth_value (1 x 207M)', timeit(lambda: ops.kth_value_batched([big], [int(big.numel() * 0.7)])), 4 * n_total, 'global-threshold variant: one segment')
+# --- losses, B=256, A=3129
+B, A = 256, 3129
+logits = torch.randn(B, A, device=dev); labels = (torch.rand(B, A, device=dev) > 0.999).float(); bias = torch.rand(B, A, device=dev) * 0.01
+ml = labels.argmax(1); fac = torch.randn(B, 1, device=dev)
+rec('vqa_loss_bce fwd+bwd', timeit(lambda: ops.vqa_loss_bce(logits, labels), flush_l2=False), 12 * B * A, 'logit + label in, dlogit out; 2 launches')
+rec('vqa_loss_lpf fwd+bwd', timeit(lambda: ops.vqa_loss_lpf(logits, bias, ml, 5.0, labels), flush_l2=False), 8 * B * A, 'logit in, dlogit out')
+rec('vqa_loss_lmh fwd+bwd', timeit(lambda: ops.vqa_loss_lmh(logits, bias, labels, fac, 0.27, 0.36), flush_l2=False), 16 * B * A, 'logit, bias, label in, dlogit out')
+# --- optimiser + mask refresh over the arena
+n = n_total
+p_, g_, m_, v_, s_ = (torch.randn(n, device=dev) * 0.01 for _ in range(5))
+m_.abs_(); v_.abs_()
+sq = torch.ones((), device=dev)
+rec('adamw_step (arena)', timeit(lambda: ops.adamw_step_flat(p_, g_, m_, v_, s_, 5e-5, 10, 0.9, 0.999, 1e-8, 0.0, sq, 1.0)), 36 * n, 'p,g,m,v,sum read; p,m,v,sum written')
+acc = torch.zeros((), device=dev)
+rec('sumsq (grad norm)', timeit(lambda: ops.sumsq_into(g_, acc)), 4 * n)
+w16 = torch.randn(n, device=dev).bfloat16(); wm = torch.empty_like(w16)
+chunks = torch.tensor([((i * 8192) // 8, min(8192, n - i * 8192), 0, 0) for i in range((n + 8191) // 8192)], dtype=torch.int32, device=dev)
+thrv = torch.tensor([0.01], device=dev)
+rec('apply_mask_segmented', timeit(lambda: ops.apply_mask_segmented(w16, p_, thrv, chunks, wm)), 8 * n, 'S fp32 + W bf16 in, Wm bf16 out')
+# --- layer kernels at M=9216, H=768
+M, H = 9216, 768
+ln = torch.nn.LayerNorm(H, eps=1e-12).to(dev); ln.weight.requires_grad_(False); ln.bias.requires_grad_(False)
+gg = torch.randn(M, H, device=dev).bfloat16().requires_grad_(True); res = torch.randn(M, H, device=dev, requires_grad=True)
+fused.RngState.get(dev).advance()
+rec('ln_fwd (drop+res+LN)', timeit(lambda: fused.drop_add_layernorm(gg, res, ln, 0.1, 3, True)), (2 + 4 + 4 + 2) * M * H, 'g bf16 + res fp32 in, y fp32 + y bf16 out')
+y32, y16 = fused.drop_add_layernorm(gg, res, ln, 0.1, 3, True)
+d32, d16 = torch.randn_like(y32), torch.randn_like(y16)
+rec('ln_bwd', timeit(lambda: torch.autograd.grad([y32, y16], [gg, res], [d32, d16], retain_graph=True)), (4 + 2 + 2 + 4 + 2 + 4) * M * H, 'dy32, dy16, g, res in; dg bf16, dres fp32 out')
+u = torch.randn(M, 3072, device=dev).bfloat16()
+rec('gelu_fwd bf16', timeit(lambda: fused.gelu_bf16(u)), 4 * M * 3072)
+qkv = (torch.randn(256, 36, 2304, device=dev) * 0.5).bfloat16().requires_grad_(True)
+rec('attention_fwd S=36', timeit(lambda: fused.small_attention(0, 12, None, 0.1, 5, True, qkv)), 2 * 256 * 36 * 768 * 4, 'q,k,v in, o out (bf16)')
+o_ = fused.small_attention(0, 12, None, 0.1, 5, True, qkv); do = torch.randn_like(o_)
+rec('attention_bwd S=36', timeit(lambda: torch.autograd.grad(o_, qkv, do, retain_graph=True)), 2 * 256 * 36 * 768 * 7, 'q,k,v,do in; dq,dk,dv out (bf16)')
+os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+json.dump({'peak_hbm_gbs': peak, 'kernels': out}, open(os.path.join(ROOT, 'gpurun_out', 'kernels.json'), 'w'), indent=1)

@@ -70,6 +70,82 @@ def test_kth_value_sortedness_property_large():
     assert below < k <= upto
 
 
+def _kth_ref(x, k, use_abs=False):
+    v = x.abs() if use_abs else x
+    return torch.kthvalue(v.reshape(-1).float(), k).values
+
+
+def test_kth_value_front_end_edge_cases():
+    """Segments large enough for the sample -> filter -> select front end: NaN / inf members, ranks at both ends
+    (open pivot windows), |x| keys, an unaligned segment, pivots that tie massively, and a segment whose
+    stratified sample is unrepresentative on purpose (every sampled run holds huge values), which must fall
+    back to the full radix select.  All bit-exact against torch.kthvalue."""
+    from crvqa import ops
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    n = 700001
+    base = torch.randn(n, device="cuda", generator=gen) * 0.01
+    with_inf = base.clone(); with_inf[::1000] = float("inf"); with_inf[1::1000] = float("-inf")
+    with_nan = base.clone(); with_nan[5::997] = float("nan")
+    ties = torch.where(torch.rand(n, device="cuda", generator=gen) < 0.7, 0.0, 0.02)
+    ties[::3] += torch.randn(ties[::3].numel(), device="cuda", generator=gen) * 1e-3
+    unaligned = torch.randn(n + 3, device="cuda", generator=gen)[3:]
+    assert unaligned.data_ptr() % 16 != 0
+    adversarial = torch.randn(589824, device="cuda", generator=gen) * 0.01
+    idx = torch.arange(589824, device="cuda")
+    run = 589824 // 2048
+    adversarial[(idx % run) < 8] = 1000.0          # exactly the elements the sampler looks at
+    neg_zero = torch.zeros(n, device="cuda"); neg_zero[::2] = -0.0; neg_zero[::7] = 1.0; neg_zero[::11] = -1.0
+    cases = [(base, 1), (base, n), (base, 3), (base, n - 2), (base, n // 2), (with_inf, 600), (with_inf, n - 500),
+             (with_inf, n // 3), (with_nan, n - 5), (with_nan, n // 2), (ties, int(n * 0.7)), (ties, int(n * 0.2)),
+             (ties, int(n * 0.9)), (unaligned, n // 5), (adversarial, int(589824 * 0.7)), (adversarial, 589824 - 100),
+             (neg_zero, n // 2), (torch.full((n,), 0.02, device="cuda"), n // 2)]
+    for use_abs in (False, True):
+        got = ops.kth_value_batched([c[0] for c in cases], [c[1] for c in cases], use_abs=use_abs)
+        for i, (x, k) in enumerate(cases):
+            ref = _kth_ref(x, k, use_abs)
+            if torch.isnan(ref):
+                assert torch.isnan(got[i]), (i, use_abs)
+            else:
+                assert float(got[i]) == float(ref), (i, use_abs, float(got[i]), float(ref))
+
+
+def test_kth_value_small_workspace_takes_radix_core():
+    """With the count-only workspace size of the C ABI every segment takes the 3-pass radix core; same answers."""
+    import ctypes
+    from crvqa import _lib, ops
+    gen = torch.Generator(device="cuda").manual_seed(12)
+    segs = [torch.randn(900001, device="cuda", generator=gen), torch.rand(40000, device="cuda", generator=gen),
+            torch.randn(300000, device="cuda", generator=gen).abs()]
+    ks = [450000, 17, 299999]
+    count = len(segs)
+    nbytes = _lib.lib.crv_kth_value_workspace_bytes(count)
+    ns = (ctypes.c_longlong * count)(*[s.numel() for s in segs])
+    assert nbytes < _lib.lib.crv_kth_value_workspace_bytes_for(ns, count)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    out = torch.empty(count, device="cuda")
+    ptrs = (ctypes.c_void_p * count)(*[s.data_ptr() for s in segs])
+    kk = (ctypes.c_longlong * count)(*ks)
+    _lib.check(_lib.lib.crv_kth_value_batched(ptrs, ns, kk, count, 0, out.data_ptr(), ws.data_ptr(), nbytes, None), "kth")
+    for i, (x, k) in enumerate(zip(segs, ks)):
+        assert float(out[i]) == float(_kth_ref(x, k))
+    assert torch.equal(out, ops.kth_value_batched(segs, ks))
+
+
+def test_kth_plan_reuse_tracks_changing_scores():
+    """The cached plan (trainer path) holds pointers, not values: new scores and new ranks give new thresholds."""
+    from crvqa import ops
+    gen = torch.Generator(device="cuda").manual_seed(13)
+    segs = [torch.randn(589824, device="cuda", generator=gen) for _ in range(5)] + [torch.randn(3072, device="cuda", generator=gen)]
+    plan = ops.KthPlan(segs)
+    for rate in (0.3, 0.7, 0.95):
+        for s in segs:
+            s.add_(torch.randn(s.shape, device="cuda", generator=gen) * 0.1)
+        ks = [max(1, int(s.numel() * rate)) for s in segs]
+        got = plan(ks)
+        for i, (x, k) in enumerate(zip(segs, ks)):
+            assert float(got[i]) == float(_kth_ref(x, k)), (rate, i)
+
+
 def test_magnitude_init(g):
     from crvqa import ops
     w = dev(g["ml_weight"])
