@@ -3,10 +3,12 @@
 // section 8; hg_transformers/modeling_lxmert.py:798-827).
 //
 // Library flash kernels tile 128 x 128 and spend > 90 % of their work on padding at these lengths (cuDNN
-// SDPA measured 7.8 ms per training step, 28 % of it).  Here ONE WARP owns one (batch, head) pair: the
-// small matmuls run on the tensor cores (mma.sync m16n8k16, bf16 in / fp32 accumulate), scores and
-// probabilities stay in registers, softmax / dropout are fp32, and the backward recomputes P (both in
-// row and in transposed orientation) instead of storing it.  No block-level barrier (only __syncwarp).
+// SDPA measured 7.8 ms per training step, 28 % of it).  Here one (batch, head) pair is owned by a GROUP of
+// KT2 = ceil(S / 16) warps that share the pair's Q / K / V / dO tiles in shared memory; each warp owns one
+// 16-row block (query rows in the forward and in pass A of the backward, key rows in pass B).  The small
+// matmuls run on the tensor cores (mma.sync m16n8k16, bf16 in / fp32 accumulate), scores and probabilities
+// stay in registers, softmax / dropout are fp32, and the backward recomputes P (both in row and in transposed
+// orientation) instead of storing it.  One block barrier after the tile load, one between the passes.
 // Inputs are read in place from the fused QKV projection ([B, S, 3H] row stride) and gradients are written
 // straight into the fused dQKV tensor, so no split / concat copies exist.
 #include <mma.h>
@@ -46,8 +48,8 @@ struct AttnParams {
 
 // ---------------------------------------------------------------------------------------------------
 // Register-resident formulation (flash-attention-2 style, specialised for S <= 64):
-// one warp per (batch, head); scores / probabilities never leave registers; K, V (and Q, dO in the
-// backward) are staged once per warp in shared memory with 16-byte loads and read back as MMA fragments
+// one warp per 16-row block of a (batch, head) pair; scores / probabilities never leave registers; K, V (and
+// Q, dO in the backward) are staged once per pair in shared memory with 16-byte loads and read back as MMA fragments
 // with ldmatrix; mma.sync.m16n8k16 (bf16 x bf16 -> fp32).  Lane = 4 g + t:
 //   A (16x16): a0 (row g, k 2t..2t+1)  a1 (row g+8, same k)  a2 (row g, k+8)  a3 (row g+8, k+8)
 //   B (16x8) : b0 (k 2t..2t+1, n g)    b1 (k 2t+8.., n g)
@@ -101,8 +103,8 @@ struct AttnSmem {
 // rows [0, S) of a [S][64] bf16 global tile -> smem [SP][72]; rows >= S zero-filled
 template <int SP>
 __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, long long row_stride, int S,
-                                          int lane) {
-  for (int i = lane; i < SP * 8; i += 32) {
+                                          int tid, int nthreads) {
+  for (int i = tid; i < SP * 8; i += nthreads) {
     const int r = i >> 3, c = i & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (r < S) v = __ldg(reinterpret_cast<const uint4*>(src + r * row_stride) + c);
@@ -110,16 +112,27 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat1
   }
 }
 
+// Dropout decisions come four to a hash: the 64-bit mix of a 2 x 2 block (query pair, key pair) of the
+// probability matrix carries one 16-bit field per element.  An MMA lane holds two elements of such a block in
+// both orientations of the problem (same row, adjacent keys in the forward / pass A; adjacent queries, same key
+// in pass B), so every hash serves two elements.
 struct DropKey {
   uint64_t key;
   uint32_t thresh;
   float scale;
-  __device__ __forceinline__ bool keep(uint64_t idx) const {
-    return thresh == 0 || (amix64(key + idx * 0x9E3779B97F4A7C15ull) & 0xFFFFu) >= thresh;
+  int half_sk;               // ceil(Sk / 2)
+  uint64_t pair_base;        // pair * ceil(Sq / 2)
+  __device__ __forceinline__ uint64_t bits(int i, int j) const {      // hash of the block holding (i, j)
+    const uint64_t grp = (pair_base + static_cast<uint64_t>(i >> 1)) * half_sk + (j >> 1);
+    return amix64(key + grp * 0x9E3779B97F4A7C15ull);
+  }
+  __device__ __forceinline__ bool keep(uint64_t h, int i, int j) const {
+    return ((h >> (16 * ((i & 1) * 2 + (j & 1)))) & 0xFFFFu) >= thresh;
   }
 };
-__device__ __forceinline__ DropKey make_key(const unsigned long long* state, int site, float p) {
-  DropKey r{0, 0, 1.f};
+__device__ __forceinline__ DropKey make_key(const unsigned long long* state, int site, float p, int pair, int Sq,
+                                            int Sk) {
+  DropKey r{0, 0, 1.f, (Sk + 1) >> 1, static_cast<uint64_t>(pair) * ((Sq + 1) >> 1)};
   if (state != nullptr && p > 0.f) {
     r.key = (state[0] * 0xD1342543DE82EF95ull) ^ (state[1] * 0xA24BAED4963EE407ull) ^ (static_cast<uint64_t>(site) << 40);
     r.thresh = static_cast<uint32_t>(fminf(p, 0.9999f) * 65536.0f);
@@ -145,28 +158,31 @@ __device__ __forceinline__ void scores_16(float (&acc)[2 * KT2][4], const uint32
   }
 }
 
-template <int KT2, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int KT2, int PAIRS>
+__global__ void __launch_bounds__(PAIRS * KT2 * 32)
 attn_fwd_kernel(const AttnParams p) {
   using L = AttnSmem<KT2>;
   constexpr int SP = L::SP, NT = 2 * KT2;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = blockIdx.x * WARPS + warp;
-  if (pair >= p.B * p.heads) return;
-  const int b = pair / p.heads, h = pair % p.heads;
+  const int slot = warp / KT2, tile = warp % KT2;      // pair slot inside the CTA, 16-row block inside the pair
+  const int pair = blockIdx.x * PAIRS + slot;
+  const bool valid = pair < p.B * p.heads;
+  const int b = valid ? pair / p.heads : 0, h = valid ? pair % p.heads : 0;
   const int g = lane >> 2, t = lane & 3;
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem + warp * L::kFwd);
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem + slot * L::kFwd);
   __nv_bfloat16* sV = sK + SP * kLdH;
-  load_tile<SP>(sK, p.k + b * p.k_bs + h * kHeadDim, p.k_ss, p.Sk, lane);
-  load_tile<SP>(sV, p.v + b * p.v_bs + h * kHeadDim, p.v_ss, p.Sk, lane);
-  __syncwarp();
-  const DropKey dk = make_key(p.rng_state, p.site, p.p_drop);
+  if (valid) {
+    load_tile<SP>(sK, p.k + b * p.k_bs + h * kHeadDim, p.k_ss, p.Sk, tile * 32 + lane, KT2 * 32);
+    load_tile<SP>(sV, p.v + b * p.v_bs + h * kHeadDim, p.v_ss, p.Sk, tile * 32 + lane, KT2 * 32);
+  }
+  __syncthreads();
+  const DropKey dk = make_key(p.rng_state, p.site, p.p_drop, pair, p.Sq, p.Sk);
   const __nv_bfloat16* qb = p.q + b * p.q_bs + h * kHeadDim;
   const float* mrow = p.mask ? p.mask + static_cast<long long>(b) * p.Sk : nullptr;
   const long long HD = static_cast<long long>(p.heads) * kHeadDim;
-  const int MT = (p.Sq + 15) >> 4;
-  for (int mt = 0; mt < MT; ++mt) {
+  const int mt = tile;
+  if (valid && mt * 16 < p.Sq) {
     const int r0 = mt * 16 + g, r1 = r0 + 8;
     uint32_t a[4][4];
 #pragma unroll
@@ -207,15 +223,15 @@ attn_fwd_kernel(const AttnParams p) {
     }
     const float i0 = 1.f / quad_sum(l0), i1 = 1.f / quad_sum(l1);
     uint32_t pa[KT2][4];
-    const uint64_t ib0 = (static_cast<uint64_t>(pair) * p.Sq + r0) * p.Sk, ib1 = ib0 + 8ull * p.Sk;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       float v[4];
+      const int jb = nt * 8 + 2 * t;
+      const uint64_t h0 = dk.thresh ? dk.bits(r0, jb) : 0ull, h1 = dk.thresh ? dk.bits(r1, jb) : 0ull;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int j = nt * 8 + 2 * t + e;
-        v[e] = dk.keep(ib0 + j) ? s[nt][e] * i0 * dk.scale : 0.f;
-        v[2 + e] = dk.keep(ib1 + j) ? s[nt][2 + e] * i1 * dk.scale : 0.f;
+        v[e] = dk.keep(h0, r0, jb + e) ? s[nt][e] * i0 * dk.scale : 0.f;
+        v[2 + e] = dk.keep(h1, r1, jb + e) ? s[nt][2 + e] * i1 * dk.scale : 0.f;
       }
       pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(v[0], v[1]);
       pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(v[2], v[3]);
@@ -237,18 +253,19 @@ attn_fwd_kernel(const AttnParams p) {
   }
 }
 
-template <int KT2, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int KT2, int PAIRS>
+__global__ void __launch_bounds__(PAIRS * KT2 * 32)
 attn_bwd_kernel(const AttnParams p) {
   using L = AttnSmem<KT2>;
   constexpr int SP = L::SP, NT = 2 * KT2;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = blockIdx.x * WARPS + warp;
-  if (pair >= p.B * p.heads) return;
-  const int b = pair / p.heads, h = pair % p.heads;
+  const int slot = warp / KT2, tile = warp % KT2;
+  const int pair = blockIdx.x * PAIRS + slot;
+  const bool valid = pair < p.B * p.heads;
+  const int b = valid ? pair / p.heads : 0, h = valid ? pair % p.heads : 0;
   const int g = lane >> 2, t = lane & 3;
-  uint8_t* base = smem + warp * L::kBwd;
+  uint8_t* base = smem + slot * L::kBwd;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(base);
   __nv_bfloat16* sK = sQ + SP * kLdH;
   __nv_bfloat16* sV = sK + SP * kLdH;
@@ -257,17 +274,20 @@ attn_bwd_kernel(const AttnParams p) {
   float* sL = sM + SP;
   float* sD = sL + SP;
   const long long HD = static_cast<long long>(p.heads) * kHeadDim;
-  load_tile<SP>(sQ, p.q + b * p.q_bs + h * kHeadDim, p.q_ss, p.Sq, lane);
-  load_tile<SP>(sK, p.k + b * p.k_bs + h * kHeadDim, p.k_ss, p.Sk, lane);
-  load_tile<SP>(sV, p.v + b * p.v_bs + h * kHeadDim, p.v_ss, p.Sk, lane);
-  load_tile<SP>(sdO, p.dout + static_cast<long long>(b) * p.Sq * HD + h * kHeadDim, HD, p.Sq, lane);
-  __syncwarp();
-  const DropKey dk = make_key(p.rng_state, p.site, p.p_drop);
+  if (valid) {
+    const int gt = tile * 32 + lane;
+    load_tile<SP>(sQ, p.q + b * p.q_bs + h * kHeadDim, p.q_ss, p.Sq, gt, KT2 * 32);
+    load_tile<SP>(sK, p.k + b * p.k_bs + h * kHeadDim, p.k_ss, p.Sk, gt, KT2 * 32);
+    load_tile<SP>(sV, p.v + b * p.v_bs + h * kHeadDim, p.v_ss, p.Sk, gt, KT2 * 32);
+    load_tile<SP>(sdO, p.dout + static_cast<long long>(b) * p.Sq * HD + h * kHeadDim, HD, p.Sq, gt, KT2 * 32);
+  }
+  __syncthreads();
+  const DropKey dk = make_key(p.rng_state, p.site, p.p_drop, pair, p.Sq, p.Sk);
   const float* mrow = p.mask ? p.mask + static_cast<long long>(b) * p.Sk : nullptr;
-  const int MT = (p.Sq + 15) >> 4, JT = (p.Sk + 15) >> 4;
 
-  // ---- pass A: query-row blocks.  P, dP, D_i = sum_j dP_ij P_ij, dS -> dQ; row statistics to smem
-  for (int mt = 0; mt < MT; ++mt) {
+  // ---- pass A: this warp's query-row block.  P, dP, D_i = sum_j dP_ij P_ij, dS -> dQ; row statistics to smem
+  const int mt = tile;
+  if (valid && mt * 16 < p.Sq) {
     const int r0 = mt * 16 + g, r1 = r0 + 8;
     uint32_t a[4][4];
 #pragma unroll
@@ -309,17 +329,18 @@ attn_bwd_kernel(const AttnParams p) {
     for (int kt = 0; kt < 4; ++kt) ld_a(a[kt], sdO, mt * 16, kt * 16, lane);
     float dp[NT][4];
     scores_16<KT2>(dp, a, sV, lane);
-    const uint64_t ib0 = (static_cast<uint64_t>(pair) * p.Sq + r0) * p.Sk, ib1 = ib0 + 8ull * p.Sk;
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
+      const int jb = nt * 8 + 2 * t;
+      const uint64_t h0 = dk.thresh ? dk.bits(r0, jb) : 0ull, h1 = dk.thresh ? dk.bits(r1, jb) : 0ull;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int j = nt * 8 + 2 * t + e;
+        const int j = jb + e;
         s[nt][e] *= i0;            // P
         s[nt][2 + e] *= i1;
-        dp[nt][e] = (j < p.Sk && dk.keep(ib0 + j)) ? dp[nt][e] * dk.scale : 0.f;
-        dp[nt][2 + e] = (j < p.Sk && dk.keep(ib1 + j)) ? dp[nt][2 + e] * dk.scale : 0.f;
+        dp[nt][e] = (j < p.Sk && dk.keep(h0, r0, j)) ? dp[nt][e] * dk.scale : 0.f;
+        dp[nt][2 + e] = (j < p.Sk && dk.keep(h1, r1, j)) ? dp[nt][2 + e] * dk.scale : 0.f;
         d0 += dp[nt][e] * s[nt][e];
         d1 += dp[nt][2 + e] * s[nt][2 + e];
       }
@@ -348,10 +369,11 @@ attn_bwd_kernel(const AttnParams p) {
       if (r1 < p.Sq) *reinterpret_cast<uint32_t*>(qo + r1 * p.dq_ss + c) = pack_bf16x2(o[2], o[3]);
     }
   }
-  __syncwarp();
+  __syncthreads();   // every row block's statistics are in shared memory
 
-  // ---- pass B: key-row blocks on the transposed problem.  P^T, dP^T -> dV = Pd^T dO, dK = dS^T Q
-  for (int jt = 0; jt < JT; ++jt) {
+  // ---- pass B: this warp's key-row block on the transposed problem.  P^T, dP^T -> dV = Pd^T dO, dK = dS^T Q
+  const int jt = tile;
+  if (valid && jt * 16 < p.Sk) {
     const int j0 = jt * 16 + g, j1 = j0 + 8;
     uint32_t a[4][4];
 #pragma unroll
@@ -367,15 +389,16 @@ attn_bwd_kernel(const AttnParams p) {
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       float pv[4], dv[4];
+      const int ib = nt * 8 + 2 * t;
+      const uint64_t h0 = dk.thresh ? dk.bits(ib, j0) : 0ull, h1 = dk.thresh ? dk.bits(ib, j1) : 0ull;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int i = nt * 8 + 2 * t + e;
+        const int i = ib + e;
         const bool iv = i < p.Sq;
         const float mi = iv ? sM[i] : 0.f, li = iv ? 1.f / sL[i] : 0.f, Di = iv ? sD[i] : 0.f;
-        const uint64_t ib = (static_cast<uint64_t>(pair) * p.Sq + i) * p.Sk;
         const float p0 = (iv && j0 < p.Sk) ? __expf(s[nt][e] * p.scale + add0 - mi) * li : 0.f;
         const float p1 = (iv && j1 < p.Sk) ? __expf(s[nt][2 + e] * p.scale + add1 - mi) * li : 0.f;
-        const bool k0 = iv && j0 < p.Sk && dk.keep(ib + j0), k1 = iv && j1 < p.Sk && dk.keep(ib + j1);
+        const bool k0 = iv && j0 < p.Sk && dk.keep(h0, i, j0), k1 = iv && j1 < p.Sk && dk.keep(h1, i, j1);
         pv[e] = k0 ? p0 * dk.scale : 0.f;
         pv[2 + e] = k1 ? p1 * dk.scale : 0.f;
         const float dp0 = k0 ? dp[nt][e] * dk.scale : 0.f, dp1 = k1 ? dp[nt][2 + e] * dk.scale : 0.f;
@@ -413,18 +436,18 @@ attn_bwd_kernel(const AttnParams p) {
   }
 }
 
-template <int KT2, int WARPS, bool BWD>
+template <int KT2, int PAIRS, bool BWD>
 static int launch_attn(const AttnParams& p, cudaStream_t st) {
   using L = AttnSmem<KT2>;
-  constexpr int smem = WARPS * (BWD ? L::kBwd : L::kFwd);
-  auto kern = BWD ? attn_bwd_kernel<KT2, WARPS> : attn_fwd_kernel<KT2, WARPS>;
+  constexpr int smem = PAIRS * (BWD ? L::kBwd : L::kFwd);
+  auto kern = BWD ? attn_bwd_kernel<KT2, PAIRS> : attn_fwd_kernel<KT2, PAIRS>;
   static bool configured = false;
   if (!configured) {
     CRV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int pairs = p.B * p.heads;
-  kern<<<(pairs + WARPS - 1) / WARPS, WARPS * 32, smem, st>>>(p);
+  kern<<<(pairs + PAIRS - 1) / PAIRS, PAIRS * KT2 * 32, smem, st>>>(p);
   return launch_status();
 }
 
@@ -455,9 +478,9 @@ extern "C" int crv_attention_fwd(const uint16_t* q, long long q_bs, long long q_
   if (!out || !aligned16(out)) return CRV_E_BADARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int S = Sq > Sk ? Sq : Sk;
-  if (S <= 32) return launch_attn<2, 8, false>(p, st);
-  if (S <= 48) return launch_attn<3, 8, false>(p, st);
-  return launch_attn<4, 8, false>(p, st);
+  if (S <= 32) return launch_attn<2, 4, false>(p, st);
+  if (S <= 48) return launch_attn<3, 2, false>(p, st);
+  return launch_attn<4, 2, false>(p, st);
 }
 
 extern "C" int crv_attention_bwd(const uint16_t* q, long long q_bs, long long q_ss, const uint16_t* k, long long k_bs,
@@ -481,7 +504,7 @@ extern "C" int crv_attention_bwd(const uint16_t* q, long long q_bs, long long q_
   if ((dq_ss | dk_ss | dv_ss | dq_bs | dk_bs | dv_bs) & 7) return CRV_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int S = Sq > Sk ? Sq : Sk;
-  if (S <= 32) return launch_attn<2, 4, true>(p, st);
-  if (S <= 48) return launch_attn<3, 4, true>(p, st);
-  return launch_attn<4, 4, true>(p, st);
+  if (S <= 32) return launch_attn<2, 2, true>(p, st);
+  if (S <= 48) return launch_attn<3, 2, true>(p, st);
+  return launch_attn<4, 2, true>(p, st);
 }

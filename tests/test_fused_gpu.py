@@ -197,3 +197,38 @@ def test_small_attention_dropout_is_unbiased_and_replayable():
         acc += fused.small_attention(0, heads, None, 0.1, 5, True, qkv).float()
     rel = float((acc / n - base).norm() / base.norm())
     assert rel < 0.1, rel                                       # E[dropout(P)] = P
+
+
+@pytest.mark.parametrize("Sq,Sk", [(36, 36), (20, 36), (36, 20), (56, 56)])
+def test_small_attention_dropout_forward_and_backward_use_one_mask(Sq, Sk):
+    """Training-mode parity: the dropout mask depends only on (rng state, site, batch, head, i, j), so it can be
+    read back by running the forward with one-hot V rows; torch attention with THAT mask is then the reference
+    for the forward and for dQ / dK / dV (pass A and pass B of the backward regenerate the same mask)."""
+    from crvqa import fused
+    torch.manual_seed(Sq + Sk)
+    B, heads, H, p = 4, 12, 768, 0.1
+    d = H // heads
+    srcs = tuple((torch.randn(B, s, H, device="cuda") * 0.7).bfloat16().requires_grad_(True) for s in (Sq, Sk, Sk))
+    q, k, v = (t.detach() for t in srcs)
+    rng = fused.RngState.get(q.device)
+    rng.advance()
+    onehot = torch.zeros(B, Sk, heads, d, device="cuda")
+    onehot[:, torch.arange(Sk), :, torch.arange(Sk)] = 1.0          # V[b, j, h, :] = e_j  (Sk <= 64 = d)
+    probe = fused.small_attention(2, heads, None, p, 9, True, q, k, onehot.view(B, Sk, H).bfloat16())
+    keep = (probe.view(B, Sq, heads, d)[..., :Sk] != 0).permute(0, 2, 1, 3).float()   # [B, heads, Sq, Sk]
+    share = 1.0 - float(keep.mean())
+    assert abs(share - p) < 0.02, share
+    out = fused.small_attention(2, heads, None, p, 9, True, *srcs)
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    qh = qr.view(B, Sq, heads, d).transpose(1, 2)
+    kh = kr.view(B, Sk, heads, d).transpose(1, 2)
+    vh = vr.view(B, Sk, heads, d).transpose(1, 2)
+    pd = torch.softmax(qh @ kh.transpose(-1, -2) / d ** 0.5, -1) * keep / (1.0 - p)
+    ref = (pd @ vh).transpose(1, 2).reshape(B, Sq, H)
+    assert float((out.float() - ref).abs().max() / ref.abs().max()) < 2e-2
+    do = torch.randn_like(out)
+    out.backward(do)
+    ref.backward(do.float())
+    for t, r in zip(srcs, (qr, kr, vr)):
+        rel = float((t.grad.float() - r.grad).norm() / r.grad.norm())
+        assert rel < 2e-2, rel
