@@ -153,6 +153,11 @@ class TrainerCore:
         if self.tb_writer is None and is_tensorboard_available() and self.is_world_master() and self.args.logging_dir:
             self.tb_writer = SummaryWriter(log_dir=self.args.logging_dir)
         set_seed(self.args.seed)
+        # The dense (unmasked, trainable) answer head goes through torch matmul: let it use TF32 tensor cores rather
+        # than SIMT fp32 (0.3 ms of a 18 ms step); every masked layer already multiplies in bf16 with fp32
+        # accumulation, so this is the most precise GEMM of the step either way.  CRVQA_TF32=0 keeps strict fp32.
+        if os.environ.get("CRVQA_TF32", "1") != "0":
+            torch.backends.cuda.matmul.allow_tf32 = True
         if self.is_world_master():
             os.makedirs(self.args.output_dir, exist_ok=True)
 

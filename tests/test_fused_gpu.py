@@ -70,7 +70,12 @@ def test_gelu_bf16():
     u = (torch.randn(4096, 3072, device="cuda") * 2).bfloat16().requires_grad_(True)
     y = fused.gelu_bf16(u)
     ref = F.gelu(u.detach().float())
-    assert torch.equal(y, ref.bfloat16())
+    # the kernel's erf is Abramowitz-Stegun 7.1.26 (|erf error| < 1.5e-7) on SFU rcp / ex2, so the fp32 value is within
+    # 5e-7 ABSOLUTE of torch's.  Tolerance: that plus one bf16 rounding step (2^-8 relative); in the lower tail
+    # (gelu(-3) = -0.004) 5e-7 absolute is a few 1e-5 relative, enough to land on the neighbouring bf16 value there.
+    diff = (y.float() - ref).abs()
+    assert bool((diff <= ref.abs() * 2.0 ** -8 + 1e-6).all())
+    assert float((y.float() != ref.bfloat16().float()).float().mean()) < 0.05
     dy = torch.randn_like(y)
     y.backward(dy)
     u_ref = u.detach().float().requires_grad_(True)
