@@ -114,11 +114,19 @@ class GroupLinearFn(torch.autograd.Function):
         g = ctx.group
         dy2 = dy.reshape(-1, g.N)
         dy2 = ops.to_bf16(dy2) if dy2.dtype != torch.bfloat16 else (dy2 if dy2.is_contiguous() else dy2.contiguous())
+        lane = ops.ds_lane(dy2.device) if ctx.need_dx else None
+        if lane is not None:
+            lane.fork()                      # dY is ready here; dS need not wait for dX (see ops._DsLane)
         dx = None
         if ctx.need_dx:
             dx = ops.masked_linear_bwd_dx(dy2, g.wm, None, None, torch.bfloat16).view(ctx.x_shape)
         dirty = g.modules[0]._grad_dirty
-        ops.masked_linear_bwd_ds(dy2, x2, g.w16, out=g.grad, accumulate=dirty)
+        if lane is not None:
+            with torch.cuda.stream(lane.stream):
+                ops.masked_linear_bwd_ds(dy2, x2, g.w16, out=g.grad, accumulate=dirty)
+            lane.hold(dy2, x2)
+        else:
+            ops.masked_linear_bwd_ds(dy2, x2, g.w16, out=g.grad, accumulate=dirty)
         for m in g.modules:
             ops._sink_done(m)
         return dx, None, None, None

@@ -3,6 +3,7 @@
 loss graphs of the trainers.  Every op runs on torch's current CUDA stream."""
 import ctypes
 import math
+import os
 
 import torch
 
@@ -221,6 +222,57 @@ def _sink_done(sink):
         sync.module_backward_done(sink)
 
 
+class _DsLane:
+    """Second stream for the score-gradient GEMMs of the backward pass.
+
+    dX feeds the next layer's backward; dS is only read by the gradient exchange / optimiser at the end of the
+    step.  The stage-2 GEMMs are short (one wave of 256 x 256 tiles, 10 - 40 us) and more than half of such a
+    launch is pipeline fill, epilogue and drain, so dS runs on its own stream and its fixed costs overlap the dX
+    chain instead of extending it.  fork() orders the lane after dY's producer; the operands are held until
+    join(), which the arena calls before anything reads the gradients (ScoreArena.finalize_grads,
+    GradSync._launch).  Inside a CUDA-graph capture this is an ordinary fork / join of the capturing stream.
+    CRVQA_DS_STREAM=0 keeps everything on one stream."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device)
+        self.held = []
+        self.open = False
+
+    def fork(self):
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        self.open = True
+
+    def hold(self, *tensors):
+        self.held.extend(tensors)
+
+    def join(self):
+        if self.open:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+            self.open = False
+        self.held.clear()
+
+
+_ds_lanes = {}
+
+
+def ds_lane(device):
+    """The dS lane of `device`, or None when disabled."""
+    if os.environ.get("CRVQA_DS_STREAM", "1") == "0":
+        return None
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    lane = _ds_lanes.get(key)
+    if lane is None:
+        lane = _ds_lanes[key] = _DsLane(torch.device("cuda", key))
+    return lane
+
+
+def ds_lane_join():
+    """Make the current stream wait for every outstanding dS launch (cheap no-op when none is)."""
+    for lane in _ds_lanes.values():
+        lane.join()
+
+
 class MaskedLinearFn(torch.autograd.Function):
     """y = F.linear(x, weight * binarize(scores, thr), bias) with the straight-through score gradient.
 
@@ -251,6 +303,10 @@ class MaskedLinearFn(torch.autograd.Function):
     def backward(ctx, dy):
         x2, scores, w_bf16, thr_t = ctx.saved_tensors
         dy2 = to_bf16(dy.reshape(-1, dy.shape[-1]))
+        sink_grad = _sink_grad(ctx.sink) if ctx.needs_input_grad[1] else None
+        lane = ds_lane(dy.device) if (sink_grad is not None and ctx.need_dx) else None
+        if lane is not None:
+            lane.fork()                      # dY is ready here; dS need not wait for dX
         dx = None
         if ctx.need_dx:
             if ctx.wm is not None:
@@ -259,9 +315,13 @@ class MaskedLinearFn(torch.autograd.Function):
                 dx = masked_linear_bwd_dx(dy2, w_bf16, scores.detach(), thr_t, torch.float32).view(ctx.x_shape)
         ds = None
         if ctx.needs_input_grad[1]:
-            sink_grad = _sink_grad(ctx.sink)
             if sink_grad is not None:
-                masked_linear_bwd_ds(dy2, x2, w_bf16, out=sink_grad, accumulate=ctx.sink._grad_dirty)
+                if lane is not None:
+                    with torch.cuda.stream(lane.stream):
+                        masked_linear_bwd_ds(dy2, x2, w_bf16, out=sink_grad, accumulate=ctx.sink._grad_dirty)
+                    lane.hold(dy2, x2)
+                else:
+                    masked_linear_bwd_ds(dy2, x2, w_bf16, out=sink_grad, accumulate=ctx.sink._grad_dirty)
                 _sink_done(ctx.sink)
             else:
                 ds = masked_linear_bwd_ds(dy2, x2, w_bf16)

@@ -153,7 +153,9 @@ class ScoreArena:
 
     def finalize_grads(self):
         """Modules that received no gradient this step (e.g. the vision side of the last cross layer,
-        which nothing downstream reads) must contribute zeros."""
+        which nothing downstream reads) must contribute zeros.  Also the point where the dS lane (ops._DsLane)
+        rejoins the current stream: every reader of the gradients comes after this call."""
+        ops.ds_lane_join()
         for m in self.modules:
             if not m._grad_dirty:
                 m._arena_grad.zero_()
@@ -230,6 +232,7 @@ class GradSync:
             return
         lo, hi = self.bucket_ranges[b]
         view = self.arena.grads[lo:hi]
+        ops.ds_lane_join()               # the bucket's dS GEMMs run on the dS lane
         if dist.get_backend(self.group) == "nccl":
             self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
         else:
