@@ -38,6 +38,7 @@ _PROTOS = {
     "crv_masked_linear_small_k_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "crv_masked_embedding_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, _P]),
     "crv_masked_embedding_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_longlong, _P]),
+    "crv_mul_cast_bf16": (c_int, [_P, _P, _P, c_int64, _P]),
     "crv_kth_value_workspace_bytes": (c_size_t, [c_int]),
     "crv_kth_value_workspace_bytes_for": (c_size_t, [_P, c_int]),
     "crv_kth_value_batched": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, c_size_t, _P]),

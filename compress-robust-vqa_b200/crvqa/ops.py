@@ -73,6 +73,18 @@ def to_bf16(x):
     return out
 
 
+def mul_cast_bf16(w, mask):
+    """bf16(w * mask), product in fp32 (stage-3 pruned operand, crv_mul_cast_bf16)."""
+    _need_cuda(w)
+    w = w.detach().contiguous()
+    mask = mask.contiguous()
+    if w.dtype != torch.float32 or mask.dtype != torch.float32 or w.shape != mask.shape:
+        raise ValueError("mul_cast_bf16 needs fp32 weight and fp32 0/1 mask of the same shape")
+    out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    check(lib.crv_mul_cast_bf16(_p(w), _p(mask), _p(out), w.numel(), _stream()), "crv_mul_cast_bf16")
+    return out
+
+
 def as_thr(thr, device):
     """The reference keeps thresholds as 0-dim tensors (possibly on CPU); the kernels read a device float."""
     if not torch.is_tensor(thr):

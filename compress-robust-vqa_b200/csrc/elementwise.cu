@@ -39,6 +39,27 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, uint16_t* __
   }
 }
 
+// stage-3 pruned operand: dst = bf16(w * m), the product formed in fp32 exactly as torch.nn.utils.prune's
+// forward pre-hook does (weight = weight_orig * weight_mask) before the operand is rounded for the MMA
+__global__ void mul_cast_bf16_kernel(const float* __restrict__ w, const float* __restrict__ m, uint16_t* __restrict__ dst,
+                                     int64_t n) {
+  const int64_t nvec = n >> 3;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(w) + 2 * i + 1);
+    const float4 ma = __ldg(reinterpret_cast<const float4*>(m) + 2 * i);
+    const float4 mb = __ldg(reinterpret_cast<const float4*>(m) + 2 * i + 1);
+    reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16(a.x * ma.x, a.y * ma.y), pack_bf16(a.z * ma.z, a.w * ma.w),
+                                                  pack_bf16(b.x * mb.x, b.y * mb.y), pack_bf16(b.z * mb.z, b.w * mb.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const int64_t i = (nvec << 3) + threadIdx.x;
+    __nv_bfloat16 t = __float2bfloat16_rn(w[i] * m[i]);
+    dst[i] = *reinterpret_cast<uint16_t*>(&t);
+  }
+}
+
 __global__ void binarize_kernel(const float* __restrict__ s, const float* __restrict__ thr_p,
                                 float* __restrict__ mf, uint8_t* __restrict__ mb, long long* __restrict__ kept,
                                 int64_t n) {
@@ -341,6 +362,14 @@ extern "C" int crv_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, 
   if (n == 0) return CRV_OK;
   if (!aligned16(src) || !aligned16(dst)) return CRV_E_ALIGN;
   cast_f32_bf16_kernel<<<stream_grid(n >> 3), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n);
+  return launch_status();
+}
+
+extern "C" int crv_mul_cast_bf16(const float* w, const float* mask, uint16_t* dst, int64_t n, void* stream) {
+  if (!w || !mask || !dst || n < 0) return CRV_E_BADARG;
+  if (n == 0) return CRV_OK;
+  if (!aligned16(w) || !aligned16(mask) || !aligned16(dst)) return CRV_E_ALIGN;
+  mul_cast_bf16_kernel<<<stream_grid(n >> 3), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(w, mask, dst, n);
   return launch_status();
 }
 

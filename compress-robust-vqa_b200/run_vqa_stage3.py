@@ -1,0 +1,83 @@
+"""Stage-3 driver pieces of the reference's ``run_vqa_stage3.py`` that the frozen-mask fine-tune needs
+(SURVEY.md section 8(f) rank 2): the same function names, arguments and results, with the pruned modules of
+``masking/pruned.py`` underneath instead of ``torch.nn.utils.prune`` hooks.
+
+    pruning_model_with_mask(model, mask_dict, model_type)    run_vqa_stage3.py:227-297   (FT_trainedMask)
+    mag_pruning(model, px)                                   run_vqa_stage3.py:205-225   (FT_randMask)
+    see_weight_rate(model, model_type)                       run_vqa_stage3.py:75-178
+    init_optimizer(model, training_args, num_train_data)     run_vqa_stage3.py:577-598
+
+The trainer is the stage-2 one (``hg_transformers.mask_trainer_VQA.Trainer``, as the reference imports at :45)
+with ``training_type`` in {FT_trainedMask, FT_randMask} and no masker; dataset / argument parsing of the
+reference driver is out of scope.
+"""
+import torch
+
+from hg_transformers.optimization import get_linear_schedule_with_warmup
+from masking.pruned import PrunedEmbedding, PrunedLinear, custom_from_mask, l1_unstructured_mask
+
+_ATT = ("attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense",
+        "intermediate.dense", "output.dense")
+_XSUB = ("visual_attention.att.query", "visual_attention.att.key", "visual_attention.att.value",
+         "visual_attention.output.dense", "lang_self_att.self.query", "lang_self_att.self.key",
+         "lang_self_att.self.value", "lang_self_att.output.dense", "visn_self_att.self.query",
+         "visn_self_att.self.key", "visn_self_att.self.value", "visn_self_att.output.dense",
+         "lang_inter.dense", "lang_output.dense", "visn_inter.dense", "visn_output.dense")
+
+
+def trained_mask_module_names():
+    """The modules pruning_model_with_mask reparametrises, in the reference's order (:231-294)."""
+    names = [f"encoder.layer.{i}.{s}" for i in range(9) for s in _ATT]
+    names += [f"encoder.r_layers.{i}.{s}" for i in range(5) for s in _ATT]
+    names += [f"encoder.x_layers.{i}.{s}" for i in range(5) for s in _XSUB]
+    return names + ["pooler.dense", "embeddings.word_embeddings", "encoder.visn_fc.visn_fc", "encoder.visn_fc.box_fc"]
+
+
+def pruning_model_with_mask(model, mask_dict, model_type):
+    """`model` is the bare encoder (``model.lxmert``); `mask_dict` is what stage 2's save_model_mask wrote
+    (keys '<model_type>.<module>.weight_mask', bool) or a state_dict-style dict (suffix '.weight')."""
+    suffix = ".weight_mask" if "_mask" in list(mask_dict.keys())[0] else ".weight"
+    for name in trained_mask_module_names():
+        custom_from_mask(model, name, mask_dict["%s.%s%s" % (model_type, name, suffix)])
+
+
+def mag_pruning(model, px):
+    """prune.l1_unstructured(amount=px) on the language layers that exist, the pooler and the word embeddings --
+    exactly the module list of the reference (it never names r_layers / x_layers)."""
+    print("Start magnitude pruning with zero rate %.2f" % px)
+    wanted = [f"encoder.layer.{i}.{s}" for i in range(12) for s in _ATT] + ["pooler.dense"]
+    existing = dict(model.named_modules())
+    for name in wanted:
+        if name in existing:
+            custom_from_mask(model, name, l1_unstructured_mask(existing[name].weight, px))
+    emb = model.embeddings.word_embeddings
+    custom_from_mask(model, "embeddings.word_embeddings", l1_unstructured_mask(emb.weight, px))
+
+
+def see_weight_rate(model, model_type):
+    """Percentage of zeros over the weight masks of the trained-mask module set (read from state_dict, :75-178)."""
+    sd = model.state_dict()
+    total = zeros = 0.0
+    for name in trained_mask_module_names():
+        m = sd["%s.%s.weight_mask" % (model_type, name)]
+        total += float(m.nelement())
+        zeros += float(torch.sum(m == 0))
+    return 100 * zeros / total
+
+
+def init_optimizer(model, training_args, num_train_data):
+    """torch.optim.Adam with one param group per tensor + linear schedule (:577-598)."""
+    params = [{"params": [value], "name": key, "weight_decay": training_args.weight_decay,
+               "param_size": value.size(), "nelement": value.nelement(), "lr": training_args.learning_rate}
+              for key, value in model.named_parameters() if value.requires_grad]
+    optimizer = torch.optim.Adam(params, lr=training_args.learning_rate, betas=(0.9, 0.999),
+                                 eps=training_args.adam_epsilon)
+    num_training_steps = int(int(num_train_data / (max(1, training_args.n_gpu) * training_args.per_gpu_train_batch_size) + 1)
+                             * training_args.num_train_epochs)
+    scheduler = get_linear_schedule_with_warmup(optimizer, num_warmup_steps=training_args.warmup_steps,
+                                                num_training_steps=num_training_steps)
+    return optimizer, scheduler
+
+
+__all__ = ["PrunedLinear", "PrunedEmbedding", "pruning_model_with_mask", "mag_pruning", "see_weight_rate",
+           "init_optimizer", "trained_mask_module_names"]

@@ -49,6 +49,12 @@ unsigned long long crv_launch_count(void);   /* kernels this library has launche
 /* fp32 -> bf16 (round-to-nearest-even) operand conversion in front of the bf16 MMAs. */
 int crv_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);
 
+/* Stage-3 frozen-mask fine-tune (run_vqa_stage3.py:227-300: torch.nn.utils.prune.CustomFromMask, whose forward
+ * pre-hook sets weight = weight_orig * weight_mask): dst = bf16(w * mask), product in fp32, one pass.  The
+ * masked GEMMs then take dst as their plain operand and crv_masked_linear_bwd_ds with w_bf16 = bf16(mask)
+ * yields dW = (dY^T X) (.) mask, the gradient autograd gives weight_orig. */
+int crv_mul_cast_bf16(const float* w, const float* mask, uint16_t* dst, int64_t n, void* stream);
+
 /* binarizer_fn1 (masking/maskers.py:325-329): mask[i] = scores[i] > *thr ? 1 : 0 (strict >),
  * written as fp32 0/1 (mask_f32) and/or bytes (mask_u8) -- either may be NULL.  Also the body of
  * Trainer.save_model_mask / Trainer.binarizer_fn1 (hg_transformers/mask_trainer_VQA.py:930-968).

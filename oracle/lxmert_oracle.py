@@ -135,8 +135,11 @@ def forward(c, ids, feats, pos, l_layers=9, r_layers=5, x_layers=5):
         words = _ops.masked_embedding(ids, c.S[emb_name], c.P[emb_name + ".weight"], c.T[emb_name], 0)
     else:
         words = F.embedding(ids, c.P[emb_name + ".weight"], padding_idx=0)
-    position = c.P["lxmert.embeddings.position_embeddings.weight"][:T].unsqueeze(0)
-    token_type = c.P["lxmert.embeddings.token_type_embeddings.weight"][0].view(1, 1, -1)
+    # both tables are nn.Embedding(..., padding_idx=0) (modeling_lxmert.py:735-736): row 0 never receives a
+    # gradient -- invisible in stage 2 (frozen) but part of the stage-3 fine-tune
+    position = F.embedding(torch.arange(T, device=ids.device).unsqueeze(0).expand(ids.shape),
+                           c.P["lxmert.embeddings.position_embeddings.weight"], padding_idx=0)
+    token_type = F.embedding(torch.zeros_like(ids), c.P["lxmert.embeddings.token_type_embeddings.weight"], padding_idx=0)
     lang = c.drop(c.ln("lxmert.embeddings.LayerNorm", words + position + token_type), c.p_hidden)
     vf = "lxmert.encoder.visn_fc."
     visn = (c.ln(vf + "visn_layer_norm", c.lin(vf + "visn_fc", feats)) + c.ln(vf + "box_layer_norm", c.lin(vf + "box_fc", pos))) / 2
