@@ -132,7 +132,7 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -337,11 +337,27 @@ def run_ours(args):
             "gpu_launches": int(launches), "roofline": roofline}
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    emit(line)
     finish()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; see main()."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries print banners to fd 1 (NCCL: "NCCL version ..." when NCCL_DEBUG is set in the environment): keep
+    # stdout for the JSON line only -- everything else that lands on fd 1 is sent to stderr.
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -18,6 +18,8 @@ GradSync
     backward pass has produced every module of a bucket, its slice is all-reduced asynchronously (NCCL
     over NVLink / NVSwitch) while the remaining dS / dX GEMMs run.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 
@@ -232,12 +234,23 @@ class GradSync:
             return
         lo, hi = self.bucket_ranges[b]
         view = self.arena.grads[lo:hi]
-        ops.ds_lane_join()               # the bucket's dS GEMMs run on the dS lane
-        if dist.get_backend(self.group) == "nccl":
-            self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        # The bucket's dS GEMMs run on the dS lane.  Issue the collective FROM the lane (ordered after the current
+        # stream as well, for the few gradients written there): NCCL then waits for exactly the work that
+        # produced the bucket, and the dX chain on the current stream is not held up at bucket boundaries.
+        lane = ops.ds_lane(view.device) if view.is_cuda else None
+        if lane is not None:
+            lane.stream.wait_stream(torch.cuda.current_stream(view.device))
+            ctx = torch.cuda.stream(lane.stream)
         else:
-            h = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            self._handles.append((h, view))
+            ctx = contextlib.nullcontext()
+        with ctx:
+            if dist.get_backend(self.group) == "nccl":
+                self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+            else:
+                h = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self._handles.append((h, view))
+        if lane is not None:
+            lane.open = True           # the lane holds work the current stream has to join before reading gradients
 
     def module_backward_done(self, module):
         """One backward invocation of `module` finished writing its dS."""
