@@ -161,6 +161,8 @@ __device__ __forceinline__ void scores_16(float (&acc)[2 * KT2][4], const uint32
 template <int KT2, int PAIRS>
 __global__ void __launch_bounds__(PAIRS * KT2 * 32)
 attn_fwd_kernel(const AttnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   using L = AttnSmem<KT2>;
   constexpr int SP = L::SP, NT = 2 * KT2;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -256,6 +258,8 @@ attn_fwd_kernel(const AttnParams p) {
 template <int KT2, int PAIRS>
 __global__ void __launch_bounds__(PAIRS * KT2 * 32)
 attn_bwd_kernel(const AttnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   using L = AttnSmem<KT2>;
   constexpr int SP = L::SP, NT = 2 * KT2;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -447,7 +451,7 @@ static int launch_attn(const AttnParams& p, cudaStream_t st) {
     configured = true;
   }
   const int pairs = p.B * p.heads;
-  kern<<<(pairs + PAIRS - 1) / PAIRS, PAIRS * KT2 * 32, smem, st>>>(p);
+  CRV_CUDA(launch_pdl(kern, dim3((pairs + PAIRS - 1) / PAIRS), dim3(PAIRS * KT2 * 32), smem, st, p));
   return launch_status();
 }
 

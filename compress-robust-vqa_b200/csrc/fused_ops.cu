@@ -79,6 +79,7 @@ ln_fwd_kernel(const void* __restrict__ g, int g_bf16, const float* __restrict__ 
               const float* __restrict__ beta, float eps, float p, const unsigned long long* __restrict__ rng_state,
               int site, float* __restrict__ y32, uint16_t* __restrict__ y16, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, int M, int H) {
+  pdl_wait();
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -98,6 +99,7 @@ ln_fwd_kernel(const void* __restrict__ g, int g_bf16, const float* __restrict__ 
     z[i] = gv;
     s += gv.x + gv.y + gv.z + gv.w;
   }
+  pdl_launch_dependents();     // inputs are in registers
   const float mean = warp_sum(s) / H;
   float v = 0.f;
 #pragma unroll
@@ -129,6 +131,7 @@ ln_bwd_kernel(const float* __restrict__ dy32, const uint16_t* __restrict__ dy16,
               const float* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, float p, const unsigned long long* __restrict__ rng_state, int site,
               void* __restrict__ dg, int dg_bf16, float* __restrict__ dres, int M, int H) {
+  pdl_wait();
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -159,6 +162,7 @@ ln_bwd_kernel(const float* __restrict__ dy32, const uint16_t* __restrict__ dy16,
     s1 += d.x + d.y + d.z + d.w;
     s2 += d.x * xh[i].x + d.y * xh[i].y + d.z * xh[i].z + d.w * xh[i].w;
   }
+  pdl_launch_dependents();     // inputs are in registers
   const float m1 = warp_sum(s1) / H, m2 = warp_sum(s2) / H;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -207,6 +211,7 @@ __device__ __forceinline__ float gelu_grad_f(float u) {   // Phi(u) + u phi(u)
 }
 
 __global__ void gelu_fwd_kernel(const uint16_t* __restrict__ u, uint16_t* __restrict__ y, int64_t n) {
+  pdl_wait();
   const int64_t nvec = n >> 3;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
@@ -219,6 +224,7 @@ __global__ void gelu_fwd_kernel(const uint16_t* __restrict__ u, uint16_t* __rest
 
 __global__ void gelu_bwd_kernel(const uint16_t* __restrict__ u, const uint16_t* __restrict__ dy,
                                 uint16_t* __restrict__ du, int64_t n) {
+  pdl_wait();
   const int64_t nvec = n >> 3;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
@@ -261,8 +267,9 @@ extern "C" int crv_ln_fwd(const void* g, int g_dtype, const float* res, const fl
   const int grid = (M + kRowsPerBlock - 1) / kRowsPerBlock;
   return dispatch_vec(H, [&](auto v) {
     constexpr int VEC = decltype(v)::value;
-    ln_fwd_kernel<VEC><<<grid, kRowsPerBlock * 32, 0, st>>>(g, g_dtype == CRV_DTYPE_BF16, res, gamma, beta, eps, p_drop,
-                                                            rng_state, site, y_f32, y_bf16, mean, rstd, M, H);
+    CRV_CUDA(launch_pdl(ln_fwd_kernel<VEC>, dim3(grid), dim3(kRowsPerBlock * 32), 0, st, g,
+                        static_cast<int>(g_dtype == CRV_DTYPE_BF16), res, gamma, beta, eps, p_drop, rng_state, site, y_f32,
+                        y_bf16, mean, rstd, M, H));
     return launch_status();
   });
 }
@@ -277,9 +284,9 @@ extern "C" int crv_ln_bwd(const float* dy_f32, const uint16_t* dy_bf16, const vo
   const int grid = (M + kRowsPerBlock - 1) / kRowsPerBlock;
   return dispatch_vec(H, [&](auto v) {
     constexpr int VEC = decltype(v)::value;
-    ln_bwd_kernel<VEC><<<grid, kRowsPerBlock * 32, 0, st>>>(dy_f32, dy_bf16, g, g_dtype == CRV_DTYPE_BF16, res, gamma,
-                                                            mean, rstd, p_drop, rng_state, site, dg,
-                                                            dg_dtype == CRV_DTYPE_BF16, dres, M, H);
+    CRV_CUDA(launch_pdl(ln_bwd_kernel<VEC>, dim3(grid), dim3(kRowsPerBlock * 32), 0, st, dy_f32, dy_bf16, g,
+                        static_cast<int>(g_dtype == CRV_DTYPE_BF16), res, gamma, mean, rstd, p_drop, rng_state, site, dg,
+                        static_cast<int>(dg_dtype == CRV_DTYPE_BF16), dres, M, H));
     return launch_status();
   });
 }
@@ -290,7 +297,7 @@ extern "C" int crv_gelu_fwd(const uint16_t* u, uint16_t* y, int64_t n, void* str
   if (n == 0) return CRV_OK;
   int64_t blocks = ((n >> 3) + 255) / 256;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  gelu_fwd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(u, y, n);
+  CRV_CUDA(launch_pdl(gelu_fwd_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), u, y, n));
   return launch_status();
 }
 
@@ -300,7 +307,7 @@ extern "C" int crv_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du,
   if (n == 0) return CRV_OK;
   int64_t blocks = ((n >> 3) + 255) / 256;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  gelu_bwd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(u, dy, du, n);
+  CRV_CUDA(launch_pdl(gelu_bwd_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), u, dy, du, n));
   return launch_status();
 }
 

@@ -150,6 +150,7 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // barriers, TMEM and descriptors are set up; operands of a predecessor from here on
   long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = gtime();  // setup done
 
@@ -192,6 +193,7 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
       }
+      pdl_launch_dependents();   // every load of this CTA is in flight: let the next grid be scheduled
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
@@ -497,6 +499,7 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // barriers, TMEM and descriptors are set up; operands of a predecessor from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -529,6 +532,7 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      pdl_launch_dependents();   // every load of this CTA is in flight: let the next grid be scheduled
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
@@ -726,7 +730,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   p.dbg = g_dbg;
   const int tiles = p.num_m * p.num_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, XFORM ? 320 : 192, L::kTotal, stream>>>(tmA, tmB, tmS, tmOut, p);
+  CRV_CUDA(launch_pdl(kern, dim3(grid), dim3(XFORM ? 320 : 192), L::kTotal, stream, tmA, tmB, tmS, tmOut, p));
   return launch_status();
 }
 
@@ -751,13 +755,15 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = Smem2::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   CRV_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, p));
   return launch_status();
 }

@@ -38,6 +38,26 @@ def masked_modules_of(model):
     return out
 
 
+def execution_order(named_modules):
+    """Arena (and therefore bucket) order = the order the fused LXMERT forward executes the modules: vision
+    stack, language stack, cross layers, pooler (modeling_lxmert._forward_fast).  The backward pass completes
+    gradients in the reverse order, so the bucket that finishes LAST is the small head of the vision stack and the
+    94 MB word-embedding gradient is exchanged while the vision layers are still in backward.  Other models
+    (VisualBERT: one stack) keep named_modules order."""
+    def key(item):
+        name = item[0]
+        if "visn_fc" in name or ".r_layers." in name:
+            return 0
+        if ".x_layers." in name:
+            return 2
+        if "pooler" in name:
+            return 3
+        return 1
+    if not any(".r_layers." in n for n, _ in named_modules):
+        return list(named_modules)
+    return sorted(named_modules, key=key)          # stable: named_modules order inside each group
+
+
 class ScoreArena:
     def __init__(self, named_modules, device=None):
         self.names = [n for n, _ in named_modules]
@@ -187,7 +207,7 @@ class ScoreArena:
 class GradSync:
     """Bucketed asynchronous all-reduce(mean) of an arena's gradient buffer + a few loose tensors."""
 
-    def __init__(self, arena, bucket_bytes=64 << 20, group=None):
+    def __init__(self, arena, bucket_bytes=32 << 20, group=None):
         self.arena = arena
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1

@@ -32,7 +32,7 @@ from torch.utils.data.sampler import Sampler
 
 from crvqa import ops
 
-from ._engine import GradSync, GraphedStep, InputPrefetcher, ScoreArena, masked_modules_of
+from ._engine import execution_order, GradSync, GraphedStep, InputPrefetcher, ScoreArena, masked_modules_of
 from .data.data_collator import DataCollator, DefaultDataCollator, TrimCollator  # noqa: F401
 from .optimization import AdamW, get_constant_schedule, get_linear_schedule_with_warmup  # noqa: F401
 from .trainer_utils import PREFIX_CHECKPOINT_DIR, EvalPrediction, PredictionOutput, TrainOutput
@@ -232,8 +232,17 @@ class TrainerCore:
             self._kth_plan = plan
         thr = plan[1](ks)
         arena = getattr(self, "arena", None)
-        if arena is not None and [m for _, m in mods] == arena.modules:
-            arena.set_thresholds(thr)          # one device vector; module.threshold = 0-dim views of it
+        modules = [m for _, m in mods]
+        if arena is not None and len(modules) == len(arena.modules) and set(map(id, modules)) == set(map(id, arena.modules)):
+            # one device vector in ARENA order (the arena follows execution order, not named_modules order);
+            # module.threshold = 0-dim views of it
+            pos = {id(m): i for i, m in enumerate(modules)}
+            perm = [pos[id(m)] for m in arena.modules]
+            if perm != list(range(len(perm))):
+                thr_arena = thr[torch.tensor(perm, device=thr.device)]
+            else:
+                thr_arena = thr
+            arena.set_thresholds(thr_arena)
             arena.refresh_masked()
         else:
             for i, (_, module) in enumerate(mods):
@@ -293,7 +302,7 @@ class TrainerCore:
                 if m.weight_mask.requires_grad and m.weight_mask.is_cuda and getattr(m, "unstructured_masked", False)]
         if not mods:
             return
-        self.arena = ScoreArena(mods)
+        self.arena = ScoreArena(execution_order(mods))
         if os.environ.get("CRVQA_MASK_MODE", "cached") == "cached":
             self.arena.enable_mask_cache()
         if hasattr(optimizer, "attach_arena"):

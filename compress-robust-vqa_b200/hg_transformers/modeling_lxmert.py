@@ -189,10 +189,16 @@ class LxmertEncoder(nn.Module):
         self.r_layers = nn.ModuleList([LxmertLayer(config) for _ in range(config.r_layers)])
 
     def forward(self, lang, lang_mask, visual_feats, visual_pos, visn_mask=None):
+        """`lang` is the language embedding output or a callable producing it.  LxmertModel passes a callable so the
+        fast path can create the embedding node AFTER the vision stack: autograd runs later-created nodes first,
+        which puts the 94 MB word-embedding gradient before the vision stack in the backward pass instead of at
+        its very end, where its all-reduce could overlap nothing (_engine.execution_order)."""
         visn = self.visn_fc(visual_feats, visual_pos)
-        fast = self._fast_plans() if lang.is_cuda else None
+        fast = self._fast_plans() if visn.is_cuda else None
         if fast is not None:
             return self._forward_fast(fast, lang, lang_mask, visn, visn_mask)
+        if callable(lang):
+            lang = lang()
         for blk in self.layer:
             lang = blk(lang, lang_mask)
         for blk in self.r_layers:
@@ -238,13 +244,18 @@ class LxmertEncoder(nn.Module):
 
     def _forward_fast(self, plans, lang32, lang_mask, visn32, visn_mask):
         tr = self.training
-        lang16, visn16 = lang32.to(torch.bfloat16), visn32.to(torch.bfloat16)
-        for att, ffn in plans["lang"]:
-            a32, a16 = att.self_attention(lang32, lang16, lang_mask, tr)
-            lang32, lang16 = ffn(a32, a16, tr)
+        visn16 = visn32.to(torch.bfloat16)
+        # vision stack first: independent of the language stack, and this way the backward pass ends with the
+        # small vision head instead of the 94 MB word-embedding gradient (see _engine.execution_order)
         for att, ffn in plans["visn"]:
             a32, a16 = att.self_attention(visn32, visn16, visn_mask, tr)
             visn32, visn16 = ffn(a32, a16, tr)
+        if callable(lang32):
+            lang32 = lang32()
+        lang16 = lang32.to(torch.bfloat16)
+        for att, ffn in plans["lang"]:
+            a32, a16 = att.self_attention(lang32, lang16, lang_mask, tr)
+            lang32, lang16 = ffn(a32, a16, tr)
         for cross, site_l, site_v, ls, vs, lf, vf in plans["cross"]:
             lx32, lx16 = cross.cross_attention(lang32, lang16, visn16, visn_mask, tr, site_l)
             vx32, vx16 = cross.cross_attention(visn32, visn16, lang16, lang_mask, tr, site_v)
@@ -323,8 +334,8 @@ class LxmertModel(LxmertPreTrainedModel):
         visn_mask = None
         if visual_attention_mask is not None:
             visn_mask = (1.0 - visual_attention_mask[:, None, None, :].to(visual_feats.dtype)) * -10000.0
-        emb = self.embeddings(input_ids, token_type_ids)
-        lang, visn = self.encoder(emb, lang_mask, visual_feats, visual_pos, visn_mask)
+        lang, visn = self.encoder(lambda: self.embeddings(input_ids, token_type_ids), lang_mask, visual_feats,
+                                  visual_pos, visn_mask)
         return lang, visn, self.pooler(lang)
 
 
