@@ -508,7 +508,7 @@ extern "C" int crv_attention_bwd(const uint16_t* q, long long q_bs, long long q_
   if ((dq_ss | dk_ss | dv_ss | dq_bs | dk_bs | dv_bs) & 7) return CRV_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int S = Sq > Sk ? Sq : Sk;
-  if (S <= 32) return launch_attn<2, 2, true>(p, st);
-  if (S <= 48) return launch_attn<3, 2, true>(p, st);
-  return launch_attn<4, 2, true>(p, st);
+  if (S <= 32) return launch_attn<2, 1, true>(p, st);
+  if (S <= 48) return launch_attn<3, 1, true>(p, st);
+  return launch_attn<4, 1, true>(p, st);
 }

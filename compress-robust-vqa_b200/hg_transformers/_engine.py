@@ -212,15 +212,17 @@ class GradSync:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.enabled = self.world > 1
-        # buckets = runs of consecutive modules (arena order == forward order)
+        # buckets = runs of consecutive modules (arena order == execution order).  The FIRST buckets of the arena are
+        # the last ones the backward pass completes, and only their all-reduce is exposed at the end of the step, so
+        # they start small (bucket_bytes / 4, / 2, then bucket_bytes).
         self.bucket_of, self.bucket_ranges, self.bucket_members = [], [], []
         start_mod, start_off, cur = 0, 0, 0
-        limit = bucket_bytes // 4
         n = len(arena.modules)
         for i in range(n):
             end = arena.offsets[i + 1] if i + 1 < n else arena.total
             cur = end - start_off
             self.bucket_of.append(len(self.bucket_ranges))
+            limit = (bucket_bytes >> max(0, 2 - len(self.bucket_ranges))) // 4
             if cur >= limit or i == n - 1:
                 self.bucket_ranges.append((start_off, end))
                 self.bucket_members.append(list(range(start_mod, i + 1)))
