@@ -220,6 +220,8 @@ class TrainerCore:
         mods = masked_modules_of(model)
         if not mods:
             return float("nan")
+        if self.threshold_mode == "union":
+            return self._reset_threshold_union(mods, init_sparsity)
         ks = []
         for name, module in mods:
             k = int(module.weight.nelement() * self._sparsity_of(name, init_sparsity))
@@ -248,6 +250,27 @@ class TrainerCore:
             for i, (_, module) in enumerate(mods):
                 module.threshold = thr[i]
         return float(thr.mean())
+
+    def _reset_threshold_union(self, mods, tgt_sparsity):
+        """global_mask_trainer_VQA.py:421-443: one threshold = k-th smallest of ALL scores together."""
+        if not getattr(self.model_args, "global_prune", False):
+            raise AssertionError("this function is designed for GLOBAL_MASKER, plz check it again whether run the "
+                                 "wrong py-files")
+        from masking._core import global_kth_value
+        tensors = [m.weight_mask.data for _, m in mods]
+        k = int(sum(t.numel() for t in tensors) * tgt_sparsity)
+        thr = global_kth_value(tensors, k)                      # 1-element device tensor
+        arena = getattr(self, "arena", None)
+        modules = [m for _, m in mods]
+        if arena is not None and len(modules) == len(arena.modules) and set(map(id, modules)) == set(map(id, arena.modules)):
+            arena.set_thresholds(thr.expand(len(modules)).contiguous())
+            arena.refresh_masked()
+        else:
+            shared = thr[0]
+            for m in modules:
+                m.threshold = shared
+        # the reference returns the fp32 mean of the per-module list (all entries identical)
+        return float(torch.tensor([float(thr[0])] * len(modules)).mean())
 
     def binarizer_fn1(self, inputs, threshold):
         return ops.binarize(inputs, threshold)

@@ -306,17 +306,34 @@ class MaskedLinearX(nn.Module):
         raise NotImplementedError
 
 
-def finish_magnitude_init(modules):
-    """One batched exact select over |W| of every pending module, then S = 2*thr where |W| > kth else 0."""
+def global_kth_value(tensors, k, use_abs=False):
+    """k-th smallest over the UNION of the tensors (reference: torch.cat([...]).kthvalue(k), global_maskers.py:536-541,
+    global_mask_trainer_VQA.py:424-429): one contiguous copy, then a single-segment exact select (the
+    sample / filter path reads it once)."""
+    flat = torch.cat([ops._stage(t.detach()).reshape(-1) for t in tensors])
+    return ops.kth_value_batched([flat], [int(k)], use_abs=use_abs)
+
+
+def finish_magnitude_init(modules, global_sparsity=None):
+    """One batched exact select over |W| of every pending module, then S = 2*thr where |W| > kth else 0.
+    With `global_sparsity` (global_maskers.Masker, global_prune=True) ONE magnitude cut is taken over the union of
+    all pending weights instead (reference global_maskers.py:219-231,531-541); returns that cut (0-dim tensor)."""
     pend = [m for m in modules if getattr(m, "_pending_magnitude", False)]
     if not pend:
-        return
-    ks = [MaskedLinearX.num_zero_elements(m.weight, m._init_sparsity) for m in pend]
-    w_thr = ops.kth_value_batched([m.weight.detach() for m in pend], ks, use_abs=True)
+        return None
+    cut = None
+    if global_sparsity is not None:
+        total = sum(m.weight.numel() for m in pend)
+        cut = global_kth_value([m.weight for m in pend], int(total * global_sparsity), use_abs=True)
+        w_thr = cut.expand(len(pend))
+    else:
+        ks = [MaskedLinearX.num_zero_elements(m.weight, m._init_sparsity) for m in pend]
+        w_thr = ops.kth_value_batched([m.weight.detach() for m in pend], ks, use_abs=True)
     for i, m in enumerate(pend):
         thr = float(m.threshold)
-        m.weight_mask.data = ops.magnitude_init(m.weight, w_thr[i:i + 1], 2.0 * thr, 0.0 * thr)
+        m.weight_mask.data = ops.magnitude_init(m.weight, w_thr[i:i + 1].contiguous(), 2.0 * thr, 0.0 * thr)
         m._pending_magnitude = False
+    return cut[0] if cut is not None else None
 
 
 class MaskedLinear0(nn.Module):
@@ -446,7 +463,10 @@ class MaskerBase(object):
         masked_linear_cls = _MASKED_CLASSES[name_of_masker]
         self._created = []
         self.replace(model, "", names_tobe_masked, masked_linear_cls)
-        finish_magnitude_init(self._created)
+        if getattr(self, "global_prune", False):
+            self.global_threshold = finish_magnitude_init(self._created, self.masker_scheduler.init_sparsity)
+        else:
+            finish_magnitude_init(self._created)
         self.masked_linear_cls = masked_linear_cls
 
         self.logger.info("Check the trainable status.")

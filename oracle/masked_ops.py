@@ -36,6 +36,22 @@ def kth_value(values, k, use_abs=False):
     return np.float32(np.partition(a, k - 1)[k - 1])
 
 
+def global_kth_value(tensors, k, use_abs=False):
+    """k-th smallest over the union of the tensors -- torch.cat([...]).kthvalue(k) as called at
+    masking/global_maskers.py:536-541 (|W|) and hg_transformers/global_mask_trainer_VQA.py:424-429 (scores)."""
+    flat = torch.cat([t.detach().reshape(-1) for t in tensors])
+    return kth_value(flat, k, use_abs=use_abs)
+
+
+def magnitude_init_global(weight, w_cut, threshold):
+    """_magnitude_global -- masking/global_maskers.py:219-231: S = 2*thr where |W| > the global cut, else 0."""
+    thr = float(threshold)
+    s = torch.zeros_like(weight)
+    keep = weight.abs() > float(w_cut)
+    s[keep] = 2.0 * thr
+    return s
+
+
 def magnitude_init(weight, init_sparsity, threshold):
     """MaskedLinearX.controlled_init._magnitude -- masking/maskers.py:204-215:
     S = 2*thr where |W| > kthvalue(|W|, int(n*sparsity)) else 0*thr."""

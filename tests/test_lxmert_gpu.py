@@ -316,3 +316,50 @@ def test_visualbert_stage2_trainer_runs(tmp_path):
     for n, m in mods:                                               # thresholds refreshed at step 3 (logging_steps)
         k = max(1, int(m.weight.nelement() * 0.7))
         assert float(m.threshold) == float(o.kth_value(m.weight_mask.detach().cpu(), k)), n
+
+
+def test_global_threshold_variant_on_gpu():
+    """masking.global_maskers.Masker (one magnitude cut over all masked weights) and the union reset_threshold of
+    hg_transformers.global_mask_trainer_VQA against the reference's outputs (tests/golden/global_tiny.pt): bit-exact
+    cut, kept counts and thresholds."""
+    import logging
+    import types
+    from hg_transformers import global_mask_trainer_VQA as gt
+    from hg_transformers.modeling_lxmert import LxmertConfig, LxmertForMultipleChoice
+    from masking import global_maskers as gm
+    from masking.sparsity_control import MaskerScheduler
+    g = torch.load(os.path.join(GOLD, "global_tiny.pt"), weights_only=False)
+    tiny = torch.load(os.path.join(GOLD, "tiny_lxmert.pt"), weights_only=False)
+    model = LxmertForMultipleChoice(LxmertConfig(**tiny["config"]))
+    model.load_state_dict(tiny["state_dict"])
+    model.cuda()
+    conf = types.SimpleNamespace(
+        masking_scheduler_conf_={"lambdas_lr": 0.0, "sparsity_warmup": "automated_gradual_sparsity",
+                                 "sparsity_warmup_interval_epoch": 0.1, "init_epoch": 0.0, "final_epoch": 1.0,
+                                 "final_sparsity": 0.7},
+        logger=logging.getLogger("t"), num_epochs=20)
+    masker = gm.Masker(masker_scheduler=MaskerScheduler(conf), logger=logging.getLogger("t"), mask_biases=False,
+                       structured_masking_info={"structured_masking": None, "structured_masking_types": None,
+                                                "force_masking": "bert"},
+                       threshold=1e-2, init_scale=2e-2, which_ptl="lxmert", controlled_init="magnitude")
+    assert masker.global_prune is True
+    from oracle.lxmert_oracle import LXMERT_WEIGHT_TYPES
+    names = gm.chain_module_names("lxmert", list(range(12)), LXMERT_WEIGHT_TYPES)
+    masker.patch_modules(model=model, names_tobe_masked=names, name_of_masker="MaskedLinear1")
+    mods = [(n, m) for n, m in model.named_modules() if hasattr(m, "threshold")]
+    assert [n for n, _ in mods] == g["module_names"]
+    assert float(masker.global_threshold) == float(g["global_weight_threshold"])
+    assert {n: int((m.weight_mask.detach() > 1e-2).sum()) for n, m in mods} == g["kept_init"]
+    gen = torch.Generator().manual_seed(g["noise_seed"])
+    for n, m in mods:
+        m.weight_mask.data.add_((torch.randn(m.weight_mask.shape, generator=gen) * 5e-3).cuda())
+    tr = gt.Trainer.__new__(gt.Trainer)
+    tr.model_args = types.SimpleNamespace(global_prune=True)
+    tr.masker = masker
+    for rate in (0.7, 0.35):
+        mean_thr = tr.reset_threshold(model, rate)
+        assert mean_thr == g[f"union_threshold_{rate}"]
+        assert {n: int((m.weight_mask.detach() > m.threshold).sum()) for n, m in mods} == g[f"kept_after_{rate}"]
+    tr.model_args = types.SimpleNamespace(global_prune=False)
+    with pytest.raises(AssertionError):
+        tr.reset_threshold(model, 0.7)

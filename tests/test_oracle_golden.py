@@ -207,3 +207,24 @@ def test_full_lxmert_config1_matches_reference_and_survey_known_answers():
     assert int((out["grads"][0] != 0).sum()) == 486912              # embedding dS nnz, SURVEY 8(c)
     lpf = lxo.compute_loss("lpf", out["logits"], out["pooled"], batch)
     assert abs(float(lpf) - 7.543721) < 1e-4
+
+
+def test_global_threshold_variant_matches_reference(tiny_gold):
+    """masking/global_maskers.py + global_mask_trainer_VQA.py on the tiny LXMERT (tests/golden/global_tiny.pt)."""
+    g = torch.load(os.path.join(GOLD, "global_tiny.pt"), weights_only=False)
+    sd = tiny_gold["state_dict"]
+    names = g["module_names"]
+    ws = [sd[n + ".weight"] for n in names]
+    total = sum(w.numel() for w in ws)
+    cut = o_ops.global_kth_value(ws, int(total * g["init_sparsity"]), use_abs=True)
+    assert same_value(cut, g["global_weight_threshold"])
+    scores = {n: o_ops.magnitude_init_global(w, cut, 1e-2) for n, w in zip(names, ws)}
+    assert {n: int((s > 1e-2).sum()) for n, s in scores.items()} == g["kept_init"]
+    gen = torch.Generator().manual_seed(g["noise_seed"])
+    for n in names:
+        scores[n] = scores[n] + torch.randn(scores[n].shape, generator=gen) * 5e-3
+    for rate in (0.7, 0.35):
+        thr = o_ops.global_kth_value(list(scores.values()), int(total * rate))
+        # the reference returns float(torch.tensor([thr] * n_modules).mean()): fp32 mean of identical values
+        assert float(torch.tensor([float(thr)] * len(names)).mean()) == g[f"union_threshold_{rate}"]
+        assert {n: int((s > float(thr)).sum()) for n, s in scores.items()} == g[f"kept_after_{rate}"]
