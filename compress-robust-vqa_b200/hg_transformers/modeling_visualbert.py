@@ -53,7 +53,7 @@ class VisualBertSelfAttention(nn.Module):
         h = config.hidden_size
         self.num_attention_heads = config.num_attention_heads
         self.attention_head_size = h // config.num_attention_heads
-        self.all_head_size = h
+        self.all_head_size = self.head_size = h
         self.query, self.key, self.value = nn.Linear(h, h), nn.Linear(h, h), nn.Linear(h, h)
         self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
 
@@ -131,9 +131,38 @@ class VisualBertEncoder(nn.Module):
         self.layer = nn.ModuleList([VisualBertLayer(config) for _ in range(config.num_hidden_layers)])
 
     def forward(self, hidden_states, attention_mask=None):
+        fast = self._fast_plans() if hidden_states.is_cuda else None
+        if fast is not None:
+            # engine fast path (crvqa.fused), the same building blocks as LXMERT's single-modality layers: grouped QKV
+            # GEMM, small-sequence attention (20 tokens + 36 regions = 56 <= 64), fused dropout+residual+LayerNorm, GELU
+            x32, x16 = hidden_states, hidden_states.to(torch.bfloat16)
+            for att, ffn in fast:
+                a32, a16 = att.self_attention(x32, x16, attention_mask, self.training)
+                x32, x16 = ffn(a32, a16, self.training)
+            return x32
         for blk in self.layer:
             hidden_states = blk(hidden_states, attention_mask)
         return hidden_states
+
+    def _fast_plans(self):
+        """Layer plans when every masked module of the stack sits in a ScoreArena with a valid mask cache (stage-2
+        training engine); None selects the generic per-module path (also with CRVQA_FUSED=0)."""
+        import os
+        if os.environ.get("CRVQA_FUSED", "1") == "0":
+            return None
+        from crvqa import fused
+        plans = getattr(self, "_plans", None)
+        if plans is None:
+            plans = [(fused.AttentionPlan(b.attention.self, b.attention.output), fused.FfnPlan(b.intermediate, b.output))
+                     for b in self.layer]
+            self._plans = plans
+        try:
+            for att, ffn in plans:
+                if not (att.ready() and ffn.ready()):
+                    return None
+        except AttributeError:      # modules are not MaskedLinear1 (model not patched)
+            return None
+        return plans
 
 
 class VisualBertPooler(nn.Module):

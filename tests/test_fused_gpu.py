@@ -237,3 +237,66 @@ def test_small_attention_dropout_forward_and_backward_use_one_mask(Sq, Sk):
     for t, r in zip(srcs, (qr, kr, vr)):
         rel = float((t.grad.float() - r.grad).norm() / r.grad.norm())
         assert rel < 2e-2, rel
+
+
+def test_visualbert_fast_path_matches_generic_path():
+    """VisualBERT (BASELINE config 3 in miniature, 20 + 36 = 56 tokens): fused fast path vs generic per-module path on
+    the same scores, dropout off -- logits, loss and every score gradient."""
+    import logging
+    import os
+    import types
+    from crvqa import ops
+    from hg_transformers._engine import ScoreArena, masked_modules_of
+    from hg_transformers.modeling_visualbert import VisualBertForMultipleChoice, visualBERTConfig
+    from masking import maskers_visualBert as mk
+    from masking import sparsity_control as spc
+    torch.manual_seed(7)
+    cfg = visualBERTConfig(vocab_size=1000, hidden_size=256, num_hidden_layers=3, num_attention_heads=4,
+                           intermediate_size=512, visual_embedding_dim=128, ans_num=96, max_position_embeddings=64)
+    model = VisualBertForMultipleChoice(cfg).cuda()
+    conf = types.SimpleNamespace(masking_scheduler_conf_={"final_sparsity": 0.7, "sparsity_warmup_interval_epoch": 0.1,
+                                                          "lambdas_lr": 0.0, "init_epoch": 0, "final_epoch": 1},
+                                 logger=logging.getLogger("vb"), num_epochs=1)
+    log = logging.getLogger("vb"); log.setLevel(logging.ERROR)
+    masker = mk.Masker(masker_scheduler=spc.MaskerScheduler(conf), logger=log, mask_biases=False,
+                       structured_masking_info={"structured_masking": None, "structured_masking_types": None,
+                                                "force_masking": "bert"},
+                       threshold=1e-2, init_scale=2e-2, which_ptl="visual_bert", controlled_init="magnitude")
+    masker.patch_modules(model, mk.chain_module_names("visual_bert", list(range(12)), ["K", "Q", "V", "AO", "I", "O", "P", "E"]),
+                         "MaskedLinear1")
+    model.eval()
+    B, T, R = 16, 20, 36
+    ids = torch.randint(1, 1000, (B, T), device="cuda")
+    feats = torch.randn(B, R, 128, device="cuda")
+    target = (torch.rand(B, 96, device="cuda") > 0.97).float()
+
+    def run(zero=True):
+        if zero:
+            model.zero_grad()
+        out = model(input_ids=ids, visual_embeds=feats, labels=target)
+        logits = out[1]
+        loss, _ = ops.vqa_loss_bce(logits, target)
+        loss.backward()
+        return logits.detach().clone(), float(loss.detach())
+
+    lg0, l0 = run()
+    mods = masked_modules_of(model)
+    plain = {n: (m.weight_mask.grad.clone() if m.weight_mask.grad is not None else None) for n, m in mods}
+    arena = ScoreArena(mods)
+    arena.enable_mask_cache()
+    assert model.visual_bert.encoder._fast_plans() is not None
+    arena.begin_step()
+    lg1, l1 = run(zero=False)
+    arena.finalize_grads()
+    assert float((lg1 - lg0).abs().max() / lg0.abs().max()) < 2e-2      # bf16 intermediates vs fp32 ones
+    assert abs(l1 - l0) <= 1e-3 * abs(l0)
+    for n, m in mods:
+        if plain[n] is None:
+            continue
+        rel = float((m.weight_mask.grad - plain[n]).double().norm() / (plain[n].double().norm() + 1e-30))
+        assert rel < 8e-2, (n, rel)
+    os.environ["CRVQA_FUSED"] = "0"
+    try:
+        assert model.visual_bert.encoder._fast_plans() is None
+    finally:
+        os.environ.pop("CRVQA_FUSED")
