@@ -36,9 +36,11 @@ g = torch.Generator(device='cuda').manual_seed(1)
 scores = [torch.where(torch.rand(s, device=dev, generator=g) < 0.7, 0.0, 0.02) + torch.randn(s, device=dev, generator=g) * 3e-3 for s in shapes]
 n_total = sum(s.numel() for s in scores)
 ks = [max(1, int(s.numel() * 0.7)) for s in scores]
-rec('kth_value_batched (168 seg)', timeit(lambda: ops.kth_value_batched(scores, ks)), 4 * n_total, f'{n_total} floats, exact radix select, 3 passes')
+plan = ops.KthPlan(scores)   # what Trainer.reset_threshold holds on to: pointers + workspace, ranks marshalled per call
+rec('kth_value_batched (168 seg)', timeit(lambda: plan(ks)), 4 * n_total, f'{n_total} floats, exact: sample -> one filter pass -> select of ~3 % candidates (host enqueue of 16 launches included)')
 init = [torch.where(torch.rand(s, device=dev, generator=g) < 0.7, 0.0, 0.02) for s in shapes]
-rec('kth_value_batched (ties)', timeit(lambda: ops.kth_value_batched(init, ks)), 4 * n_total, 'scores exactly {0, 0.02} (state before the first optimiser step)')
+plan_t = ops.KthPlan(init)
+rec('kth_value_batched (ties)', timeit(lambda: plan_t(ks)), 4 * n_total, 'scores exactly {0, 0.02} (state before the first optimiser step)')
 big = torch.cat([s.reshape(-1) for s in scores])
 rec('kth_value (1 x 207M)', timeit(lambda: ops.kth_value_batched([big], [int(big.numel() * 0.7)])), 4 * n_total, 'global-threshold variant: one segment')
 # --- losses, B=256, A=3129
