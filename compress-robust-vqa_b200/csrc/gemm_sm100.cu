@@ -451,12 +451,13 @@ struct Smem2 {
   static constexpr int kB = 128 * BK * 2;       // 16 KB: this CTA's half of the 256 B columns
   static constexpr int kStage = kA + kB;
   static constexpr int kStages = 6;
-  static constexpr int kEpi = 4 * 2 * 4096;
+  static constexpr int kEpiWarps = 8;            // two per TMEM lane quadrant: each drains 32 rows x 128 columns
+  static constexpr int kEpi = kEpiWarps * 4096;  // one 4 KB staging buffer per epilogue warp
   static constexpr int kTotal = kStages * kStage + kEpi + 256 + 1024;
 };
 
 template <bool A_MN, bool B_MN, int EPI, bool OUT_BF16>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(64 + 32 * Smem2::kEpiWarps, 1)
 masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const GemmParams p) {
   using L = Smem2;
@@ -489,7 +490,7 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 8);
+      mbar_init(&tmem_empty_bar[a], 2 * L::kEpiWarps);   // every epilogue warp of both CTAs
     }
     fence_mbar_init();
   }
@@ -570,10 +571,12 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
-    const int q = warp & 3;
-    uint8_t* stage_buf = epi_base + (warp - 2) * 8192;
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;       // which 128 of the tile's 256 columns
+    uint8_t* buf = epi_base + (warp - 2) * 4096;
     constexpr int COLS = OUT_BF16 ? 64 : 32;
-    int tcount = 0, chunk_no = 0;
+    constexpr int HALF_N = BN / 2;
+    int tcount = 0;
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tcount) {
       const TileCoord tc = tile_coord(p, tile, BN);
       const int acc = tcount & 1;
@@ -583,8 +586,9 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / COLS; ++c, ++chunk_no) {
-        const int nb = tc.n0 + c * COLS;
+      for (int c = 0; c < HALF_N / COLS; ++c) {
+        const int col0 = half * HALF_N + c * COLS;
+        const int nb = tc.n0 + col0;
         uint32_t r[32];
         uint32_t pk[32];
         float bias_lo = 0.f, bias_hi = 0.f;
@@ -592,10 +596,10 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (nb + lane < p.NN) bias_lo = __ldg(p.bias + nb + lane);
           if (OUT_BF16 && nb + 32 + lane < p.NN) bias_hi = __ldg(p.bias + nb + 32 + lane);
         }
-        tmem_ld_32x32(t_addr + c * COLS, r);
+        tmem_ld_32x32(t_addr + col0, r);
         if (OUT_BF16) {
           uint32_t r2[32];
-          tmem_ld_32x32(t_addr + c * COLS + 32, r2);
+          tmem_ld_32x32(t_addr + col0 + 32, r2);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -637,8 +641,7 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
-        uint8_t* buf = stage_buf + (chunk_no & 1) * 4096;
-        if (lane == 0) bulk_wait_read<1>();
+        if (lane == 0) bulk_wait_read<0>();     // the previous chunk's TMA store has read the staging buffer
         __syncwarp();
         const int sw = lane & 7;
 #pragma unroll
@@ -752,7 +755,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(64 + 32 * Smem2::kEpiWarps);
   cfg.dynamicSmemBytes = Smem2::kTotal;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
