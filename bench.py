@@ -216,8 +216,13 @@ def run_ours(args):
     # operands, same order), re-issue them back to back as one CUDA graph and time the replays with CUDA events
     c0 = lib.crv_launch_count()
     ops.RECORD = []
+    # this one eager step is also the cudaProfilerStart/Stop range: `ncu --profile-from-start off ... bench.py` lists
+    # exactly the launches of one training step (same kernels the graph replays) and nothing else
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
     one_step(dev_inputs, force_eager=True)
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     record, ops.RECORD = ops.RECORD, None
     if graphed is not None:
         launches = (lib.crv_launch_count() - c0) * args.steps  # replays launch from the graph, not from Python
