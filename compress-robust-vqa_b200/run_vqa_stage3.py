@@ -12,6 +12,7 @@ with ``training_type`` in {FT_trainedMask, FT_randMask} and no masker; dataset /
 reference driver is out of scope.
 """
 import torch
+from torch.optim._functional import adam as _adam_functional
 
 from hg_transformers.optimization import get_linear_schedule_with_warmup
 from masking.pruned import PrunedEmbedding, PrunedLinear, custom_from_mask, l1_unstructured_mask
@@ -65,13 +66,48 @@ def see_weight_rate(model, model_type):
     return 100 * zeros / total
 
 
+class GroupedAdam(torch.optim.Adam):
+    """torch.optim.Adam whose step() updates every parameter group with the same hyper-parameters in ONE fused
+    multi-tensor call.  The reference builds one group per tensor (~500 groups); stepped group by group, each launch
+    covers a single small tensor with a few dozen CTAs (measured: 15 ms for 6 GB of optimiser traffic).  The update
+    rule, the state layout (`exp_avg`, `exp_avg_sq`, `step`) and `param_groups` are torch.optim.Adam's."""
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        buckets = {}
+        for group in self.param_groups:
+            key = (group["lr"] if not torch.is_tensor(group["lr"]) else id(group["lr"]), group["betas"], group["eps"],
+                   group["weight_decay"], group["amsgrad"], group["maximize"], group.get("decoupled_weight_decay", False))
+            b = buckets.setdefault(key, (group, [], [], [], [], [], []))
+            self._init_group(group, b[1], b[2], b[3], b[4], b[5], b[6])
+        for group, params, grads, exp_avgs, exp_avg_sqs, max_sqs, steps in buckets.values():
+            if not params:
+                continue
+            beta1, beta2 = group["betas"]
+            _adam_functional(params, grads, exp_avgs, exp_avg_sqs, max_sqs, steps, amsgrad=group["amsgrad"],
+                                  has_complex=False, beta1=beta1, beta2=beta2, lr=group["lr"],
+                                  weight_decay=group["weight_decay"], eps=group["eps"], maximize=group["maximize"],
+                                  foreach=group["foreach"], capturable=group["capturable"],
+                                  differentiable=group["differentiable"], fused=group["fused"],
+                                  grad_scale=getattr(self, "grad_scale", None), found_inf=getattr(self, "found_inf", None),
+                                  decoupled_weight_decay=group.get("decoupled_weight_decay", False))
+        return loss
+
+
 def init_optimizer(model, training_args, num_train_data):
     """torch.optim.Adam with one param group per tensor + linear schedule (:577-598)."""
     params = [{"params": [value], "name": key, "weight_decay": training_args.weight_decay,
                "param_size": value.size(), "nelement": value.nelement(), "lr": training_args.learning_rate}
               for key, value in model.named_parameters() if value.requires_grad]
-    optimizer = torch.optim.Adam(params, lr=training_args.learning_rate, betas=(0.9, 0.999),
-                                 eps=training_args.adam_epsilon)
+    # same update rule as the reference's torch.optim.Adam(params, lr, betas, eps): fused implementation on CUDA, and
+    # all groups stepped by one multi-tensor call (GroupedAdam)
+    on_cuda = all(g["params"][0].is_cuda for g in params) and len(params) > 0
+    optimizer = GroupedAdam(params, lr=training_args.learning_rate, betas=(0.9, 0.999),
+                            eps=training_args.adam_epsilon, **({"fused": True} if on_cuda else {}))
     num_training_steps = int(int(num_train_data / (max(1, training_args.n_gpu) * training_args.per_gpu_train_batch_size) + 1)
                              * training_args.num_train_epochs)
     scheduler = get_linear_schedule_with_warmup(optimizer, num_warmup_steps=training_args.warmup_steps,
@@ -79,5 +115,5 @@ def init_optimizer(model, training_args, num_train_data):
     return optimizer, scheduler
 
 
-__all__ = ["PrunedLinear", "PrunedEmbedding", "pruning_model_with_mask", "mag_pruning", "see_weight_rate",
+__all__ = ["GroupedAdam", "PrunedLinear", "PrunedEmbedding", "pruning_model_with_mask", "mag_pruning", "see_weight_rate",
            "init_optimizer", "trained_mask_module_names"]

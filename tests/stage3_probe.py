@@ -38,3 +38,17 @@ t0 = time.perf_counter(); e0.record()
 for _ in range(n): loss = step()
 e1.record(); torch.cuda.synchronize(); t1 = time.perf_counter()
 print(f'stage3 B={B}: {e0.elapsed_time(e1)/n:.1f} ms/step (device), {(t1-t0)*1e3/n:.1f} ms/step (wall), {B*n/(t1-t0):.0f} samples/s, loss {float(loss):.4f}')
+if os.environ.get('PROFILE'):
+    import collections, re
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        step(); torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            name = re.sub(r'<.*', '', ev.name)[:70]
+            agg[name][0] += 1; agg[name][1] += ev.device_time if hasattr(ev, 'device_time') else ev.cuda_time
+    tot = sum(v[1] for v in agg.values())
+    print('total kernel us', tot)
+    for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:25]:
+        print(f'{t:9.1f} us {100*t/tot:5.1f}% n={c:4d} avg={t/c:7.1f} {k}')

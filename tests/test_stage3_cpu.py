@@ -144,3 +144,25 @@ def test_driver_functions_need_no_kernel_for_given_masks(gold):
     torch.testing.assert_close(q.weight, q.weight_orig * q.weight_mask)
     with pytest.raises(RuntimeError):
         q(torch.zeros(2, 768))                                   # no CPU fallback
+
+
+def test_grouped_adam_is_torch_adam():
+    """run_vqa_stage3.init_optimizer's GroupedAdam steps all one-tensor groups with one multi-tensor call: same
+    numbers, state and schedule behaviour as torch.optim.Adam built the reference's way."""
+    import run_vqa_stage3 as s3
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(s)) for s in [(5, 3), (7,), (2, 2, 2)]]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    a = torch.optim.Adam([{"params": [p], "name": str(i)} for i, p in enumerate(ps)], lr=1e-3, eps=1e-8)
+    b = s3.GroupedAdam([{"params": [p], "name": str(i)} for i, p in enumerate(qs)], lr=1e-3, eps=1e-8)
+    sa = torch.optim.lr_scheduler.LambdaLR(a, lambda s: 1 - s / 10)
+    sb = torch.optim.lr_scheduler.LambdaLR(b, lambda s: 1 - s / 10)
+    for _ in range(4):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p)
+            p.grad, q.grad = g.clone(), g.clone()
+        a.step(); b.step(); sa.step(); sb.step()
+    for p, q in zip(ps, qs):
+        assert torch.equal(p, q)
+        assert torch.equal(a.state[p]["exp_avg_sq"], b.state[q]["exp_avg_sq"])
+    assert [g["name"] for g in b.param_groups] == ["0", "1", "2"]
