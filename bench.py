@@ -196,6 +196,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     trainer._zero_grad(optimizer)
+    # The step graph is captured on the call after GraphedStep's own eager warm-up steps: do those (and the capture)
+    # before the W warm-up steps the caller asked for, so no --warmup value can put the capture in the timed region.
+    if graphed is not None:
+        while graphed.graph is None:
+            one_step(dev_inputs)
+        one_step(dev_inputs)
     for _ in range(args.warmup):
         one_step(dev_inputs)
     barrier()
