@@ -100,15 +100,23 @@ struct AttnSmem {
   static constexpr int kBwd = 4 * kTile + 3 * SP * 4;     // Q, K, V, dO + row max / row sum / D
 };
 
-// rows [0, S) of a [S][64] bf16 global tile -> smem [SP][72]; rows >= S zero-filled
+// rows [0, S) of a [S][64] bf16 global tile -> smem [SP][72]; rows >= S zero-filled.  cp.async (16 B, L2 only): all
+// of a thread's chunks are in flight at once and nothing is staged through registers -- with plain loads the
+// load -> st.shared pairs of the (not unrollable) loop ran one global round trip after the other.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int bytes = valid ? 16 : 0;      // 0 source bytes: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sptr(smem_dst)), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 template <int SP>
 __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, long long row_stride, int S,
                                           int tid, int nthreads) {
   for (int i = tid; i < SP * 8; i += nthreads) {
     const int r = i >> 3, c = i & 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < S) v = __ldg(reinterpret_cast<const uint4*>(src + r * row_stride) + c);
-    *reinterpret_cast<uint4*>(dst + r * kLdH + c * 8) = v;
+    const bool valid = r < S;
+    cp_async16(dst + r * kLdH + c * 8, src + (valid ? r : 0) * row_stride + c * 8, valid);
   }
 }
 
@@ -178,6 +186,7 @@ attn_fwd_kernel(const AttnParams p) {
     load_tile<SP>(sK, p.k + b * p.k_bs + h * kHeadDim, p.k_ss, p.Sk, tile * 32 + lane, KT2 * 32);
     load_tile<SP>(sV, p.v + b * p.v_bs + h * kHeadDim, p.v_ss, p.Sk, tile * 32 + lane, KT2 * 32);
   }
+  cp_async_wait_all();
   __syncthreads();
   const DropKey dk = make_key(p.rng_state, p.site, p.p_drop, pair, p.Sq, p.Sk);
   const __nv_bfloat16* qb = p.q + b * p.q_bs + h * kHeadDim;
@@ -285,6 +294,7 @@ attn_bwd_kernel(const AttnParams p) {
     load_tile<SP>(sV, p.v + b * p.v_bs + h * kHeadDim, p.v_ss, p.Sk, gt, KT2 * 32);
     load_tile<SP>(sdO, p.dout + static_cast<long long>(b) * p.Sq * HD + h * kHeadDim, HD, p.Sq, gt, KT2 * 32);
   }
+  cp_async_wait_all();
   __syncthreads();
   const DropKey dk = make_key(p.rng_state, p.site, p.p_drop, pair, p.Sq, p.Sk);
   const float* mrow = p.mask ? p.mask + static_cast<long long>(b) * p.Sk : nullptr;
