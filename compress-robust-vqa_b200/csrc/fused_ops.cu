@@ -74,7 +74,7 @@ __device__ __forceinline__ uint2 pack4(float4 v) {
 }
 
 template <int VEC>  // VEC = H / 128 float4 chunks per lane
-__global__ void __launch_bounds__(kRowsPerBlock * 32)
+__global__ void __launch_bounds__(kRowsPerBlock * 32, 2)
 ln_fwd_kernel(const void* __restrict__ g, int g_bf16, const float* __restrict__ res, const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, float p, const unsigned long long* __restrict__ rng_state,
               int site, float* __restrict__ y32, uint16_t* __restrict__ y16, float* __restrict__ mean_out,
@@ -84,18 +84,22 @@ ln_fwd_kernel(const void* __restrict__ g, int g_bf16, const float* __restrict__ 
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const Rng rng = make_rng(rng_state, site, p);
-  float4 z[VEC];
+  // every load of the row is issued before the first dependent instruction (the dropout hash between the loads
+  // made ptxas serialise them: one global round trip per chunk)
+  float4 z[VEC], rv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int64_t e = static_cast<int64_t>(row) * H + (i * 32 + lane) * 4;
+    z[i] = load4(g, g_bf16, e);
+    rv[i] = res ? __ldg(reinterpret_cast<const float4*>(res + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    const int col = (i * 32 + lane) * 4;
-    const int64_t e = static_cast<int64_t>(row) * H + col;
-    float4 gv = load4(g, g_bf16, e);
+    const int64_t e = static_cast<int64_t>(row) * H + (i * 32 + lane) * 4;
+    float4 gv = z[i];
     if (rng.thresh) rng.drop4(gv, e);
-    if (res) {
-      const float4 rv = __ldg(reinterpret_cast<const float4*>(res + e));
-      gv.x += rv.x; gv.y += rv.y; gv.z += rv.z; gv.w += rv.w;
-    }
+    gv.x += rv[i].x; gv.y += rv[i].y; gv.z += rv[i].z; gv.w += rv[i].w;
     z[i] = gv;
     s += gv.x + gv.y + gv.z + gv.w;
   }
@@ -126,7 +130,7 @@ ln_fwd_kernel(const void* __restrict__ g, int g_bf16, const float* __restrict__ 
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kRowsPerBlock * 32)
+__global__ void __launch_bounds__(kRowsPerBlock * 32, 2)
 ln_bwd_kernel(const float* __restrict__ dy32, const uint16_t* __restrict__ dy16, const void* __restrict__ g, int g_bf16,
               const float* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, float p, const unsigned long long* __restrict__ rng_state, int site,
@@ -137,25 +141,27 @@ ln_bwd_kernel(const float* __restrict__ dy32, const uint16_t* __restrict__ dy16,
   if (row >= M) return;
   const Rng rng = make_rng(rng_state, site, p);
   const float mean = mean_in[row], rstd = rstd_in[row];
-  float4 xh[VEC], dyg[VEC];
+  // all loads first (see ln_fwd_kernel)
+  float4 xh[VEC], dyg[VEC], rv[VEC], d2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int64_t e = static_cast<int64_t>(row) * H + (i * 32 + lane) * 4;
+    xh[i] = load4(g, g_bf16, e);
+    rv[i] = res ? __ldg(reinterpret_cast<const float4*>(res + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dyg[i] = dy32 ? __ldg(reinterpret_cast<const float4*>(dy32 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    d2[i] = dy16 ? load4(dy16, 1, e) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const int col = (i * 32 + lane) * 4;
     const int64_t e = static_cast<int64_t>(row) * H + col;
-    float4 gv = load4(g, g_bf16, e);
+    float4 gv = xh[i];
     if (rng.thresh) rng.drop4(gv, e);
-    if (res) {
-      const float4 rv = __ldg(reinterpret_cast<const float4*>(res + e));
-      gv.x += rv.x; gv.y += rv.y; gv.z += rv.z; gv.w += rv.w;
-    }
+    gv.x += rv[i].x; gv.y += rv[i].y; gv.z += rv[i].z; gv.w += rv[i].w;
     xh[i] = make_float4((gv.x - mean) * rstd, (gv.y - mean) * rstd, (gv.z - mean) * rstd, (gv.w - mean) * rstd);
-    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (dy32) d = __ldg(reinterpret_cast<const float4*>(dy32 + e));
-    if (dy16) {
-      const float4 d2 = load4(dy16, 1, e);
-      d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
-    }
+    float4 d = dyg[i];
+    d.x += d2[i].x; d.y += d2[i].y; d.z += d2[i].z; d.w += d2[i].w;
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + col));
     d.x *= ga.x; d.y *= ga.y; d.z *= ga.z; d.w *= ga.w;
     dyg[i] = d;
