@@ -618,13 +618,19 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 32; ++j)
             pk[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lo, j));
         } else {
-          tmem_ld_wait();
           const bool row_ok = m < p.MM;
           const __nv_bfloat16* wrow = p.w + static_cast<size_t>(row_ok ? m : 0) * p.NN + nb;
-          if (row_ok && nb + 32 <= p.NN && (p.NN & 7) == 0) {
+          const bool fast = row_ok && nb + 32 <= p.NN && (p.NN & 7) == 0;
+          uint4 wq[4];
+          if (fast) {      // the multiplier row is fetched while the TMEM load is in flight, not after it
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wq[j] = __ldg(reinterpret_cast<const uint4*>(wrow + 8 * j));
+          }
+          tmem_ld_wait();
+          if (fast) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wrow + j));
+              const uint4 wv = wq[j >> 3];
               const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
