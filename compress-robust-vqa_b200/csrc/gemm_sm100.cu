@@ -393,7 +393,7 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // 48 KB per 512 MMA cycles, which is what the L2 -> SM path sustains (measured ~62 B/cycle/SM: the
 // 1-CTA 128 x 256 kernel above needs 94 and runs its mainloop at 67 %).  The leader CTA's single thread
 // issues tcgen05.mma.cta_group::2 (M = 256); each CTA's TMEM holds its own 128 accumulator rows and its
-// own four epilogue warps drain them.  Barriers: both producers signal the LEADER's full barrier (2SM TMA
+// own eight epilogue warps (two per TMEM lane quadrant, 128 columns each) drain them.  Barriers: both producers signal the LEADER's full barrier (2SM TMA
 // with the peer bit cleared); the MMA commit multicasts to both CTAs' empty / tmem-full barriers; both
 // CTAs' epilogue warps arrive remotely on the leader's tmem-empty barrier.
 // ------------------------------------------------------------------------------------------------
