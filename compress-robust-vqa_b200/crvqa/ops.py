@@ -257,6 +257,8 @@ class _DsLane:
 
     def hold(self, *tensors):
         self.held.extend(tensors)
+        if len(self.held) > 4096:        # nobody joined for ~10 backward passes (arena gradients read without
+            self.join()                  # finalize_grads): join here rather than pin activations without bound
 
     def join(self):
         if self.open:
