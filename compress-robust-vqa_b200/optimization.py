@@ -6,7 +6,6 @@ replaced by ONE fused kernel per parameter tensor (crv_adamw_step), or one launc
 arena when the parameters are arena views (hg_transformers._engine.ScoreArena).  A clip coefficient
 prepared by the trainer (``set_clip``) is folded into the same pass, so clip_grad_norm_ never rewrites
 the gradients in HBM."""
-import math
 
 import torch
 from torch.optim import Optimizer

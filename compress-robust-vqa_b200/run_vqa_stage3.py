@@ -15,7 +15,7 @@ import torch
 from torch.optim._functional import adam as _adam_functional
 
 from hg_transformers.optimization import get_linear_schedule_with_warmup
-from masking.pruned import PrunedEmbedding, PrunedLinear, custom_from_mask, l1_unstructured_mask
+from masking.pruned import PrunedEmbedding, PrunedLinear, custom_from_mask, l1_unstructured_mask  # noqa: F401 (re-exported)
 
 _ATT = ("attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense",
         "intermediate.dense", "output.dense")
