@@ -312,3 +312,23 @@ def test_execution_order_puts_the_vision_stack_first():
     vb = [("visual_bert.embeddings.word_embeddings", 0), ("visual_bert.encoder.layer.0.attention.self.query", 1),
           ("visual_bert.pooler.dense", 2)]
     assert execution_order(vb) == vb
+
+
+def test_secondary_debias_losses_match_reference():
+    """RUBI_loss and BiasProduct are plain torch graphs in the drop-in: same values and
+    logit gradients as the reference (tests/golden/secondary_losses.pt, make_golden_secondary_losses.py)."""
+    from hg_transformers._trainer_core import RUBI_loss
+    from hg_transformers.vqa_debias_loss_functions import BiasProduct
+    g = torch.load(os.path.join(GOLD, "secondary_losses.pt"), weights_only=False)
+    logits = g["logits"].clone().requires_grad_(True)
+    loss = RUBI_loss(logits, g["bias"], g["max_label"])
+    loss.backward()
+    torch.testing.assert_close(loss.detach(), g["rubi"], rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(logits.grad, g["rubi_dlogits"], rtol=1e-5, atol=1e-8)
+    logits.grad = None
+    bp = BiasProduct()
+    assert torch.equal(bp.smooth_param.detach(), g["bp_smooth_param"])
+    loss = bp(g["hidden"], logits, g["bias"], g["labels"])
+    loss.backward()
+    torch.testing.assert_close(loss.detach(), g["bp"], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(logits.grad, g["bp_dlogits"], rtol=1e-5, atol=1e-8)
