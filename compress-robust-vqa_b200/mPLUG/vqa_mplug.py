@@ -1,0 +1,128 @@
+"""Mask-training pieces of the reference's ``mPLUG/vqa_mplug.py``.
+
+Kept with the reference's names and semantics: ``load_mask_and_prune`` (:44-52), ``encode_maskconfig`` (:54-57),
+``init_masker`` (:59-128: scheduler wiring, the four towers' weight types / layers, ``_m`` twins), the mask-update
+block of the training loop (:202-210, here ``update_masks``) and ``train`` (:130-217) over batches that are already
+tokenised.  The reference driver itself needs DeepSpeed, the CLIP / BERT checkpoints and the VQA image datasets (none
+shipped); the engine of ``engine.py`` stands where the DeepSpeed engine stands.
+"""
+import logging
+import os
+
+import torch
+
+if __package__:                                     # imported as mPLUG.vqa_mplug (package root on sys.path)
+    from . import param_parser
+    from .masking import maskers
+    from .masking import sparsity_control as sp_control
+    from .masking.mask_config import MaskConfigs
+    from .masking.pruned import custom_from_mask
+else:                                               # the reference's layout: mPLUG/ itself is on sys.path
+    import param_parser
+    from masking import maskers
+    from masking import sparsity_control as sp_control
+    from masking.mask_config import MaskConfigs
+    from masking.pruned import custom_from_mask
+
+reset_threshold, save_model_mask, see_sparsity = maskers.reset_threshold, maskers.save_model_mask, maskers.see_sparsity
+
+# which Linear layers of which tower are masked (:105-116)
+WEIGHT_TYPES = {
+    "visual_encoder": ["I_visual", "O_visual"],
+    "text_encoder": ["K", "Q", "V", "AO", "I", "O"],
+    "fusion_encoder": ["SK", "SQ", "SV", "SAO", "CK", "CQ", "CV", "CAO", "I", "O"],
+    "text_decoder": ["SK", "SQ", "SV", "SAO", "CK", "CQ", "CV", "CAO", "I", "O"],
+}
+LAYERS_TO_MASK = {
+    "visual_encoder": list(range(12)),
+    "text_encoder": list(range(6)),
+    "fusion_encoder": list(range(6, 12)),
+    "text_decoder": list(range(12)),
+}
+
+
+def load_mask_and_prune(mask_dir, model):
+    """Freeze a saved mask into the network: every ``<module>.weight`` entry of mask.pt reparametrises that module as
+    ``weight_orig * weight_mask`` (the reference uses prune.CustomFromMask; same parameter / buffer names here)."""
+    print("Loading mask from %s" % mask_dir)
+    masks = torch.load(os.path.join(mask_dir, "mask.pt"))
+    for k, m in masks.items():
+        custom_from_mask(model, k.replace("module.", "").replace(".weight", ""), m.bool())
+    return model
+
+
+def encode_maskconfig(obj):
+    return obj.__dict__ if isinstance(obj, MaskConfigs) else obj
+
+
+def names_to_mask(conf, weight_types=None, layers_to_mask=None):
+    weight_types = WEIGHT_TYPES if weight_types is None else weight_types
+    layers_to_mask = LAYERS_TO_MASK if layers_to_mask is None else layers_to_mask
+    names = set()
+    for tower, abbres in weight_types.items():
+        names.update(maskers.chain_module_names(tower, layers_to_mask[tower], abbres))
+    if conf.mask_classifier:
+        names.add("text_decoder_m.cls.predictions.transform.dense")
+    return names
+
+
+def init_masker(conf, model, weight_types=None, layers_to_mask=None):
+    """Build the scheduler and the masker from a MaskConfigs and patch ``model`` in place.  ``weight_types`` /
+    ``layers_to_mask`` default to the reference's tables (they are literals inside the reference function)."""
+    mask_logger = logging.getLogger(__name__)
+    conf.masking_scheduler_conf_ = (param_parser.dict_parser(conf.masking_scheduler_conf)
+                                    if conf.masking_scheduler_conf is not None else None)
+    conf.masking_scheduler_conf_["final_sparsity"] = conf.zero_rate
+    conf.masking_scheduler_conf_["final_epoch"] = conf.final_sparsity_epoch
+    if conf.init_sparsity is not None:
+        conf.masking_scheduler_conf_["init_sparsity"] = conf.init_sparsity
+    if conf.masking_scheduler_conf is not None:
+        for k, v in conf.masking_scheduler_conf_.items():
+            setattr(conf, f"masking_scheduler_{k}", v)
+    conf.logger = mask_logger
+    masker_scheduler = sp_control.MaskerScheduler(conf)
+
+    assert not (conf.train_classifier and conf.mask_classifier), \
+        "If the classifier is masked, don't train its weights!"
+    masker = maskers.Masker(
+        masker_scheduler=masker_scheduler, logger=mask_logger, mask_biases=conf.mask_biases,
+        structured_masking_info={"structured_masking": conf.structured_masking,
+                                 "structured_masking_types": conf.structured_masking_types,
+                                 "force_masking": conf.force_masking},
+        threshold=conf.threshold, init_scale=conf.init_scale, controlled_init=conf.controlled_init,
+        train_classifier=conf.train_classifier, global_prune=conf.global_prune)
+    masker.patch_modules(model=model, names_tobe_masked=names_to_mask(conf, weight_types, layers_to_mask),
+                         name_of_masker=conf.name_of_masker)
+    return masker
+
+
+def update_masks(model, masker, epoch, output_dir=None):
+    """The block the reference runs every ``masker_update_step`` optimiser steps (:202-210): advance the sparsity
+    schedule, refresh every threshold for the new target, export the masks, report the sparsity."""
+    _, target_sparsity, _ = masker.masker_scheduler.step(cur_epoch=epoch)
+    mean_thresh = reset_threshold(model, target_sparsity)
+    save_model_mask(model, is_save=False)
+    if output_dir is not None:
+        save_model_mask(model, is_save=True, output_dir=output_dir)
+    print({"mean_thresh": mean_thresh})
+    see_sparsity(model)
+    return mean_thresh, target_sparsity
+
+
+def train(model, data_loader, epoch, masker=None, masker_update_step=5, output_dir=None, log=None):
+    """One epoch of the reference loop (:130-217) on an engine (``engine.MaskTrainEngine``): every batch is the tuple
+    of positional arguments of ``model(...)`` and yields the loss; forward -> backward -> step, and the mask update
+    whenever ``global_steps`` is a multiple of ``masker_update_step``.  Returns the mean loss."""
+    model.train()
+    total, count = None, 0
+    for batch in data_loader:
+        loss = model(*batch)
+        model.backward(loss)
+        model.step()
+        total = loss.detach() if total is None else total + loss.detach()
+        count += 1
+        if masker is not None and model.global_steps % masker_update_step == 0:
+            update_masks(model, masker, epoch, output_dir)
+        if log is not None:
+            log(model.global_steps, loss)
+    return float(total / count) if count else float("nan")

@@ -292,7 +292,8 @@ class MaskedLinearX(nn.Module):
             # the reference then dies in `None + tensor`; the scales are unused with a controlled init.
             return (0.0, 0.0)
         if scheme_idx == "MaskedLinear1":
-            return (-init_scale, (init_scale + float(self.threshold)) / init_sparsity - init_scale)
+            top = init_scale + float(self.threshold)   # the reference divides a tensor: sparsity 0 gives inf, no error
+            return (-init_scale, (top / init_sparsity if init_sparsity else math.copysign(math.inf, top)) - init_scale)
         if scheme_idx == "MaskedLinear2":
             warnings.warn(f"we cannot control the initial sparsity for {scheme_idx}.")
             return (-init_scale, init_scale)

@@ -1,0 +1,386 @@
+"""mPLUG masking path, CPU tier:
+
+* oracle/mplug_masking.py against the reference's outputs (tests/golden/mplug_skeleton.pt, make_golden_mplug.py);
+* the host logic of the drop-in ``mPLUG/masking/maskers.py`` / ``vqa_mplug.py`` / ``engine.py`` with the oracle
+  injected as a fake kernel backend (no CUDA compute runs here), against the same golden file;
+* the bf16-score comparison threshold as a brute-force property.
+"""
+import contextlib
+import hashlib
+import io
+import logging
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import mplug_skeleton as sk  # noqa: E402
+from oracle import masked_ops as o_ops  # noqa: E402
+from oracle import mplug_masking as om  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mplug_skeleton.pt")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLD, weights_only=False)
+
+
+def digest(tensors):
+    h = hashlib.sha256()
+    for k in sorted(tensors):
+        h.update(k.encode())
+        h.update(tensors[k].detach().cpu().float().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def masked(model):
+    return [(n, m) for n, m in model.named_modules() if hasattr(m, "threshold")]
+
+
+def thr_record(model):
+    rec = {}
+    for n, m in masked(model):
+        t = m.threshold
+        rec[n] = (float(t), str(t.dtype).replace("torch.", "") if torch.is_tensor(t) else type(t).__name__)
+    return rec
+
+
+def perturb(model, seed, scale):
+    g = torch.Generator().manual_seed(seed)
+    for _, m in masked(model):
+        m.weight_mask.data.add_((torch.randn(m.weight_mask.shape, generator=g) * scale).to(m.weight_mask.device))
+
+
+def kept(model):
+    return {n: int(m.get_masks()[0].sum()) for n, m in masked(model)}
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def fresh(gold):
+    model = sk.build(gold["skeleton_seed"])
+    assert digest(model.state_dict()) == gold["state_dict_sha256"], "skeleton weights differ from the golden run"
+    return model
+
+
+# ----------------------------------------------------------------------------- oracle vs reference
+def test_oracle_chain_module_names(gold):
+    abbr = {"visual_encoder": ["AO_visual", "I_visual", "O_visual", "AO", "I", "O", "E"],
+            "text_encoder": ["K", "Q", "V", "AO", "I", "O", "E"],
+            "fusion_encoder": ["SK", "SQ", "SV", "SAO", "CK", "CQ", "CV", "CAO", "I", "O", "E"],
+            "text_decoder": ["SK", "SQ", "SV", "SAO", "CK", "CQ", "CV", "CAO", "I", "O", "E"]}
+    for tower, ab in abbr.items():
+        assert sorted(om.chain_module_names(tower, list(range(3)), ab)) == gold["chain"][tower]
+
+
+def _oracle_train_state(model):
+    for p in model.parameters():
+        p.grad = None
+    model.train()
+    loss = model(*sk.batch())
+    loss.backward()
+    return float(loss.detach()), {n: m.weight_mask.grad for n, m in masked(model)}
+
+
+def test_oracle_variant_a_matches_reference(gold):
+    A = gold["A"]
+    model = fresh(gold)
+    names = sk.names_to_mask(om.chain_module_names)
+    assert sorted(names) == A["names_tobe_masked"]
+    om.patch(model, names, init_sparsity=A["init_sparsity"], controlled_init="magnitude_soft")
+    assert [n for n, _ in masked(model)] == A["module_names"]
+    assert sorted(n for n, p in model.named_parameters() if p.requires_grad) == A["trainable"]
+    assert thr_record(model) == A["init_thresholds"]
+    assert kept(model) == A["kept_init"]
+    for n, m in masked(model):      # Masker.init_masks: binarised against the MASKER's 1e-2, not the module's threshold
+        assert np.array_equal(om.packed(om.mask_of(m.weight_mask, 1e-2)), A["init_masks"][f"{n}_weight_mask"])
+    loss, grads = _oracle_train_state(model)
+    assert loss == pytest.approx(A["loss"], rel=1e-5)
+    for n, g in grads.items():
+        if A["grads"][n] is None:
+            assert g is None                    # attn.out_proj: nn.MultiheadAttention reads .weight, never calls it
+        else:
+            assert torch.allclose(g, A["grads"][n], rtol=1e-4, atol=1e-7), n
+    masks = [m.get_masks()[0] for _, m in masked(model)]
+    sizes = [(n, p.numel()) for n, p in model.named_parameters()]
+    assert round(om.see_sparsity(masks, sizes), 2) == A["start_see_sparsity"]
+    assert round(om.zero_rate(masks), 2) == A["start_zero_rate"]
+
+    perturb(model, *A["perturb"])
+    for r in A["resets"]:
+        mean = om.reset_threshold(model, r["rate"])
+        assert thr_record(model) == r["thresholds"]
+        assert kept(model) == r["kept"]
+        assert mean == r["mean"]
+    for n, m in masked(model):
+        assert np.array_equal(om.packed(m.get_masks()[0]), A["after_masks"][n + ".weight"])
+    before = thr_record(model)
+    om.reset_threshold(model, 1e-4)
+    assert (before == thr_record(model)) == A["tiny_rate_moves_nothing"]
+    loss, grads = _oracle_train_state(model)
+    assert loss == pytest.approx(A["after_train"]["loss"], rel=1e-5)
+    for n, g in grads.items():
+        want = A["after_train"]["grad_norms"][n]
+        assert (g is None) if want is None else float(g.norm()) == pytest.approx(want, rel=1e-4)
+
+    # (D) the same scores seen through a bf16 model copy
+    D = gold["D"]
+    assert digest({n: m.weight_mask for n, m in masked(model)}) == D["fp32_scores_sha256"]
+    assert thr_record(model) == D["fp32_thresholds"]
+    for _, m in masked(model):
+        m.score_dtype = torch.bfloat16
+    assert kept(model) == D["kept_before"]
+    for r in D["resets"]:
+        mean = om.reset_threshold(model, r["rate"])
+        assert thr_record(model) == r["thresholds"]
+        assert mean == r["mean"]
+        for n, m in masked(model):
+            assert np.array_equal(om.packed(m.get_masks()[0]), r["masks"][n]), n
+
+
+def test_oracle_ramp_and_global_variants_match_reference(gold):
+    from masking import sparsity_control as sp   # the drop-in's scheduler: pure host code
+    import types
+    B0 = gold["B0"]
+    model = fresh(gold)
+    names = sk.names_to_mask(om.chain_module_names)
+    om.patch(model, names, init_sparsity=0.0, controlled_init="magnitude_soft")
+    assert thr_record(model) == B0["init_thresholds"] and kept(model) == B0["kept_init"]
+    assert all(v == (0.0, "int") for v in B0["init_thresholds"].values())
+    assert B0["reset_at_zero"].startswith("RuntimeError")         # the reference cannot average a list of ints
+
+    B = gold["B"]
+    model = fresh(gold)
+    om.patch(model, names, init_sparsity=B["init_sparsity"], controlled_init="magnitude_soft")
+    conf = types.SimpleNamespace(
+        masking_scheduler_conf_={"lambdas_lr": 0.0, "sparsity_warmup": "automated_gradual_sparsity",
+                                 "sparsity_warmup_interval_epoch": 0.1, "init_epoch": 0.0, "final_epoch": 4,
+                                 "final_sparsity": 0.7, "init_sparsity": 0.1},
+        logger=logging.getLogger("t"))
+    sched = sp.MaskerScheduler(conf)
+    for r in B["ramp"]:
+        _, target, changed = sched.step(cur_epoch=r["epoch"])
+        assert target == r["target"] and changed == r["changed"]
+        mean = om.reset_threshold(model, target)
+        assert thr_record(model) == r["thresholds"] and kept(model) == r["kept"] and mean == r["mean"]
+    cs = B["constant_scores"]
+    mod = dict(masked(model))[cs["module"]]
+    mod.weight_mask.data.fill_(0.25)
+    om.reset_threshold(model, 0.5)
+    assert float(mod.threshold) == cs["threshold_after"] == cs["threshold_before"]
+
+    C = gold["C"]
+    model = fresh(gold)
+    cut = om.patch(model, names, init_sparsity=C["init_sparsity"], controlled_init="magnitude", global_prune=True)
+    assert cut == C["global_weight_threshold"]
+    assert kept(model) == C["kept_init"] and thr_record(model) == C["init_thresholds"]
+    loss, grads = _oracle_train_state(model)
+    assert loss == pytest.approx(C["loss"], rel=1e-5)
+    for n, g in grads.items():
+        want = C["grad_norms"][n]
+        assert (g is None) if want is None else float(g.norm()) == pytest.approx(want, rel=1e-4)
+    perturb(model, *C["perturb"])
+    for r in C["global_resets"]:
+        mean = om.reset_threshold(model, r["rate"], global_prune=True)
+        assert thr_record(model) == r["thresholds"] and kept(model) == r["kept"] and mean == r["mean"]
+
+
+# ----------------------------------------------------------------------------- bf16 comparison threshold
+def test_bf16_score_threshold_is_exact():
+    """bf16(S) > bf16(t)  <=>  S > T for every fp32 S, checked on dense neighbourhoods of both rounding boundaries."""
+    from mPLUG.masking.maskers import bf16_score_threshold
+    g = torch.Generator().manual_seed(0)
+    ts = torch.cat([torch.randn(400, generator=g) * 0.05, torch.randn(100, generator=g) * 30,
+                    torch.tensor([0.0, -0.0, 1e-2, 1.0, -1.0, 0.0078125, 0.00390625, 1e-40, -1e-40, 3e-39])])
+    T = bf16_score_threshold(ts)
+    assert T.dtype == torch.float32 and T.shape == ts.shape
+    offs = torch.cat([torch.arange(-70000, 70000, 13), torch.arange(-33000, -32500), torch.arange(32500, 33000),
+                      torch.arange(-4, 5)]).to(torch.int64)
+    for t, Ti in zip(ts, T):
+        t16 = t.to(torch.bfloat16)
+        base = int(t16.float().view(torch.int32))
+        key = (-(base & 0x7FFFFFFF) if base < 0 else base) + offs         # monotone integer image of fp32
+        bits = torch.where(key < 0, (-key) | 0x80000000, key)
+        bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+        S = bits.view(torch.float32)
+        S = S[torch.isfinite(S)]
+        assert torch.equal(S.to(torch.bfloat16) > t16, S > Ti), float(t)
+
+
+# ----------------------------------------------------------------------------- drop-in host logic, oracle as backend
+@pytest.fixture()
+def oracle_backend(monkeypatch):
+    from crvqa import ops
+
+    def kth(tensors, ks, use_abs=False):
+        return torch.tensor([float(o_ops.kth_value(t, int(k), use_abs=use_abs)) for t, k in zip(tensors, ks)])
+
+    def mag(weight, w_thr, hi, lo):
+        keep = weight.detach().abs() > float(w_thr)
+        return torch.where(keep, torch.full_like(weight, hi), torch.full_like(weight, lo))
+
+    def binz(scores, thr, want_count=False, as_bool=False):
+        m = o_ops.binarize(scores.detach(), float(thr))
+        out = m.bool() if as_bool else m
+        return (out, m.sum().long()) if want_count else out
+
+    monkeypatch.setattr(ops, "kth_value_batched", kth)
+    monkeypatch.setattr(ops, "magnitude_init", mag)
+    monkeypatch.setattr(ops, "binarize", binz)
+    monkeypatch.setattr(ops, "_stage", lambda t: t)
+    return ops
+
+
+def _conf(**over):
+    from mPLUG.masking.mask_config import MaskConfigs
+    conf = MaskConfigs()
+    for k, v in over.items():
+        setattr(conf, k, v)
+    return conf
+
+
+def _init(model, **over):
+    from mPLUG import vqa_mplug
+    return quiet(vqa_mplug.init_masker, _conf(**over), model, weight_types=sk.WEIGHT_TYPES,
+                 layers_to_mask=sk.LAYERS)
+
+
+def test_dropin_chain_names_and_config(gold):
+    from mPLUG.masking import maskers
+    from mPLUG.masking.mask_config import MaskConfigs
+    from mPLUG import vqa_mplug
+    for tower, names in gold["chain"].items():
+        ab = {"visual_encoder": ["AO_visual", "I_visual", "O_visual", "AO", "I", "O", "E"],
+              "text_encoder": ["K", "Q", "V", "AO", "I", "O", "E"]}.get(
+            tower, ["SK", "SQ", "SV", "SAO", "CK", "CQ", "CV", "CAO", "I", "O", "E"])
+        assert sorted(maskers.chain_module_names(tower, list(range(3)), ab)) == names
+    c = MaskConfigs()
+    assert (c.zero_rate, c.threshold, c.controlled_init, c.masker_update_step, c.train_classifier) == \
+        (0.5, 1e-2, "magnitude_soft", 100, True)
+    assert vqa_mplug.encode_maskconfig(c) is c.__dict__ and vqa_mplug.encode_maskconfig(3) == 3
+    full = vqa_mplug.names_to_mask(c)
+    # 12 x 2 ViT MLPs + 6 x 6 text + 6 x 10 fusion + 12 x 10 decoder, each with its _m twin
+    assert len(full) == 2 * (24 + 36 + 60 + 120)
+    c.mask_classifier = True
+    assert "text_decoder_m.cls.predictions.transform.dense" in vqa_mplug.names_to_mask(c)
+
+
+def test_dropin_masker_host_logic_variant_a(gold, oracle_backend):
+    from mPLUG.masking import maskers
+    A = gold["A"]
+    model = fresh(gold)
+    masker = _init(model, zero_rate=0.7)
+    assert sorted(masker.masker_scheduler.conf.masking_scheduler_conf_) == sorted(
+        ["lambdas_lr", "sparsity_warmup", "sparsity_warmup_interval_epoch", "init_epoch", "final_epoch",
+         "final_sparsity"])
+    assert [n for n, _ in masked(model)] == A["module_names"]
+    assert sorted(n for n, p in model.named_parameters() if p.requires_grad) == A["trainable"]
+    assert thr_record(model) == A["init_thresholds"]
+    assert kept(model) == A["kept_init"]
+    for n, m in masked(model):
+        assert np.array_equal(om.packed(masker.init_masks[f"{n}_weight_mask"]), A["init_masks"][f"{n}_weight_mask"])
+        assert m.weight is dict(model.named_parameters())[n + ".weight"] and not m.weight.requires_grad
+        assert isinstance(m, maskers.MaskedLinear1)
+    assert round(quiet(maskers.see_sparsity, model), 2) == A["start_see_sparsity"]
+    assert round(quiet(maskers.save_model_mask, model, is_save=False), 2) == A["start_zero_rate"]
+
+    perturb(model, *A["perturb"])
+    for r in A["resets"]:
+        mean = maskers.reset_threshold(model, r["rate"])
+        assert thr_record(model) == r["thresholds"]
+        assert kept(model) == r["kept"]
+        assert mean == r["mean"]
+    before = thr_record(model)
+    maskers.reset_threshold(model, 1e-4)
+    assert before == thr_record(model)
+
+    # bf16 score mode: fp32 master scores, masks and thresholds of the reference's bf16 model copy
+    D = gold["D"]
+    maskers.set_score_dtype(model, torch.bfloat16)
+    assert kept(model) == D["kept_before"]
+    for r in D["resets"]:
+        mean = maskers.reset_threshold(model, r["rate"])
+        assert thr_record(model) == r["thresholds"]
+        assert mean == r["mean"]
+        for n, m in masked(model):
+            assert np.array_equal(om.packed(m.get_masks()[0]), r["masks"][n]), n
+
+
+def test_dropin_masker_host_logic_ramp_global_and_export(gold, oracle_backend, tmp_path):
+    from mPLUG import vqa_mplug
+    from mPLUG.masking import maskers
+    B0 = gold["B0"]
+    model = fresh(gold)
+    _init(model, zero_rate=0.7, init_sparsity=0.0, final_sparsity_epoch=4)
+    assert thr_record(model) == B0["init_thresholds"] and kept(model) == B0["kept_init"]
+    assert maskers.reset_threshold(model, 0.0) == 0.0   # documented difference: the reference raises here
+
+    B = gold["B"]
+    model = fresh(gold)
+    masker = _init(model, zero_rate=0.7, init_sparsity=0.1, final_sparsity_epoch=4)
+    out_dir = str(tmp_path / "masks")
+    for r in B["ramp"]:
+        mean, target = quiet(vqa_mplug.update_masks, model, masker, r["epoch"], out_dir)
+        assert target == r["target"] and mean == r["mean"]
+        assert thr_record(model) == r["thresholds"] and kept(model) == r["kept"]
+    saved = torch.load(os.path.join(out_dir, "mask.pt"))
+    assert sorted(saved) == sorted(n + ".weight" for n, _ in masked(model))
+    for n, m in masked(model):
+        assert saved[n + ".weight"].dtype == torch.float32 and torch.equal(saved[n + ".weight"], m.get_masks()[0])
+    cs = B["constant_scores"]
+    mod = dict(masked(model))[cs["module"]]
+    mod.weight_mask.data.fill_(0.25)
+    maskers.reset_threshold(model, 0.5)
+    assert float(mod.threshold) == cs["threshold_after"]
+
+    C = gold["C"]
+    model = fresh(gold)
+    masker = _init(model, zero_rate=0.6, init_sparsity=0.5, controlled_init="magnitude", global_prune=True)
+    assert float(masker.global_threshold) == C["global_weight_threshold"]
+    assert kept(model) == C["kept_init"] and thr_record(model) == C["init_thresholds"]
+    perturb(model, *C["perturb"])
+    for r in C["global_resets"]:
+        mean = maskers.reset_threshold(model, r["rate"], global_prune=True)
+        assert thr_record(model) == r["thresholds"] and kept(model) == r["kept"] and mean == r["mean"]
+
+
+def test_load_mask_and_prune_reparametrises_the_named_modules(gold, oracle_backend, tmp_path):
+    from mPLUG import vqa_mplug
+    from mPLUG.masking.pruned import PrunedLinear   # the shared module, as this package sees it
+    model = fresh(gold)
+    g = torch.Generator().manual_seed(1)
+    target = "text_encoder.encoder.layer.0.intermediate.dense"
+    mask = (torch.rand(model.text_encoder.encoder.layer[0].intermediate.dense.weight.shape, generator=g) > 0.5).float()
+    torch.save({"module." + target + ".weight": mask}, tmp_path / "mask.pt")
+    quiet(vqa_mplug.load_mask_and_prune, str(tmp_path), model)
+    mod = model.text_encoder.encoder.layer[0].intermediate.dense
+    assert isinstance(mod, PrunedLinear) and torch.equal(mod.weight_mask, mask)
+    assert "text_encoder.encoder.layer.0.intermediate.dense.weight_orig" in dict(model.named_parameters())
+
+
+def test_engine_step_protocol_on_cpu():
+    """The DeepSpeed-engine stand-in: backward / clip / optimiser step / counters, on a plain module."""
+    from mPLUG.engine import MaskTrainEngine
+    torch.manual_seed(0)
+    net = torch.nn.Linear(8, 4)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    eng = MaskTrainEngine(net, opt, gradient_clipping=0.5)
+    x = torch.randn(16, 8)
+    w0 = net.weight.detach().clone()
+    loss = eng(x).pow(2).sum()
+    eng.backward(loss)
+    g = net.weight.grad.clone()
+    gb = net.bias.grad.clone()
+    norm = torch.sqrt(g.pow(2).sum() + gb.pow(2).sum())
+    eng.step()
+    assert eng.global_steps == 1 and net.weight.grad is None
+    assert float(eng.last_grad_norm) == pytest.approx(float(norm), rel=1e-6)
+    assert torch.allclose(net.weight, w0 - 0.1 * g * (0.5 / (norm + 1e-6)), atol=1e-7)
+    assert [n for n, _ in eng.named_parameters()] == ["weight", "bias"]
