@@ -1,0 +1,144 @@
+"""``MPLUG`` -- the VQA network of the reference (mPLUG/models/model_vqa_mplug.py:13-173), training path.
+
+Same constructor arguments, sub-module names (``visual_encoder.visual``, ``text_encoder``, ``fusion_encoder``,
+``text_decoder`` and their ``_m`` momentum twins) and ``forward(image, question, answer, alpha, k, weights, train,
+bias)`` semantics: CLIP ViT image states -> BERT text encoder -> skip-connected fusion encoder -> [image; question]
+states repeated ``k[b]`` times -> causal answer decoder; loss = sum_b weights * nll (optionally (1 - bias) weighted)
+/ batch.  With ``config['distill']`` the momentum twins are updated every step as in the reference -- but the
+reference never forwards ``alpha`` to the decoder (:96-104), so its distillation term is multiplied by the decoder's
+default ``alpha=0`` and the loss is the plain one; the twins' forward pass, whose only product is that zero-weighted
+term, is therefore skipped here (``MPLUG.run_unused_distill_forward = True`` runs it anyway).
+
+The reference initialises from checkpoints (``from_pretrained`` of bert-base-uncased, ``ckpts/ViT-B-16.tar``); none
+ship, so the stacks are randomly initialised and ``load_state_dict`` of a reference checkpoint works key for key
+(except the CLIP text tower, which mPLUG-VQA never runs and this package does not build).  ``train=False`` (beam-search
+generation, mPLUG/models/predictor.py) is not built.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .modeling_mplug import BertConfig, BertLMHeadModel, BertModel, FusionModel
+from .visual_transformers import initialize_clip
+
+
+class MPLUG(nn.Module):
+    run_unused_distill_forward = False
+
+    def __init__(self, tokenizer=None, config=None):
+        super().__init__()
+        self.tokenizer = tokenizer
+        self.pad_token_id = getattr(tokenizer, "pad_token_id", 0) if tokenizer is not None else 0
+        self.module_setting(config)
+        self.visual_encoder, _ = initialize_clip(config)
+        self.text_encoder = BertModel(self.config_encoder, add_pooling_layer=False)
+        self.fusion_encoder = FusionModel(self.config_fusion, add_pooling_layer=False)
+        self.text_decoder = BertLMHeadModel(self.config_decoder)
+        self.init_distill(config)
+
+    # -- configuration ---------------------------------------------------------------------------
+    @staticmethod
+    def _bert_config(config):
+        src = config["bert_config"]
+        return BertConfig(**src) if isinstance(src, dict) else BertConfig.from_json_file(src)
+
+    def module_setting(self, config):
+        self.config_encoder = self._bert_config(config)
+        self.config_encoder.num_hidden_layers = self.config_encoder.text_encoder_layers
+        self.config_fusion = self._bert_config(config)
+        self.config_decoder = self._bert_config(config)
+        self.config_decoder.add_cross_attention = True
+        self.config_decoder.num_hidden_layers = self.config_decoder.text_decode_layers
+        self.large = False
+        if self.config_encoder.hidden_size != config["vision_width"]:
+            self.visn_fc = nn.Linear(config["vision_width"], self.config_encoder.hidden_size)
+            self.visn_layer_norm = nn.LayerNorm(self.config_encoder.hidden_size, eps=1e-12)
+            self.dropout = nn.Dropout(self.config_encoder.hidden_dropout_prob)
+            self.large = True
+        self.use_checkpoint = config.get("use_checkpoint", True)
+
+    def init_distill(self, config):
+        self.distill = config["distill"]
+        if not self.distill:
+            return
+        self.visual_encoder_m, _ = initialize_clip(config)
+        self.text_encoder_m = BertModel(self.config_encoder, add_pooling_layer=False)
+        self.fusion_encoder_m = FusionModel(self.config_fusion, add_pooling_layer=False)
+        self.text_decoder_m = BertLMHeadModel(self.config_decoder)
+        # the reference pairs exactly these three (the fusion twin is initialised separately and never updated)
+        self.model_pairs = [[self.visual_encoder, self.visual_encoder_m], [self.text_encoder, self.text_encoder_m],
+                            [self.text_decoder, self.text_decoder_m]]
+        if self.large:
+            self.visn_fc_m = nn.Linear(config["vision_width"], self.config_encoder.hidden_size)
+            self.visn_layer_norm_m = nn.LayerNorm(self.config_encoder.hidden_size, eps=1e-12)
+            self.dropout_m = nn.Dropout(self.config_encoder.hidden_dropout_prob)
+            self.model_pairs.extend([[self.visn_fc, self.visn_fc_m], [self.visn_layer_norm, self.visn_layer_norm_m]])
+        self.copy_params()
+        self.momentum = 0.995
+
+    @torch.no_grad()
+    def copy_params(self):
+        for online, twin in self.model_pairs:
+            for p, p_m in zip(online.parameters(), twin.parameters()):
+                p_m.data.copy_(p.data)
+                p_m.requires_grad = False
+
+    @torch.no_grad()
+    def _momentum_update(self):
+        for online, twin in self.model_pairs:
+            for p, p_m in zip(online.parameters(), twin.parameters()):
+                p_m.data = p_m.data * self.momentum + p.data * (1.0 - self.momentum)
+
+    # -- towers ----------------------------------------------------------------------------------
+    def _image_states(self, image, twin=False):
+        enc = self.visual_encoder_m if twin else self.visual_encoder
+        x = enc.visual(image, skip_last_layer=True, use_checkpoint=False)
+        if self.large:
+            fc, ln, drop = ((self.visn_fc_m, self.visn_layer_norm_m, self.dropout_m) if twin
+                            else (self.visn_fc, self.visn_layer_norm, self.dropout))
+            x = drop(ln(fc(x)))
+        return x
+
+    def _question_states(self, image_embeds, image_atts, question, twin=False):
+        text_enc = self.text_encoder_m if twin else self.text_encoder
+        fusion = self.fusion_encoder_m if twin else self.fusion_encoder
+        text = text_enc(question.input_ids, attention_mask=question.attention_mask).last_hidden_state
+        image_out, question_out = fusion(encoder_embeds=text, attention_mask=question.attention_mask,
+                                         encoder_hidden_states=image_embeds, encoder_attention_mask=image_atts)
+        return torch.cat([image_out, question_out], 1)
+
+    @staticmethod
+    def _repeat(x, k):
+        """Row b repeated k[b] times (the reference builds Python lists and stacks them, :54-60)."""
+        k = torch.as_tensor(k, device=x.device)
+        return x.repeat_interleave(k, dim=0)
+
+    def forward(self, image, question, answer=None, alpha=0, k=None, weights=None, train=True, bias=None):
+        image = image.to(dtype=next(self.parameters()).dtype)
+        image_embeds = self._image_states(image)
+        image_atts = torch.ones(image_embeds.size()[:-1], dtype=torch.long, device=image.device)
+        if not train:
+            raise NotImplementedError("beam-search answer generation (mPLUG/models/predictor.py) is not built")
+
+        answer_targets = answer.input_ids.masked_fill(answer.input_ids == self.pad_token_id, -100)
+        question_states = self._repeat(self._question_states(image_embeds, image_atts, question), k)
+        question_atts = self._repeat(torch.cat([image_atts, question.attention_mask], 1), k)
+
+        soft_labels = None
+        if self.distill:
+            self._momentum_update()
+        if self.distill and self.run_unused_distill_forward:
+            with torch.no_grad():
+                image_embeds_m = self._image_states(image, twin=True)
+                states_m = self._repeat(self._question_states(image_embeds_m, image_atts, question, twin=True), k)
+                logits_m = self.text_decoder_m(answer.input_ids, attention_mask=answer.attention_mask,
+                                               encoder_hidden_states=states_m, encoder_attention_mask=question_atts,
+                                               return_logits=True)
+                soft_labels = F.softmax(logits_m, dim=-1)
+        out = self.text_decoder(answer.input_ids, attention_mask=answer.attention_mask,
+                                encoder_hidden_states=question_states, encoder_attention_mask=question_atts,
+                                labels=answer_targets, return_dict=True, soft_labels=soft_labels, reduction="none")
+        loss = weights * out.loss
+        if bias is not None:
+            loss = (1 - bias) * loss
+        return loss.sum() / image.size(0)

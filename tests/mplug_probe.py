@@ -1,0 +1,80 @@
+"""BASELINE config 5 probe: mPLUG-base (ViT-B/16 at 384 px + 6/6/12 BERT layers) masked training on one GPU, synthetic
+batch, zero rate 0.7: ms/step and samples/s of forward + backward + engine step.  Not a test; prints one JSON line.
+    python tests/mplug_probe.py [batch] [steps]
+"""
+import json
+import os
+import sys
+import time
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "compress-robust-vqa_b200"))
+
+
+def main():
+    from mPLUG import vqa_mplug
+    from mPLUG.engine import MaskTrainEngine
+    from mPLUG.masking.mask_config import MaskConfigs
+    from mPLUG.models.model_vqa_mplug import MPLUG
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    torch.manual_seed(49)
+    config = dict(image_res=384, vision_width=768, distill=True, clip_name="ViT-B-16",
+                  bert_config=dict(stride_layer=3, fusion_layers=6, text_encoder_layers=6, text_decode_layers=12))
+    t0 = time.time()
+    with torch.device("cuda"):
+        model = MPLUG(config=config, tokenizer=types.SimpleNamespace(pad_token_id=0))
+    conf = MaskConfigs()
+    conf.zero_rate = 0.7
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        masker = vqa_mplug.init_masker(conf, model)
+    n_scores = sum(p.numel() for n, p in model.named_parameters() if p.requires_grad and n.endswith("weight_mask"))
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=3e-5, weight_decay=0.02)
+    eng = MaskTrainEngine(model, opt, gradient_clipping=1.0, bf16=True)
+    model.train()
+    g = torch.Generator(device="cuda").manual_seed(49)
+    image = torch.randn(B, 3, 384, 384, device="cuda", generator=g)
+    q = types.SimpleNamespace(input_ids=torch.randint(1, 30522, (B, 16), device="cuda", generator=g),
+                              attention_mask=torch.ones(B, 16, dtype=torch.long, device="cuda"))
+    k = [2] * B
+    a = types.SimpleNamespace(input_ids=torch.randint(1, 30522, (2 * B, 6), device="cuda", generator=g),
+                              attention_mask=torch.ones(2 * B, 6, dtype=torch.long, device="cuda"))
+    w = torch.rand(2 * B, device="cuda", generator=g)
+    setup_s = time.time() - t0
+
+    def step():
+        loss = eng(image, q, a, train=True, alpha=0.4, k=k, weights=w)
+        eng.backward(loss)
+        eng.step()
+        return loss
+
+    for _ in range(3):
+        loss = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    with contextlib.redirect_stdout(io.StringIO()):
+        t1 = time.time()
+        vqa_mplug.update_masks(eng, masker, 0)
+        torch.cuda.synchronize()
+        upd = time.time() - t1
+    print(json.dumps({"workload": "mPLUG-base masked training, 384 px (577 image tokens), 16 question / 6 answer "
+                                  "tokens, 2 answers per question, distill twins updated, zero rate 0.7",
+                      "batch": B, "steps": steps, "ms_per_step": ms, "samples_per_s": B / ms * 1e3,
+                      "masked_modules": len([1 for _, m in model.named_modules() if hasattr(m, "threshold")]),
+                      "trainable_scores": n_scores, "loss": float(loss), "setup_s": setup_s,
+                      "mask_update_s": upd, "max_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+
+
+if __name__ == "__main__":
+    main()

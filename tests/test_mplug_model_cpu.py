@@ -1,0 +1,129 @@
+"""mPLUG-VQA network, CPU tier: the drop-in ``mPLUG/models`` (plain torch until the masker patches it) against the
+reference's network run in the build container (tests/golden/mplug_model_tiny.pt, make_golden_mplug_model.py): same
+state_dict keys (strict load), same loss and per-parameter gradient norms; then the host logic of masking it, with the
+oracle as the fake kernel backend."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from test_mplug_cpu import kept, masked, oracle_backend, quiet, thr_record  # noqa: E402,F401
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mplug_model_tiny.pt")
+TWINS = ("visual_encoder", "text_encoder", "fusion_encoder", "text_decoder")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLD, weights_only=False)
+
+
+def build(gold, device="cpu"):
+    from mPLUG.models.model_vqa_mplug import MPLUG
+    config = dict(gold["config"], bert_config=dict(gold["bert"]))
+    model = MPLUG(config=config, tokenizer=types.SimpleNamespace(pad_token_id=0))
+    assert sorted(model.state_dict()) == gold["state_dict_keys"]
+    full = dict(gold["online"])
+    for k, v in gold["online"].items():             # the twins start as copies of the online towers
+        tower = k.split(".")[0]
+        if tower in TWINS:
+            full[tower + "_m" + k[len(tower):]] = v
+    model.load_state_dict(full, strict=True)
+    return model.eval().to(device)                  # dropout off, as in the golden run; gradients still flow
+
+
+def batch(gold, device="cpu"):
+    B, res, V = 4, gold["config"]["image_res"], gold["bert"]["vocab_size"]
+    g = torch.Generator().manual_seed(5)
+    image = torch.randn(B, 3, res, res, generator=g)
+    q_ids = torch.randint(1, V, (B, 7), generator=g)
+    q_att = torch.ones(B, 7, dtype=torch.long)
+    q_att[1, 5:] = 0
+    q_ids[1, 5:] = 0
+    k = [2, 1, 3, 2]
+    n = sum(k)
+    a_ids = torch.randint(1, V, (n, 5), generator=g)
+    a_att = torch.ones(n, 5, dtype=torch.long)
+    a_ids[0, 3:] = 0
+    a_att[0, 3:] = 0
+    a_ids[5, 4:] = 0
+    a_att[5, 4:] = 0
+    weights = torch.rand(n, generator=g) + 0.2
+    bias = torch.rand(n, generator=g) * 0.5
+    d = torch.device(device)
+    question = types.SimpleNamespace(input_ids=q_ids.to(d), attention_mask=q_att.to(d))
+    answer = types.SimpleNamespace(input_ids=a_ids.to(d), attention_mask=a_att.to(d))
+    return image.to(d), question, answer, k, weights.to(d), bias.to(d)
+
+
+def run(model, gold, with_bias, device="cpu"):
+    image, question, answer, k, weights, bias = batch(gold, device)
+    for p in model.parameters():
+        p.grad = None
+    loss = model(image, question, answer, train=True, alpha=0.4, k=k, weights=weights, bias=bias if with_bias else None)
+    loss.backward()
+    return float(loss.detach()), {n: float(p.grad.norm()) for n, p in model.named_parameters() if p.grad is not None}
+
+
+def test_dense_network_matches_reference(gold):
+    model = build(gold)
+    assert (model.text_decoder.cls.predictions.decoder.weight
+            is model.text_decoder.bert.embeddings.word_embeddings.weight) == gold["tied"]
+    twin0 = {k: v.clone() for k, v in model.state_dict().items() if k.startswith("text_encoder_m.")}
+    loss, norms = run(model, gold, with_bias=False)
+    assert loss == pytest.approx(gold["dense_loss"], rel=1e-5)
+    assert sorted(norms) == sorted(gold["dense_grad_norms"])
+    for n, want in gold["dense_grad_norms"].items():
+        assert norms[n] == pytest.approx(want, rel=2e-4, abs=1e-9), n
+    loss_b, _ = run(model, gold, with_bias=True)
+    assert loss_b == pytest.approx(gold["dense_loss_bias"], rel=1e-5)
+    moved = any(not torch.equal(v, twin0[k]) for k, v in model.state_dict().items() if k in twin0)
+    assert moved == gold["twin_moved"]              # the momentum update runs although its logits are never weighted in
+    # the skipped twin forward changes nothing: with it switched on the loss is identical
+    type(model).run_unused_distill_forward = True
+    try:
+        again, _ = run(model, gold, with_bias=True)
+    finally:
+        type(model).run_unused_distill_forward = False
+    assert again == pytest.approx(loss_b, rel=1e-6)
+    with pytest.raises(NotImplementedError):
+        model(batch(gold)[0], None, train=False)
+
+
+def test_full_size_configuration_builds_the_reference_census():
+    """mPLUG-base at 384 px on the meta device: parameter count and the census of maskable modules."""
+    from mPLUG import vqa_mplug
+    from mPLUG.masking.mask_config import MaskConfigs
+    from mPLUG.models.model_vqa_mplug import MPLUG
+    config = dict(image_res=384, vision_width=768, distill=True, clip_name="ViT-B-16",
+                  bert_config=dict(stride_layer=3, fusion_layers=6, text_encoder_layers=6, text_decode_layers=12))
+    with torch.device("meta"):
+        model = MPLUG(config=config)
+    names = vqa_mplug.names_to_mask(MaskConfigs())
+    found = [n for n, m in model.named_modules() if n in names]
+    assert len(found) == len(names) == 480          # every name the reference tables produce exists in the network
+    assert all(isinstance(dict(model.named_modules())[n], torch.nn.Linear) for n in found)
+    assert model.visual_encoder.visual.positional_embedding.shape == (577, 768)
+    online = sum(p.numel() for n, p in model.named_parameters() if "_m." not in n)
+    assert 420e6 < online < 435e6                   # ViT-B/16 86 M, text 6 layers, fusion and decoder 12 each, 3 tables
+
+
+def test_masking_the_network_host_logic(gold, oracle_backend):
+    from mPLUG import vqa_mplug
+    from mPLUG.masking.mask_config import MaskConfigs
+    from mPLUG.masking import maskers
+    G = gold["masked"]
+    model = build(gold)
+    conf = MaskConfigs()
+    conf.zero_rate = 0.5
+    quiet(vqa_mplug.init_masker, conf, model, layers_to_mask=gold["layers_to_mask"])
+    assert [n for n, _ in masked(model)] == G["module_names"]
+    assert sorted(n for n, p in model.named_parameters() if p.requires_grad) == G["trainable"]
+    assert thr_record(model) == G["thresholds"]
+    assert kept(model) == G["kept"]
+    mean = maskers.reset_threshold(model, 0.7)
+    r = G["reset_0.7"]
+    assert mean == r["mean"] and thr_record(model) == r["thresholds"] and kept(model) == r["kept"]
