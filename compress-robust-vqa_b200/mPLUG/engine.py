@@ -12,6 +12,11 @@ What DeepSpeed does there (mPLUG/configs/ds_config.json: bf16, ZeRO-2, gradient_
 * gradient all-reduce  ->  one all-reduce(mean) of the flattened trainable gradients (scores + LM head; frozen
   weights have none) when ``torch.distributed`` is initialised with more than one rank.
 * gradient_clipping  ->  global-norm clip over the (reduced) trainable gradients before the optimiser step.
+
+Scores only change in ``step()``, thresholds only in ``reset_threshold``; so every masked module keeps its masked bf16
+operand ``W (.) M`` between steps (one streaming pass per module and step) and forward / dX run as plain tcgen05 GEMMs
+instead of re-deriving the mask inside every GEMM call.  Code that edits scores behind the engine's back must call
+``invalidate_masks()``.
 """
 import torch
 import torch.distributed as dist
@@ -24,7 +29,8 @@ else:
 
 
 class MaskTrainEngine:
-    def __init__(self, module, optimizer, lr_scheduler=None, gradient_clipping=1.0, bf16=True, process_group=None):
+    def __init__(self, module, optimizer, lr_scheduler=None, gradient_clipping=1.0, bf16=True, process_group=None,
+                 hold_masks=True):
         self.module = module
         self.optimizer = optimizer
         self.lr_scheduler = lr_scheduler
@@ -33,6 +39,9 @@ class MaskTrainEngine:
         self.global_steps = 0
         self.last_grad_norm = None
         maskers.set_score_dtype(module, torch.bfloat16 if bf16 else torch.float32)
+        self._masked = [m for m in module.modules() if hasattr(m, "hold_masked_weight")]
+        for m in self._masked:
+            m.hold_masked_weight(hold_masks)
 
     # -- the nn.Module face the loop uses -------------------------------------------------------
     def __call__(self, *args, **kwargs):
@@ -75,4 +84,10 @@ class MaskTrainEngine:
             self.last_grad_norm = torch.nn.utils.clip_grad_norm_(params, self.gradient_clipping)
         self.optimizer.step()
         self.optimizer.zero_grad(set_to_none=True)
+        self.invalidate_masks()
         self.global_steps += 1
+
+    def invalidate_masks(self):
+        """The scores moved: the next forward of every masked module rebuilds its masked operand."""
+        for m in self._masked:
+            m.drop_masked_weight()

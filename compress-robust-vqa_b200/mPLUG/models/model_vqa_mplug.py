@@ -85,9 +85,19 @@ class MPLUG(nn.Module):
 
     @torch.no_grad()
     def _momentum_update(self):
-        for online, twin in self.model_pairs:
-            for p, p_m in zip(online.parameters(), twin.parameters()):
-                p_m.data = p_m.data * self.momentum + p.data * (1.0 - self.momentum)
+        """p_m <- p_m * momentum + p * (1 - momentum) for every paired parameter (:152-156), as three multi-tensor
+        launches per dtype / device group instead of three launches per parameter; same products, same sum, same
+        rounding as the per-parameter expression."""
+        online, twins = [], []
+        for a, b in self.model_pairs:
+            for p, p_m in zip(a.parameters(), b.parameters()):
+                online.append(p.data)
+                twins.append(p_m.data)
+        if not twins:
+            return
+        fresh = torch._foreach_mul(online, 1.0 - self.momentum)
+        torch._foreach_mul_(twins, self.momentum)
+        torch._foreach_add_(twins, fresh)
 
     # -- towers ----------------------------------------------------------------------------------
     def _image_states(self, image, twin=False):
@@ -110,8 +120,8 @@ class MPLUG(nn.Module):
     @staticmethod
     def _repeat(x, k):
         """Row b repeated k[b] times (the reference builds Python lists and stacks them, :54-60)."""
-        k = torch.as_tensor(k, device=x.device)
-        return x.repeat_interleave(k, dim=0)
+        total = int(sum(int(v) for v in k))          # known on the host: no device sync to size the output
+        return x.repeat_interleave(torch.as_tensor(k, device=x.device), dim=0, output_size=total)
 
     def forward(self, image, question, answer=None, alpha=0, k=None, weights=None, train=True, bias=None):
         image = image.to(dtype=next(self.parameters()).dtype)

@@ -408,8 +408,31 @@ class MaskedLinear1(MaskedLinearX):
         if self.weight.shape[1] % 8 != 0:
             return ops.MaskedLinearSmallKFn.apply(x, self.weight_mask, self.weight, thr, self.bias, sink)
         arena = getattr(self, "_arena", None)
-        wm = arena.cached_masked_weight(self) if arena is not None else None
+        wm = arena.cached_masked_weight(self) if arena is not None else self._held_masked_weight(thr)
         return ops.MaskedLinearFn.apply(x, self.weight_mask, self._weight_bf16(), thr, self.bias, sink, wm)
+
+    # -- per-module mask cache for engines without a score arena (mPLUG/engine.py) --------------------------------
+    def hold_masked_weight(self, on=True):
+        """Opt in: keep W (.) M as a bf16 operand between calls, so forward and dX run as plain GEMMs.  Whoever changes
+        the scores (the engine, after its optimiser step) must call drop_masked_weight(); a new threshold object or
+        an in-place threshold update is noticed here."""
+        self._hold_wm = bool(on)
+        self.drop_masked_weight()
+
+    def drop_masked_weight(self):
+        self._wm = None
+        self._wm_key = None
+
+    def _held_masked_weight(self, thr):
+        if not getattr(self, "_hold_wm", False):
+            return None
+        t = self.threshold               # the source object: alive as long as it is current, so its id is not reused
+        key = (id(t), t._version if torch.is_tensor(t) else t, getattr(self, "score_dtype", None),
+               self.weight_mask.data_ptr(), thr.device)
+        if self._wm is None or self._wm_key != key:
+            self._wm = ops.apply_mask_bf16(self._weight_bf16(), self.weight_mask.detach(), thr)
+            self._wm_key = key
+        return self._wm
 
 
 class MaskedLinear2(MaskedLinearX):

@@ -21,7 +21,10 @@ def main():
     from mPLUG.models.model_vqa_mplug import MPLUG
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    profile_to = sys.argv[3] if len(sys.argv) > 3 else None      # path for a torch.profiler kernel table of 2 steps
+    hold = os.environ.get("CRVQA_MPLUG_HOLD_MASKS", "1") != "0"
     torch.manual_seed(49)
+    torch.backends.cuda.matmul.allow_tf32 = True      # the UNMASKED torch GEMMs (ViT qkv, heads); the reference runs bf16
     config = dict(image_res=384, vision_width=768, distill=True, clip_name="ViT-B-16",
                   bert_config=dict(stride_layer=3, fusion_layers=6, text_encoder_layers=6, text_decode_layers=12))
     t0 = time.time()
@@ -35,7 +38,7 @@ def main():
         masker = vqa_mplug.init_masker(conf, model)
     n_scores = sum(p.numel() for n, p in model.named_parameters() if p.requires_grad and n.endswith("weight_mask"))
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=3e-5, weight_decay=0.02)
-    eng = MaskTrainEngine(model, opt, gradient_clipping=1.0, bf16=True)
+    eng = MaskTrainEngine(model, opt, gradient_clipping=1.0, bf16=True, hold_masks=hold)
     model.train()
     g = torch.Generator(device="cuda").manual_seed(49)
     image = torch.randn(B, 3, 384, 384, device="cuda", generator=g)
@@ -63,6 +66,19 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    busy = None
+    if profile_to:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+        ka = prof.key_averages()
+        busy = sum(e.self_device_time_total for e in ka) / 2 / 1e3
+        with open(profile_to, "w") as f:
+            f.write(f"# mplug_probe batch {B}: {ms:.1f} ms/step unprofiled; GPU-busy {busy:.1f} ms/step (sum of kernel "
+                    f"time over 2 profiled steps / 2)\n")
+            f.write(ka.table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=70))
     with contextlib.redirect_stdout(io.StringIO()):
         t1 = time.time()
         vqa_mplug.update_masks(eng, masker, 0)
@@ -70,7 +86,8 @@ def main():
         upd = time.time() - t1
     print(json.dumps({"workload": "mPLUG-base masked training, 384 px (577 image tokens), 16 question / 6 answer "
                                   "tokens, 2 answers per question, distill twins updated, zero rate 0.7",
-                      "batch": B, "steps": steps, "ms_per_step": ms, "samples_per_s": B / ms * 1e3,
+                      "batch": B, "steps": steps, "ms_per_step": ms, "hold_masks": hold,
+                      "gpu_busy_ms_per_step": busy, "samples_per_s": B / ms * 1e3,
                       "masked_modules": len([1 for _, m in model.named_modules() if hasattr(m, "threshold")]),
                       "trainable_scores": n_scores, "loss": float(loss), "setup_s": setup_s,
                       "mask_update_s": upd, "max_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))

@@ -167,6 +167,16 @@ def test_mplug_engine_trains_scores_and_head_only(gold):
             assert torch.equal(m.get_masks()[0].cpu(), want), n
     assert eng.global_steps == 12
     assert losses[-1] < losses[0]
+    # the operand every masked GEMM holds between steps is exactly bf16(W) (.) current mask
+    loss = eng(*batch)
+    held = [m for _, m in masked(model) if getattr(m, "_wm", None) is not None]
+    assert len(held) >= 40
+    for m in held:
+        assert torch.equal(m._wm.float(), m._weight_bf16().float() * m.get_masks()[0])
+    # and with the cache off (mask re-derived inside every GEMM call) the same step gives the same loss
+    for m in held:
+        m.hold_masked_weight(False)
+    assert float(eng(*batch)) == pytest.approx(float(loss), rel=1e-3)
     for n, p in model.named_parameters():
         if n in frozen:
             assert torch.equal(p, frozen[n]), n
