@@ -3,10 +3,16 @@ parameter names (``conv1``, ``class_embedding``, ``positional_embedding``, ``ln_
 {attn,ln_1,mlp.c_fc,mlp.c_proj,ln_2}``, ``ln_post``, ``proj``), so reference checkpoints load with ``strict=True`` and
 the masker finds ``mlp.c_fc`` / ``mlp.c_proj`` by name.  Plain torch modules: the masked layers become sm_100a masked
 GEMMs when ``Masker.patch_modules`` swaps them."""
+import contextlib
+import os
 from collections import OrderedDict
 
 import torch
 from torch import nn
+
+# see modeling_mplug.BF16_ATTENTION: the attention sub-block (in_proj, softmax(QK^T)V, out_proj) runs under bf16 autocast
+# on a GPU, as the whole network does in the reference's DeepSpeed-bf16 run
+BF16_ATTENTION = os.environ.get("CRVQA_MPLUG_BF16_ATTENTION", "1") != "0"
 
 
 class LayerNorm(nn.LayerNorm):
@@ -34,7 +40,10 @@ class ResidualAttentionBlock(nn.Module):
     def attention(self, x, text_mask=None):
         if text_mask is None and self.attn_mask is not None:
             text_mask = self.attn_mask.to(dtype=x.dtype, device=x.device)
-        return self.attn(x, x, x, need_weights=False, attn_mask=text_mask)[0]
+        bf16 = (torch.autocast("cuda", dtype=torch.bfloat16) if BF16_ATTENTION and x.is_cuda
+                else contextlib.nullcontext())
+        with bf16:
+            return self.attn(x, x, x, need_weights=False, attn_mask=text_mask)[0].to(x.dtype)
 
     def forward(self, x, text_mask=None):
         x = x + self.attention(self.ln_1(x), text_mask=text_mask)

@@ -9,12 +9,18 @@ Everything here is plain torch; the Linear layers named by the masker become sm_
 relative position embeddings, the TF checkpoint loader and the other task heads of the reference file.
 """
 import json
-import math
+import os
 from types import SimpleNamespace
 
 import torch
 import torch.nn.functional as F
 from torch import nn
+
+
+# The reference trains under DeepSpeed bf16: every attention there is a bf16 computation.  On a GPU the attention cores
+# (not the projections) therefore run in bf16 through the fused SDPA kernels; fp32 attention at 577 image tokens was
+# half of the step (profiles/r01_mplug_profile_fp32_attention.txt).  CRVQA_MPLUG_BF16_ATTENTION=0 keeps fp32.
+BF16_ATTENTION = os.environ.get("CRVQA_MPLUG_BF16_ATTENTION", "1") != "0"
 
 
 class BertConfig:
@@ -85,11 +91,14 @@ class BertSelfAttention(nn.Module):
         src = hidden_states if encoder_hidden_states is None else encoder_hidden_states
         mask = attention_mask if encoder_hidden_states is None else encoder_attention_mask
         q, k, v = self._heads(self.query(hidden_states)), self._heads(self.key(src)), self._heads(self.value(src))
+        out_dtype = q.dtype
+        if BF16_ATTENTION and q.is_cuda and q.dtype == torch.float32:
+            q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
         if mask is not None:
             mask = mask.to(q.dtype)
         ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=mask,
                                              dropout_p=self.dropout.p if self.training else 0.0)
-        return ctx.transpose(1, 2).reshape(hidden_states.shape[0], hidden_states.shape[1], -1)
+        return ctx.transpose(1, 2).reshape(hidden_states.shape[0], hidden_states.shape[1], -1).to(out_dtype)
 
 
 class BertSelfOutput(nn.Module):

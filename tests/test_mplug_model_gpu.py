@@ -28,7 +28,7 @@ def test_masked_network_matches_reference(gold):
     G = gold["masked"]
     model = build(gold, "cuda")
     dense, _ = run(model, gold, with_bias=True, device="cuda")
-    assert dense == pytest.approx(gold["dense_loss_bias"], rel=1e-4)       # torch modules only: fp32 on the GPU
+    assert dense == pytest.approx(gold["dense_loss_bias"], rel=2e-3)       # torch modules; attention cores in bf16
     conf = MaskConfigs()
     conf.zero_rate = 0.5
     masker = quiet(vqa_mplug.init_masker, conf, model, layers_to_mask=gold["layers_to_mask"])
