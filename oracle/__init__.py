@@ -14,4 +14,6 @@ only third-party boundary is PyTorch itself.  The oracle is therefore pinned aga
 UNMODIFIED reference modules imported in the build container: tests/golden/make_golden.py (committed)
 runs them on seeded synthetic inputs and writes tests/golden/*.pt; tests/test_oracle_golden.py checks
 every oracle function against those files, and SURVEY.md 8(c)'s known-answer values are asserted too.
+mplug_masking.py (the mPLUG masker / threshold refresh) is pinned the same way by tests/golden/make_golden_mplug.py ->
+mplug_skeleton.pt (tests/test_mplug_cpu.py).
 """

@@ -132,15 +132,11 @@ class OracleMasked(nn.Module):
         self.operand = operand
         self.score_dtype = torch.float32
 
-    def effective_threshold(self):
-        return self.threshold
-
     def get_masks(self):
         return mask_of(self.weight_mask, self.threshold, self.score_dtype), None
 
     def forward(self, x):
         m = self.get_masks()[0]
-        # route the mask through masked_ops by handing it scores that binarise to it: S' = M, threshold 0.5
         if "embedding" in self.name:
             return _MaskedEmbeddingWithMask.apply(x, self.weight_mask, self.weight, m, self.padding_idx)
         return _MaskedLinearWithMask.apply(x, self.weight_mask, self.weight, m, self.bias, self.operand)
