@@ -302,13 +302,19 @@ class MaskedLinearFn(torch.autograd.Function):
         shp = x.shape
         x2 = to_bf16(x.reshape(-1, shp[-1]))
         thr_t = as_thr(thr, x.device)
+        # bf16 activations (a bf16 input, or a caller running under bf16 autocast, where nn.Linear would answer in bf16
+        # too) -> bf16 out; dX always comes back in the input's own dtype: no fp32 round trips between bf16 layers
+        autocast16 = (x.is_cuda and torch.is_autocast_enabled("cuda")
+                      and torch.get_autocast_dtype("cuda") == torch.bfloat16)
+        io = torch.bfloat16 if (x.dtype == torch.bfloat16 or autocast16) else torch.float32
         if wm_bf16 is not None:   # mask cache: W (.) M was materialised for this (scores, threshold) state
-            y = masked_linear_fwd(x2, wm_bf16, None, None, bias, torch.float32)
+            y = masked_linear_fwd(x2, wm_bf16, None, None, bias, io)
         else:
-            y = masked_linear_fwd(x2, w_bf16, scores.detach(), thr_t, bias, torch.float32)
+            y = masked_linear_fwd(x2, w_bf16, scores.detach(), thr_t, bias, io)
         ctx.save_for_backward(x2, scores, w_bf16, thr_t)
         ctx.wm = wm_bf16
         ctx.x_shape = shp
+        ctx.dx_dtype = torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32
         ctx.need_dx = x.requires_grad
         ctx.sink = sink
         return y.view(*shp[:-1], w_bf16.shape[0])
@@ -324,9 +330,9 @@ class MaskedLinearFn(torch.autograd.Function):
         dx = None
         if ctx.need_dx:
             if ctx.wm is not None:
-                dx = masked_linear_bwd_dx(dy2, ctx.wm, None, None, torch.float32).view(ctx.x_shape)
+                dx = masked_linear_bwd_dx(dy2, ctx.wm, None, None, ctx.dx_dtype).view(ctx.x_shape)
             else:
-                dx = masked_linear_bwd_dx(dy2, w_bf16, scores.detach(), thr_t, torch.float32).view(ctx.x_shape)
+                dx = masked_linear_bwd_dx(dy2, w_bf16, scores.detach(), thr_t, ctx.dx_dtype).view(ctx.x_shape)
         ds = None
         if ctx.needs_input_grad[1]:
             if sink_grad is not None:

@@ -14,6 +14,8 @@ ship, so the stacks are randomly initialised and ``load_state_dict`` of a refere
 (except the CLIP text tower, which mPLUG-VQA never runs and this package does not build).  ``train=False`` (beam-search
 generation, mPLUG/models/predictor.py) is not built.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -24,6 +26,11 @@ from .visual_transformers import initialize_clip
 
 class MPLUG(nn.Module):
     run_unused_distill_forward = False
+    # Opt-in (CRVQA_MPLUG_BF16_ACTIVATIONS=1): run the whole forward under bf16 autocast on a GPU, which is the
+    # reference's DeepSpeed-bf16 arithmetic -- bf16 activations between the masked GEMMs (which then read and write bf16
+    # directly), LayerNorm / softmax / loss still in fp32.  Default off: fp32 activations, bf16 only inside the masked
+    # GEMMs and the attention cores.
+    bf16_activations = os.environ.get("CRVQA_MPLUG_BF16_ACTIVATIONS", "0") == "1"
 
     def __init__(self, tokenizer=None, config=None):
         super().__init__()
@@ -124,6 +131,10 @@ class MPLUG(nn.Module):
         return x.repeat_interleave(torch.as_tensor(k, device=x.device), dim=0, output_size=total)
 
     def forward(self, image, question, answer=None, alpha=0, k=None, weights=None, train=True, bias=None):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(self.bf16_activations and image.is_cuda)):
+            return self._forward(image, question, answer, alpha, k, weights, train, bias)
+
+    def _forward(self, image, question, answer, alpha, k, weights, train, bias):
         image = image.to(dtype=next(self.parameters()).dtype)
         image_embeds = self._image_states(image)
         image_atts = torch.ones(image_embeds.size()[:-1], dtype=torch.long, device=image.device)

@@ -7,7 +7,9 @@ from crvqa import ops
 dev = 'cuda'
 torch.manual_seed(0)
 SHAPES = [(9216, 768, 768), (5120, 768, 768), (9216, 3072, 768), (9216, 768, 3072), (9216, 768, 2048)]
-if len(sys.argv) > 1: SHAPES = SHAPES[:int(sys.argv[1])]
+if len(sys.argv) > 1 and sys.argv[1] == 'mplug':   # mPLUG-base, batch 32: ViT MLPs (577 tokens), cross-attention K/V, connected fusion layer
+    SHAPES = [(18464, 3072, 768), (18464, 768, 3072), (37952, 768, 768), (18976, 768, 768)]
+elif len(sys.argv) > 1: SHAPES = SHAPES[:int(sys.argv[1])]
 def timeit(fn, iters=20):
     for _ in range(3): fn()
     torch.cuda.synchronize()
