@@ -384,3 +384,91 @@ def test_engine_step_protocol_on_cpu():
     assert float(eng.last_grad_norm) == pytest.approx(float(norm), rel=1e-6)
     assert torch.allclose(net.weight, w0 - 0.1 * g * (0.5 / (norm + 1e-6)), atol=1e-7)
     assert [n for n, _ in eng.named_parameters()] == ["weight", "bias"]
+
+
+# ----------------------------------------------------------------------------- engine: data parallel (gloo, 2 ranks)
+def _engine_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    "compress-robust-vqa_b200"))
+    from mPLUG.engine import MaskTrainEngine
+    torch.manual_seed(0)                                   # identical replicas
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    net[0].bias.requires_grad = False                      # a frozen tensor must stay out of the exchange
+    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.05)
+    eng = MaskTrainEngine(net, opt, gradient_clipping=1e9)
+    g = torch.Generator().manual_seed(100)
+    xs = [torch.randn(4, 6, generator=g) for _ in range(world)]       # every rank knows every shard
+    # what one process would do on the concatenated batch (mean of per-rank mean losses == mean over the union)
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    ref.load_state_dict(net.state_dict())
+    for step in range(2):
+        loss = eng(xs[rank]).pow(2).mean()
+        eng.backward(loss)
+        eng.step()
+        ref.zero_grad()
+        torch.stack([ref(x).pow(2).mean() for x in xs]).mean().backward()
+        with torch.no_grad():
+            for n, p in ref.named_parameters():
+                if n != "0.bias":
+                    p -= 0.05 * p.grad
+        for (n, p), (_, pr) in zip(net.named_parameters(), ref.named_parameters()):
+            assert torch.allclose(p, pr, atol=1e-6), (rank, step, n)
+    assert eng.global_steps == 2
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put(rank)
+
+
+def test_engine_allreduces_trainable_gradients_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_engine_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5) for _ in range(2)) == [0, 1]
+
+
+def test_held_masked_operand_is_rebuilt_exactly_when_it_must(gold, oracle_backend, monkeypatch):
+    """The engine-managed operand cache of the masked modules: built once, reused while nothing changes, rebuilt after
+    the engine's step (drop), after a threshold refresh (new threshold object) and after a score-dtype switch."""
+    from mPLUG.engine import MaskTrainEngine
+    from mPLUG.masking import maskers
+    calls = []
+
+    def fake_apply(w16, scores, thr):
+        calls.append(float(thr))
+        return (w16.float() * (scores > thr).float()).to(torch.bfloat16)
+
+    monkeypatch.setattr(oracle_backend, "apply_mask_bf16", fake_apply)
+    monkeypatch.setattr(oracle_backend, "to_bf16", lambda x: x.to(torch.bfloat16))
+    model = fresh(gold)
+    _init(model, zero_rate=0.7)
+    mod = dict(masked(model))["text_encoder.encoder.layer.0.intermediate.dense"]
+    dev = torch.device("cpu")
+    assert mod._held_masked_weight(mod._threshold_on(dev)) is None            # off until an engine opts in
+    eng = MaskTrainEngine(model, torch.optim.SGD([mod.weight_mask], lr=0.1), bf16=False)
+    a = mod._held_masked_weight(mod._threshold_on(dev))
+    b = mod._held_masked_weight(mod._threshold_on(dev))
+    assert a is b and len(calls) == 1
+    assert torch.equal(a.float(), mod.weight.bfloat16().float() * mod.get_masks()[0])
+    mod.weight_mask.grad = torch.ones_like(mod.weight_mask)
+    eng.step()                                                                # scores moved
+    c = mod._held_masked_weight(mod._threshold_on(dev))
+    assert c is not a and len(calls) == 2
+    maskers.reset_threshold(model, 0.5)                                       # new threshold objects
+    d = mod._held_masked_weight(mod._threshold_on(dev))
+    assert d is not c and len(calls) == 3 and calls[-1] == float(mod.threshold)
+    maskers.set_score_dtype(model, torch.bfloat16)                            # same threshold, other comparison
+    e = mod._held_masked_weight(mod._threshold_on(dev))
+    assert e is not d and len(calls) == 4
+    assert calls[-1] == float(maskers.bf16_score_threshold(torch.tensor(float(mod.threshold))))
+    eng.invalidate_masks()
+    assert mod._wm is None
