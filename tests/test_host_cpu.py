@@ -53,6 +53,21 @@ def test_cabi_argument_errors_are_reported_before_any_cuda_work():
         _lib.check(-3, "x")
 
 
+def test_every_entry_point_rejects_null_arguments_without_touching_cuda():
+    """All-null pointers and zero sizes: each int-returning entry point answers CRV_E_ARG (-1) on a box without a GPU,
+    i.e. before any CUDA call.  (crv_gemm_debug_timestamps(NULL) is the documented way to switch the debug aid off.)"""
+    from crvqa import _lib
+    seen = 0
+    for name, (res, args) in _lib._PROTOS.items():
+        if res is not ctypes.c_int or not args or name == "crv_gemm_debug_timestamps":
+            continue
+        vals = [ctypes.c_void_p(0) if a is ctypes.c_void_p else (0.0 if a is ctypes.c_float else 0) for a in args]
+        assert getattr(_lib.lib, name)(*vals) == -1, name
+        seen += 1
+    assert seen >= 25
+    assert _lib.lib.crv_gemm_debug_timestamps(ctypes.c_void_p(0)) == 0
+
+
 def test_product_ops_fail_loudly_without_cuda():
     if torch.cuda.is_available():
         pytest.skip("this check is for the CPU-only tier")
