@@ -12,7 +12,7 @@ term, is therefore skipped here (``MPLUG.run_unused_distill_forward = True`` run
 The reference initialises from checkpoints (``from_pretrained`` of bert-base-uncased, ``ckpts/ViT-B-16.tar``); none
 ship, so the stacks are randomly initialised and ``load_state_dict`` of a reference checkpoint works key for key
 (except the CLIP text tower, which mPLUG-VQA never runs and this package does not build).  ``train=False`` (beam-search
-generation, mPLUG/models/predictor.py) is not built.
+generation, mPLUG/models/predictor.py) is not built; the closed-set alternative ``rank_answer`` (:188-245) is.
 """
 import os
 
@@ -163,3 +163,40 @@ class MPLUG(nn.Module):
         if bias is not None:
             loss = (1 - bias) * loss
         return loss.sum() / image.size(0)
+
+    # -- closed-set inference --------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_question(self, image, question):
+        """[image; question] states and their attention mask, as the ``train=False`` branch builds them (:122-134)."""
+        image = image.to(dtype=next(self.parameters()).dtype)
+        image_embeds = self._image_states(image)
+        image_atts = torch.ones(image_embeds.size()[:-1], dtype=torch.long, device=image.device)
+        states = self._question_states(image_embeds, image_atts, question)
+        return states, torch.cat([image_atts, question.attention_mask], 1)
+
+    def rank_answer(self, question_states, question_atts, answer_ids, answer_atts, k):
+        """Rank a fixed candidate list (:188-245): the k candidates whose FIRST token is most probable after [BOS] are
+        re-scored by the full sequence log-likelihood; returns (topk_ids [Q, k] into the candidate list, topk_probs)."""
+        num_ques = question_states.size(0)
+        start_ids = answer_ids[0, 0].repeat(num_ques, 1)                       # the shared [BOS] token
+        start = self.text_decoder(start_ids, encoder_hidden_states=question_states,
+                                  encoder_attention_mask=question_atts, return_dict=True, reduction="none")
+        first_token_probs = F.softmax(start.logits[:, 0, :], dim=1).index_select(dim=1, index=answer_ids[:, 1])
+        topk_probs, topk_ids = first_token_probs.topk(k, dim=1)
+
+        input_ids = answer_ids.index_select(0, topk_ids.reshape(-1))           # [Q * k, L], question-major
+        input_atts = answer_atts.index_select(0, topk_ids.reshape(-1))
+        targets = input_ids.masked_fill(input_ids == self.pad_token_id, -100)
+        out = self.text_decoder(input_ids, attention_mask=input_atts,
+                                encoder_hidden_states=tile(question_states, 0, k),
+                                encoder_attention_mask=tile(question_atts, 0, k),
+                                labels=targets, return_dict=True, reduction="none")
+        answer_loss = out.loss.view(input_ids.size(0), -1)
+        log_probs = torch.cat([topk_probs.view(-1, 1).log(), -answer_loss], dim=1).sum(1).view(num_ques, k)
+        topk_probs, rerank = F.softmax(log_probs, dim=-1).topk(k, dim=1)
+        return torch.gather(topk_ids, 1, rerank), topk_probs
+
+
+def tile(x, dim, n_tile):
+    """Each slice along ``dim`` repeated ``n_tile`` times in place: [a, b] -> [a, a, b, b] (:247-253)."""
+    return x.repeat_interleave(n_tile, dim=dim)

@@ -15,7 +15,7 @@ Shims (all outside the reference tree; the reference pins transformers==4.14.1, 
   * checkpoints are not shipped -> ``from_pretrained`` builds from the config, ``initialize_clip`` builds the CLIP visual
     tower at the test resolution (both random init under the seed).
 Recorded: the dense network's loss and per-parameter gradient norms (distill on: the loss must NOT depend on the momentum
-twins), then the same network patched by the reference mPLUG masker: module census, trainable set, thresholds, kept
+twins), the closed-set ``rank_answer`` output, then the same network patched by the reference mPLUG masker: module census, trainable set, thresholds, kept
 counts, masked loss and score-gradient norms.
 """
 import contextlib
@@ -150,6 +150,24 @@ def main():
     gold["dense_loss_bias"], _ = run(model, with_bias=True)
     twin_after = {k: v.clone() for k, v in model.state_dict().items() if k.startswith("text_encoder_m.")}
     gold["twin_moved"] = any(not torch.equal(v, sd[k]) for k, v in twin_after.items())
+
+    # ---- closed-set ranking on the dense network (rank_answer :188-245, tile :247-253)
+    with torch.no_grad():
+        image, question, answer, k, weights, bias = batch()
+        image_embeds = model.visual_encoder.visual(image, skip_last_layer=True, use_checkpoint=False)
+        image_atts = torch.ones(image_embeds.size()[:-1], dtype=torch.long)
+        text = model.text_encoder(question.input_ids, attention_mask=question.attention_mask,
+                                  return_dict=True).last_hidden_state
+        img_out, q_out = model.fusion_encoder(encoder_embeds=text, attention_mask=question.attention_mask,
+                                      encoder_hidden_states=image_embeds, encoder_attention_mask=image_atts,
+                                      return_dict=False)
+        states, atts = torch.cat([img_out, q_out], 1), torch.cat([image_atts, question.attention_mask], 1)
+        cand_ids = answer.input_ids.clone()
+        cand_ids[:, 0] = 7                                  # a shared [BOS] token, as the tokenizer would emit
+        ids, probs = model.rank_answer(states, atts, cand_ids, answer.attention_mask, 3)
+        gold["rank"] = {"bos": 7, "k": 3, "topk_ids": ids.clone(), "topk_probs": probs.clone(),
+                        "states_norm": float(states.norm())}
+        gold["tile"] = mv.tile(torch.arange(6).view(2, 3), 0, 3).clone()
 
     # ---- masked: the reference masker with init_masker's wiring (vqa_mplug.py:59-128) on a fresh copy of the weights
     torch.manual_seed(13)

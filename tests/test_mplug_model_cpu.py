@@ -93,6 +93,22 @@ def test_dense_network_matches_reference(gold):
         model(batch(gold)[0], None, train=False)
 
 
+def test_rank_answer_matches_reference(gold):
+    from mPLUG.models.model_vqa_mplug import tile
+    model = build(gold)
+    image, question, answer, k, weights, bias = batch(gold)
+    states, atts = model.encode_question(image, question)
+    R = gold["rank"]
+    assert float(states.norm()) == pytest.approx(R["states_norm"], rel=1e-5)
+    cand = answer.input_ids.clone()
+    cand[:, 0] = R["bos"]
+    with torch.no_grad():
+        ids, probs = model.rank_answer(states, atts, cand, answer.attention_mask, R["k"])
+    assert torch.equal(ids, R["topk_ids"])
+    assert torch.allclose(probs, R["topk_probs"], rtol=1e-4, atol=1e-7)
+    assert torch.equal(tile(torch.arange(6).view(2, 3), 0, 3), gold["tile"])
+
+
 def test_full_size_configuration_builds_the_reference_census():
     """mPLUG-base at 384 px on the meta device: parameter count and the census of maskable modules."""
     from mPLUG import vqa_mplug
