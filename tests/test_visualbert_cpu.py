@@ -61,3 +61,40 @@ def test_visualbert_oracle_matches_reference():
         t = o_ops.kth_value(after[n], k)
         assert float(t) == float(g["thresholds_after"][n]), n
         assert int((after[n] > float(t)).sum()) == g["kept_after"][n], n
+
+
+def test_visualbert_driver_init_masker_host_logic(monkeypatch):
+    """prune_debias_VQA_visualBERT.init_masker (uniform zero rate, K/Q/V/AO/I/O/P/E) with the oracle as the fake kernel
+    backend: same module census, trainable set and initial kept counts as the reference masker produced."""
+    import logging
+
+    import pytest
+    from crvqa import ops
+    from hg_transformers.modeling_visualbert import VisualBertForMultipleChoice, visualBERTConfig
+    from prune_debias_VQA_visualBERT import ModelArguments, init_masker
+
+    def kth(tensors, ks, use_abs=False):
+        return torch.tensor([float(o_ops.kth_value(t, int(k), use_abs=use_abs)) for t, k in zip(tensors, ks)])
+
+    def mag(weight, w_thr, hi, lo):
+        keep = weight.detach().abs() > float(w_thr)
+        return torch.where(keep, torch.full_like(weight, hi), torch.full_like(weight, lo))
+
+    monkeypatch.setattr(ops, "kth_value_batched", kth)
+    monkeypatch.setattr(ops, "magnitude_init", mag)
+    monkeypatch.setattr(ops, "binarize", lambda s, t, want_count=False, as_bool=False: o_ops.binarize(s.detach(), float(t)))
+    g = torch.load(os.path.join(GOLD, "visualbert_tiny.pt"), weights_only=False)
+    model = VisualBertForMultipleChoice(visualBERTConfig(**g["config"]))
+    model.load_state_dict(g["state_dict"], strict=True)
+    log = logging.getLogger("t")
+    log.setLevel(logging.ERROR)
+    margs = ModelArguments(model_type="visual_bert", zero_rate=0.7)
+    masker = init_masker(margs, model, log)
+    mods = [(n, m) for n, m in model.named_modules() if hasattr(m, "threshold")]
+    assert [n for n, _ in mods] == g["module_names"]
+    assert sorted(n for n, p in model.named_parameters() if p.requires_grad) == g["trainable"]
+    assert {n: int((m.weight_mask > 1e-2).sum()) for n, m in mods} == g["kept_init"]
+    assert masker.masker_scheduler.init_sparsity == 0.7 and margs.layers_to_mask_ == list(range(12))
+    margs2 = ModelArguments(model_type="visual_bert", mask_classifier=True)
+    with pytest.raises(AssertionError):
+        init_masker(margs2, VisualBertForMultipleChoice(visualBERTConfig(**g["config"])), log)
