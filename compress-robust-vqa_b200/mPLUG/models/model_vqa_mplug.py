@@ -11,8 +11,8 @@ term, is therefore skipped here (``MPLUG.run_unused_distill_forward = True`` run
 
 The reference initialises from checkpoints (``from_pretrained`` of bert-base-uncased, ``ckpts/ViT-B-16.tar``); none
 ship, so the stacks are randomly initialised and ``load_state_dict`` of a reference checkpoint works key for key
-(except the CLIP text tower, which mPLUG-VQA never runs and this package does not build).  ``train=False`` (beam-search
-generation, mPLUG/models/predictor.py) is not built; the closed-set alternative ``rank_answer`` (:188-245) is.
+(except the CLIP text tower, which mPLUG-VQA never runs and this package does not build).  ``train=False`` runs the
+beam search of ``predictor.TextGenerator``; the closed-set alternative ``rank_answer`` (:188-245) is built too.
 """
 import os
 
@@ -21,6 +21,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .modeling_mplug import BertConfig, BertLMHeadModel, BertModel, FusionModel
+from .predictor import TextGenerator
 from .visual_transformers import initialize_clip
 
 
@@ -42,6 +43,11 @@ class MPLUG(nn.Module):
         self.fusion_encoder = FusionModel(self.config_fusion, add_pooling_layer=False)
         self.text_decoder = BertLMHeadModel(self.config_decoder)
         self.init_distill(config)
+        # generation settings: the reference's driver copies --beam_size / --min_length / --max_length into the config
+        # (vqa_mplug.py:494-496, defaults 5 / 1 / 10)
+        self.beam_generator = TextGenerator(
+            {"beam_size": config.get("beam_size", 5), "min_length": config.get("min_length", 1),
+             "max_length": config.get("max_length", 10)}, self.text_decoder)
 
     # -- configuration ---------------------------------------------------------------------------
     @staticmethod
@@ -139,7 +145,8 @@ class MPLUG(nn.Module):
         image_embeds = self._image_states(image)
         image_atts = torch.ones(image_embeds.size()[:-1], dtype=torch.long, device=image.device)
         if not train:
-            raise NotImplementedError("beam-search answer generation (mPLUG/models/predictor.py) is not built")
+            states = self._question_states(image_embeds, image_atts, question)
+            return self.generation(states, torch.cat([image_atts, question.attention_mask], 1))
 
         answer_targets = answer.input_ids.masked_fill(answer.input_ids == self.pad_token_id, -100)
         question_states = self._repeat(self._question_states(image_embeds, image_atts, question), k)
@@ -163,6 +170,10 @@ class MPLUG(nn.Module):
         if bias is not None:
             loss = (1 - bias) * loss
         return loss.sum() / image.size(0)
+
+    def generation(self, question_states, question_atts):
+        """Beam search over the answer decoder (:181-184): per question a list of token-id tensors and their scores."""
+        return self.beam_generator.translate_batch([question_states, question_atts])
 
     # -- closed-set inference --------------------------------------------------------------------
     @torch.no_grad()

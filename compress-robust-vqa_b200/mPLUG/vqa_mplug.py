@@ -2,10 +2,12 @@
 
 Kept with the reference's names and semantics: ``load_mask_and_prune`` (:44-52), ``encode_maskconfig`` (:54-57),
 ``init_masker`` (:59-128: scheduler wiring, the four towers' weight types / layers, ``_m`` twins), the mask-update
-block of the training loop (:202-210, here ``update_masks``) and ``train`` (:130-217) over batches that are already
-tokenised.  The reference driver itself needs DeepSpeed, the CLIP / BERT checkpoints and the VQA image datasets (none
+block of the training loop (:202-210, here ``update_masks``), ``train`` (:130-217) over batches that are already
+tokenised, and the generation-side helpers ``evaluation`` (:219-246), ``evaluate`` (:248-290), ``cal_metric``
+(:292-306) and ``save_result`` (:309-311).  The reference driver itself needs DeepSpeed, the CLIP / BERT checkpoints and the VQA image datasets (none
 shipped); the engine of ``engine.py`` stands where the DeepSpeed engine stands.
 """
+import json
 import logging
 import os
 
@@ -126,3 +128,57 @@ def train(model, data_loader, epoch, masker=None, masker_update_step=5, output_d
         if log is not None:
             log(model.global_steps, loss)
     return float(total / count) if count else float("nan")
+
+
+# --------------------------------------------------------------------------- generation-side helpers
+def _decode(tokenizer, ids):
+    text = tokenizer.decode(ids)
+    return text.replace("[SEP]", "").replace("[CLS]", "").replace("[PAD]", "").strip()
+
+
+@torch.no_grad()
+def evaluation(model, data_loader, tokenizer, device, config):
+    """Generate one answer per question: [{"question_id", "answer"}] (beam search, best hypothesis)."""
+    model.eval()
+    result = []
+    for image, question, question_id in data_loader:
+        image = image.to(device, non_blocking=True)
+        question_input = tokenizer(question, padding="longest", return_tensors="pt").to(device)
+        topk_ids, _ = model(image, question_input, None, train=False, k=config["k_test"])
+        for ques_id, topk_id in zip(question_id, topk_ids):
+            result.append({"question_id": int(ques_id.item() if torch.is_tensor(ques_id) else ques_id),
+                           "answer": _decode(tokenizer, topk_id[0])})
+    return result
+
+
+def cal_metric(vqa_result, val_file):
+    """Mean soft VQA score of the generated answers against ``val_file[0]`` (a JSON list of {question_id, label})."""
+    with open(val_file[0], "r") as f:
+        id2datum = {each["question_id"]: each["label"] for each in json.load(f)}
+    score = 0.0
+    for each in vqa_result:
+        label = id2datum[each["question_id"]]
+        if each["answer"] in label:
+            score += label[each["answer"]]
+    return score / len(vqa_result)
+
+
+def save_result(result, output_file):
+    with open(output_file, "w") as f:
+        json.dump(result, f)
+
+
+@torch.no_grad()
+def evaluate(model, data_loader, dataset, tokenizer, device, config, output_dir):
+    """Generate, score every batch against the label file ``dataset`` and write ``vqa_answer.json``; returns
+    ``{"acc": "<mean over questions, 4 decimals>"}`` like the reference's metric logger."""
+    model.eval()
+    results, total, count = [], 0.0, 0
+    for image, question, question_id in data_loader:
+        batch = evaluation(model, [(image, question, question_id)], tokenizer, device, config)
+        results += batch
+        total += cal_metric(batch, dataset) * len(batch)
+        count += len(batch)
+    os.makedirs(output_dir, exist_ok=True)
+    save_result(results, os.path.join(output_dir, "vqa_answer.json"))
+    return {"acc": "{:.4f}".format(total / max(count, 1))}

@@ -89,8 +89,6 @@ def test_dense_network_matches_reference(gold):
     finally:
         type(model).run_unused_distill_forward = False
     assert again == pytest.approx(loss_b, rel=1e-6)
-    with pytest.raises(NotImplementedError):
-        model(batch(gold)[0], None, train=False)
 
 
 def test_rank_answer_matches_reference(gold):
@@ -143,3 +141,94 @@ def test_masking_the_network_host_logic(gold, oracle_backend):
     mean = maskers.reset_threshold(model, 0.7)
     r = G["reset_0.7"]
     assert mean == r["mean"] and thr_record(model) == r["thresholds"] and kept(model) == r["kept"]
+
+
+def test_beam_search_generation_matches_reference():
+    """MPLUG.forward(train=False) -> predictor.TextGenerator: same token sequences and scores as the reference's beam
+    search for three (beam, min_length, max_length) settings, the full ranked lists, and the early-close case where
+    finished questions leave the batch (tests/golden/mplug_generation_tiny.pt, make_golden_mplug_generation.py)."""
+    from mPLUG.models.model_vqa_mplug import MPLUG
+    g = torch.load(os.path.join(os.path.dirname(GOLD), "mplug_generation_tiny.pt"), weights_only=False)
+    config = dict(g["config"], bert_config=dict(g["bert"]))
+    model = MPLUG(config=config, tokenizer=types.SimpleNamespace(pad_token_id=0))
+    model.load_state_dict(g["state_dict"], strict=True)
+    model.eval()
+    B, res = 5, g["config"]["image_res"]
+    gen = torch.Generator().manual_seed(9)
+    image = torch.randn(B, 3, res, res, generator=gen)
+    q_ids = torch.randint(1, 100, (B, 6), generator=gen)
+    q_att = torch.ones(B, 6, dtype=torch.long)
+    q_att[2, 4:] = 0
+    q_ids[2, 4:] = 0
+    image = image * torch.arange(1, B + 1).view(-1, 1, 1, 1).float()
+    question = types.SimpleNamespace(input_ids=q_ids, attention_mask=q_att)
+
+    def same(ids, scores, want):
+        assert [[t.tolist() for t in q] for q in ids] == [[t.tolist() for t in q] for q in want["ids"]]
+        for got_q, want_q in zip(scores, want["scores"]):
+            assert [float(s) for s in got_q] == pytest.approx(want_q, rel=1e-4)
+
+    bg = model.beam_generator
+    for key in ((3, 1, 6), (2, 0, 4), (1, 2, 5)):
+        bg.beam_size, bg.min_length, bg.max_length = key
+        ids, scores = model(image, question, None, train=False, k=None)
+        same(ids, scores, g["runs"][key])
+    bg.beam_size, bg.min_length, bg.max_length = 3, 1, 6
+    states, atts = model.encode_question(image, question)
+    same(*bg.translate_batch([states, atts], out_size=3), g["runs"]["ranked3"])
+    with torch.no_grad():
+        model.text_decoder.cls.predictions.bias[102] = g["runs"]["early_close_bias"]
+    ids, scores = bg.translate_batch([states, atts], out_size=3)
+    same(ids, scores, g["runs"]["early_close"])
+    assert sorted({len(t) for q in ids for t in q}) != [7]          # some hypotheses ended before max_length
+    with pytest.raises(NotImplementedError):
+        bg.translate_batch([states, atts], do_sample=True)
+
+
+def test_evaluation_loop_with_a_toy_tokenizer(tmp_path):
+    """vqa_mplug.evaluation / evaluate / cal_metric / save_result on the generation fixture: answers are the decoded best
+    hypotheses without the special tokens; the accuracy is the mean soft score from the label file."""
+    import json
+
+    from mPLUG import vqa_mplug
+    from mPLUG.models.model_vqa_mplug import MPLUG
+    g = torch.load(os.path.join(os.path.dirname(GOLD), "mplug_generation_tiny.pt"), weights_only=False)
+    model = MPLUG(config=dict(g["config"], bert_config=dict(g["bert"])), tokenizer=types.SimpleNamespace(pad_token_id=0))
+    model.load_state_dict(g["state_dict"], strict=True)
+    bg = model.beam_generator
+    bg.beam_size, bg.min_length, bg.max_length = 3, 1, 6
+
+    class Enc(types.SimpleNamespace):
+        def to(self, device):
+            return Enc(input_ids=self.input_ids.to(device), attention_mask=self.attention_mask.to(device))
+
+    class Tok:
+        special = {101: "[CLS]", 102: "[SEP]", 0: "[PAD]"}
+
+        def __call__(self, questions, padding="longest", return_tensors="pt", **kw):
+            ids = torch.stack(questions)
+            return Enc(input_ids=ids, attention_mask=(ids != 0).long())
+
+        def decode(self, ids):
+            return " ".join(self.special.get(int(t), f"w{int(t)}") for t in ids)
+
+    B, res = 5, g["config"]["image_res"]
+    gen = torch.Generator().manual_seed(9)
+    image = torch.randn(B, 3, res, res, generator=gen)
+    q_ids = torch.randint(1, 100, (B, 6), generator=gen)
+    q_ids[2, 4:] = 0
+    image = image * torch.arange(1, B + 1).view(-1, 1, 1, 1).float()
+    loader = [(image[:3], list(q_ids[:3]), torch.tensor([10, 11, 12])), (image[3:], list(q_ids[3:]), torch.tensor([13, 14]))]
+    out = vqa_mplug.evaluation(model, loader, Tok(), torch.device("cpu"), {"k_test": 128})
+    want = g["runs"][(3, 1, 6)]["ids"]
+    assert [r["question_id"] for r in out] == [10, 11, 12, 13, 14]
+    for r, q in zip(out, want):
+        assert r["answer"] == " ".join(f"w{int(t)}" for t in q[0] if int(t) not in (0, 101, 102))
+    labels = [{"question_id": r["question_id"], "label": {r["answer"]: 0.5 + 0.1 * i}} for i, r in enumerate(out)]
+    labels[1]["label"] = {"something else": 1.0}
+    (tmp_path / "labels.json").write_text(json.dumps(labels))
+    assert vqa_mplug.cal_metric(out, [str(tmp_path / "labels.json")]) == pytest.approx((0.5 + 0.7 + 0.8 + 0.9) / 5)
+    stats = vqa_mplug.evaluate(model, loader, [str(tmp_path / "labels.json")], Tok(), torch.device("cpu"),
+                               {"k_test": 128}, str(tmp_path / "out"))
+    assert stats == {"acc": "{:.4f}".format((0.5 + 0.7 + 0.8 + 0.9) / 5)}
+    assert json.loads((tmp_path / "out" / "vqa_answer.json").read_text()) == out
