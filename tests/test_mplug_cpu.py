@@ -472,3 +472,48 @@ def test_held_masked_operand_is_rebuilt_exactly_when_it_must(gold, oracle_backen
     assert calls[-1] == float(maskers.bf16_score_threshold(torch.tensor(float(mod.threshold))))
     eng.invalidate_masks()
     assert mod._wm is None
+
+
+def test_optimizer_groups_and_cosine_schedule_match_reference():
+    """mPLUG/optim + mPLUG/scheduler against the reference packages (tests/golden/mplug_host.json): same parameter
+    groups (members, lr, weight decay) for create_optimizer / create_two_optimizer, same learning rate after every
+    scheduler.step(t) incl. the warm-up line, repeated / out-of-order calls, restarts with t_mul and decay_rate."""
+    import json
+    import types
+
+    from mPLUG.optim import create_optimizer, create_two_optimizer
+    from mPLUG.scheduler import create_scheduler
+    with open(os.path.join(os.path.dirname(GOLD), "mplug_host.json")) as f:
+        G = json.load(f)
+    model = sk.build()
+    for n, p in model.named_parameters():
+        p.requires_grad = ("predictions" in n) or n.endswith("intermediate.dense.weight")
+    names = {id(p): n for n, p in model.named_parameters()}
+    vis = {id(p): "visual_encoder." + n for n, p in model.visual_encoder.named_parameters()}
+
+    def groups(opt):
+        return [{"lr": g["lr"], "weight_decay": g["weight_decay"],
+                 "params": [names.get(id(p), vis.get(id(p))) for p in g["params"]]} for g in opt.param_groups]
+
+    a = types.SimpleNamespace(**G["opt"])
+    two = create_two_optimizer(a, model)
+    assert groups(two) == G["two_optimizer_groups"]
+    one = create_optimizer(a, model)
+    assert groups(one) == G["optimizer_groups"]
+    assert isinstance(one, torch.optim.AdamW) and isinstance(two, torch.optim.AdamW)
+    sch, epochs = create_scheduler(types.SimpleNamespace(**G["sched"]), two)
+    assert epochs == G["num_epochs"]
+    assert [g["lr"] for g in two.param_groups] == G["lr_after_init"]
+    for t, want in G["lr_by_step"]:
+        sch.step(t)
+        assert [g["lr"] for g in two.param_groups] == pytest.approx(want, rel=1e-12, abs=0), t
+    sch2, _ = create_scheduler(types.SimpleNamespace(**dict(G["sched"], warmup_epochs=0, lr_cycle_limit=2,
+                                                            lr_cycle_mul=2.0, decay_rate=0.5, epochs=3)), one)
+    for t, want in G["lr_by_step_cycles"]:
+        sch2.step(t)
+        assert [g["lr"] for g in one.param_groups] == pytest.approx(want, rel=1e-12, abs=0), t
+    assert sch2.get_cycle_length() == G["cycle_length"]
+    with pytest.raises(NotImplementedError):
+        create_scheduler(types.SimpleNamespace(**dict(G["sched"], sched="tanh")), one)
+    with pytest.raises(NotImplementedError):
+        create_optimizer(types.SimpleNamespace(**dict(G["opt"], opt="lookahead_adam")), model)
