@@ -1,0 +1,53 @@
+"""Batch formats of the mPLUG VQA loaders (reference mPLUG/dataset/__init__.py:116-135) and a synthetic dataset of the
+same item format.  The reference's image datasets, transforms and samplers need the VQA / COCO / VG files (not shipped)."""
+import torch
+from torch.utils.data import Dataset
+
+
+def vqa_collate_fn(batch):
+    """[(image, question, answers, weights)] -> (images [B,3,H,W], questions, flat answers, flat weights, answers per
+    question)."""
+    images, questions, answers, weights, n = [], [], [], [], []
+    for image, question, answer, weight in batch:
+        images.append(image)
+        questions.append(question)
+        answers += answer
+        weights += weight
+        n.append(len(answer))
+    return torch.stack(images, dim=0), questions, answers, torch.Tensor(weights), n
+
+
+def vqa_bias_collate_fn(batch):
+    """The same with one language-prior bias value per answer appended (VQA-CP debiasing)."""
+    images, questions, answers, weights, n, biases = [], [], [], [], [], []
+    for image, question, answer, weight, bias in batch:
+        images.append(image)
+        questions.append(question)
+        answers += answer
+        weights += weight
+        n.append(len(answer))
+        biases += bias
+    return torch.stack(images, dim=0), questions, answers, torch.Tensor(weights), n, torch.Tensor(biases)
+
+
+class SyntheticVQAImageDataset(Dataset):
+    """Items shaped like the reference's vqa_dataset in training mode: (image [3,res,res], question string, list of
+    answer strings, list of answer weights[, list of biases]); text is made of the given vocabulary words."""
+
+    def __init__(self, n, image_res=384, words=("what", "color", "is", "the", "cat", "two", "red", "yes", "no", "dog"),
+                 with_bias=True, seed=49, eos="[SEP]"):
+        g = torch.Generator().manual_seed(seed)
+        self.images = torch.randn(n, 3, image_res, image_res, generator=g)
+        pick = lambda k: " ".join(words[int(i)] for i in torch.randint(0, len(words), (k,), generator=g))  # noqa: E731
+        self.questions = [pick(int(torch.randint(3, 9, (1,), generator=g))) for _ in range(n)]
+        counts = torch.randint(1, 4, (n,), generator=g)
+        self.answers = [[pick(int(torch.randint(1, 3, (1,), generator=g))) + eos for _ in range(int(c))] for c in counts]
+        self.weights = [[float(w) for w in torch.rand(int(c), generator=g)] for c in counts]
+        self.biases = [[float(b) * 0.5 for b in torch.rand(int(c), generator=g)] for c in counts] if with_bias else None
+
+    def __len__(self):
+        return len(self.questions)
+
+    def __getitem__(self, i):
+        item = (self.images[i], self.questions[i], self.answers[i], self.weights[i])
+        return item + (self.biases[i],) if self.biases is not None else item

@@ -2,8 +2,8 @@
 
 Kept with the reference's names and semantics: ``load_mask_and_prune`` (:44-52), ``encode_maskconfig`` (:54-57),
 ``init_masker`` (:59-128: scheduler wiring, the four towers' weight types / layers, ``_m`` twins), the mask-update
-block of the training loop (:202-210, here ``update_masks``), ``train`` (:130-217) over batches that are already
-tokenised, and the generation-side helpers ``evaluation`` (:219-246), ``evaluate`` (:248-290), ``cal_metric``
+block of the training loop (:202-210, here ``update_masks``), ``train`` (:130-217, same signature; plus
+``train_pretokenized`` for batches that already are model arguments), and the generation-side helpers ``evaluation`` (:219-246), ``evaluate`` (:248-290), ``cal_metric``
 (:292-306) and ``save_result`` (:309-311).  The reference driver itself needs DeepSpeed, the CLIP / BERT checkpoints and the VQA image datasets (none
 shipped); the engine of ``engine.py`` stands where the DeepSpeed engine stands.
 """
@@ -111,23 +111,77 @@ def update_masks(model, masker, epoch, output_dir=None):
     return mean_thresh, target_sparsity
 
 
-def train(model, data_loader, epoch, masker=None, masker_update_step=5, output_dir=None, log=None):
-    """One epoch of the reference loop (:130-217) on an engine (``engine.MaskTrainEngine``): every batch is the tuple
-    of positional arguments of ``model(...)`` and yields the loss; forward -> backward -> step, and the mask update
-    whenever ``global_steps`` is a multiple of ``masker_update_step``.  Returns the mean loss."""
+def _train_step(model, args, masker, masker_update_step, epoch, output_dir):
+    loss = model(*args[0], **args[1])
+    model.backward(loss)
+    model.step()
+    if masker is not None and model.global_steps % masker_update_step == 0:
+        update_masks(model, masker, epoch, output_dir)
+    return loss.detach()
+
+
+def train_pretokenized(model, data_loader, epoch, masker=None, masker_update_step=5, output_dir=None, log=None):
+    """One epoch on an engine (``engine.MaskTrainEngine``) over batches that are already the positional arguments of
+    ``model(...)``: forward -> backward -> step, and the mask update whenever ``global_steps`` is a multiple of
+    ``masker_update_step``.  Returns the mean loss."""
     model.train()
     total, count = None, 0
     for batch in data_loader:
-        loss = model(*batch)
-        model.backward(loss)
-        model.step()
-        total = loss.detach() if total is None else total + loss.detach()
+        loss = _train_step(model, (batch, {}), masker, masker_update_step, epoch, output_dir)
+        total = loss if total is None else total + loss
         count += 1
-        if masker is not None and model.global_steps % masker_update_step == 0:
-            update_masks(model, masker, epoch, output_dir)
         if log is not None:
             log(model.global_steps, loss)
     return float(total / count) if count else float("nan")
+
+
+def train(model, data_loader, optimizer, tokenizer, epoch, warmup_steps, device, scheduler, config, do_amp=False,
+          do_two_optim=False, do_accum=False, accum_steps=1, masker=None, masker_update_step=5, output_dir=None,
+          max_input_length=25):
+    """One epoch of the reference loop with its own signature (:130-217).  Batches come from ``vqa_collate_fn`` /
+    ``vqa_bias_collate_fn`` (image, questions, answers, weights, n[, bias]); questions and answers are tokenised here;
+    the distillation weight ramps over epoch 0 when ``config['warm_up']``; during epoch 0 the scheduler is stepped every
+    100 iterations up to ``warmup_steps * 100``; the masks are refreshed every ``masker_update_step`` optimiser steps.
+    ``model`` is the engine (``model(...)``, ``.backward``, ``.step``, ``.global_steps``); ``do_amp`` / ``do_accum`` /
+    ``accum_steps`` are accepted and, as in the reference (whose code for them is commented out), unused.  Returns the
+    reference's stats dict: {"lr" | "lr1", "lr2", "loss"} as formatted averages."""
+    model.train()
+    step_size = 100
+    warmup_iterations = warmup_steps * step_size
+    losses, lr_log = [], []
+    n_batches = len(data_loader)
+    for i, data in enumerate(data_loader):
+        if len(data) == 5:
+            image, question, answer, weights, n = data
+            bias = None
+        else:
+            image, question, answer, weights, n, bias = data
+            bias = bias.to(device, non_blocking=True)
+        image, weights = image.to(device, non_blocking=True), weights.to(device, non_blocking=True)
+        question_input = tokenizer(question, padding="longest", truncation=True,
+                                   max_length=max_input_length if config.get("add_ocr") else 25,
+                                   return_tensors="pt").to(device)
+        answer_input = tokenizer(answer, padding="longest", return_tensors="pt").to(device)
+        if epoch > 0 or not config["warm_up"]:
+            alpha = config["alpha"]
+        else:
+            alpha = config["alpha"] * min(1, i / n_batches)
+        kwargs = dict(train=True, alpha=alpha, k=n, weights=weights, bias=bias)
+        loss = _train_step(model, ((image, question_input, answer_input), kwargs), masker, masker_update_step, epoch,
+                           output_dir)
+        losses.append(loss)
+        lr_log.append((optimizer.param_groups[0]["lr"], optimizer.param_groups[2]["lr"] if do_two_optim else None))
+        if epoch == 0 and i % step_size == 0 and i <= warmup_iterations:
+            scheduler.step(i // step_size)
+    mean = float(torch.stack(losses).mean()) if losses else float("nan")
+    stats = {"loss": "{:.3f}".format(mean)}
+    if lr_log:
+        if do_two_optim:
+            stats["lr1"] = "{:.3f}".format(sum(a for a, _ in lr_log) / len(lr_log))
+            stats["lr2"] = "{:.3f}".format(sum(b for _, b in lr_log) / len(lr_log))
+        else:
+            stats["lr"] = "{:.3f}".format(sum(a for a, _ in lr_log) / len(lr_log))
+    return stats
 
 
 # --------------------------------------------------------------------------- generation-side helpers

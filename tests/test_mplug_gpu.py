@@ -159,7 +159,7 @@ def test_mplug_engine_trains_scores_and_head_only(gold):
     batch = tuple(t.cuda() for t in sk.batch())
     losses = []
     for epoch in range(3):
-        mean = quiet(vqa_mplug.train, eng, [batch] * 4, epoch, masker=masker, masker_update_step=2)
+        mean = quiet(vqa_mplug.train_pretokenized, eng, [batch] * 4, epoch, masker=masker, masker_update_step=2)
         losses.append(mean)
         for n, m in masked(model):
             want = om.mask_of(m.weight_mask.detach().cpu(), m.threshold.cpu() if torch.is_tensor(m.threshold)

@@ -232,3 +232,76 @@ def test_evaluation_loop_with_a_toy_tokenizer(tmp_path):
                                {"k_test": 128}, str(tmp_path / "out"))
     assert stats == {"acc": "{:.4f}".format((0.5 + 0.7 + 0.8 + 0.9) / 5)}
     assert json.loads((tmp_path / "out" / "vqa_answer.json").read_text()) == out
+
+
+class _ToyTokenizer:
+    """Whitespace tokenizer over a tiny vocabulary with BERT's special ids ([PAD] 0, [CLS] 101 -> here 1, [SEP] 2)."""
+    pad_token_id = 0
+
+    def __init__(self, words):
+        self.ids = {w: i + 3 for i, w in enumerate(words)}
+
+    def __call__(self, texts, padding="longest", truncation=False, max_length=None, return_tensors="pt"):
+        rows = []
+        for t in texts:
+            toks = [1] + [self.ids[w] for w in t.replace("[SEP]", " ").split()] + [2]
+            rows.append(toks[:max_length] if truncation and max_length else toks)
+        width = max(len(r) for r in rows)
+        ids = torch.tensor([r + [0] * (width - len(r)) for r in rows])
+
+        class Enc(types.SimpleNamespace):
+            def to(self, device):
+                return Enc(input_ids=self.input_ids.to(device), attention_mask=self.attention_mask.to(device))
+
+        return Enc(input_ids=ids, attention_mask=(ids != 0).long())
+
+
+def test_reference_signature_train_loop_on_cpu(gold):
+    """vqa_mplug.train with the reference's argument list on the dense tiny network (plain torch on the CPU): collate ->
+    tokenise -> engine step, alpha ramp and scheduler warm-up calls in epoch 0, stats dict; train_pretokenized too."""
+    from torch.utils.data import DataLoader
+
+    from mPLUG import vqa_mplug
+    from mPLUG.dataset import SyntheticVQAImageDataset, vqa_bias_collate_fn, vqa_collate_fn
+    from mPLUG.engine import MaskTrainEngine
+    from mPLUG.optim import create_two_optimizer
+    from mPLUG.scheduler import create_scheduler
+    model = build(gold)
+    words = ("what", "color", "is", "the", "cat", "two", "red", "yes", "no", "dog")
+    tok = _ToyTokenizer(words)
+    data = SyntheticVQAImageDataset(6, image_res=gold["config"]["image_res"], words=words, with_bias=True, seed=3)
+    item = data[0]
+    assert item[0].shape == (3, 64, 64) and isinstance(item[1], str) and len(item[2]) == len(item[3]) == len(item[4])
+    loader = DataLoader(data, batch_size=3, collate_fn=vqa_bias_collate_fn)
+    image, questions, answers, weights, n, bias = next(iter(loader))
+    assert image.shape[0] == 3 and len(questions) == 3 and sum(n) == len(answers) == weights.numel() == bias.numel()
+    plain = vqa_collate_fn([d[:4] for d in (data[0], data[1])])
+    assert len(plain) == 5 and plain[4] == [len(data[0][2]), len(data[1][2])]
+
+    opt = create_two_optimizer(types.SimpleNamespace(lr1=1e-3, lr2=1e-4, weight_decay=0.02), model)
+    sch, _ = create_scheduler(types.SimpleNamespace(sched="cosine", lr=1e-3, epochs=8, min_lr=1e-6, decay_rate=1,
+                                                    warmup_lr=1e-5, warmup_epochs=4, cooldown_epochs=0), opt)
+    eng = MaskTrainEngine(model, opt, gradient_clipping=1.0, bf16=False)
+    alphas = []
+    fwd = model.forward
+
+    def spy(*a, **k):
+        alphas.append(k["alpha"])
+        return fwd(*a, **k)
+
+    model.forward = spy
+    cfg = {"alpha": 0.4, "warm_up": True, "add_ocr": False}
+    s0 = vqa_mplug.train(eng, loader, opt, tok, 0, 4, torch.device("cpu"), sch, cfg, do_two_optim=True)
+    assert alphas == [0.0, 0.2] and eng.global_steps == 2                    # alpha * min(1, i / len(loader))
+    assert set(s0) == {"loss", "lr1", "lr2"}
+    assert opt.param_groups[0]["lr"] == pytest.approx(1e-5)                    # scheduler.step(0) at i == 0: warm-up start
+    s1 = vqa_mplug.train(eng, loader, opt, tok, 1, 4, torch.device("cpu"), sch, cfg, do_two_optim=True)
+    assert alphas[2:] == [0.4, 0.4] and eng.global_steps == 4
+    assert float(s1["loss"]) > 0 and float(s1["lr1"]) == 0.0                 # "{:.3f}" of 1e-5, as the reference logs it
+    model.forward = fwd
+    q = tok(questions)
+    a = tok(answers)
+    mean = vqa_mplug.train_pretokenized(eng, [(image, q, a, 0.4, n, weights)] * 2, 2)
+    assert eng.global_steps == 6 and mean > 0
+    assert not torch.equal(model.text_decoder.cls.predictions.transform.dense.weight,
+                           gold["online"]["text_decoder.cls.predictions.transform.dense.weight"])
