@@ -51,3 +51,39 @@ class SyntheticVQAImageDataset(Dataset):
     def __getitem__(self, i):
         item = (self.images[i], self.questions[i], self.answers[i], self.weights[i])
         return item + (self.biases[i],) if self.biases is not None else item
+
+
+WORDS = ("what", "color", "is", "the", "cat", "two", "red", "yes", "no", "dog")
+
+
+class WhitespaceTokenizer:
+    """Stand-in for the BERT tokenizer on synthetic text (no vocabulary file ships): whitespace words of a fixed list,
+    BERT's special ids ([PAD] 0, [CLS] 101, [SEP] 102 -- the ids the beam search hard-codes), ``padding='longest'``
+    batches with ``input_ids`` / ``attention_mask`` and ``.to(device)``, and ``decode``."""
+    pad_token_id, cls_token_id, sep_token_id = 0, 101, 102
+
+    def __init__(self, words=WORDS, first_id=103):
+        self.ids = {w: first_id + i for i, w in enumerate(words)}
+        self.words = {i: w for w, i in self.ids.items()}
+        self.words.update({0: "[PAD]", 101: "[CLS]", 102: "[SEP]"})
+        self.vocab_size = first_id + len(words)
+
+    class Encoding:
+        def __init__(self, input_ids, attention_mask):
+            self.input_ids, self.attention_mask = input_ids, attention_mask
+
+        def to(self, device):
+            return WhitespaceTokenizer.Encoding(self.input_ids.to(device), self.attention_mask.to(device))
+
+    def __call__(self, texts, padding="longest", truncation=False, max_length=None, return_tensors="pt"):
+        rows = []
+        for text in texts:
+            body = [self.ids[w] for w in text.replace("[SEP]", " ").split()]
+            row = [self.cls_token_id] + body + [self.sep_token_id]
+            rows.append(row[:max_length] if truncation and max_length else row)
+        width = max(len(r) for r in rows)
+        ids = torch.tensor([r + [self.pad_token_id] * (width - len(r)) for r in rows])
+        return self.Encoding(ids, (ids != self.pad_token_id).long())
+
+    def decode(self, ids):
+        return " ".join(self.words.get(int(t), "[UNK]") for t in ids)

@@ -7,9 +7,11 @@ block of the training loop (:202-210, here ``update_masks``), ``train`` (:130-21
 (:292-306) and ``save_result`` (:309-311).  The reference driver itself needs DeepSpeed, the CLIP / BERT checkpoints and the VQA image datasets (none
 shipped); the engine of ``engine.py`` stands where the DeepSpeed engine stands.
 """
+import argparse
 import json
 import logging
 import os
+import types
 
 import torch
 
@@ -236,3 +238,68 @@ def evaluate(model, data_loader, dataset, tokenizer, device, config, output_dir)
     os.makedirs(output_dir, exist_ok=True)
     save_result(results, os.path.join(output_dir, "vqa_answer.json"))
     return {"acc": "{:.4f}".format(total / max(count, 1))}
+
+
+# --------------------------------------------------------------------------- synthetic entry point
+TINY = dict(clip_width=64, clip_layers=2, clip_heads=4, clip_output_dim=32, clip_patch_size=16, vision_width=64,
+            bert_config=dict(vocab_size=128, hidden_size=64, num_hidden_layers=4, num_attention_heads=4,
+                             intermediate_size=128, max_position_embeddings=32, encoder_width=64, fusion_layers=2,
+                             stride_layer=1, text_encoder_layers=2, text_decode_layers=2))
+TINY_LAYERS = {"visual_encoder": [0, 1], "text_encoder": [0, 1], "fusion_encoder": [2, 3], "text_decoder": [0, 1]}
+
+
+def main(argv=None):
+    """The reference's main() flow (:313-460) on synthetic image-VQA data and random init: model -> init_masker ->
+    create_two_optimizer -> create_scheduler -> engine (in place of deepspeed.initialize) -> train()."""
+    if __package__:
+        from .dataset import SyntheticVQAImageDataset, WhitespaceTokenizer, vqa_bias_collate_fn
+        from .engine import MaskTrainEngine
+        from .models.model_vqa_mplug import MPLUG
+        from .optim import create_two_optimizer
+        from .scheduler import create_scheduler
+    else:
+        from dataset import SyntheticVQAImageDataset, WhitespaceTokenizer, vqa_bias_collate_fn
+        from engine import MaskTrainEngine
+        from models.model_vqa_mplug import MPLUG
+        from optim import create_two_optimizer
+        from scheduler import create_scheduler
+    ap = argparse.ArgumentParser(description="synthetic mPLUG masked training")
+    ap.add_argument("--image_res", type=int, default=384)
+    ap.add_argument("--batch_size", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--masker_update_step", type=int, default=2)
+    ap.add_argument("--zero_rate", type=float, default=0.7)
+    ap.add_argument("--tiny", action="store_true", help="a miniature network (smoke runs)")
+    ap.add_argument("--no_mask", action="store_true", help="dense network, no masker (runs on a CPU)")
+    ap.add_argument("--output_dir", default=None)
+    ap.add_argument("--device", default="cuda" if torch.cuda.is_available() else "cpu")
+    ap.add_argument("--seed", type=int, default=42)
+    a = ap.parse_args(argv)
+    torch.manual_seed(a.seed)
+    device = torch.device(a.device)
+    config = dict(image_res=a.image_res, vision_width=768, distill=True, clip_name="ViT-B-16", alpha=0.4, warm_up=True,
+                  add_ocr=False, bert_config=dict(stride_layer=3, fusion_layers=6, text_encoder_layers=6,
+                                                  text_decode_layers=12))
+    if a.tiny:
+        config.update(TINY)
+    tokenizer = WhitespaceTokenizer()
+    model = MPLUG(config=config, tokenizer=tokenizer).to(device)
+    masker = None
+    if not a.no_mask:
+        conf = MaskConfigs()
+        conf.zero_rate = a.zero_rate
+        masker = init_masker(conf, model, layers_to_mask=TINY_LAYERS if a.tiny else None)
+    optimizer = create_two_optimizer(types.SimpleNamespace(lr1=3e-5, lr2=5e-6, weight_decay=0.02), model)
+    scheduler, _ = create_scheduler(types.SimpleNamespace(sched="cosine", lr=3e-5, epochs=8, min_lr=1e-6, decay_rate=1,
+                                                          warmup_lr=1e-5, warmup_epochs=4, cooldown_epochs=0), optimizer)
+    engine = MaskTrainEngine(model, optimizer, gradient_clipping=1.0, bf16=True)
+    data = SyntheticVQAImageDataset(a.batch_size * a.steps, image_res=a.image_res, seed=a.seed)
+    loader = torch.utils.data.DataLoader(data, batch_size=a.batch_size, collate_fn=vqa_bias_collate_fn)
+    stats = train(engine, loader, optimizer, tokenizer, 0, 4, device, scheduler, config, do_two_optim=True,
+                  masker=masker, masker_update_step=a.masker_update_step, output_dir=a.output_dir)
+    print(stats)
+    return stats
+
+
+if __name__ == "__main__":
+    main()

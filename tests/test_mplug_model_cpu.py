@@ -305,3 +305,16 @@ def test_reference_signature_train_loop_on_cpu(gold):
     assert eng.global_steps == 6 and mean > 0
     assert not torch.equal(model.text_decoder.cls.predictions.transform.dense.weight,
                            gold["online"]["text_decoder.cls.predictions.transform.dense.weight"])
+
+
+def test_synthetic_main_runs_dense_on_cpu(capsys):
+    """python mPLUG/vqa_mplug.py --tiny --no_mask: the whole driver flow on the CPU (dense, no CUDA ops)."""
+    from mPLUG import vqa_mplug
+    from mPLUG.dataset import WhitespaceTokenizer
+    stats = vqa_mplug.main(["--tiny", "--no_mask", "--image_res", "32", "--batch_size", "2", "--steps", "2",
+                            "--device", "cpu"])
+    assert set(stats) == {"loss", "lr1", "lr2"} and float(stats["loss"]) > 0
+    tok = WhitespaceTokenizer()
+    enc = tok(["what color is the cat", "yes"])
+    assert enc.input_ids[1].tolist() == [101, 110, 102, 0, 0, 0, 0] and enc.attention_mask[1].tolist() == [1, 1, 1, 0, 0, 0, 0]
+    assert tok.decode(enc.input_ids[1]) == "[CLS] yes [SEP] [PAD] [PAD] [PAD] [PAD]"
