@@ -11,6 +11,7 @@ import io
 import logging
 import os
 import sys
+import types
 
 import numpy as np
 import pytest
@@ -517,3 +518,30 @@ def test_optimizer_groups_and_cosine_schedule_match_reference():
         create_scheduler(types.SimpleNamespace(**dict(G["sched"], sched="tanh")), one)
     with pytest.raises(NotImplementedError):
         create_optimizer(types.SimpleNamespace(**dict(G["opt"], opt="lookahead_adam")), model)
+
+
+def test_driver_utils():
+    from mPLUG import utils
+    d = utils.AttrDict({"opt": "adamW", "lr1": 3e-5})
+    assert d.opt == "adamW" and d["lr1"] == 3e-5
+    d.lr2 = 5e-6
+    assert d["lr2"] == 5e-6
+    assert utils.get_rank() == 0 and utils.get_world_size() == 1 and utils.is_main_process()
+    assert utils.compute_n_params(torch.nn.Linear(1000, 2000)) == "2.0M"
+    log = utils.MetricLogger(delimiter="  ")
+    log.add_meter("loss", utils.SmoothedValue(window_size=1, fmt="{value:.4f}"))
+    seen = []
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        for x in log.log_every([1.0, 3.0], 1, "hdr"):
+            log.update(loss=torch.tensor(x), lr=0.5)
+            seen.append(x)
+    assert seen == [1.0, 3.0] and "loss: 3.0000" in out.getvalue()
+    assert log.meters["loss"].global_avg == 2.0 and log.global_avg() == "loss: 2.0000  lr: 0.5000"
+    args = types.SimpleNamespace()
+    for k in ("RANK", "WORLD_SIZE"):
+        os.environ.pop(k, None)
+    with contextlib.redirect_stdout(io.StringIO()):
+        utils.init_distributed_mode(args)
+    assert args.distributed is False
