@@ -8,7 +8,6 @@ import os
 import sys
 import types
 
-import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(os.path.dirname(HERE)))

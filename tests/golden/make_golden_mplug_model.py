@@ -57,7 +57,7 @@ def load_reference_model_classes():
     sys.modules.setdefault("ftfy", types.ModuleType("ftfy"))
     vit = types.ModuleType("models.vit")
     vit.VisionTransformer = object
-    import models                                           # the reference's mPLUG/models package
+    import models  # noqa: F401  (the reference mPLUG/models package must be the one in sys.modules)
     sys.modules["models.vit"] = vit
     import models.modeling_mplug as mm
     import models.clip.model as cm
