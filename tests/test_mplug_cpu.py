@@ -545,3 +545,30 @@ def test_driver_utils():
     with contextlib.redirect_stdout(io.StringIO()):
         utils.init_distributed_mode(args)
     assert args.distributed is False
+
+
+def test_bf16_score_threshold_property_random_bit_patterns():
+    """Same equivalence on uniformly random fp32 BIT PATTERNS for both threshold and score (all exponents, both signs,
+    subnormals), plus scores placed exactly on and next to the two rounding boundaries of every threshold."""
+    from mPLUG.masking.maskers import bf16_score_threshold
+    g = torch.Generator().manual_seed(123)
+    tbits = torch.randint(-2 ** 31, 2 ** 31 - 1, (4000,), generator=g, dtype=torch.int64).to(torch.int32)
+    t = tbits.view(torch.float32)
+    t = t[torch.isfinite(t) & (t.abs() < 1e38)]
+    T = bf16_score_threshold(t)
+    t16 = t.to(torch.bfloat16)
+    sbits = torch.randint(-2 ** 31, 2 ** 31 - 1, (t.numel(), 64), generator=g, dtype=torch.int64).to(torch.int32)
+    S = sbits.view(torch.float32)
+    ok = torch.isfinite(S)
+    want = S.to(torch.bfloat16) > t16[:, None]
+    got = S > T[:, None]
+    assert torch.equal(want[ok], got[ok])
+    # the boundary itself and its two fp32 neighbours, for every threshold
+    for delta in (-1, 0, 1):
+        Tb = T.view(torch.int32).to(torch.int64)
+        key = torch.where(Tb < 0, -(Tb & 0x7FFFFFFF), Tb) + delta
+        bits = torch.where(key < 0, (-key) | 0x80000000, key)
+        bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+        Sb = bits.view(torch.float32)
+        fin = torch.isfinite(Sb)
+        assert torch.equal((Sb.to(torch.bfloat16) > t16)[fin], (Sb > T)[fin]), delta
