@@ -241,6 +241,36 @@ def test_reset_threshold_modes(oracle_backend):
     assert [float(net.a.threshold), float(net.b.threshold), float(net.c.threshold)] == [7.0, 70.0, 2.0]
 
 
+def test_save_model_mask_host_logic(oracle_backend, tmp_path):
+    """Trainer.save_model_mask: mask.pt holds one CPU BoolTensor per masked module (`S > thr`), the return value is the
+    overall zero rate in percent, per-modality bookkeeping follows masker.name_in_module (incl. DataParallel's
+    'module.' prefix)."""
+    from hg_transformers import mask_trainer_Robust_VQA as robust
+
+    class M(torch.nn.Module):
+        def __init__(self, scores, thr):
+            super().__init__()
+            self.weight_mask = torch.nn.Parameter(torch.tensor(scores))
+            self.threshold = torch.tensor(thr)
+
+    net = torch.nn.Module()
+    net.module = torch.nn.Module()
+    net.module.a = M([[0.0, 0.02, 0.02, 0.0]], 1e-2)        # 2 of 4 kept
+    net.module.b = M([[0.5, 0.1], [0.3, 0.31]], 0.3)        # strict >: 0.3 itself is dropped -> 2 of 4 kept
+    net.c = M([[1.0, 2.0, 3.0]], 0.0)                       # all kept
+    t = robust.Trainer.__new__(robust.Trainer)
+    t.model = net
+    t.masker = types.SimpleNamespace(name_in_module={"a": "Lang", "b": "Fus", "c": "P"})
+    t.args = types.SimpleNamespace(output_dir=str(tmp_path / "unused"))
+    rate = t.save_model_mask(str(tmp_path / "m"))
+    assert float(rate) == pytest.approx(100.0 * 4 / 11)
+    saved = torch.load(tmp_path / "m" / "mask.pt")
+    assert sorted(saved) == ["c.weight", "module.a.weight", "module.b.weight"]
+    assert saved["module.b.weight"].dtype == torch.bool
+    assert saved["module.b.weight"].tolist() == [[True, False], [False, True]]
+    assert saved["module.a.weight"].tolist() == [[False, True, True, False]] and saved["c.weight"].all()
+
+
 # ----------------------------------------------------------------------------- data parallel (gloo, 2 ranks)
 def _sync_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
