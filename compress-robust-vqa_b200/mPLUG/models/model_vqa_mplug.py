@@ -111,6 +111,13 @@ class MPLUG(nn.Module):
         fresh = torch._foreach_mul(online, 1.0 - self.momentum)
         torch._foreach_mul_(twins, self.momentum)
         torch._foreach_add_(twins, fresh)
+        # the twins' frozen weights and scores just moved underneath their masked modules (through .data, which does not
+        # bump the version counters those modules key their bf16 operand caches on): drop the caches
+        for _, twin in self.model_pairs:
+            for m in twin.modules():
+                if hasattr(m, "drop_masked_weight"):
+                    m._w16 = None
+                    m.drop_masked_weight()
 
     # -- towers ----------------------------------------------------------------------------------
     def _image_states(self, image, twin=False):

@@ -318,3 +318,24 @@ def test_synthetic_main_runs_dense_on_cpu(capsys):
     enc = tok(["what color is the cat", "yes"])
     assert enc.input_ids[1].tolist() == [101, 110, 102, 0, 0, 0, 0] and enc.attention_mask[1].tolist() == [1, 1, 1, 0, 0, 0, 0]
     assert tok.decode(enc.input_ids[1]) == "[CLS] yes [SEP] [PAD] [PAD] [PAD] [PAD]"
+
+
+def test_momentum_update_drops_the_twins_operand_caches(gold, oracle_backend):
+    """The EMA writes the twins' weights through .data; their masked modules must not keep bf16 operands derived from
+    the old values (matters only when the optional twin forward is switched on)."""
+    from mPLUG import vqa_mplug
+    from mPLUG.masking.mask_config import MaskConfigs
+    model = build(gold)
+    conf = MaskConfigs()
+    conf.zero_rate = 0.5
+    quiet(vqa_mplug.init_masker, conf, model, layers_to_mask=gold["layers_to_mask"])
+    twin = model.text_encoder_m.encoder.layer[0].intermediate.dense
+    online = model.text_encoder.encoder.layer[0].intermediate.dense
+    twin._w16, twin._wm = torch.zeros(1), torch.zeros(1)
+    online._w16 = torch.zeros(1)
+    with torch.no_grad():
+        online.weight_mask.add_(1.0)
+    before = twin.weight_mask.detach().clone()
+    model._momentum_update()
+    assert twin._w16 is None and twin._wm is None and online._w16 is not None
+    assert torch.allclose(twin.weight_mask, before * 0.995 + online.weight_mask * 0.005)
