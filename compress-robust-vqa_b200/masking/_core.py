@@ -428,7 +428,7 @@ class MaskedLinear1(MaskedLinearX):
             return None
         t = self.threshold               # the source object: alive as long as it is current, so its id is not reused
         key = (id(t), t._version if torch.is_tensor(t) else t, getattr(self, "score_dtype", None),
-               self.weight_mask.data_ptr(), thr.device)
+               self.weight_mask.data_ptr(), self.weight_mask._version, thr.device)   # optimisers bump _version
         if self._wm is None or self._wm_key != key:
             self._wm = ops.apply_mask_bf16(self._weight_bf16(), self.weight_mask.detach(), thr)
             self._wm_key = key
