@@ -377,3 +377,51 @@ def test_secondary_debias_losses_match_reference():
     loss.backward()
     torch.testing.assert_close(loss.detach(), g["bp"], rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(logits.grad, g["bp_dlogits"], rtol=1e-5, atol=1e-8)
+
+
+# ----------------------------------------------------------------------------- bench.py contract
+_LINE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "cpu_baseline"}
+
+
+def test_recorded_bench_lines_follow_the_contract():
+    """The committed bench lines (profiles/r01_bench_{1,2,4,8}gpu.json) carry every key of the bench contract with
+    consistent values: whole-job throughput = global batch / step time, roofline fraction = achieved / peak, e2e measured
+    with host-to-device traffic, weak scaling, a CPU baseline on rank 0 / N = 1 only."""
+    for n in (1, 2, 4, 8):
+        with open(os.path.join(ROOT, "profiles", f"r01_bench_{n}gpu.json")) as f:
+            line = json.loads(f.read().strip().splitlines()[-1])
+        assert _LINE_KEYS - {"cpu_baseline"} <= set(line), n
+        assert line["n_gpus"] == n and line["higher_is_better"] is True and line["scaling"] == "weak"
+        assert line["unit"] == "samples/s" and line["vs_baseline"] is None and line["data"] == "synthetic"
+        assert "workload" in line["config"] and line["config"]["global_batch"] == 256 * n
+        assert line["value"] == pytest.approx(256 * n / line["ms_per_step"] * 1e3, rel=1e-6)
+        assert line["warmup"] >= 3 and line["gpu_launches"] > 0
+        e2e = line["e2e"]
+        assert e2e["unit"] == "samples/s" and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
+        assert e2e["value"] <= line["value"] * 1.02
+        assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if n == 1:
+            r = line["roofline"]
+            assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["traffic"] is not None
+            assert r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-9) and 0.6 < r["frac"] < 1.0
+            c = line["cpu_baseline"]
+            assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "batch 32" in c["sample"]
+    ref = {n: json.loads(open(os.path.join(ROOT, "profiles", f"r01_bench_{n}gpu.json")).read().strip().splitlines()[-1])
+           for n in (1, 8)}
+    assert ref[8]["value"] / ref[1]["value"] > 7.0          # the north_star's scaling target, as recorded
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs the oracle port of the reference step on the host cores (here) and prints one
+    JSON line with impl = reference, its own cpu_baseline block and an e2e block without copies."""
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and _LINE_KEYS <= set(line)
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and line["dtype"] == "f32"
