@@ -228,6 +228,31 @@ def main():
                                    "kept": {n: int(m.get_masks()[0].float().sum()) for n, m in masked(model)}})
     gold["C"] = C
 
+    # (T) a short training trajectory: AdamW on scores + LM head, mask update (scheduler.step -> reset_threshold) every
+    # two steps, bf16-free (fp32 scores): losses, thresholds and kept counts along the way
+    model, masker, sched, T = variant(M, SP, zero_rate=0.7, init_sparsity=0.3, final_epoch=2,
+                                      controlled_init="magnitude_soft", global_prune=False)
+    T.pop("grads")
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=2e-3, weight_decay=0.0)
+    T["lr"], T["steps"] = 2e-3, []
+    data = sk.batch()
+    model.train()
+    for step in range(6):
+        loss = model(*data)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad and p.grad is not None], 1.0)
+        opt.step()
+        rec = {"loss": float(loss.detach())}
+        if (step + 1) % 2 == 0:
+            _, target, _ = masker.masker_scheduler.step(cur_epoch=(step + 1) // 2)
+            rec["target"] = target
+            rec["mean"] = M.reset_threshold(model, target)
+            rec["thresholds"] = thr_record(model)
+            rec["kept"] = {n: int(m.get_masks()[0].float().sum()) for n, m in masked(model)}
+        T["steps"].append(rec)
+    gold["T"] = T
+
     # host-only vectors: chain_module_names per tower
     gold["chain"] = {t: sorted(M.chain_module_names(t, list(range(3)), ab)) for t, ab in {
         "visual_encoder": ["AO_visual", "I_visual", "O_visual", "AO", "I", "O", "E"],
@@ -242,6 +267,7 @@ def main():
     print("B0", B0["reset_at_zero"], "B ramp", [(r["epoch"], round(r["target"], 4), r["mean"]) for r in B["ramp"]], B["constant_scores"])
     print("C", C["global_weight_threshold"], [(r["rate"], r["mean"]) for r in C["global_resets"]])
     print("D", [(r["rate"], r["mean"]) for r in D["resets"]])
+    print("T", [round(r["loss"], 4) for r in T["steps"]], [r.get("target") for r in T["steps"]])
 
 
 if __name__ == "__main__":

@@ -572,3 +572,38 @@ def test_bf16_score_threshold_property_random_bit_patterns():
         Sb = bits.view(torch.float32)
         fin = torch.isfinite(Sb)
         assert torch.equal((Sb.to(torch.bfloat16) > t16)[fin], (Sb > T)[fin]), delta
+
+
+def test_oracle_training_trajectory_matches_reference(gold):
+    """Six AdamW steps on scores + LM head with a mask update every two steps (scheduler.step -> reset_threshold): the
+    oracle-patched network follows the reference's losses, thresholds (bf16, exact) and kept counts."""
+    import types
+
+    from masking import sparsity_control as sp
+    T = gold["T"]
+    model = fresh(gold)
+    om.patch(model, sk.names_to_mask(om.chain_module_names), init_sparsity=T["init_sparsity"],
+             controlled_init="magnitude_soft")
+    assert thr_record(model) == T["init_thresholds"] and kept(model) == T["kept_init"]
+    sched = sp.MaskerScheduler(types.SimpleNamespace(
+        masking_scheduler_conf_={"lambdas_lr": 0.0, "sparsity_warmup": "automated_gradual_sparsity",
+                                 "sparsity_warmup_interval_epoch": 0.1, "init_epoch": 0.0, "final_epoch": 2,
+                                 "final_sparsity": 0.7, "init_sparsity": 0.3}, logger=logging.getLogger("t")))
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=T["lr"], weight_decay=0.0)
+    data = sk.batch()
+    model.train()
+    for step, want in enumerate(T["steps"]):
+        loss = model(*data)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad and p.grad is not None], 1.0)
+        opt.step()
+        assert float(loss.detach()) == pytest.approx(want["loss"], rel=1e-4), step
+        if "target" in want:
+            _, target, _ = sched.step(cur_epoch=(step + 1) // 2)
+            assert target == want["target"]
+            mean = om.reset_threshold(model, target)
+            assert thr_record(model) == want["thresholds"], step
+            assert mean == want["mean"]
+            got = kept(model)
+            assert all(abs(got[n] - want["kept"][n]) <= 2 for n in got), step
