@@ -43,24 +43,26 @@ class CosineLRScheduler:
         for group, value in zip(self.optimizer.param_groups, values):
             group["lr"] = value
 
+    def _cycle(self, t):
+        """(index of the cosine cycle that contains t, its length, position inside it)."""
+        period, growth = self.t_initial, self.t_mul
+        if growth == 1:
+            index = t // period
+            return index, period, t - period * index
+        index = math.floor(math.log(1 - t / period * (1 - growth), growth))
+        start = (1 - growth ** index) / (1 - growth) * period
+        return index, growth ** index * period, t - start
+
     def _get_lr(self, t):
-        if t < self.warmup_t:
-            return [self.warmup_lr_init + t * s for s in self.warmup_steps]
-        if self.warmup_prefix:
-            t = t - self.warmup_t
-        if self.t_mul != 1:
-            i = math.floor(math.log(1 - t / self.t_initial * (1 - self.t_mul), self.t_mul))
-            t_i = self.t_mul ** i * self.t_initial
-            t_curr = t - (1 - self.t_mul ** i) / (1 - self.t_mul) * self.t_initial
-        else:
-            i = t // self.t_initial
-            t_i = self.t_initial
-            t_curr = t - self.t_initial * i
-        if self.cycle_limit != 0 and i >= self.cycle_limit:
-            return [self.lr_min for _ in self.base_values]
-        gamma = self.decay_rate ** i
-        low = self.lr_min * gamma
-        return [low + 0.5 * (v * gamma - low) * (1 + math.cos(math.pi * t_curr / t_i)) for v in self.base_values]
+        if t < self.warmup_t:                                   # the warm-up line
+            return [self.warmup_lr_init + t * slope for slope in self.warmup_steps]
+        index, length, pos = self._cycle(t - self.warmup_t if self.warmup_prefix else t)
+        if self.cycle_limit != 0 and index >= self.cycle_limit:  # past the last restart
+            return [self.lr_min] * len(self.base_values)
+        shrink = self.decay_rate ** index
+        floor = self.lr_min * shrink
+        wave = 0.5 * (1 + math.cos(math.pi * pos / length))
+        return [floor + (base * shrink - floor) * wave for base in self.base_values]
 
     def step(self, epoch, metric=None):
         self.metric = metric
