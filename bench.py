@@ -3,11 +3,13 @@
 samples/s at 1/2/4/8 B200; masked-GEMM tensor utilisation).
 
   python bench.py --gpus N --steps K --warmup W                 # this framework (one rank per GPU under torchrun)
-  python bench.py --impl reference --gpus N --steps K --warmup W # the reference algorithm on the host CPU cores
+  python bench.py --impl reference --gpus N --steps K --warmup W # the reference's own modules on the host CPU cores
+  python bench.py --impl torch-gpu --precision fp32|tf32|bf16-autocast   # same-box bar: reference modules on one B200
 
 One "step" = one full stage-2 training step on one synthetic batch: forward (188 masked-module calls),
-LPF loss, backward (dX + straight-through dS), gradient exchange (N > 1), global-norm clip + AdamW, and
-the per-modality threshold refresh at the reference's cadence (every 100 steps).  Prints ONE JSON line.
+LPF loss, backward (dX + straight-through dS), gradient exchange (N > 1), global-norm clip + AdamW; the
+per-modality threshold refresh of the reference's cadence (every 100 steps) is timed separately and its amortised
+share added to ms_per_step.  Prints ONE JSON line.
 """
 import argparse
 import json
@@ -33,13 +35,16 @@ def workload_name(batch, ans_num, loss):
 
 
 def measured_peaks():
+    """Burst figure for a kernel family timed alone (the roofline object), sustained one beside it."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
             d = json.load(f)
-        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm_gbs": d.get("hbm_gbs"),
-                "source": "measured (MEASURED_PEAKS.json, sustained)"}
-    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        burst = d.get("bf16_tflops")
+        return {"bf16_tflops": burst, "bf16_tflops_sustained": d.get("bf16_tflops_sustained", burst),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json: burst; sustained beside it)"}
+    return {"bf16_tflops": 1650.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
 
 
 # --------------------------------------------------------------------------- clocks
@@ -88,10 +93,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# --------------------------------------------------------------------------- CPU arm (oracle port of the reference)
-def cpu_reference_arm(steps, warmup, batch, ans_num, loss, quiet=False):
-    """The reference's stage-2 step (fwd -> loss -> backward -> clip_grad_norm_ -> AdamW -> zero_grad) restated
-    in oracle/ (kind 'port': the reference is Python and does not travel to the GPU box), all host threads."""
+# --------------------------------------------------------------------------- reference arms
+def cpu_port_arm(steps, warmup, batch, ans_num, loss):
+    """Fallback when the reference's own modules are not staged (oracle/_ref absent): the oracle's restatement of
+    the reference step (fwd -> loss -> backward -> clip_grad_norm_ -> AdamW -> zero_grad), all host threads."""
     import torch
     from hg_transformers.modeling_lxmert import LxmertConfig, LxmertForMultipleChoice
     from oracle import lxmert_oracle as lxo
@@ -118,21 +123,64 @@ def cpu_reference_arm(steps, warmup, batch, ans_num, loss, quiet=False):
             "ms_per_step": 1000.0 * dt / steps}
 
 
+def cpu_reference_arm(steps, warmup, batch, ans_num, loss):
+    """The reference's OWN modules (oracle/_ref: unmodified masking/maskers_Robust.py, hg_transformers/modeling_lxmert.py,
+    LPF_loss, root optimization.AdamW) on the host cores: kind 'reference'.  Falls back to the port when not staged."""
+    from oracle import ref_runner
+    if ref_runner.reference_root() is None:
+        return cpu_port_arm(steps, warmup, batch, ans_num, loss)
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run = ref_runner.ReferenceStage2(ans_num, device="cpu")
+    dt, _ = run.timed(batch, steps, warmup, loss)
+    return {"value": batch * steps / dt, "unit": "samples/s", "cores": cores, "kind": "reference",
+            "sample": f"{steps} steps of batch {batch} (A={ans_num}, {loss} loss, fp32, dropout on) after {warmup} warm-up; "
+                      f"unmodified reference modules from {os.path.relpath(run.root, ROOT) if run.root.startswith(ROOT) else run.root}",
+            "ms_per_step": 1000.0 * dt / steps}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cpu_batch = 32
+    cpu_batch = args.cpu_batch
     r = cpu_reference_arm(args.steps, args.warmup, cpu_batch, args.ans_num, args.loss)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.batch, args.ans_num, args.loss),
-                       "note": f"reference algorithm on the host CPU; each step is a bounded sample of batch {cpu_batch}"},
+                       "note": f"reference implementation on the host CPU; each step is a bounded sample of batch {cpu_batch}"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def run_torch_gpu(args):
+    """Same-box bar: the reference's own modules on cuda:0 under stock PyTorch -- fp32 as the
+    reference runs them, or under bf16 autocast.  None of this repository's kernels are on this path."""
+    import torch
+    from oracle import ref_runner
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if ref_runner.reference_root() is None or not torch.cuda.is_available():
+        emit({"impl": "torch-gpu", "unavailable": "reference modules not staged (oracle/_ref) or no CUDA device"})
+        return
+    torch.cuda.set_device(0)
+    torch.backends.cuda.matmul.allow_tf32 = args.precision == "tf32"
+    run = ref_runner.ReferenceStage2(args.ans_num, device="cuda:0")
+    dt, last = run.timed(args.batch, args.steps, args.warmup, args.loss, autocast_bf16=args.precision == "bf16-autocast")
+    v = args.batch * args.steps / dt
+    emit({"impl": "torch-gpu", "precision": args.precision, "metric": METRIC, "value": v, "unit": "samples/s",
+          "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": {"fp32": "f32", "tf32": "tf32", "bf16-autocast": "bf16"}[args.precision], "data": "synthetic",
+          "config": {"workload": workload_name(args.batch, args.ans_num, args.loss),
+                     "note": "unmodified reference modules (oracle/_ref) on one B200 under stock PyTorch kernels, inputs "
+                             "resident in HBM"},
+          "last_loss": last, "gpu_launches": 0})
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -144,8 +192,7 @@ def run_ours(args):
     from hg_transformers.data.metrics import vqa_compute_metrics
     from hg_transformers.mask_trainer_Robust_VQA import Trainer
     from hg_transformers.training_args import TrainingArguments
-    from oracle import lxmert_oracle as lxo  # synthetic batch recipe only; not on the timed path
-    from prune_debias_VQA import build_stage2, init_optimizer
+    from prune_debias_VQA import batch_tuple, build_stage2, init_optimizer, synthetic_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -168,12 +215,10 @@ def run_ours(args):
     trainer._setup_engine(optimizer)
     trainer.global_step = 0
 
-    host = lxo.synthetic_batch(B, A, seed=49 + rank)
-    order = ["ids", "feats", "pos", "target", None, None, "bias", "max_label"]
-    qid = torch.arange(B)
-    host_inputs = [host[k].pin_memory() if k else qid.pin_memory() for k in order]
+    host = synthetic_batch(B, A, seed=49 + rank)
+    host_inputs = [t.pin_memory() for t in batch_tuple(host)]
     dev_inputs = [t.to(dev) for t in host_inputs]
-    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in order if k)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_inputs)
 
     graphed = None if args.eager else trainer._make_graphed_step(model, optimizer, scheduler)
 
@@ -181,14 +226,15 @@ def run_ours(args):
         if graphed is not None and not force_eager:
             loss, score = graphed.step(inputs)
         elif graphed is not None:
-            loss, score = graphed._eager(inputs)
+            loss, score = graphed.eager_step(inputs)
         else:
             loss, score = trainer._device_step(model, inputs, optimizer)
             scheduler.step()
         trainer.global_step += 1
-        if trainer.global_step % targs.logging_steps == 0:
-            trainer.reset_threshold(model, masker.masker_scheduler.init_sparsity)
         return loss
+
+    def refresh():
+        trainer.reset_threshold(model, masker.masker_scheduler.init_sparsity)
 
     def barrier():
         if world > 1:
@@ -218,6 +264,18 @@ def run_ours(args):
     ev1.record()
     barrier()
     launches = lib.crv_launch_count() - launches0
+    # ---- threshold refresh (reset_threshold: 168 exact selects + mask-cache refresh), every `logging_steps` = 100
+    # steps in the recipe: a K-step region cannot hold 1/100 of one, so it is timed here (CUDA events, host enqueue
+    # included) and its amortised share is ADDED to ms_per_step / value below
+    refresh()
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(3):
+        refresh()
+    r1.record()
+    torch.cuda.synchronize()
+    refresh_ms = r0.elapsed_time(r1) / 3
     # ---- masked-GEMM family alone: record every GEMM launch of one eager step of the same workload (same
     # operands, same order), re-issue them back to back as one CUDA graph and time the replays with CUDA events
     c0 = lib.crv_launch_count()
@@ -256,7 +314,7 @@ def run_ours(args):
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms)
+    ms_total = float(ms) + args.steps * refresh_ms / targs.logging_steps
     clock_info = clocks.stop() if rank == 0 else None
 
     # ---- timed region 2: end to end (pinned host inputs -> H2D every step, loss read back every step)
@@ -288,7 +346,7 @@ def run_ours(args):
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    ms_e2e = float(ms2)
+    ms_e2e = float(ms2) + args.steps * refresh_ms / targs.logging_steps
 
     def finish():
         """Multi-rank teardown: NCCL communicators referenced by a live CUDA graph can block in
@@ -312,14 +370,21 @@ def run_ours(args):
         d[0] += 1
         d[1] += 2.0 * m * n * k
     achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, from an `ncu --set full` capture of the launches of
+    # ONE PROFILED TRAINING STEP of this very command (profiles/r02_gemm_traffic.json names the capture); null when
+    # no capture of the current kernels exists
+    traffic, traffic_alg = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("masked_gemm_dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic, traffic_alg = tj.get("dram_bytes_per_launch"), tj.get("algorithmic_bytes_per_launch")
     roofline = {"kernel": "masked_gemm2_kernel / masked_gemm_kernel (fwd + dX + dS instantiations: every launch of one step)",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"] if peaks["bf16_tflops"] else None, "traffic": traffic,
+                "traffic_algorithmic": traffic_alg,
+                "peak_sustained": peaks["bf16_tflops_sustained"],
+                "frac_sustained": achieved / peaks["bf16_tflops_sustained"] if peaks["bf16_tflops_sustained"] else None,
                 "peak_source": peaks["source"], "launches_per_step": len(record),
                 "avg_launch_us": 1000.0 * gemm_ms / max(1, len(record)),
                 "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / (ms_total / args.steps),
@@ -329,14 +394,16 @@ def run_ours(args):
                 "by_kernel": {k: {"launches": v[0], "gflop": v[1] / 1e9} for k, v in by_kind.items()}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_arm(2, 1, 32, A, args.loss)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = cpu_baseline_subprocess(A, args.loss)
     value = world * B * args.steps / (ms_total * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(B, A, args.loss), "global_batch": B * world,
-                       "parallelism": f"dp{world}", "threshold_refresh_every": targs.logging_steps,
+                       "parallelism": f"dp{world}",
+                       "threshold_refresh": {"every_steps": targs.logging_steps, "refresh_ms": refresh_ms,
+                                             "amortised_ms_per_step": refresh_ms / targs.logging_steps,
+                                             "included_in_value_and_e2e": True},
                        "step_execution": "eager" if graphed is None else "cuda-graph replay of the whole step",
                        "mask_mode": os.environ.get("CRVQA_MASK_MODE", "cached"),
                        "l2": "per-step working set (weights 0.4 GB + scores/grads/Adam 4 GB) far exceeds the 126 MB L2",
@@ -350,6 +417,21 @@ def run_ours(args):
         line["cpu_baseline"] = cpu
     emit(line)
     finish()
+
+
+def cpu_baseline_subprocess(ans_num, loss, steps=5, warmup=1, batch=32):
+    """cpu_baseline of the GPU line: the reference arm on a bounded sample (5 steps of batch 32 after one warm-up,
+    ~15-30 s of CPU work) in its own process -- the reference's modules carry the same names as the product
+    package's (masking, hg_transformers, optimization), so the two never share an interpreter."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup",
+           str(warmup), "--cpu-batch", str(batch), "--ans-num", str(ans_num), "--loss", loss]
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+        return line["cpu_baseline"]
+    except Exception as e:  # the GPU line must still be printed
+        return {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "unavailable",
+                "sample": f"reference arm failed: {type(e).__name__}: {e}"}
 
 
 _JSON_OUT = None
@@ -373,7 +455,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
+    ap.add_argument("--precision", default="bf16-autocast", choices=["fp32", "tf32", "bf16-autocast"],
+                    help="--impl torch-gpu only")
+    ap.add_argument("--cpu-batch", type=int, default=32, help="--impl reference: batch of one bounded CPU step")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--ans-num", type=int, default=3129)
     ap.add_argument("--loss", default="lpf", choices=["normal", "lpf", "lmh"])
@@ -382,6 +467,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch-gpu":
+        run_torch_gpu(args)
     else:
         run_ours(args)
 

@@ -78,6 +78,7 @@ class ProjectionGroup:
         n = self.N * self.K
         self.wm = arena.wm[off0: off0 + n].view(self.N, self.K)
         self.w16 = arena.w16[off0: off0 + n].view(self.N, self.K)
+        self.w32 = arena.w32[off0: off0 + n].view(self.N, self.K)
         self.grad = arena.grads[off0: off0 + n].view(self.N, self.K)
         biases = [m.bias for m in self.modules]
         self.bias = None if any(b is None for b in biases) else torch.cat([b.detach().float() for b in biases]).contiguous()
@@ -123,10 +124,10 @@ class GroupLinearFn(torch.autograd.Function):
         dirty = g.modules[0]._grad_dirty
         if lane is not None:
             with torch.cuda.stream(lane.stream):
-                ops.masked_linear_bwd_ds(dy2, x2, g.w16, out=g.grad, accumulate=dirty)
+                ops.masked_linear_bwd_ds(dy2, x2, g.w32, out=g.grad, accumulate=dirty)
             lane.hold(dy2, x2)
         else:
-            ops.masked_linear_bwd_ds(dy2, x2, g.w16, out=g.grad, accumulate=dirty)
+            ops.masked_linear_bwd_ds(dy2, x2, g.w32, out=g.grad, accumulate=dirty)
         for m in g.modules:
             ops._sink_done(m)
         return dx, None, None, None

@@ -154,19 +154,22 @@ def masked_linear_bwd_dx(dy_bf16, w_bf16, scores, thr, out_dtype=torch.float32):
     return dx
 
 
-def masked_linear_bwd_ds(dy_bf16, x_bf16, w_bf16, out=None, accumulate=False):
-    _need_cuda(dy_bf16, x_bf16, w_bf16)
+def masked_linear_bwd_ds(dy_bf16, x_bf16, w_f32, out=None, accumulate=False):
+    """dS[N,K] (+)= (dY^T X) (.) W with W in fp32 (the reference multiplies by its fp32 Parameter)."""
+    _need_cuda(dy_bf16, x_bf16, w_f32)
     M, N = dy_bf16.shape
     K = x_bf16.shape[1]
+    if w_f32.dtype != torch.float32 or not w_f32.is_contiguous() or w_f32.shape != (N, K):
+        raise ValueError("masked_linear_bwd_ds multiplies by a contiguous fp32 [N, K] tensor")
     if out is None:
         out = torch.empty((N, K), dtype=torch.float32, device=dy_bf16.device)
         accumulate = False
     if RECORD is not None:
         scratch = torch.empty_like(out)
-        RECORD.append(("ds", M, N, K, lambda: masked_linear_bwd_ds(dy_bf16, x_bf16, w_bf16, out=scratch,
+        RECORD.append(("ds", M, N, K, lambda: masked_linear_bwd_ds(dy_bf16, x_bf16, w_f32, out=scratch,
                                                                      accumulate=accumulate)))
     with _Timed("ds", M, N, K):
-        check(lib.crv_masked_linear_bwd_ds(_p(dy_bf16), _p(x_bf16), _p(w_bf16), _p(out), int(bool(accumulate)),
+        check(lib.crv_masked_linear_bwd_ds(_p(dy_bf16), _p(x_bf16), _p(w_f32), _p(out), int(bool(accumulate)),
                                            M, N, K, _stream()), "crv_masked_linear_bwd_ds")
     return out
 
@@ -287,21 +290,42 @@ def ds_lane_join():
         lane.join()
 
 
+def operand_mode():
+    """'bf16' (product path) or 'split': every MMA operand is carried as hi + lo bf16 halves and each GEMM is issued
+    three times (hi.hi + lo.hi + hi.lo, fp32 accumulate), i.e. ~16 mantissa bits per operand through the SAME tcgen05
+    kernels.  A debugging / parity aid (CRVQA_OPERAND=split): it shows how much of the end-to-end gap to the fp32
+    reference is bf16 operand rounding and how much is the kernels (tests/test_parity_precise_gpu.py)."""
+    return os.environ.get("CRVQA_OPERAND", "bf16")
+
+
+def split_bf16(x32):
+    """x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): relative error ~2^-17."""
+    hi = to_bf16(x32)
+    lo = to_bf16(x32 - hi.float())
+    return hi, lo
+
+
 class MaskedLinearFn(torch.autograd.Function):
     """y = F.linear(x, weight * binarize(scores, thr), bias) with the straight-through score gradient.
 
     forward : bf16 tcgen05 GEMM with the mask applied in the TMA-fed prologue (fp32 accumulate)
     backward: dX = dY . (W (.) M)   and   dS = (dY^T . X) (.) W   (no dW, no db: weights are frozen,
-              masking/maskers.py:564-569,594-596)
+              masking/maskers.py:564-569,594-596); the (.) W of dS uses the fp32 weight
     `sink` is the owning module when its score gradient lives in a ScoreArena: dS is then accumulated
     in place by the GEMM epilogue and autograd receives no tensor for `scores`.
     """
 
     @staticmethod
-    def forward(ctx, x, scores, w_bf16, thr, bias, sink=None, wm_bf16=None):
+    def forward(ctx, x, scores, w_bf16, thr, bias, sink=None, wm_bf16=None, w_f32=None):
         shp = x.shape
-        x2 = to_bf16(x.reshape(-1, shp[-1]))
         thr_t = as_thr(thr, x.device)
+        if w_f32 is None:
+            w_f32 = w_bf16.float()
+        w_f32 = w_f32.detach()
+        ctx.split = operand_mode() == "split" and x.dtype == torch.float32
+        if ctx.split:
+            return MaskedLinearFn._forward_split(ctx, x, scores, w_bf16, thr_t, bias, sink, wm_bf16, w_f32)
+        x2 = to_bf16(x.reshape(-1, shp[-1]))
         # bf16 activations (a bf16 input, or a caller running under bf16 autocast, where nn.Linear would answer in bf16
         # too) -> bf16 out; dX always comes back in the input's own dtype: no fp32 round trips between bf16 layers
         autocast16 = (x.is_cuda and torch.is_autocast_enabled("cuda")
@@ -311,7 +335,7 @@ class MaskedLinearFn(torch.autograd.Function):
             y = masked_linear_fwd(x2, wm_bf16, None, None, bias, io)
         else:
             y = masked_linear_fwd(x2, w_bf16, scores.detach(), thr_t, bias, io)
-        ctx.save_for_backward(x2, scores, w_bf16, thr_t)
+        ctx.save_for_backward(x2, scores, w_bf16, thr_t, w_f32)
         ctx.wm = wm_bf16
         ctx.x_shape = shp
         ctx.dx_dtype = torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32
@@ -319,9 +343,57 @@ class MaskedLinearFn(torch.autograd.Function):
         ctx.sink = sink
         return y.view(*shp[:-1], w_bf16.shape[0])
 
+    # -- CRVQA_OPERAND=split: the same three GEMMs, each as hi.hi + lo.hi + hi.lo ------------------------------
+    @staticmethod
+    def _masked_pair(w_bf16, w_f32, scores, thr_t, wm_bf16):
+        """(hi, lo) masked bf16 halves of W (.) M."""
+        lo = to_bf16(w_f32 - w_bf16.float())
+        hi = wm_bf16 if wm_bf16 is not None else apply_mask_bf16(w_bf16, scores.detach(), thr_t)
+        return hi, apply_mask_bf16(lo, scores.detach(), thr_t)
+
+    @staticmethod
+    def _forward_split(ctx, x, scores, w_bf16, thr_t, bias, sink, wm_bf16, w_f32):
+        shp = x.shape
+        xh, xl = split_bf16(x.reshape(-1, shp[-1]).contiguous())
+        wh, wl = MaskedLinearFn._masked_pair(w_bf16, w_f32, scores, thr_t, wm_bf16)
+        y = masked_linear_fwd(xh, wh, None, None, bias, torch.float32)
+        y += masked_linear_fwd(xl, wh, None, None, None, torch.float32)
+        y += masked_linear_fwd(xh, wl, None, None, None, torch.float32)
+        ctx.save_for_backward(xh, xl, wh, wl, scores, w_f32)
+        ctx.x_shape, ctx.need_dx, ctx.sink = shp, x.requires_grad, sink
+        return y.view(*shp[:-1], w_bf16.shape[0])
+
+    @staticmethod
+    def _backward_split(ctx, dy):
+        xh, xl, wh, wl, scores, w_f32 = ctx.saved_tensors
+        dh, dl = split_bf16(dy.reshape(-1, dy.shape[-1]).contiguous().float())
+        dx = None
+        if ctx.need_dx:
+            dx = masked_linear_bwd_dx(dh, wh, None, None, torch.float32)
+            dx += masked_linear_bwd_dx(dl, wh, None, None, torch.float32)
+            dx += masked_linear_bwd_dx(dh, wl, None, None, torch.float32)
+            dx = dx.view(ctx.x_shape)
+        ds = None
+        if ctx.needs_input_grad[1]:
+            sink_grad = _sink_grad(ctx.sink)
+            if sink_grad is not None:
+                out, acc = sink_grad, ctx.sink._grad_dirty
+            else:
+                out, acc = torch.empty_like(w_f32), False
+            masked_linear_bwd_ds(dh, xh, w_f32, out=out, accumulate=acc)
+            masked_linear_bwd_ds(dl, xh, w_f32, out=out, accumulate=True)
+            masked_linear_bwd_ds(dh, xl, w_f32, out=out, accumulate=True)
+            if sink_grad is not None:
+                _sink_done(ctx.sink)
+            else:
+                ds = out
+        return dx, ds, None, None, None, None, None, None
+
     @staticmethod
     def backward(ctx, dy):
-        x2, scores, w_bf16, thr_t = ctx.saved_tensors
+        if ctx.split:
+            return MaskedLinearFn._backward_split(ctx, dy)
+        x2, scores, w_bf16, thr_t, w_f32 = ctx.saved_tensors
         dy2 = to_bf16(dy.reshape(-1, dy.shape[-1]))
         sink_grad = _sink_grad(ctx.sink) if ctx.needs_input_grad[1] else None
         lane = ds_lane(dy.device) if (sink_grad is not None and ctx.need_dx) else None
@@ -338,14 +410,14 @@ class MaskedLinearFn(torch.autograd.Function):
             if sink_grad is not None:
                 if lane is not None:
                     with torch.cuda.stream(lane.stream):
-                        masked_linear_bwd_ds(dy2, x2, w_bf16, out=sink_grad, accumulate=ctx.sink._grad_dirty)
+                        masked_linear_bwd_ds(dy2, x2, w_f32, out=sink_grad, accumulate=ctx.sink._grad_dirty)
                     lane.hold(dy2, x2)
                 else:
-                    masked_linear_bwd_ds(dy2, x2, w_bf16, out=sink_grad, accumulate=ctx.sink._grad_dirty)
+                    masked_linear_bwd_ds(dy2, x2, w_f32, out=sink_grad, accumulate=ctx.sink._grad_dirty)
                 _sink_done(ctx.sink)
             else:
-                ds = masked_linear_bwd_ds(dy2, x2, w_bf16)
-        return dx, ds, None, None, None, None, None
+                ds = masked_linear_bwd_ds(dy2, x2, w_f32)
+        return dx, ds, None, None, None, None, None, None
 
 
 class MaskedLinearSmallKFn(torch.autograd.Function):

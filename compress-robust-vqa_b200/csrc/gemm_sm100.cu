@@ -41,7 +41,7 @@ struct GemmParams {
   int num_m, num_n;        // tile counts
   const float* thr;        // device scalar (XFORM)
   const float* bias;       // [NN] or null (store epilogue)
-  const __nv_bfloat16* w;  // [MM, NN] bf16 multiplier (score-grad epilogue)
+  const float* w;          // [MM, NN] fp32 multiplier (score-grad epilogue): the reference's dS = dM * W is fp32
   int reduce_out;          // score-grad: 1 = TMA reduce-add into out, 0 = plain TMA store
   long long* dbg;          // optional per-CTA timestamps (crv_gemm_debug_timestamps), else null
 };
@@ -277,26 +277,23 @@ masked_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             pk[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lo, j));
-        } else {  // score gradient: (.) W
+        } else {  // score gradient: (.) W, W in fp32 as the reference multiplies (masking/maskers.py:337-339,365-366)
           tmem_ld_wait();
           const bool row_ok = m < p.MM;
-          const __nv_bfloat16* wrow = p.w + static_cast<size_t>(row_ok ? m : 0) * p.NN + nb;
-          if (row_ok && nb + 32 <= p.NN && (p.NN & 7) == 0) {
+          const float* wrow = p.w + static_cast<size_t>(row_ok ? m : 0) * p.NN + nb;
+          if (row_ok && nb + 32 <= p.NN && (p.NN & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wrow + j));
-              const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                pk[j + 2 * e] = __float_as_uint(__uint_as_float(r[j + 2 * e]) * __uint_as_float(ww[e] << 16));
-                pk[j + 2 * e + 1] =
-                    __float_as_uint(__uint_as_float(r[j + 2 * e + 1]) * __uint_as_float(ww[e] & 0xFFFF0000u));
-              }
+            for (int j = 0; j < 8; ++j) {
+              const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow) + j);
+              pk[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) * wv.x);
+              pk[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) * wv.y);
+              pk[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) * wv.z);
+              pk[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) * wv.w);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float wv = (row_ok && nb + j < p.NN) ? __bfloat162float(wrow[j]) : 0.f;
+              const float wv = (row_ok && nb + j < p.NN) ? __ldg(wrow + j) : 0.f;
               pk[j] = __float_as_uint(__uint_as_float(r[j]) * wv);
             }
           }
@@ -619,30 +616,26 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             pk[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lo, j));
         } else {
           const bool row_ok = m < p.MM;
-          const __nv_bfloat16* wrow = p.w + static_cast<size_t>(row_ok ? m : 0) * p.NN + nb;
-          const bool fast = row_ok && nb + 32 <= p.NN && (p.NN & 7) == 0;
-          uint4 wq[4];
-          if (fast) {      // the multiplier row is fetched while the TMEM load is in flight, not after it
+          const float* wrow = p.w + static_cast<size_t>(row_ok ? m : 0) * p.NN + nb;
+          const bool fast = row_ok && nb + 32 <= p.NN && (p.NN & 3) == 0;
+          float4 wq[8];
+          if (fast) {      // the fp32 multiplier row is fetched while the TMEM load is in flight, not after it
 #pragma unroll
-            for (int j = 0; j < 4; ++j) wq[j] = __ldg(reinterpret_cast<const uint4*>(wrow + 8 * j));
+            for (int j = 0; j < 8; ++j) wq[j] = __ldg(reinterpret_cast<const float4*>(wrow) + j);
           }
           tmem_ld_wait();
           if (fast) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 wv = wq[j >> 3];
-              const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                pk[j + 2 * e] = __float_as_uint(__uint_as_float(r[j + 2 * e]) * __uint_as_float(ww[e] << 16));
-                pk[j + 2 * e + 1] =
-                    __float_as_uint(__uint_as_float(r[j + 2 * e + 1]) * __uint_as_float(ww[e] & 0xFFFF0000u));
-              }
+            for (int j = 0; j < 8; ++j) {
+              pk[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) * wq[j].x);
+              pk[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) * wq[j].y);
+              pk[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) * wq[j].z);
+              pk[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) * wq[j].w);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float wv = (row_ok && nb + j < p.NN) ? __bfloat162float(wrow[j]) : 0.f;
+              const float wv = (row_ok && nb + j < p.NN) ? __ldg(wrow + j) : 0.f;
               pk[j] = __float_as_uint(__uint_as_float(r[j]) * wv);
             }
           }
@@ -882,7 +875,7 @@ extern "C" int crv_masked_linear_bwd_dx(const uint16_t* dy, const uint16_t* w, c
              : launch<false, true, 128, false, kEpiStore, false>(tmA, tmB, tmS, tmO, p, st);
 }
 
-extern "C" int crv_masked_linear_bwd_ds(const uint16_t* dy, const uint16_t* x, const uint16_t* w, float* dscores,
+extern "C" int crv_masked_linear_bwd_ds(const uint16_t* dy, const uint16_t* x, const float* w, float* dscores,
                                         int accumulate, int M, int N, int K, void* stream) {
   if (!dy || !x || !w || !dscores || M <= 0 || N <= 0 || K <= 0) return CRV_E_BADARG;
   if ((N % 8) || (K % 8)) return CRV_E_SHAPE;
@@ -903,7 +896,7 @@ extern "C" int crv_masked_linear_bwd_ds(const uint16_t* dy, const uint16_t* x, c
   p.MM = N; p.NN = K; p.KK = M;
   p.kb_per_split = (num_kb + splits - 1) / splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
-  p.w = reinterpret_cast<const __nv_bfloat16*>(w);
+  p.w = w;
   p.reduce_out = (p.splits > 1 || accumulate) ? 1 : 0;
   if (p.splits > 1 && !accumulate)
     CRV_CUDA(cudaMemsetAsync(dscores, 0, static_cast<size_t>(N) * K * sizeof(float), st));

@@ -91,7 +91,7 @@ class ScoreArena:
         # mask cache (enable_mask_cache): bf16 weights and W (.) M, same element offsets as the scores
         self.cache_on = False
         self.epoch = 0
-        self.w16 = self.wm = self.chunks = None
+        self.w16 = self.wm = self.w32 = self.chunks = None
 
     def _view(self, flat, i):
         p = self.modules[i].weight_mask
@@ -134,11 +134,19 @@ class ScoreArena:
         dev = self.scores.device
         self.w16 = torch.zeros(self.total, dtype=torch.bfloat16, device=dev)
         self.wm = torch.zeros(self.total, dtype=torch.bfloat16, device=dev)
+        # the frozen fp32 weights move into a flat buffer with the scores' element offsets too (the Parameters become
+        # views, no second copy): the dS epilogue multiplies by fp32 W, and a projection group (query|key|value) needs
+        # its three weights as one contiguous [sum N, K] multiplier
+        self.w32 = torch.zeros(self.total, dtype=torch.float32, device=dev)
         rows = []
         for i, m in enumerate(self.modules):
             if not self._gemm_module(m):
                 continue
             n, off = m.weight_mask.numel(), self.offsets[i]
+            if m.weight.dtype == torch.float32:
+                w32 = self.w32[off: off + n].view(m.weight.shape)
+                w32.copy_(m.weight.detach())
+                m.weight.data = w32
             self.w16[off: off + n].view(m.weight.shape).copy_(ops.to_bf16(m.weight.detach()))
             m._w16 = self.w16[off: off + n].view(m.weight.shape)
             m._w16_key = (m.weight.data_ptr(), m.weight._version, m.weight.device)
@@ -202,6 +210,8 @@ class ScoreArena:
             p.grad = None
             m._arena_grad = None
             m._arena = None
+            if self.w32 is not None and self._gemm_module(m):
+                m.weight.data = m.weight.data.clone()
 
 
 class GradSync:
@@ -326,6 +336,7 @@ class GraphedStep:
     """
 
     TENSOR_SLOTS = (0, 1, 2, 3, 6, 7)  # ids, feats, pos, target, bias, max_label of the 8-tuple batch
+    HYPER_SLOTS = 8
 
     def __init__(self, trainer, model, optimizer, scheduler, warmup_steps=3):
         self.trainer, self.model, self.optimizer, self.scheduler = trainer, model, optimizer, scheduler
@@ -336,7 +347,12 @@ class GraphedStep:
         self.static_out = None
         dev = trainer.args.device
         self.hyper = torch.zeros(2, dtype=torch.float32, device=dev)
-        self.hyper_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        # {lr, step_size} of step n travel through a RING of pinned buffers: the host runs many steps ahead of the GPU
+        # (no sync between logging steps), so one reused buffer would be overwritten with step n+k's values while the
+        # copy for step n is still queued.  A slot is rewritten only after the event behind its last copy completed.
+        self.hyper_ring = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(self.HYPER_SLOTS)]
+        self.hyper_events = [None] * self.HYPER_SLOTS
+        self.hyper_turn = 0
         self.shapes = None
         # warm-up steps and the capture share one side stream, so the AccumulateGrad nodes of the loose
         # (classifier) parameters live on the capture stream, as torch.cuda.graph requires
@@ -348,8 +364,16 @@ class GraphedStep:
 
     def _upload_hyper(self):
         lr, step_size = self.optimizer.hyper_values(self._next_step_index())
-        self.hyper_host[0], self.hyper_host[1] = lr, step_size
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        i = self.hyper_turn
+        self.hyper_turn = (i + 1) % self.HYPER_SLOTS
+        if self.hyper_events[i] is not None:
+            self.hyper_events[i].synchronize()      # returns at once unless the GPU is HYPER_SLOTS steps behind
+        buf = self.hyper_ring[i]
+        buf[0], buf[1] = lr, step_size
+        self.hyper.copy_(buf, non_blocking=True)
+        ev = self.hyper_events[i] or torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.hyper_events[i] = ev
 
     def _shape_key(self, inputs):
         return tuple((tuple(inputs[i].shape), inputs[i].dtype) for i in self.TENSOR_SLOTS)
@@ -358,7 +382,7 @@ class GraphedStep:
         """Returns (loss, score) as 0-dim device tensors, like Trainer._training_step."""
         t = self.trainer
         if self.graph is not None and self._shape_key(inputs) != self.shapes:
-            return self._eager(inputs)  # odd-sized last batch of an epoch
+            return self.eager_step(inputs)  # odd-sized last batch of an epoch
         if self.graph is None and self.seen < self.warmup_steps:
             self.seen += 1
             cur = torch.cuda.current_stream()
@@ -391,6 +415,16 @@ class GraphedStep:
         self.optimizer.advance_steps(1)
         self.scheduler.step()
         return self.static_out
+
+    def eager_step(self, inputs):
+        """One eager step on the capture stream (profiling, odd-sized batches): the AccumulateGrad nodes of the loose
+        parameters were created on that stream, and autograd warns when their producer runs on another one."""
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            out = self._eager(inputs)
+        cur.wait_stream(self.stream)
+        return out
 
     def _eager(self, inputs):
         self.optimizer.use_device_hyper(None)

@@ -509,7 +509,10 @@ class TrainerCore:
                 results_at_best_score)
 
     def _save_best(self, model, eval_output):
-        """What the reference does on a new best eval accuracy (mask_trainer_VQA.py:697-742)."""
+        """What the reference does on a new best eval accuracy (mask_trainer_VQA.py:697-742).  The threshold refresh
+        changes the masks every rank trains with, so ALL ranks run it; only the file writes are the master's."""
+        if self.args.training_type == "Masker" and self.masker:
+            self.reset_threshold(model, self.masker.masker_scheduler.init_sparsity)
         if not self.is_world_master():
             return
         try:
@@ -522,7 +525,6 @@ class TrainerCore:
         if kind == "Masker":
             if not self.masker:
                 raise AssertionError("When you are training the masker, please pass the initialed masker into trainer()")
-            self.reset_threshold(model, self.masker.masker_scheduler.init_sparsity)
             self.save_model_mask(self.args.output_dir)
             head = getattr(model, "classifier", None) or getattr(model, "cls", None)
             if head is None:

@@ -8,7 +8,7 @@ These modules keep exactly that state (same parameter / buffer names, so ``state
 
     forward   bf16(weight_orig * weight_mask) in ONE pass (crv_mul_cast_bf16), then the tcgen05 GEMM
     dX        dY . (W (.) M)                           (crv_masked_linear_bwd_dx)
-    dW_orig   (dY^T . X) (.) M                         (crv_masked_linear_bwd_ds with bf16(M) as the multiplier)
+    dW_orig   (dY^T . X) (.) M                         (crv_masked_linear_bwd_ds with the fp32 mask as the multiplier)
     db        column sums of dY
 
 No CPU fallback: on a CPU tensor the ops raise (crvqa.ops._need_cuda).
@@ -22,29 +22,29 @@ from crvqa import ops
 
 class PrunedLinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight_orig, mask, mask16, bias):
+    def forward(ctx, x, weight_orig, mask, bias):
         shp = x.shape
         x2 = ops.to_bf16(x.reshape(-1, shp[-1]))
         wm = ops.mul_cast_bf16(weight_orig, mask)
         y = ops.masked_linear_fwd(x2, wm, None, None, bias, torch.float32)
-        ctx.save_for_backward(x2, wm, mask16)
+        ctx.save_for_backward(x2, wm, mask)
         ctx.x_shape = shp
         ctx.has_bias = bias is not None
         return y.view(*shp[:-1], wm.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        x2, wm, mask16 = ctx.saved_tensors
+        x2, wm, mask = ctx.saved_tensors
         d = dy.reshape(-1, dy.shape[-1])
         dy2 = ops.to_bf16(d)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = ops.masked_linear_bwd_dx(dy2, wm, None, None, torch.float32).view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            dw = ops.masked_linear_bwd_ds(dy2, x2, mask16)      # (dY^T X) (.) M: the multiplier is the 0/1 mask
-        if ctx.has_bias and ctx.needs_input_grad[4]:
+            dw = ops.masked_linear_bwd_ds(dy2, x2, mask)        # (dY^T X) (.) M: the multiplier is the 0/1 mask
+        if ctx.has_bias and ctx.needs_input_grad[3]:
             db = d.sum(0)
-        return dx, dw, None, None, db
+        return dx, dw, None, db
 
 
 class PrunedLinear(nn.Module):
@@ -56,24 +56,16 @@ class PrunedLinear(nn.Module):
         self.register_buffer("weight_mask", weight_mask.to(dtype=weight_orig.dtype, device=weight_orig.device))
         self.bias = bias
         self.out_features, self.in_features = weight_orig.shape
-        self._mask16 = None
 
     @property
     def weight(self):
         return self.weight_orig * self.weight_mask
 
-    def _mask_bf16(self):
-        m = self.weight_mask
-        if self._mask16 is None or self._mask16.device != m.device or self._mask16_ver != m._version:
-            self._mask16 = m.to(torch.bfloat16).contiguous()  # 0 / 1 are exact in bf16
-            self._mask16_ver = m._version
-        return self._mask16
-
     def forward(self, x):
         if self.in_features % 8 != 0:
             # box_fc (K = 4) cannot be a TMA operand; 3 K-element rows of torch math on the device
             return F.linear(x, self.weight_orig * self.weight_mask, self.bias)
-        return PrunedLinearFn.apply(x, self.weight_orig, self.weight_mask, self._mask_bf16(), self.bias)
+        return PrunedLinearFn.apply(x, self.weight_orig, self.weight_mask.contiguous(), self.bias)
 
     def extra_repr(self):
         return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}"

@@ -59,7 +59,14 @@ class AdamW(Optimizer):
                 self.state[p]["step"] += n
 
     def hyper_values(self, next_step):
+        """{lr, step_size} of the next step for the device hyper vector.  ONE pair serves every parameter group, so
+        the groups must agree on lr / betas / correct_bias (they do under the reference's init_optimizer, which
+        builds every group from the same TrainingArguments and steps them with one LambdaLR)."""
         g = self.param_groups[0]
+        for other in self.param_groups[1:]:
+            if (other["lr"], other["betas"], other["correct_bias"]) != (g["lr"], g["betas"], g["correct_bias"]):
+                raise RuntimeError("device-side {lr, step_size} (CUDA-graph replay) needs one lr schedule for all "
+                                   "parameter groups; set CRVQA_CUDA_GRAPH=0 for per-group schedules")
         return g["lr"], ops.adam_step_size(g["lr"], next_step, g["betas"][0], g["betas"][1], g["correct_bias"])
 
     def attach_arena(self, arena):

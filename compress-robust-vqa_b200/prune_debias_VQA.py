@@ -133,6 +133,26 @@ class SyntheticVQADataset(Dataset):
                 self.bias[i], self.max_label[i])
 
 
+def synthetic_batch(B, ans_num, seed=49, tokens=20, regions=36, feat_dim=2048, vocab=30522):
+    """One synthetic VQA-CP-shaped batch as a dict (the recipe of SURVEY.md section 8(d); the order of the draws
+    matters -- it is the batch the reference goldens were generated on): ids [B,T] int64, feats [B,R,feat] fp32,
+    pos [B,R,4] in [0,1), target [B,A] sparse soft labels, bias [B,A], max_label [B]."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, vocab, (B, tokens), generator=g)
+    feats = torch.randn(B, regions, feat_dim, generator=g)
+    pos = torch.rand(B, regions, 4, generator=g)
+    target = (torch.rand(B, ans_num, generator=g) > 0.999).float() * torch.rand(B, ans_num, generator=g)
+    bias = torch.rand(B, ans_num, generator=g) * 0.01
+    return {"ids": ids, "feats": feats, "pos": pos, "target": target, "bias": bias, "max_label": target.argmax(1)}
+
+
+def batch_tuple(batch):
+    """The dict above as the 8-tuple the trainers index (dataset_LXM.VQAFeatureDataset.__getitem__, :282)."""
+    qid = torch.arange(batch["ids"].shape[0])
+    return [batch["ids"], batch["feats"], batch["pos"], batch["target"], qid, qid.clone(), batch["bias"],
+            batch["max_label"]]
+
+
 def build_stage2(ans_num=2274, model_args=None, device=None, seed=49, config_kwargs=None, quiet=True):
     """Model + masker for a synthetic stage-2 run: random-init LXMERT under `seed`, moved to `device`,
     then patched (so the magnitude init runs on the GPU)."""

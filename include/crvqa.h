@@ -51,7 +51,7 @@ int crv_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* strea
 
 /* Stage-3 frozen-mask fine-tune (run_vqa_stage3.py:227-300: torch.nn.utils.prune.CustomFromMask, whose forward
  * pre-hook sets weight = weight_orig * weight_mask): dst = bf16(w * mask), product in fp32, one pass.  The
- * masked GEMMs then take dst as their plain operand and crv_masked_linear_bwd_ds with w_bf16 = bf16(mask)
+ * masked GEMMs then take dst as their plain operand and crv_masked_linear_bwd_ds with w_f32 = the fp32 0/1 mask
  * yields dW = (dY^T X) (.) mask, the gradient autograd gives weight_orig. */
 int crv_mul_cast_bf16(const float* w, const float* mask, uint16_t* dst, int64_t n, void* stream);
 
@@ -98,11 +98,13 @@ int crv_masked_linear_bwd_dx(const uint16_t* dy_bf16, const uint16_t* w_bf16, co
 
 /* Straight-through score gradient (autograd of masking/maskers.py:337-339,365-366):
  *     dS[N,K] (+)= (dY[M,N]^T . X[M,K]) (.) W[N,K]
- * The (.)W happens in the GEMM epilogue; accumulate != 0 adds into dS (second invocation of the
- * shared cross-attention modules, hg_transformers/modeling_lxmert.py:947-958), otherwise dS is
- * overwritten.  The reduction over M may be split across CTAs (fp32 atomics).
- * Requirements: N % 8 == 0, K % 8 == 0. */
-int crv_masked_linear_bwd_ds(const uint16_t* dy_bf16, const uint16_t* x_bf16, const uint16_t* w_bf16,
+ * The (.)W happens in the GEMM epilogue with W in FP32, as the reference multiplies (dM * self.weight, an fp32
+ * Parameter): only the MMA operands dY and X are bf16.  accumulate != 0 adds into dS (second invocation of the
+ * shared cross-attention modules, hg_transformers/modeling_lxmert.py:947-958), otherwise dS is overwritten.
+ * The reduction over M may be split across CTAs (TMA reduce-add, fp32): the summation order of the splits is
+ * not fixed, so dS is reproducible to fp32 rounding of a handful of partial sums, not bit for bit.
+ * Requirements: N % 8 == 0, K % 8 == 0; W 16-byte aligned. */
+int crv_masked_linear_bwd_ds(const uint16_t* dy_bf16, const uint16_t* x_bf16, const float* w_f32,
                              float* dscores, int accumulate, int M, int N, int K, void* stream);
 
 /* Same three operations for inner dimensions the TMA path cannot take (box_fc has K = 4,

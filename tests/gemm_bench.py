@@ -20,7 +20,7 @@ def timeit(fn, iters=20):
     return e0.elapsed_time(e1) / iters
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for (M, N, K) in SHAPES:
-    x = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) * 0.02).bfloat16()
+    x = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) * 0.02).bfloat16(); w32 = w.float()
     s = torch.rand(N, K, device=dev); thr = torch.tensor(0.7, device=dev); dy = torch.randn(M, N, device=dev).bfloat16()
     b = torch.randn(N, device=dev); ds = torch.zeros(N, K, device=dev)
     fl = 2.0 * M * N * K
@@ -32,7 +32,7 @@ for (M, N, K) in SHAPES:
     res['dx masked f32'] = timeit(lambda: ops.masked_linear_bwd_dx(dy, w, s, thr))
     res['dx plain f32'] = timeit(lambda: ops.masked_linear_bwd_dx(dy, w, None, thr))
     res['dx plain bf16'] = timeit(lambda: ops.masked_linear_bwd_dx(dy, w, None, thr, torch.bfloat16))
-    res['ds store'] = timeit(lambda: ops.masked_linear_bwd_ds(dy, x, w, out=ds, accumulate=False))
-    res['ds accum'] = timeit(lambda: ops.masked_linear_bwd_ds(dy, x, w, out=ds, accumulate=True))
+    res['ds store'] = timeit(lambda: ops.masked_linear_bwd_ds(dy, x, w32, out=ds, accumulate=False))
+    res['ds accum'] = timeit(lambda: ops.masked_linear_bwd_ds(dy, x, w32, out=ds, accumulate=True))
     res['torch bf16 mm'] = timeit(lambda: torch.matmul(x, w.t()))
     print(f'M={M} N={N} K={K}: ' + ' | '.join(f'{k} {v*1e3:.0f}us {fl/v/1e9:.0f}TF' for k, v in res.items()), flush=True)

@@ -19,6 +19,6 @@ for (M,N,K) in [(128,128,64),(128,128,128),(256,256,256),(640,768,768)]:
             print('dx ',M,N,K,masked, rel(dx, dy.float()@wm))
         except Exception as e: print('dx FAIL',M,N,K,masked,e)
     try:
-        ds = ops.masked_linear_bwd_ds(dy,x,w); torch.cuda.synchronize()
+        ds = ops.masked_linear_bwd_ds(dy,x,w.float()); torch.cuda.synchronize()
         print('ds ',M,N,K, rel(ds, (dy.float().t()@x.float())*w.float()))
     except Exception as e: print('ds FAIL',M,N,K,e)

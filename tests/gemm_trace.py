@@ -22,9 +22,9 @@ def run(name, fn):
     print(f'{name}: entry {entry.mean():.2f} (min {entry.min():.2f}) event {e0.elapsed_time(e1)*1e3:.1f}us ctas={len(d)} tiles/cta={d[:,6].float().mean():.2f} | setup_done {rel[:,0].mean():.2f} (max {rel[:,0].max():.2f}) first_tma {rel[:,1].mean():.2f} stage0_landed {rel[:,2].mean():.2f} acc0_ready {rel[:,3].mean():.2f} epi0_drained {rel[:,4].mean():.2f} all_done {rel[:,5].mean():.2f} (max {rel[:,5].max():.2f}) us')
 import os
 for (M, N, K) in [(5120, 768, 768), (9216, 768, 768)]:
-    x = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) * 0.02).bfloat16()
+    x = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) * 0.02).bfloat16(); w32 = w.float()
     dy = torch.randn(M, N, device=dev).bfloat16(); b = torch.randn(N, device=dev); ds = torch.zeros(N, K, device=dev)
     run(f'fwd bf16 {M}x{N}x{K}', lambda: ops.masked_linear_fwd(x, w, None, None, b, torch.bfloat16))
     run(f'fwd nobias {M}x{N}x{K}', lambda: ops.masked_linear_fwd(x, w, None, None, None, torch.bfloat16))
     run(f'dx  bf16 {M}x{N}x{K}', lambda: ops.masked_linear_bwd_dx(dy, w, None, None, torch.bfloat16))
-    run(f'ds       {M}x{N}x{K}', lambda: ops.masked_linear_bwd_ds(dy, x, w, out=ds, accumulate=False))
+    run(f'ds       {M}x{N}x{K}', lambda: ops.masked_linear_bwd_ds(dy, x, w32, out=ds, accumulate=False))

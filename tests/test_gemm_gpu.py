@@ -60,13 +60,24 @@ def test_dx(M, N, K, masked):
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_ds(M, N, K):
+    """dS = (dY^T X) (.) W with the UN-ROUNDED fp32 W, as the reference multiplies (masking/maskers.py:337-339 +
+    autograd of `self.weight * M_w`): only the MMA operands dY and X are bf16.  A bf16-rounded multiplier would sit
+    2^-9 = 2e-3 away element-wise, which the element-wise check below would catch."""
     from crvqa import ops
     x, w, _, _, _, dy = _mk(M, N, K, 3)
-    xb, wb, dyb = x.bfloat16(), w.bfloat16(), dy.bfloat16()
-    ref = (dyb.float().t() @ xb.float()) * wb.float()
-    ds = ops.masked_linear_bwd_ds(dyb, xb, wb)
+    xb, dyb = x.bfloat16(), dy.bfloat16()
+    acc = dyb.float().t() @ xb.float()
+    ref = acc * w
+    ds = ops.masked_linear_bwd_ds(dyb, xb, w)
     torch.cuda.synchronize()
     assert _rel(ds, ref) < 2e-3, _rel(ds, ref)
+    # element-wise in units of the element's own magnitude: the multiplier is exact fp32, so what remains is the
+    # fp32 summation order of the accumulator (|acc| can cancel to ~0, hence the absolute floor of 1e-3 max|dS|)
+    floor = 1e-3 * float(ref.abs().max())
+    elem = ((ds - ref).abs() / (ref.abs() + floor)).max()
+    assert float(elem) < 5e-4, float(elem)
+    rounded = acc * w.bfloat16().float()
+    assert float(((rounded - ref).abs() / (ref.abs() + floor)).max()) > 1e-3   # the check can see a bf16 multiplier
     # accumulate: second invocation of a shared module adds
-    ds2 = ops.masked_linear_bwd_ds(dyb, xb, wb, out=ds.clone(), accumulate=True)
+    ds2 = ops.masked_linear_bwd_ds(dyb, xb, w, out=ds.clone(), accumulate=True)
     assert _rel(ds2, 2 * ref) < 2e-3

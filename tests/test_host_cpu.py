@@ -413,15 +413,18 @@ def test_recorded_bench_lines_follow_the_contract():
 
 
 def test_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` runs the oracle port of the reference step on the host cores (here) and prints one
-    JSON line with impl = reference, its own cpu_baseline block and an e2e block without copies."""
+    """`bench.py --impl reference` runs the reference's own stage-2 modules (oracle/_ref, or /root/reference where it
+    exists; the oracle port only when neither does) on the host cores and prints one JSON line with impl = reference,
+    its own cpu_baseline block and an e2e block without copies."""
     import subprocess
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--warmup", "0", "--cpu-batch", "4"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-500:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and _LINE_KEYS <= set(line)
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"] > 0
+    from oracle import ref_runner
+    want = "reference" if ref_runner.reference_root() is not None else "port"
+    assert line["cpu_baseline"]["kind"] == want and line["cpu_baseline"]["value"] == line["value"] > 0
     assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0 and line["dtype"] == "f32"

@@ -279,3 +279,38 @@ def test_cast_and_apply_mask():
     w = torch.randn(4099, generator=gen).bfloat16()
     out = ops.apply_mask_bf16(dev(w), dev(s), torch.tensor(0.5))
     assert torch.equal(out.cpu(), torch.where(s > 0.5, w, torch.zeros_like(w)))
+
+
+def test_apply_mask_segmented_bit_exact():
+    """The launch that writes EVERY masked operand of the timed step (ScoreArena.refresh_masked): per-module
+    thresholds, ragged module sizes, ties at the threshold, +-0 -- bit for bit against oracle binarize x W."""
+    from crvqa import ops
+    from oracle import masked_ops as o
+    gen = torch.Generator().manual_seed(11)
+    sizes = [8192 * 3, 768 * 768, 8, 24, 8192 + 40, 3072 * 768, 136 * 72]
+    offs, off = [], 0
+    for n in sizes:
+        offs.append(off)
+        off += (n + 63) // 64 * 64
+    w = torch.randn(off, generator=gen).bfloat16()
+    s = torch.rand(off, generator=gen) * 0.02
+    s[torch.rand(off, generator=gen) < 0.3] = 0.0
+    s[torch.rand(off, generator=gen) < 0.05] = -0.0
+    thr = torch.tensor([0.0, 0.01, 0.02, -1.0, 5e-5, 0.0139, 0.007])
+    for i, n in enumerate(sizes):           # exact ties at every module's threshold
+        s[offs[i]: offs[i] + n: 7] = thr[i]
+    rows = []
+    for i, n in enumerate(sizes):
+        for c0 in range(0, n, 8192):
+            rows.append(((offs[i] + c0) // 8, min(8192, n - c0), i, 0))
+    chunks = torch.tensor(rows, dtype=torch.int32)
+    wm = torch.full((off,), 7.0).bfloat16().cuda()
+    ops.apply_mask_segmented(dev(w), dev(s), dev(thr), dev(chunks), wm)
+    wm = wm.cpu()
+    for i, n in enumerate(sizes):
+        sl = slice(offs[i], offs[i] + n)
+        mask = o.binarize(s[sl], float(thr[i]))
+        want = torch.where(mask > 0, w[sl], torch.zeros_like(w[sl]))
+        assert torch.equal(wm[sl].view(torch.int16), want.view(torch.int16)), i
+        pad = wm[offs[i] + n: (offs[i + 1] if i + 1 < len(sizes) else off)]
+        assert bool((pad.float() == 7.0).all())      # alignment padding between modules is never written
