@@ -34,6 +34,7 @@ _PROTOS = {
     "crv_gemm_debug_timestamps": (c_int, [_P]),
     "crv_masked_linear_bwd_dx": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "crv_masked_linear_bwd_ds": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "crv_masked_gemm_grouped": (c_int, [_P, c_int, _P]),
     "crv_masked_linear_small_k_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "crv_masked_linear_small_k_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "crv_masked_embedding_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, _P]),
@@ -66,6 +67,14 @@ for _name, (_res, _args) in _PROTOS.items():
     _fn = getattr(lib, _name)
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+class GemmProblem(ctypes.Structure):
+    """crv_gemm_problem of include/crvqa.h."""
+    _fields_ = [("kind", c_int), ("act", c_int), ("out_dtype", c_int), ("accumulate", c_int),
+                ("M", c_int), ("N", c_int), ("K", c_int), ("reserved", c_int),
+                ("a", c_void_p), ("b", c_void_p), ("bias", c_void_p), ("w_f32", c_void_p),
+                ("out", c_void_p), ("aux", c_void_p)]
 
 
 def check(rc, what=""):

@@ -138,6 +138,104 @@ def group_linear(group, x16, out_dtype=torch.bfloat16):
     return GroupLinearFn.apply(x16, group.anchor, group, out_dtype)
 
 
+# ----------------------------------------------------------------------------- grouped launches
+def _grouped_on():
+    return os.environ.get("CRVQA_GROUPED", "1") != "0"
+
+
+class MultiLinearFn(torch.autograd.Function):
+    """n masked linears over ProjectionGroups as ONE grouped 2-CTA launch (crv_masked_gemm_grouped); their backward is
+    one grouped launch list too: dX and dS of every member read the same dY.
+
+    args = x_1 .. x_n (bf16), anchor_1 .. anchor_n (score Parameters: keep the node alive), then the pre-activations
+    u_i of the members whose spec carries `u_in` (in member order).
+    spec = (group, out_dtype, gelu_out, u_in):
+      gelu_out  the forward returns (gelu(y), y): the FFN intermediate with its activation fused into the epilogue
+      u_in      this member's INPUT is gelu(u) of the tensor u given in args; its dX epilogue multiplies by gelu'(u),
+                i.e. the gradient returned for x is ALREADY the gradient of u.  Private contract of FfnPlan: the
+                producer of x (a gelu_out member) passes its incoming gradient through unchanged."""
+
+    @staticmethod
+    def forward(ctx, specs, *args):
+        n = len(specs)
+        xs, extra = args[:n], list(args[2 * n:])
+        x2s, outs, problems, ret, u_ins = [], [], [], [], []
+        for (group, out_dtype, gelu_out, has_u), x in zip(specs, xs):
+            x2 = x.reshape(-1, x.shape[-1])
+            x2 = x2 if x2.is_contiguous() else x2.contiguous()
+            M = x2.shape[0]
+            y = torch.empty((M, group.N), dtype=out_dtype, device=x2.device)
+            u = torch.empty((M, group.N), dtype=torch.bfloat16, device=x2.device) if gelu_out else None
+            problems.append(ops.gemm_problem(ops.GEMM_FWD, x2, group.wm, y, bias=group.bias, aux=u,
+                                             act=ops.ACT_GELU if gelu_out else ops.ACT_NONE))
+            x2s.append(x2)
+            u_ins.append(extra.pop(0) if has_u else None)
+            ret.append(y.view(*x.shape[:-1], group.N))
+            if gelu_out:
+                ret.append(u.view(*x.shape[:-1], group.N))
+                outs.append(ret[-1])
+        ops.gemm_grouped(problems)
+        ctx.specs = specs
+        ctx.shapes = [x.shape for x in xs]
+        ctx.need_dx = [x.requires_grad for x in xs]
+        ctx.n_extra = len(args) - 2 * n
+        ctx.save_for_backward(*x2s, *[u for u in u_ins if u is not None])
+        ctx.has_u = [u is not None for u in u_ins]
+        if outs:
+            ctx.mark_non_differentiable(*outs)
+        return tuple(ret)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        specs, n = ctx.specs, len(ctx.specs)
+        saved = list(ctx.saved_tensors)
+        x2s, us = saved[:n], saved[n:]
+        problems, dxs, seen, k, ui = [], [], set(), 0, 0
+        for i, (group, out_dtype, gelu_out, has_u) in enumerate(specs):
+            dy = dys[k]
+            k += 2 if gelu_out else 1
+            dy2 = dy.reshape(-1, group.N)
+            dy2 = ops.to_bf16(dy2) if dy2.dtype != torch.bfloat16 else (dy2 if dy2.is_contiguous() else dy2.contiguous())
+            u = None
+            if has_u:
+                u = us[ui].reshape(-1, group.K)
+                ui += 1
+            dx = None
+            if ctx.need_dx[i]:
+                dx = torch.empty((dy2.shape[0], group.K), dtype=torch.bfloat16, device=dy2.device)
+                problems.append(ops.gemm_problem(ops.GEMM_DX, dy2, group.wm, dx, aux=u,
+                                                 act=ops.ACT_GELU if u is not None else ops.ACT_NONE))
+            dxs.append(dx)
+            key = group.grad.data_ptr()
+            acc = group.modules[0]._grad_dirty or key in seen       # second use of a shared module in this call adds
+            seen.add(key)
+            problems.append(ops.gemm_problem(ops.GEMM_DS, dy2, x2s[i], group.grad, w_f32=group.w32, accumulate=acc))
+        ops.gemm_grouped(problems)
+        for group, _, _, _ in specs:
+            for m in group.modules:
+                ops._sink_done(m)
+        grads = [dx.view(shp) if dx is not None else None for dx, shp in zip(dxs, ctx.shapes)]
+        return (None, *grads, *([None] * n), *([None] * ctx.n_extra))
+
+
+def multi_linear(items):
+    """items: (group, x16, out_dtype, gelu_out, u_in).  Returns one entry per item: y, or (gelu(y), y) for gelu_out."""
+    specs = [(g, dt, bool(gelu), u is not None) for g, _, dt, gelu, u in items]
+    for g, *_ in items:
+        g.note_forward()
+    args = [x for _, x, _, _, _ in items] + [g.anchor for g, *_ in items] + [u for *_, u in items if u is not None]
+    flat = MultiLinearFn.apply(specs, *args)
+    out, k = [], 0
+    for _, _, _, gelu, _ in items:
+        if gelu:
+            out.append((flat[k], flat[k + 1]))
+            k += 2
+        else:
+            out.append(flat[k])
+            k += 1
+    return out
+
+
 # ----------------------------------------------------------------------------- dropout + residual + LayerNorm
 class DropAddLayerNormFn(torch.autograd.Function):
     @staticmethod
@@ -268,6 +366,64 @@ class SmallAttentionFn(torch.autograd.Function):
         return (None, None, None, None, None, None) + grads
 
 
+def _attn_fwd_raw(views, m2, out, B, heads, Sq, Sk, scale, p, state, site):
+    (qt, qo), (kt, ko), (vt, vo) = views
+    check(lib.crv_attention_fwd(_off(qt, qo), qt.stride(0), qt.stride(1), _off(kt, ko), kt.stride(0), kt.stride(1),
+                                _off(vt, vo), vt.stride(0), vt.stride(1), _p(m2), _p(out), B, heads, Sq, Sk,
+                                scale, float(p), _p(state), int(site), _stream()), "crv_attention_fwd")
+
+
+def _attn_bwd_raw(views, m2, dout, gviews, B, heads, Sq, Sk, scale, p, state, site):
+    (qt, qo), (kt, ko), (vt, vo) = views
+    (dq, dqo), (dk, dko), (dv, dvo) = gviews
+    check(lib.crv_attention_bwd(_off(qt, qo), qt.stride(0), qt.stride(1), _off(kt, ko), kt.stride(0), kt.stride(1),
+                                _off(vt, vo), vt.stride(0), vt.stride(1), _p(m2), _p(dout),
+                                _off(dq, dqo), dq.stride(0), dq.stride(1), _off(dk, dko), dk.stride(0), dk.stride(1),
+                                _off(dv, dvo), dv.stride(0), dv.stride(1), B, heads, Sq, Sk, scale, p, _p(state),
+                                site, _stream()), "crv_attention_bwd")
+
+
+class CrossPairAttentionFn(torch.autograd.Function):
+    """Both directions of LxmertXLayer's cross attention (hg_transformers/modeling_lxmert.py:947-958) on the fused
+    projections qkv_l = [q|k|v](lang), qkv_v = [q|k|v](visn) of the SHARED visual_attention module:
+        ctx_l = attend(q(lang), k(visn), v(visn), visn mask)      ctx_v = attend(q(visn), k(lang), v(lang), lang mask)
+    The two backward calls write disjoint slices that together cover d(qkv_l) and d(qkv_v) exactly once, so no
+    zero-fill and no gradient add is needed although each projection feeds both directions."""
+
+    @staticmethod
+    def forward(ctx, heads, mask_l, mask_v, p, site_l, site_v, rng, qkv_l, qkv_v):
+        qkv_l = qkv_l if qkv_l.is_contiguous() else qkv_l.contiguous()
+        qkv_v = qkv_v if qkv_v.is_contiguous() else qkv_v.contiguous()
+        H = qkv_l.shape[-1] // 3
+        B, Sl, Sv = qkv_l.shape[0], qkv_l.shape[1], qkv_v.shape[1]
+        scale = 1.0 / (H // heads) ** 0.5
+        state = rng.state if (rng is not None and p > 0) else None
+        ml = mask_l.reshape(B, Sl).float().contiguous() if mask_l is not None else None
+        mv = mask_v.reshape(B, Sv).float().contiguous() if mask_v is not None else None
+        out_l = torch.empty((B, Sl, H), dtype=torch.bfloat16, device=qkv_l.device)
+        out_v = torch.empty((B, Sv, H), dtype=torch.bfloat16, device=qkv_l.device)
+        _attn_fwd_raw([(qkv_l, 0), (qkv_v, H), (qkv_v, 2 * H)], mv, out_l, B, heads, Sl, Sv, scale, p, state, site_l)
+        _attn_fwd_raw([(qkv_v, 0), (qkv_l, H), (qkv_l, 2 * H)], ml, out_v, B, heads, Sv, Sl, scale, p, state, site_v)
+        ctx.save_for_backward(qkv_l, qkv_v)
+        ctx.cfg = (heads, ml, mv, float(p), int(site_l), int(site_v), state, scale)
+        return out_l, out_v
+
+    @staticmethod
+    def backward(ctx, do_l, do_v):
+        heads, ml, mv, p, site_l, site_v, state, scale = ctx.cfg
+        qkv_l, qkv_v = ctx.saved_tensors
+        H = qkv_l.shape[-1] // 3
+        B, Sl, Sv = qkv_l.shape[0], qkv_l.shape[1], qkv_v.shape[1]
+        d_l, d_v = torch.empty_like(qkv_l), torch.empty_like(qkv_v)
+        do_l = do_l if do_l.is_contiguous() else do_l.contiguous()
+        do_v = do_v if do_v.is_contiguous() else do_v.contiguous()
+        _attn_bwd_raw([(qkv_l, 0), (qkv_v, H), (qkv_v, 2 * H)], mv, do_l, [(d_l, 0), (d_v, H), (d_v, 2 * H)],
+                      B, heads, Sl, Sv, scale, p, state, site_l)
+        _attn_bwd_raw([(qkv_v, 0), (qkv_l, H), (qkv_l, 2 * H)], ml, do_v, [(d_v, 0), (d_l, H), (d_l, 2 * H)],
+                      B, heads, Sv, Sl, scale, p, state, site_v)
+        return None, None, None, None, None, None, None, d_l, d_v
+
+
 def small_attention(kind, heads, mask, p, site, training, *srcs):
     p = float(p) if training else 0.0
     rng = RngState.get(srcs[0].device) if p > 0 else None
@@ -347,6 +503,8 @@ class AttentionPlan:
 
     def self_attention(self, x32, x16, mask, training):
         S = x16.shape[1]
+        if _grouped_on() and self.qkv is not None:
+            return self_attention_multi([(self, x32, x16, mask)], training)[0]
         if self.qkv is not None:
             ctx = self._attend(0, mask, training, self.site_att, S, S, group_linear(self.qkv, x16))
         else:
@@ -384,6 +542,64 @@ class FfnPlan:
         return True
 
     def __call__(self, x32, x16, training):
+        if _grouped_on():
+            return ffn_multi([(self, x32, x16)], training)[0]
         a = gelu_bf16(group_linear(self.gi, x16))
         o = group_linear(self.go, a)
         return drop_add_layernorm(o, x32, self.out.LayerNorm, self.out.dropout.p, self.site, training)
+
+
+# ----------------------------------------------------------------------------- lockstep helpers (grouped launches)
+def self_attention_multi(items, training):
+    """items: (AttentionPlan, x32, x16, mask) of INDEPENDENT sub-layers (language / vision stack in lockstep, the two
+    self-attention blocks of a cross layer): their QKV projections share one grouped launch, so do their output
+    projections.  Returns [(y32, y16)]."""
+    if not _grouped_on() or any(pl.qkv is None for pl, *_ in items):
+        return [pl.self_attention(x32, x16, mask, training) for pl, x32, x16, mask in items]
+    qkvs = multi_linear([(pl.qkv, x16, torch.bfloat16, False, None) for pl, _, x16, _ in items])
+    ctxs = []
+    for (pl, _, x16, mask), qkv in zip(items, qkvs):
+        S = x16.shape[1]
+        ctxs.append(pl._attend(0, mask, training, pl.site_att, S, S, qkv))
+    aos = multi_linear([(pl.ao, c, torch.bfloat16, False, None) for (pl, *_), c in zip(items, ctxs)])
+    return [drop_add_layernorm(ao, x32, pl.out.LayerNorm, pl.out.dropout.p, pl.site, training)
+            for (pl, x32, _, _), ao in zip(items, aos)]
+
+
+def ffn_multi(items, training):
+    """items: (FfnPlan, x32, x16).  FF1 of all members in one launch with bias + GELU in the epilogue (pre-activation
+    kept for the backward), FF2 likewise with gelu'(u) folded into its dX epilogue."""
+    if not _grouped_on():
+        return [f(x32, x16, training) for f, x32, x16 in items]
+    fuse = all(ops.grouped_2cta_ok(x16.numel() // x16.shape[-1], f.gi.N) and
+               ops.grouped_2cta_ok(x16.numel() // x16.shape[-1], f.go.N) for f, _, x16 in items)
+    if fuse:
+        inter = multi_linear([(f.gi, x16, torch.bfloat16, True, None) for f, _, x16 in items])
+        outs = multi_linear([(f.go, a, torch.bfloat16, False, u) for (f, _, _), (a, u) in zip(items, inter)])
+    else:
+        us = multi_linear([(f.gi, x16, torch.bfloat16, False, None) for f, _, x16 in items])
+        outs = multi_linear([(f.go, gelu_bf16(u), torch.bfloat16, False, None) for (f, _, _), u in zip(items, us)])
+    return [drop_add_layernorm(o, x32, f.out.LayerNorm, f.out.dropout.p, f.site, training)
+            for (f, x32, _), o in zip(items, outs)]
+
+
+def cross_attention_pair(plan, lang32, lang16, visn32, visn16, lang_mask, visn_mask, training, site_l, site_v):
+    """Both directions of a cross layer's shared visual_attention block: one grouped launch for [q|k|v] of both
+    modalities, the attention pair, one grouped launch for the two output projections.  Returns
+    ((lang_x32, lang_x16), (visn_x32, visn_x16))."""
+    a = plan.att
+    Sl, Sv = lang16.shape[1], visn16.shape[1]
+    if not _grouped_on() or plan.qkv is None or not plan._small(Sl, Sv):
+        return (plan.cross_attention(lang32, lang16, visn16, visn_mask, training, site_l),
+                plan.cross_attention(visn32, visn16, lang16, lang_mask, training, site_v))
+    qkv_l, qkv_v = multi_linear([(plan.qkv, lang16, torch.bfloat16, False, None),
+                                 (plan.qkv, visn16, torch.bfloat16, False, None)])
+    p = float(a.dropout.p) if training else 0.0
+    rng = RngState.get(lang16.device) if p > 0 else None
+    ctx_l, ctx_v = CrossPairAttentionFn.apply(a.num_attention_heads, lang_mask, visn_mask, p, site_l + 1, site_v + 1,
+                                              rng, qkv_l, qkv_v)
+    ao_l, ao_v = multi_linear([(plan.ao, ctx_l, torch.bfloat16, False, None),
+                               (plan.ao, ctx_v, torch.bfloat16, False, None)])
+    ln, pd = plan.out.LayerNorm, plan.out.dropout.p
+    return (drop_add_layernorm(ao_l, lang32, ln, pd, site_l, training),
+            drop_add_layernorm(ao_v, visn32, ln, pd, site_v, training))

@@ -7,7 +7,7 @@ import os
 
 import torch
 
-from ._lib import check, lib
+from ._lib import GemmProblem, check, lib
 
 DT_F32, DT_BF16 = 0, 1
 
@@ -172,6 +172,44 @@ def masked_linear_bwd_ds(dy_bf16, x_bf16, w_f32, out=None, accumulate=False):
         check(lib.crv_masked_linear_bwd_ds(_p(dy_bf16), _p(x_bf16), _p(w_f32), _p(out), int(bool(accumulate)),
                                            M, N, K, _stream()), "crv_masked_linear_bwd_ds")
     return out
+
+
+GEMM_FWD, GEMM_DX, GEMM_DS = 0, 1, 2
+ACT_NONE, ACT_GELU = 0, 1
+
+
+def grouped_2cta_ok(MM, NN):
+    """Shapes the grouped 2-CTA kernel takes (generic output extents MM x NN): whole 256-column tiles, >= 256 rows."""
+    return NN % 256 == 0 and MM >= 256 and os.environ.get("CRVQA_2CTA", "1") != "0"
+
+
+def gemm_problem(kind, a, b, out, *, bias=None, w_f32=None, aux=None, act=ACT_NONE, accumulate=False):
+    """One entry of a grouped launch.  kind FWD: a = X [M,K], b = Wm [N,K]; DX: a = dY [M,N], b = Wm [N,K];
+    DS: a = dY [M,N], b = X [M,K], w_f32 = fp32 multiplier [N,K].  Returns (struct, flop, keep-alive tensors)."""
+    if kind == GEMM_FWD:
+        (M, K), N = a.shape, b.shape[0]
+    elif kind == GEMM_DX:
+        (M, N), K = a.shape, b.shape[1]
+    else:
+        (M, N), K = a.shape, b.shape[1]
+    pr = GemmProblem(kind, act, DT_BF16 if out.dtype == torch.bfloat16 else DT_F32, int(bool(accumulate)), M, N, K, 0,
+                     a.data_ptr(), b.data_ptr(), bias.data_ptr() if bias is not None else None,
+                     w_f32.data_ptr() if w_f32 is not None else None, out.data_ptr(),
+                     aux.data_ptr() if aux is not None else None)
+    return pr, ("fwd", "dx", "ds")[kind], M, N, K, (a, b, out, bias, w_f32, aux)
+
+
+def gemm_grouped(problems):
+    """Launch a list of gemm_problem() entries as grouped 2-CTA kernels (crv_masked_gemm_grouped)."""
+    n = len(problems)
+    arr = (GemmProblem * n)(*[p[0] for p in problems])
+    if RECORD is not None:
+        for p in problems:
+            RECORD.append((p[1], p[2], p[3], p[4], None))
+        keep = [p[5] for p in problems]          # the replay reads / writes these buffers: keep them allocated
+        RECORD.append(("group", 0, 0, 0, lambda: (keep, check(lib.crv_masked_gemm_grouped(arr, n, _stream()),
+                                                              "crv_masked_gemm_grouped"))))
+    check(lib.crv_masked_gemm_grouped(arr, n, _stream()), "crv_masked_gemm_grouped")
 
 
 _kth_ws = {}
@@ -345,33 +383,33 @@ class MaskedLinearFn(torch.autograd.Function):
 
     # -- CRVQA_OPERAND=split: the same three GEMMs, each as hi.hi + lo.hi + hi.lo ------------------------------
     @staticmethod
-    def _masked_pair(w_bf16, w_f32, scores, thr_t, wm_bf16):
-        """(hi, lo) masked bf16 halves of W (.) M."""
-        lo = to_bf16(w_f32 - w_bf16.float())
-        hi = wm_bf16 if wm_bf16 is not None else apply_mask_bf16(w_bf16, scores.detach(), thr_t)
-        return hi, apply_mask_bf16(lo, scores.detach(), thr_t)
-
-    @staticmethod
     def _forward_split(ctx, x, scores, w_bf16, thr_t, bias, sink, wm_bf16, w_f32):
         shp = x.shape
         xh, xl = split_bf16(x.reshape(-1, shp[-1]).contiguous())
-        wh, wl = MaskedLinearFn._masked_pair(w_bf16, w_f32, scores, thr_t, wm_bf16)
-        y = masked_linear_fwd(xh, wh, None, None, bias, torch.float32)
-        y += masked_linear_fwd(xl, wh, None, None, None, torch.float32)
-        y += masked_linear_fwd(xh, wl, None, None, None, torch.float32)
-        ctx.save_for_backward(xh, xl, wh, wl, scores, w_f32)
+        wl = to_bf16(w_f32 - w_bf16.float())
+        if wm_bf16 is not None:      # mask cache: plain (2-CTA) kernels on materialised masked halves
+            wh, wl = wm_bf16, apply_mask_bf16(wl, scores.detach(), thr_t)
+            sc = th = None
+        else:                        # no cache: the in-kernel mask transform kernels derive the mask per call
+            wh, sc, th = w_bf16, scores.detach(), thr_t
+        y = masked_linear_fwd(xh, wh, sc, th, bias, torch.float32)
+        y += masked_linear_fwd(xl, wh, sc, th, None, torch.float32)
+        y += masked_linear_fwd(xh, wl, sc, th, None, torch.float32)
+        ctx.save_for_backward(xh, xl, wh, wl, scores, w_f32, thr_t)
+        ctx.masked_in_kernel = sc is not None
         ctx.x_shape, ctx.need_dx, ctx.sink = shp, x.requires_grad, sink
         return y.view(*shp[:-1], w_bf16.shape[0])
 
     @staticmethod
     def _backward_split(ctx, dy):
-        xh, xl, wh, wl, scores, w_f32 = ctx.saved_tensors
+        xh, xl, wh, wl, scores, w_f32, thr_t = ctx.saved_tensors
+        sc, th = (scores.detach(), thr_t) if ctx.masked_in_kernel else (None, None)
         dh, dl = split_bf16(dy.reshape(-1, dy.shape[-1]).contiguous().float())
         dx = None
         if ctx.need_dx:
-            dx = masked_linear_bwd_dx(dh, wh, None, None, torch.float32)
-            dx += masked_linear_bwd_dx(dl, wh, None, None, torch.float32)
-            dx += masked_linear_bwd_dx(dh, wl, None, None, torch.float32)
+            dx = masked_linear_bwd_dx(dh, wh, sc, th, torch.float32)
+            dx += masked_linear_bwd_dx(dl, wh, sc, th, torch.float32)
+            dx += masked_linear_bwd_dx(dh, wl, sc, th, torch.float32)
             dx = dx.view(ctx.x_shape)
         ds = None
         if ctx.needs_input_grad[1]:

@@ -25,6 +25,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "gelu.cuh"
 #include "ptx.cuh"
 
 namespace crv {
@@ -671,6 +672,380 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Grouped 2-CTA kernel: up to kMaxGroup independent GEMM problems of a layer phase in ONE persistent launch
+// (dX and dS of a module -- both read the same dY; the two sides of a cross-modality layer; the language and the
+// vision stack in lockstep).  The stage-2 step is 369 GEMMs of which a third are one-wave problems (N = K = 768:
+// 60 - 108 tile pairs on 74 CTA pairs) whose pipeline fill, epilogue and drain cost more than their mainloop; in a
+// group the tile loop runs across problem boundaries, so the epilogue of one problem's last tile overlaps the
+// mainloop of the next problem's first tile, wave quantisation applies to the SUM of the tiles, and launch + set-up
+// (TMEM allocation, barrier init, cluster sync, descriptor prefetch) is paid once per group.
+//
+// Same pipeline as masked_gemm2_kernel (2-SM TMA into 128B-swizzled tiles, tcgen05.mma.cta_group::2 from one
+// thread, double-buffered 256-column TMEM accumulators, eight epilogue warps per CTA) with the per-problem
+// properties (operand majors, epilogue kind, split of the reduction) read at run time from the problem table in
+// kernel parameter space.  Two more epilogues fuse the GELU of the FFN into the GEMMs around it:
+//   kGEpiGelu      u = D + bias -> bf16 ; out = bf16(gelu(u)) and aux = u (both TMA-stored): FF1 forward
+//   kGEpiGeluGrad  out = bf16(D * gelu'(u)), u read from aux_in: the dX of FF2 becomes dU directly
+// Staging is double-buffered per epilogue warp (2 x 4 KB), which is what the two-output epilogue needs and lets a
+// chunk be staged while the previous chunk's TMA store still reads its buffer; five 32 KB operand stages.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxGroup = 4;
+constexpr int kGEpiF32 = 0, kGEpiBf16 = 1, kGEpiScoreGrad = 2, kGEpiGelu = 3, kGEpiGeluGrad = 4;
+
+struct alignas(64) GProblem {
+  CUtensorMap tmA, tmB, tmOut, tmAux;
+  const float* bias;         // [NN] or null (store epilogues)
+  const float* w;            // [MM, NN] fp32 multiplier (score-grad epilogue)
+  const uint16_t* aux_in;    // [MM, NN] bf16 pre-activation u (gelu-grad epilogue)
+  int MM, NN, KK;
+  int kb_per_split, splits, num_m, num_n;   // num_m counts 256-row pair tiles
+  int tile_end;              // exclusive end of this problem's tiles in the group's tile numbering
+  int a_mn, b_mn, epi, reduce_out;
+};
+struct GArgs {
+  GProblem p[kMaxGroup];
+  int count, total_tiles;
+};
+
+struct SmemG {
+  static constexpr int kStage = 32768;           // A: this CTA's 128 rows; B: this CTA's half of the 256 columns
+  static constexpr int kStages = 5;
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kEpi = kEpiWarps * 2 * 4096;
+  static constexpr int kTotal = kStages * kStage + kEpi + 256 + 1024;
+};
+
+struct GTile {
+  int pi, m0, n0, kb_begin, num_kb;
+};
+
+__device__ __forceinline__ GTile gtile(const GArgs& a, int tile) {
+  int pi = 0, begin = 0;
+#pragma unroll
+  for (int i = 0; i < kMaxGroup - 1; ++i) {
+    if (pi == i && tile >= a.p[i].tile_end) {
+      begin = a.p[i].tile_end;
+      pi = i + 1;
+    }
+  }
+  const GProblem& p = a.p[pi];
+  const int local = tile - begin;
+  const int per_z = p.num_m * p.num_n;
+  const int z = local / per_z;
+  const int r = local - z * per_z;
+  const int mt = r / p.num_n;
+  const int nt = r - mt * p.num_n;
+  const int total_kb = (p.KK + BK - 1) / BK;
+  GTile t;
+  t.pi = pi;
+  t.m0 = mt * 256;
+  t.n0 = nt * 256;
+  t.kb_begin = z * p.kb_per_split;
+  int e = t.kb_begin + p.kb_per_split;
+  if (e > total_kb) e = total_kb;
+  t.num_kb = e - t.kb_begin;
+  return t;
+}
+
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// stage 32 rows x 128 bytes (one register row per lane) into a swizzled buffer and hand it to TMA
+__device__ __forceinline__ void stage_and_store(uint8_t* buf, const uint32_t (&pk)[32], int lane, const CUtensorMap* map,
+                                                int c0, int r0, bool in_range, bool reduce) {
+  if (lane == 0) bulk_wait_read<1>();   // the store issued two groups ago (same buffer) has read its data
+  __syncwarp();
+  const int sw = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ sw) << 4)) =
+        make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (in_range) {
+      if (reduce) tma_reduce_add_2d(map, buf, c0, r0);
+      else tma_store_2d(map, buf, c0, r0);
+    }
+    bulk_commit();
+  }
+}
+
+__global__ void __launch_bounds__(64 + 32 * SmemG::kEpiWarps, 1)
+grouped_gemm2_kernel(const __grid_constant__ GArgs args) {
+  using L = SmemG;
+  constexpr int STAGES = L::kStages;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_base = smem + STAGES * L::kStage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_base + L::kEpi);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_tiles = args.total_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < args.count; ++i) {
+      tma_prefetch_desc(&args.p[i].tmA);
+      tma_prefetch_desc(&args.p[i].tmB);
+      tma_prefetch_desc(&args.p[i].tmOut);
+      if (args.p[i].epi == kGEpiGelu) tma_prefetch_desc(&args.p[i].tmAux);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 2 * L::kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const GTile tc = gtile(args, tile);
+        const GProblem& p = args.p[tc.pi];
+        const int m0 = tc.m0 + rank * BM;
+        const int nh = tc.n0 + rank * 128;
+        const bool a_mn = p.a_mn != 0, b_mn = p.b_mn != 0;
+        for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * L::kStage);
+          else mbar_arrive_remote(&full_bar[s], 0);
+          uint8_t* sA = smem + s * L::kStage;
+          uint8_t* sB = sA + 16384;
+          const int kk0 = (tc.kb_begin + kb) * BK;
+          if (!a_mn) {
+            tma_load_2d_2sm(sA, &p.tmA, &full_bar[s], kk0, m0);
+          } else {
+            tma_load_2d_2sm(sA, &p.tmA, &full_bar[s], m0, kk0);
+            tma_load_2d_2sm(sA + 8192, &p.tmA, &full_bar[s], m0 + 64, kk0);
+          }
+          if (!b_mn) {
+            tma_load_2d_2sm(sB, &p.tmB, &full_bar[s], kk0, nh);
+          } else {
+            tma_load_2d_2sm(sB, &p.tmB, &full_bar[s], nh, kk0);
+            tma_load_2d_2sm(sB + 8192, &p.tmB, &full_bar[s], nh + 64, kk0);
+          }
+        }
+      }
+      pdl_launch_dependents();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (leader) {
+      int it = 0, tcount = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tcount) {
+        const GTile tc = gtile(args, tile);
+        const GProblem& p = args.p[tc.pi];
+        const bool a_mn = p.a_mn != 0, b_mn = p.b_mn != 0;
+        const uint32_t idesc = make_idesc_bf16(256, BN, a_mn ? 1 : 0, b_mn ? 1 : 0);
+        const int acc = tcount & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t aBase = smem_u32(smem + s * L::kStage);
+            const uint32_t bBase = aBase + 16384;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = a_mn ? make_sw128_desc(aBase + k * 2048, 8192, 1024)
+                                       : make_sw128_desc(aBase + k * 32, 16, 1024);
+              const uint64_t db = b_mn ? make_sw128_desc(bBase + k * 2048, 8192, 1024)
+                                       : make_sw128_desc(bBase + k * 32, 16, 1024);
+              umma_bf16_2sm(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[s]);
+            if (kb == tc.num_kb - 1) umma_commit_2sm(&tmem_full_bar[acc]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;       // which 128 of the tile's 256 columns
+    uint8_t* bufs = epi_base + (warp - 2) * 8192;
+    int tcount = 0, nstore = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tcount) {
+      const GTile tc = gtile(args, tile);
+      const GProblem& p = args.p[tc.pi];
+      const int epi = p.epi;
+      const int acc = tcount & 1;
+      const int row0 = tc.m0 + rank * BM + q * 32;
+      const int m = row0 + lane;
+      const bool row_ok = m < p.MM;
+      mbar_wait(&tmem_full_bar[acc], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      if (epi == kGEpiF32 || epi == kGEpiScoreGrad) {
+        // ---- fp32 out: 32 columns per 128-byte staging row
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = half * 128 + c * 32;
+          const int nb = tc.n0 + col0;
+          uint32_t r[32], pk[32];
+          float bias_v = 0.f;
+          float4 wq[8];
+          const bool fast = row_ok && nb + 32 <= p.NN;
+          if (epi == kGEpiF32) {
+            if (p.bias != nullptr && nb + lane < p.NN) bias_v = __ldg(p.bias + nb + lane);
+          } else if (fast) {
+            const float* wrow = p.w + static_cast<size_t>(m) * p.NN + nb;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wq[j] = __ldg(reinterpret_cast<const float4*>(wrow) + j);
+          }
+          tmem_ld_32x32(t_addr + col0, r);
+          tmem_ld_wait();
+          if (epi == kGEpiF32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              pk[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_v, j));
+          } else if (fast) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              pk[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) * wq[j].x);
+              pk[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) * wq[j].y);
+              pk[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) * wq[j].z);
+              pk[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) * wq[j].w);
+            }
+          } else {
+            const float* wrow = p.w + static_cast<size_t>(row_ok ? m : 0) * p.NN + nb;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float wv = (row_ok && nb + j < p.NN) ? __ldg(wrow + j) : 0.f;
+              pk[j] = __float_as_uint(__uint_as_float(r[j]) * wv);
+            }
+          }
+          stage_and_store(bufs + (nstore & 1) * 4096, pk, lane, &p.tmOut, nb, row0, nb < p.NN && row0 < p.MM,
+                          epi == kGEpiScoreGrad && p.reduce_out);
+          ++nstore;
+        }
+      } else {
+        // ---- bf16 out: 64 columns per 128-byte staging row
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = half * 128 + c * 64;
+          const int nb = tc.n0 + col0;
+          uint32_t r[32], r2[32], pk[32];
+          float bias_lo = 0.f, bias_hi = 0.f;
+          uint4 uq[8];
+          const bool fast = row_ok && nb + 64 <= p.NN;
+          if (epi == kGEpiGeluGrad) {
+            if (fast) {
+              const uint16_t* urow = p.aux_in + static_cast<size_t>(m) * p.NN + nb;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) uq[j] = __ldg(reinterpret_cast<const uint4*>(urow) + j);
+            }
+          } else if (p.bias != nullptr) {
+            if (nb + lane < p.NN) bias_lo = __ldg(p.bias + nb + lane);
+            if (nb + 32 + lane < p.NN) bias_hi = __ldg(p.bias + nb + 32 + lane);
+          }
+          tmem_ld_32x32(t_addr + col0, r);
+          tmem_ld_32x32(t_addr + col0 + 32, r2);
+          tmem_ld_wait();
+          if (epi == kGEpiGeluGrad) {
+            if (fast) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {        // uq[j]: u of columns 8j .. 8j+7 ; uq[4 + j]: columns 32 + 8j ..
+                const uint32_t ua[4] = {uq[j].x, uq[j].y, uq[j].z, uq[j].w};
+                const uint32_t ub[4] = {uq[4 + j].x, uq[4 + j].y, uq[4 + j].z, uq[4 + j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  pk[4 * j + e] = pack2_bf16(__uint_as_float(r[8 * j + 2 * e]) * gelu_grad_f(bf16_lo(ua[e])),
+                                             __uint_as_float(r[8 * j + 2 * e + 1]) * gelu_grad_f(bf16_hi(ua[e])));
+                  pk[16 + 4 * j + e] = pack2_bf16(__uint_as_float(r2[8 * j + 2 * e]) * gelu_grad_f(bf16_lo(ub[e])),
+                                                  __uint_as_float(r2[8 * j + 2 * e + 1]) * gelu_grad_f(bf16_hi(ub[e])));
+                }
+              }
+            } else {
+              const uint16_t* urow = p.aux_in + static_cast<size_t>(row_ok ? m : 0) * p.NN + nb;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float g[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int col = (e < 2 ? 2 * j + e : 32 + 2 * j + (e - 2));
+                  const bool ok = row_ok && nb + col < p.NN;
+                  g[e] = ok ? gelu_grad_f(__uint_as_float(static_cast<uint32_t>(__ldg(urow + col)) << 16)) : 0.f;
+                }
+                pk[j] = pack2_bf16(__uint_as_float(r[2 * j]) * g[0], __uint_as_float(r[2 * j + 1]) * g[1]);
+                pk[16 + j] = pack2_bf16(__uint_as_float(r2[2 * j]) * g[2], __uint_as_float(r2[2 * j + 1]) * g[3]);
+              }
+            }
+            stage_and_store(bufs + (nstore & 1) * 4096, pk, lane, &p.tmOut, nb, row0, nb < p.NN && row0 < p.MM, false);
+            ++nstore;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              pk[j] = pack2_bf16(__uint_as_float(r[2 * j]) + __shfl_sync(0xffffffffu, bias_lo, 2 * j),
+                                 __uint_as_float(r[2 * j + 1]) + __shfl_sync(0xffffffffu, bias_lo, 2 * j + 1));
+              pk[16 + j] = pack2_bf16(__uint_as_float(r2[2 * j]) + __shfl_sync(0xffffffffu, bias_hi, 2 * j),
+                                      __uint_as_float(r2[2 * j + 1]) + __shfl_sync(0xffffffffu, bias_hi, 2 * j + 1));
+            }
+            if (epi == kGEpiGelu) {
+              // the pre-activation goes out as it is (bf16), then the same registers become gelu(u) -- computed
+              // from the ROUNDED u, which is what the backward multiplies gelu'() of
+              stage_and_store(bufs + (nstore & 1) * 4096, pk, lane, &p.tmAux, nb, row0, nb < p.NN && row0 < p.MM, false);
+              ++nstore;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) pk[j] = pack2_bf16(gelu_f(bf16_lo(pk[j])), gelu_f(bf16_hi(pk[j])));
+            }
+            stage_and_store(bufs + (nstore & 1) * 4096, pk, lane, &p.tmOut, nb, row0, nb < p.NN && row0 < p.MM, false);
+            ++nstore;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 2 * BN);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -908,4 +1283,209 @@ extern "C" int crv_masked_linear_bwd_ds(const uint16_t* dy, const uint16_t* x, c
   if (two) return launch2<true, true, kEpiScoreGrad, false>(tmA, tmB, tmO, p, st);
   if (bn == 256) return launch<true, true, 256, false, kEpiScoreGrad, false>(tmA, tmB, tmB, tmO, p, st);
   return launch<true, true, 128, false, kEpiScoreGrad, false>(tmA, tmB, tmB, tmO, p, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// grouped launch: host side
+// ------------------------------------------------------------------------------------------------
+namespace crv {
+
+static bool group_eligible(const crv_gemm_problem& q) {
+  int MM, NN;
+  if (q.kind == CRV_GEMM_FWD) { MM = q.M; NN = q.N; }
+  else if (q.kind == CRV_GEMM_DX) { MM = q.M; NN = q.K; }
+  else { MM = q.N; NN = q.K; }
+  if (!use_2cta(MM, NN)) return false;
+  if (q.act != CRV_ACT_NONE && q.out_dtype != CRV_DTYPE_BF16) return false;
+  return true;
+}
+
+// Static round-robin over CTA pairs: tile t runs on pair t % pairs.  The split of a score-gradient problem's
+// reduction decides both how many tiles it contributes and how long each is; pick, per problem, the split that
+// minimises the longest pair (cost of a tile = its k-blocks + a constant for fill / epilogue; split tiles pay a
+// little more for the reduce-add).  Problems are few and the candidates a handful, so this is a few microseconds
+// of host time per DISTINCT group shape (memoised).
+static int simulate_makespan(const GArgs& g, int pairs) {
+  static thread_local int load[128];
+  for (int i = 0; i < pairs; ++i) load[i] = 0;
+  int t = 0;
+  for (int i = 0; i < g.count; ++i) {
+    const GProblem& p = g.p[i];
+    const int total_kb = (p.KK + BK - 1) / BK;
+    const int per_z = p.num_m * p.num_n;
+    for (int z = 0; z < p.splits; ++z) {
+      int kb = total_kb - z * p.kb_per_split;
+      if (kb > p.kb_per_split) kb = p.kb_per_split;
+      const int cost = kb + 3 + (p.epi == kGEpiScoreGrad && p.reduce_out ? 1 : 0);
+      for (int r = 0; r < per_z; ++r, ++t) load[t % pairs] += cost;
+    }
+  }
+  int mx = 0;
+  for (int i = 0; i < pairs; ++i) mx = load[i] > mx ? load[i] : mx;
+  return mx;
+}
+
+static void set_split(GProblem& p, int splits, int accumulate) {
+  const int total_kb = (p.KK + BK - 1) / BK;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (total_kb + splits - 1) / splits;
+  p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.reduce_out = (p.splits > 1 || accumulate) ? 1 : 0;
+}
+
+static void finish_tiles(GArgs& g) {
+  int t = 0;
+  for (int i = 0; i < g.count; ++i) {
+    t += g.p[i].num_m * g.p[i].num_n * g.p[i].splits;
+    g.p[i].tile_end = t;
+  }
+  g.total_tiles = t;
+}
+
+static void choose_splits(GArgs& g, const int* accumulate, int pairs) {
+  static const int cand[] = {1, 2, 3, 4, 6, 8, 9, 12, 16, 18, 24};
+  for (int i = 0; i < g.count; ++i) {
+    GProblem& p = g.p[i];
+    if (p.epi != kGEpiScoreGrad) continue;
+    const int total_kb = (p.KK + BK - 1) / BK;
+    int best = 1, best_cost = 1 << 30;
+    for (int c : cand) {
+      if (c > 1 && total_kb / c < 8) break;   // keep >= 8 k-blocks per split
+      set_split(p, c, accumulate[i]);
+      const int cost = simulate_makespan(g, pairs);
+      if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    set_split(p, best, accumulate[i]);
+  }
+}
+
+static int launch_group(GArgs& g, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    CRV_CUDA(cudaFuncSetAttribute(grouped_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemG::kTotal));
+    configured = true;
+  }
+  const int max_pairs = num_sms() / 2;
+  const int pairs = g.total_tiles < max_pairs ? g.total_tiles : max_pairs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(64 + 32 * SmemG::kEpiWarps);
+  cfg.dynamicSmemBytes = SmemG::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  CRV_CUDA(cudaLaunchKernelEx(&cfg, grouped_gemm2_kernel, g));
+  return launch_status();
+}
+
+static int single_launch(const crv_gemm_problem& q, void* stream) {
+  if (q.act != CRV_ACT_NONE) return CRV_E_SHAPE;
+  if (q.kind == CRV_GEMM_FWD)
+    return crv_masked_linear_fwd(q.a, q.b, nullptr, nullptr, q.bias, q.out, q.out_dtype, q.M, q.N, q.K, stream);
+  if (q.kind == CRV_GEMM_DX)
+    return crv_masked_linear_bwd_dx(q.a, q.b, nullptr, nullptr, q.out, q.out_dtype, q.M, q.N, q.K, stream);
+  return crv_masked_linear_bwd_ds(q.a, q.b, q.w_f32, static_cast<float*>(q.out), q.accumulate, q.M, q.N, q.K, stream);
+}
+
+}  // namespace crv
+
+extern "C" int crv_masked_gemm_grouped(const crv_gemm_problem* pr, int count, void* stream) {
+  if (!pr || count <= 0) return CRV_E_BADARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < count; ++i) {
+    const crv_gemm_problem& q = pr[i];
+    if (!q.a || !q.b || !q.out || q.M <= 0 || q.N <= 0 || q.K <= 0) return CRV_E_BADARG;
+    if (q.kind < CRV_GEMM_FWD || q.kind > CRV_GEMM_DS) return CRV_E_BADARG;
+    if (q.kind == CRV_GEMM_DS && (!q.w_f32 || q.act != CRV_ACT_NONE)) return CRV_E_BADARG;
+    if (q.act != CRV_ACT_NONE && (q.act != CRV_ACT_GELU || !q.aux)) return CRV_E_BADARG;
+    if (q.out_dtype != CRV_DTYPE_F32 && q.out_dtype != CRV_DTYPE_BF16) return CRV_E_BADARG;
+    if ((q.N % 8) || (q.K % 8)) return CRV_E_SHAPE;
+    if (!aligned16(q.a) || !aligned16(q.b) || !aligned16(q.out) || (q.aux && !aligned16(q.aux)) ||
+        (q.w_f32 && !aligned16(q.w_f32)))
+      return CRV_E_ALIGN;
+  }
+  const int pairs = num_sms() / 2;
+  int i = 0;
+  while (i < count) {
+    if (!group_eligible(pr[i])) {
+      int rc = single_launch(pr[i], stream);
+      if (rc) return rc;
+      ++i;
+      continue;
+    }
+    GArgs g{};
+    int accumulate[kMaxGroup] = {0, 0, 0, 0};
+    int src[kMaxGroup];
+    while (i < count && g.count < kMaxGroup && group_eligible(pr[i])) {
+      const crv_gemm_problem& q = pr[i];
+      GProblem& p = g.p[g.count];
+      const bool obf = q.out_dtype == CRV_DTYPE_BF16;
+      int rc;
+      if (q.kind == CRV_GEMM_FWD) {            // A = X [M,K] K-major; B = Wm [N,K] K-major
+        p.MM = q.M; p.NN = q.N; p.KK = q.K; p.a_mn = 0; p.b_mn = 0;
+        if ((rc = make_map(&p.tmA, q.a, 2, false, q.M, q.K, BM, BK))) return rc;
+        if ((rc = make_map(&p.tmB, q.b, 2, false, q.N, q.K, 128, BK))) return rc;
+        if ((rc = make_out_map(&p.tmOut, q.out, obf, q.M, q.N))) return rc;
+        p.bias = q.bias;
+        p.epi = obf ? kGEpiBf16 : kGEpiF32;
+        if (q.act == CRV_ACT_GELU) {
+          if ((rc = make_out_map(&p.tmAux, q.aux, true, q.M, q.N))) return rc;
+          p.epi = kGEpiGelu;
+        }
+      } else if (q.kind == CRV_GEMM_DX) {      // A = dY [M,N] K-major; B = Wm [N,K] = [KK][NN] MN-major
+        p.MM = q.M; p.NN = q.K; p.KK = q.N; p.a_mn = 0; p.b_mn = 1;
+        if ((rc = make_map(&p.tmA, q.a, 2, false, q.M, q.N, BM, BK))) return rc;
+        if ((rc = make_map(&p.tmB, q.b, 2, false, q.N, q.K, 64, 64))) return rc;
+        if ((rc = make_out_map(&p.tmOut, q.out, obf, q.M, q.K))) return rc;
+        p.epi = obf ? kGEpiBf16 : kGEpiF32;
+        if (q.act == CRV_ACT_GELU) {
+          p.aux_in = static_cast<const uint16_t*>(q.aux);
+          p.epi = kGEpiGeluGrad;
+        }
+      } else {                                  // A = dY [M,N] = [KK][MM] MN-major; B = X [M,K] = [KK][NN] MN-major
+        p.MM = q.N; p.NN = q.K; p.KK = q.M; p.a_mn = 1; p.b_mn = 1;
+        if ((rc = make_map(&p.tmA, q.a, 2, false, q.M, q.N, 64, 64))) return rc;
+        if ((rc = make_map(&p.tmB, q.b, 2, false, q.M, q.K, 64, 64))) return rc;
+        if ((rc = make_out_map(&p.tmOut, q.out, false, q.N, q.K))) return rc;
+        p.w = q.w_f32;
+        p.epi = kGEpiScoreGrad;
+        accumulate[g.count] = q.accumulate;
+      }
+      p.num_m = (p.MM + 255) / 256;
+      p.num_n = (p.NN + 255) / 256;
+      set_split(p, 1, accumulate[g.count]);
+      src[g.count] = i;
+      ++g.count;
+      ++i;
+    }
+    // two score-gradient problems of one group that write the same dS (a shared module applied to both modalities)
+    // run concurrently: both must reduce-add, into a buffer cleared once
+    bool dup[kMaxGroup] = {false, false, false, false};
+    for (int a = 0; a < g.count; ++a)
+      for (int b = a + 1; b < g.count; ++b)
+        if (g.p[a].epi == kGEpiScoreGrad && g.p[b].epi == kGEpiScoreGrad && pr[src[a]].out == pr[src[b]].out) {
+          dup[b] = true;
+          if (!accumulate[a]) { accumulate[a] = 2; }   // 2 = "clear first, then reduce"
+          accumulate[b] = 1;
+        }
+    finish_tiles(g);
+    choose_splits(g, accumulate, pairs);
+    finish_tiles(g);
+    for (int a = 0; a < g.count; ++a) {
+      if (g.p[a].epi != kGEpiScoreGrad || dup[a]) continue;
+      const crv_gemm_problem& q = pr[src[a]];
+      const bool clear = (accumulate[a] == 2) || (accumulate[a] == 0 && g.p[a].splits > 1);
+      if (clear) CRV_CUDA(cudaMemsetAsync(q.out, 0, static_cast<size_t>(q.N) * q.K * sizeof(float), st));
+    }
+    int rc = launch_group(g, st);
+    if (rc) return rc;
+  }
+  return CRV_OK;
 }

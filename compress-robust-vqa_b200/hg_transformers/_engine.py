@@ -39,20 +39,24 @@ def masked_modules_of(model):
 
 
 def execution_order(named_modules):
-    """Arena (and therefore bucket) order = the order the fused LXMERT forward executes the modules: vision
-    stack, language stack, cross layers, pooler (modeling_lxmert._forward_fast).  The backward pass completes
-    gradients in the reverse order, so the bucket that finishes LAST is the small head of the vision stack and the
-    94 MB word-embedding gradient is exchanged while the vision layers are still in backward.  Other models
-    (VisualBERT: one stack) keep named_modules order."""
+    """Arena (and therefore bucket) order = the order the fused LXMERT forward executes the modules: the visual
+    feature encoder and the word embeddings, then language layer i and vision layer i in lockstep, the remaining
+    language layers, the cross layers, the pooler (modeling_lxmert._forward_fast).  The backward pass completes
+    gradients in the reverse order.  Other models (VisualBERT: one stack) keep named_modules order."""
+    import re
+
     def key(item):
         name = item[0]
-        if "visn_fc" in name or ".r_layers." in name:
-            return 0
+        if "visn_fc" in name or "embeddings" in name:
+            return (0, 0, 0)
+        m = re.search(r"\.(layer|r_layers)\.(\d+)\.", name)
+        if m and ".x_layers." not in name:
+            return (1, int(m.group(2)), 0 if m.group(1) == "layer" else 1)
         if ".x_layers." in name:
-            return 2
+            return (2, 0, 0)
         if "pooler" in name:
-            return 3
-        return 1
+            return (3, 0, 0)
+        return (1, 0, 0)
     if not any(".r_layers." in n for n, _ in named_modules):
         return list(named_modules)
     return sorted(named_modules, key=key)          # stable: named_modules order inside each group
@@ -393,6 +397,12 @@ class GraphedStep:
             return out
         dev = t.args.device
         if self.graph is None:
+            # nothing may be CREATED inside the capture that has to survive it: a lazily built Adam state or dropout
+            # counter would be allocated from the graph's pool and re-initialised by every replay
+            if hasattr(self.optimizer, "ensure_state"):
+                self.optimizer.ensure_state()
+            from crvqa.fused import RngState
+            RngState.get(dev)
             self.shapes = self._shape_key(inputs)
             self.static_inputs = list(inputs)
             for i in self.TENSOR_SLOTS:

@@ -243,26 +243,37 @@ class LxmertEncoder(nn.Module):
         return plans
 
     def _forward_fast(self, plans, lang32, lang_mask, visn32, visn_mask):
+        """Language and vision stacks run in LOCKSTEP (layer i of both, then the remaining language layers): the two
+        are independent until the cross layers, so their GEMMs of one phase share a grouped launch
+        (crvqa.fused.self_attention_multi / ffn_multi); inside a cross layer the two modalities are grouped the same
+        way.  CRVQA_GROUPED=0 issues every GEMM on its own."""
+        from crvqa import fused
         tr = self.training
         visn16 = visn32.to(torch.bfloat16)
-        # vision stack first: independent of the language stack, and this way the backward pass ends with the
-        # small vision head instead of the 94 MB word-embedding gradient (see _engine.execution_order)
-        for att, ffn in plans["visn"]:
-            a32, a16 = att.self_attention(visn32, visn16, visn_mask, tr)
-            visn32, visn16 = ffn(a32, a16, tr)
         if callable(lang32):
             lang32 = lang32()
         lang16 = lang32.to(torch.bfloat16)
-        for att, ffn in plans["lang"]:
-            a32, a16 = att.self_attention(lang32, lang16, lang_mask, tr)
-            lang32, lang16 = ffn(a32, a16, tr)
+        nl, nv = len(plans["lang"]), len(plans["visn"])
+        for i in range(max(nl, nv)):
+            items = []
+            if i < nl:
+                items.append((plans["lang"][i], "l"))
+            if i < nv:
+                items.append((plans["visn"][i], "v"))
+            state = {"l": (lang32, lang16, lang_mask), "v": (visn32, visn16, visn_mask)}
+            att = fused.self_attention_multi([(pl[0], *state[k]) for pl, k in items], tr)
+            ffn = fused.ffn_multi([(pl[1], a32, a16) for (pl, _), (a32, a16) in zip(items, att)], tr)
+            for (_, k), (o32, o16) in zip(items, ffn):
+                if k == "l":
+                    lang32, lang16 = o32, o16
+                else:
+                    visn32, visn16 = o32, o16
         for cross, site_l, site_v, ls, vs, lf, vf in plans["cross"]:
-            lx32, lx16 = cross.cross_attention(lang32, lang16, visn16, visn_mask, tr, site_l)
-            vx32, vx16 = cross.cross_attention(visn32, visn16, lang16, lang_mask, tr, site_v)
-            ls32, ls16 = ls.self_attention(lx32, lx16, lang_mask, tr)
-            vs32, vs16 = vs.self_attention(vx32, vx16, visn_mask, tr)
-            lang32, lang16 = lf(ls32, ls16, tr)
-            visn32, visn16 = vf(vs32, vs16, tr)
+            (lx32, lx16), (vx32, vx16) = fused.cross_attention_pair(cross, lang32, lang16, visn32, visn16, lang_mask,
+                                                                    visn_mask, tr, site_l, site_v)
+            (ls32, ls16), (vs32, vs16) = fused.self_attention_multi([(ls, lx32, lx16, lang_mask),
+                                                                     (vs, vx32, vx16, visn_mask)], tr)
+            (lang32, lang16), (visn32, visn16) = fused.ffn_multi([(lf, ls32, ls16), (vf, vs32, vs16)], tr)
         return lang32, visn32
 
 

@@ -81,6 +81,13 @@ class AdamW(Optimizer):
                     views["sum"].copy_(st["sum"])
                     st["sum"], st["exp_avg"], st["exp_avg_sq"] = views["sum"], views["exp_avg"], views["exp_avg_sq"]
 
+    def ensure_state(self):
+        """Create exp_avg / exp_avg_sq of every trainable parameter now (instead of at its first step)."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.requires_grad:
+                    self._ensure_state(p)
+
     def _ensure_state(self, p):
         state = self.state[p]
         if "exp_avg" not in state:

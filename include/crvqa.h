@@ -107,6 +107,37 @@ int crv_masked_linear_bwd_dx(const uint16_t* dy_bf16, const uint16_t* w_bf16, co
 int crv_masked_linear_bwd_ds(const uint16_t* dy_bf16, const uint16_t* x_bf16, const float* w_f32,
                              float* dscores, int accumulate, int M, int N, int K, void* stream);
 
+/* Grouped launch of the three GEMMs above (mask-cache form: `b` is the materialised W (.) M, no scores): up to four
+ * independent problems of one layer phase run as ONE persistent 2-CTA kernel -- dX and dS of a module (both read the
+ * same dY), the two modalities of a cross layer (hg_transformers/modeling_lxmert.py:947-1009), the language and the
+ * vision stack in lockstep -- so that pipeline fill / drain and wave quantisation are paid per group, not per GEMM.
+ * Longer lists are cut into groups of four in order; problems whose shape the 2-CTA kernel does not take (output
+ * width not a multiple of 256, fewer than 256 output rows) fall back to the single entry points.
+ *   kind  CRV_GEMM_FWD  out[M,N] = a[M,K] . b[N,K]^T + bias          a = X,  b = W (.) M
+ *         CRV_GEMM_DX   out[M,K] = a[M,N] . b[N,K]                   a = dY, b = W (.) M
+ *         CRV_GEMM_DS   out[N,K] (+)= (a[M,N]^T . b[M,K]) (.) w_f32   a = dY, b = X
+ *   act   CRV_ACT_GELU  fuses the erf-GELU of LxmertIntermediate (hg_transformers/modeling_lxmert.py:876-886) into
+ *         the GEMMs around it (bf16 outputs only): FWD writes aux = y (the pre-activation, bf16) and out = gelu(y);
+ *         DX reads aux = u [M,K] (bf16) and writes out = dX (.) gelu'(u).
+ * Two DS problems of one call may name the same `out` (a shared module applied to both modalities): they reduce-add
+ * into it.  problems_host is a HOST array. */
+#define CRV_GEMM_FWD 0
+#define CRV_GEMM_DX 1
+#define CRV_GEMM_DS 2
+#define CRV_ACT_NONE 0
+#define CRV_ACT_GELU 1
+typedef struct crv_gemm_problem {
+  int kind, act, out_dtype, accumulate;
+  int M, N, K, reserved;
+  const uint16_t* a;
+  const uint16_t* b;
+  const float* bias;   /* FWD, may be NULL */
+  const float* w_f32;  /* DS */
+  void* out;
+  void* aux;           /* CRV_ACT_GELU only */
+} crv_gemm_problem;
+int crv_masked_gemm_grouped(const crv_gemm_problem* problems_host, int count, void* stream);
+
 /* Same three operations for inner dimensions the TMA path cannot take (box_fc has K = 4,
  * hg_transformers/modeling_lxmert.py:1025): fp32 in / fp32 out SIMT kernels, exact fp32 math. */
 int crv_masked_linear_small_k_fwd(const float* x, const float* w, const float* scores, const float* thr,

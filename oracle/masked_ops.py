@@ -92,7 +92,9 @@ class MaskedLinear(torch.autograd.Function):
         wr = _round(weight.detach(), operand)
         wm = wr * mask
         y = F.linear(xr, wm, bias)
-        ctx.save_for_backward(xr, wr, wm)
+        # operand == "bf16" models the MMA OPERANDS only (X, dY, W (.) M); the (.) W of dS multiplies by the fp32
+        # weight, as the reference does and as the CUDA epilogue does
+        ctx.save_for_backward(xr, weight.detach(), wm)
         ctx.operand = operand
         ctx.x_shape = x.shape
         return y.view(*x.shape[:-1], weight.shape[0])

@@ -338,22 +338,27 @@ def test_grad_sync_world2_gloo():
     assert sorted(q.get(timeout=5) for _ in range(2)) == [0, 1]
 
 
-def test_execution_order_puts_the_vision_stack_first():
-    """Arena / bucket order follows the fused forward pass (vision stack, language stack incl. the word embeddings,
-    cross layers, pooler) and is stable inside each group; single-stack models keep named_modules order."""
+def test_execution_order_follows_the_lockstep_forward():
+    """Arena / bucket order follows the fused forward pass (feature encoder + word embeddings, language layer i and
+    vision layer i in lockstep, remaining language layers, cross layers, pooler) and is stable inside each group (so
+    query | key | value of a layer stay adjacent); single-stack models keep named_modules order."""
     from hg_transformers._engine import execution_order
     from oracle import lxmert_oracle as lxo
     named = [(n, object()) for n, _ in lxo.module_names()]
     got = [n for n, _ in execution_order(named)]
     assert sorted(got) == sorted(n for n, _ in named)
-    first_lang = got.index("lxmert.embeddings.word_embeddings")
-    assert got[0] == "lxmert.encoder.visn_fc.visn_fc" and got[1] == "lxmert.encoder.visn_fc.box_fc"
-    assert all(".r_layers." in n for n in got[2:first_lang])
+    assert set(got[:3]) == {"lxmert.embeddings.word_embeddings", "lxmert.encoder.visn_fc.visn_fc",
+                            "lxmert.encoder.visn_fc.box_fc"}
     first_x = next(i for i, n in enumerate(got) if ".x_layers." in n)
-    assert all(".encoder.layer." in n for n in got[first_lang + 1:first_x])
+    stack = got[3:first_x]
+    want = []
+    for i in range(9):
+        want += [n for n, _ in named if f".encoder.layer.{i}." in n]
+        want += [n for n, _ in named if f".encoder.r_layers.{i}." in n]
+    assert stack == want
+    assert stack[0].endswith("layer.0.attention.self.query") and stack[1].endswith("layer.0.attention.self.key")
     assert got[-1] == "lxmert.pooler.dense"
-    inside = [n for n in got if ".r_layers." in n]
-    assert inside == [n for n, _ in named if ".r_layers." in n]          # stable
+    assert [n for n in got if ".x_layers." in n] == [n for n, _ in named if ".x_layers." in n]      # stable
     vb = [("visual_bert.embeddings.word_embeddings", 0), ("visual_bert.encoder.layer.0.attention.self.query", 1),
           ("visual_bert.pooler.dense", 2)]
     assert execution_order(vb) == vb

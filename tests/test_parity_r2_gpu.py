@@ -152,6 +152,10 @@ def test_split_operands_close_the_gap(cached, monkeypatch):
     from oracle import lxmert_oracle as lxo
     monkeypatch.setenv("CRVQA_OPERAND", "split")
     monkeypatch.setenv("CRVQA_FUSED", "0")             # per-module path: fp32 activations between the GEMMs
+    # the attention cores and the answer head of the per-module path are torch matmuls: strict fp32 for this test
+    # (a Trainer constructed earlier in the process switches TF32 on for the answer head)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
     g = torch.load(os.path.join(GOLD, "full_lxmert.pt"), weights_only=False)
     model, _, _, _ = _build(2274)
     arena = None
