@@ -315,6 +315,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     gemm_ms = g0.elapsed_time(g1) / reps
     del gemm_graph
+    trainer.arena.grads.zero_()     # the replays reduce-added into the gradient arena; the optimiser pass expects zeros
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -121,7 +121,7 @@ class GroupLinearFn(torch.autograd.Function):
         dx = None
         if ctx.need_dx:
             dx = ops.masked_linear_bwd_dx(dy2, g.wm, None, None, torch.bfloat16).view(ctx.x_shape)
-        dirty = g.modules[0]._grad_dirty
+        dirty = ops.ds_mode(*g.modules)
         if lane is not None:
             with torch.cuda.stream(lane.stream):
                 ops.masked_linear_bwd_ds(dy2, x2, g.w32, out=g.grad, accumulate=dirty)
@@ -190,7 +190,7 @@ class MultiLinearFn(torch.autograd.Function):
         specs, n = ctx.specs, len(ctx.specs)
         saved = list(ctx.saved_tensors)
         x2s, us = saved[:n], saved[n:]
-        problems, dxs, seen, k, ui = [], [], set(), 0, 0
+        p_dx, p_ds, dxs, seen, k, ui, held = [], [], [], set(), 0, 0, []
         for i, (group, out_dtype, gelu_out, has_u) in enumerate(specs):
             dy = dys[k]
             k += 2 if gelu_out else 1
@@ -203,14 +203,26 @@ class MultiLinearFn(torch.autograd.Function):
             dx = None
             if ctx.need_dx[i]:
                 dx = torch.empty((dy2.shape[0], group.K), dtype=torch.bfloat16, device=dy2.device)
-                problems.append(ops.gemm_problem(ops.GEMM_DX, dy2, group.wm, dx, aux=u,
-                                                 act=ops.ACT_GELU if u is not None else ops.ACT_NONE))
+                p_dx.append(ops.gemm_problem(ops.GEMM_DX, dy2, group.wm, dx, aux=u,
+                                             act=ops.ACT_GELU if u is not None else ops.ACT_NONE))
             dxs.append(dx)
             key = group.grad.data_ptr()
-            acc = group.modules[0]._grad_dirty or key in seen       # second use of a shared module in this call adds
+            acc = ops.DS_ADD if key in seen else ops.ds_mode(*group.modules)   # second use of a shared module adds
             seen.add(key)
-            problems.append(ops.gemm_problem(ops.GEMM_DS, dy2, x2s[i], group.grad, w_f32=group.w32, accumulate=acc))
-        ops.gemm_grouped(problems)
+            p_ds.append(ops.gemm_problem(ops.GEMM_DS, dy2, x2s[i], group.grad, w_f32=group.w32, accumulate=acc))
+            held += [dy2, x2s[i]]
+        # dX feeds the next layer's backward, dS only the end of the step.  Either everything shares one grouped launch
+        # list, or (CRVQA_GROUP_DS_LANE=1) the dS group runs on the dS lane beside the dX chain and the small kernels
+        # between the GEMMs (ops._DsLane).
+        lane = ops.ds_lane(dys[0].device) if (p_dx and os.environ.get("CRVQA_GROUP_DS_LANE", "0") == "1") else None
+        if lane is not None:
+            lane.fork()
+            ops.gemm_grouped(p_dx)
+            with torch.cuda.stream(lane.stream):
+                ops.gemm_grouped(p_ds)
+            lane.hold(*held)
+        else:
+            ops.gemm_grouped(p_dx + p_ds)
         for group, _, _, _ in specs:
             for m in group.modules:
                 ops._sink_done(m)

@@ -169,7 +169,7 @@ def masked_linear_bwd_ds(dy_bf16, x_bf16, w_f32, out=None, accumulate=False):
         RECORD.append(("ds", M, N, K, lambda: masked_linear_bwd_ds(dy_bf16, x_bf16, w_f32, out=scratch,
                                                                      accumulate=accumulate)))
     with _Timed("ds", M, N, K):
-        check(lib.crv_masked_linear_bwd_ds(_p(dy_bf16), _p(x_bf16), _p(w_f32), _p(out), int(bool(accumulate)),
+        check(lib.crv_masked_linear_bwd_ds(_p(dy_bf16), _p(x_bf16), _p(w_f32), _p(out), int(accumulate),
                                            M, N, K, _stream()), "crv_masked_linear_bwd_ds")
     return out
 
@@ -192,7 +192,7 @@ def gemm_problem(kind, a, b, out, *, bias=None, w_f32=None, aux=None, act=ACT_NO
         (M, N), K = a.shape, b.shape[1]
     else:
         (M, N), K = a.shape, b.shape[1]
-    pr = GemmProblem(kind, act, DT_BF16 if out.dtype == torch.bfloat16 else DT_F32, int(bool(accumulate)), M, N, K, 0,
+    pr = GemmProblem(kind, act, DT_BF16 if out.dtype == torch.bfloat16 else DT_F32, int(accumulate), M, N, K, 0,
                      a.data_ptr(), b.data_ptr(), bias.data_ptr() if bias is not None else None,
                      w_f32.data_ptr() if w_f32 is not None else None, out.data_ptr(),
                      aux.data_ptr() if aux is not None else None)
@@ -266,6 +266,21 @@ def magnitude_init(weight, w_thr, hi, lo):
 def _sink_grad(sink):
     """Arena gradient view of a masked module (hg_transformers._engine.ScoreArena), or None."""
     return getattr(sink, "_arena_grad", None) if sink is not None else None
+
+
+DS_OVERWRITE, DS_ADD, DS_ZEROED = 0, 1, 3
+
+
+def ds_mode(*modules):
+    """`accumulate` of the next score-gradient GEMM into these modules' arena gradient: add when an earlier invocation
+    of this step already wrote it, ZEROED when the optimiser pass cleared it (no memset before a split reduction),
+    overwrite otherwise.  Consumes the zeroed state."""
+    if any(m._grad_dirty for m in modules):
+        return DS_ADD
+    zeroed = all(getattr(m, "_grad_zero", False) for m in modules)
+    for m in modules:
+        m._grad_zero = False
+    return DS_ZEROED if zeroed else DS_OVERWRITE
 
 
 def _sink_done(sink):
@@ -415,7 +430,7 @@ class MaskedLinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             sink_grad = _sink_grad(ctx.sink)
             if sink_grad is not None:
-                out, acc = sink_grad, ctx.sink._grad_dirty
+                out, acc = sink_grad, ds_mode(ctx.sink)
             else:
                 out, acc = torch.empty_like(w_f32), False
             masked_linear_bwd_ds(dh, xh, w_f32, out=out, accumulate=acc)
@@ -448,10 +463,10 @@ class MaskedLinearFn(torch.autograd.Function):
             if sink_grad is not None:
                 if lane is not None:
                     with torch.cuda.stream(lane.stream):
-                        masked_linear_bwd_ds(dy2, x2, w_f32, out=sink_grad, accumulate=ctx.sink._grad_dirty)
+                        masked_linear_bwd_ds(dy2, x2, w_f32, out=sink_grad, accumulate=ds_mode(ctx.sink))
                     lane.hold(dy2, x2)
                 else:
-                    masked_linear_bwd_ds(dy2, x2, w_f32, out=sink_grad, accumulate=ctx.sink._grad_dirty)
+                    masked_linear_bwd_ds(dy2, x2, w_f32, out=sink_grad, accumulate=ds_mode(ctx.sink))
                 _sink_done(ctx.sink)
             else:
                 ds = masked_linear_bwd_ds(dy2, x2, w_f32)
@@ -521,7 +536,7 @@ class MaskedEmbeddingFn(torch.autograd.Function):
         sink_grad = _sink_grad(ctx.sink)
         if sink_grad is not None:
             ds = sink_grad
-            if not ctx.sink._grad_dirty:
+            if ds_mode(ctx.sink) == DS_OVERWRITE:
                 ds.zero_()
         else:
             ds = torch.zeros((vocab, dim), dtype=torch.float32, device=weight.device)
@@ -621,3 +636,13 @@ def adamw_step_flat(p, g, m, v, s, lr, step, beta1, beta2, eps, weight_decay, to
     check(lib.crv_adamw_step(_p(p), _p(g), _p(m), _p(v), _p(s), p.numel(), float(lr), float(step_size),
                              float(beta1), float(beta2), float(eps), float(weight_decay), _p(total_sumsq),
                              float(max_norm), _p(hyper), _stream()), "crv_adamw_step")
+
+
+def adamw_segmented(p, g, m, v, s, chunks, thr_vec, w16, wm, lr, step, beta1, beta2, eps, weight_decay,
+                    total_sumsq=None, max_norm=1.0, correct_bias=True, hyper=None, zero_grad=False):
+    """crv_adamw_segmented: clip + AdamW over a score arena + masked-operand refresh (+ gradient clearing)."""
+    step_size = adam_step_size(lr, step, beta1, beta2, correct_bias)
+    check(lib.crv_adamw_segmented(_p(p), _p(g), _p(m), _p(v), _p(s), _p(chunks), chunks.shape[0], _p(thr_vec), _p(w16),
+                                  _p(wm), float(lr), float(step_size), float(beta1), float(beta2), float(eps),
+                                  float(weight_decay), _p(total_sumsq), float(max_norm), _p(hyper), int(bool(zero_grad)),
+                                  _stream()), "crv_adamw_segmented")

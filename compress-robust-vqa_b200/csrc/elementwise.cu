@@ -231,6 +231,75 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+
+// Fused clip + AdamW over a whole score arena, segment aware: the same pass refreshes the masked bf16 operand
+// Wm = W16 (.) (S_new > thr[segment]) (the scores are in registers here; a separate pass would re-read 4 B per score)
+// and, optionally, clears the gradient after consuming it (model.zero_grad() of the reference loop,
+// hg_transformers/mask_trainer_VQA.py:659) so that next step's split-K score-gradient GEMMs reduce-add into zeros
+// without a memset per module.  chunks = {start / 8, length, segment, flags}; flags bit 0 = segment has a bf16
+// operand to refresh.  40 B per score: p, g, m, v, sum read; p, m, v, sum (+ g) written; W16 read, Wm written.
+__global__ void __launch_bounds__(kThreads)
+adamw_segmented_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       float* __restrict__ sum, const int4* __restrict__ chunks, int nchunks,
+                       const float* __restrict__ thr_vec, const uint16_t* __restrict__ w16, uint16_t* __restrict__ wm,
+                       AdamArgs a, const float* __restrict__ total_sumsq, const float* __restrict__ hyper,
+                       int zero_grad) {
+  if (hyper) {
+    a.lr = __ldg(hyper);
+    a.step_size = __ldg(hyper + 1);
+  }
+  float clip = 1.0f;
+  if (total_sumsq) {
+    const float c = a.max_norm / (sqrtf(__ldg(total_sumsq)) + 1e-6f);
+    clip = c < 1.0f ? c : 1.0f;
+  }
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int4 ch = __ldg(chunks + c);
+    const float thr = __ldg(thr_vec + ch.z);
+    const bool has_wm = (ch.w & 1) != 0;
+    const int64_t base = static_cast<int64_t>(ch.x) * 8;
+    const int nvec = ch.y >> 3;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const int64_t e = base + static_cast<int64_t>(i) * 8;
+      float4 pp[2], gg[2], mm[2], vv[2], ss[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        pp[h] = reinterpret_cast<const float4*>(p + e)[h];
+        gg[h] = reinterpret_cast<const float4*>(g + e)[h];
+        mm[h] = reinterpret_cast<const float4*>(m + e)[h];
+        vv[h] = reinterpret_cast<const float4*>(v + e)[h];
+        ss[h] = sum ? reinterpret_cast<const float4*>(sum + e)[h] : make_float4(0, 0, 0, 0);
+      }
+      uint4 wv = has_wm ? __ldg(reinterpret_cast<const uint4*>(w16 + e)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        adam_one(pp[h].x, gg[h].x, mm[h].x, vv[h].x, sum ? &ss[h].x : nullptr, a, clip);
+        adam_one(pp[h].y, gg[h].y, mm[h].y, vv[h].y, sum ? &ss[h].y : nullptr, a, clip);
+        adam_one(pp[h].z, gg[h].z, mm[h].z, vv[h].z, sum ? &ss[h].z : nullptr, a, clip);
+        adam_one(pp[h].w, gg[h].w, mm[h].w, vv[h].w, sum ? &ss[h].w : nullptr, a, clip);
+        reinterpret_cast<float4*>(p + e)[h] = pp[h];
+        reinterpret_cast<float4*>(m + e)[h] = mm[h];
+        reinterpret_cast<float4*>(v + e)[h] = vv[h];
+        if (sum) reinterpret_cast<float4*>(sum + e)[h] = ss[h];
+        if (zero_grad) reinterpret_cast<float4*>(g + e)[h] = make_float4(0, 0, 0, 0);
+      }
+      if (has_wm) {
+        wv.x &= (pp[0].x > thr ? 0x0000FFFFu : 0u) | (pp[0].y > thr ? 0xFFFF0000u : 0u);
+        wv.y &= (pp[0].z > thr ? 0x0000FFFFu : 0u) | (pp[0].w > thr ? 0xFFFF0000u : 0u);
+        wv.z &= (pp[1].x > thr ? 0x0000FFFFu : 0u) | (pp[1].y > thr ? 0xFFFF0000u : 0u);
+        wv.w &= (pp[1].z > thr ? 0x0000FFFFu : 0u) | (pp[1].w > thr ? 0xFFFF0000u : 0u);
+        *reinterpret_cast<uint4*>(wm + e) = wv;
+      }
+    }
+    for (int i = (nvec << 3) + threadIdx.x; i < ch.y; i += blockDim.x) {
+      const int64_t e = base + i;
+      adam_one(p[e], g[e], m[e], v[e], sum ? sum + e : nullptr, a, clip);
+      if (zero_grad) g[e] = 0.f;
+      if (has_wm) wm[e] = p[e] > thr ? w16[e] : uint16_t(0);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ tiny-K masked linear (box_fc, K = 4)
 __global__ void small_k_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                    const float* __restrict__ s, const float* __restrict__ thr_p,
@@ -432,6 +501,25 @@ extern "C" int crv_adamw_step(float* p, const float* g, float* m, float* v, floa
   AdamArgs a{lr, step_size, beta1, beta2, eps, weight_decay, max_norm};
   adamw_kernel<<<stream_grid(n >> 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, sum, n, a,
                                                                                          total_sumsq, hyper_dev);
+  return launch_status();
+}
+
+extern "C" int crv_adamw_segmented(float* p, float* g, float* m, float* v, float* sum, const int* chunks, int nchunks,
+                                   const float* thr_vec, const uint16_t* w_bf16, uint16_t* wm_bf16, float lr,
+                                   float step_size, float beta1, float beta2, float eps, float weight_decay,
+                                   const float* total_sumsq, float max_norm, const float* hyper_dev, int zero_grad,
+                                   void* stream) {
+  if (!p || !g || !m || !v || !chunks || !thr_vec || nchunks < 0) return CRV_E_BADARG;
+  if ((w_bf16 == nullptr) != (wm_bf16 == nullptr)) return CRV_E_BADARG;
+  if (nchunks == 0) return CRV_OK;
+  if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (sum && !aligned16(sum)) ||
+      !aligned16(chunks) || (w_bf16 && (!aligned16(w_bf16) || !aligned16(wm_bf16))))
+    return CRV_E_ALIGN;
+  AdamArgs a{lr, step_size, beta1, beta2, eps, weight_decay, max_norm};
+  const int grid = nchunks < num_sms() * 8 ? nchunks : num_sms() * 8;
+  adamw_segmented_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, sum, reinterpret_cast<const int4*>(chunks), nchunks, thr_vec, w_bf16, wm_bf16, a, total_sumsq,
+      hyper_dev, zero_grad);
   return launch_status();
 }
 

@@ -709,11 +709,13 @@ struct GArgs {
   int count, total_tiles;
 };
 
+template <int STAGES_, int NBUF_>
 struct SmemG {
   static constexpr int kStage = 32768;           // A: this CTA's 128 rows; B: this CTA's half of the 256 columns
-  static constexpr int kStages = 5;
+  static constexpr int kStages = STAGES_;        // 6 stages + single staging, or 5 stages + double staging (227 KB)
+  static constexpr int kBufs = NBUF_;
   static constexpr int kEpiWarps = 8;
-  static constexpr int kEpi = kEpiWarps * 2 * 4096;
+  static constexpr int kEpi = kEpiWarps * NBUF_ * 4096;
   static constexpr int kTotal = kStages * kStage + kEpi + 256 + 1024;
 };
 
@@ -757,9 +759,12 @@ __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
 // stage 32 rows x 128 bytes (one register row per lane) into a swizzled buffer and hand it to TMA
-__device__ __forceinline__ void stage_and_store(uint8_t* buf, const uint32_t (&pk)[32], int lane, const CUtensorMap* map,
-                                                int c0, int r0, bool in_range, bool reduce) {
-  if (lane == 0) bulk_wait_read<1>();   // the store issued two groups ago (same buffer) has read its data
+template <int NBUF>
+__device__ __forceinline__ void stage_and_store(uint8_t* bufs, int& nstore, const uint32_t (&pk)[32], int lane,
+                                                const CUtensorMap* map, int c0, int r0, bool in_range, bool reduce) {
+  uint8_t* buf = bufs + (NBUF == 2 ? (nstore & 1) * 4096 : 0);
+  ++nstore;
+  if (lane == 0) bulk_wait_read<NBUF - 1>();   // the previous store that used this buffer has read its data
   __syncwarp();
   const int sw = lane & 7;
 #pragma unroll
@@ -777,9 +782,10 @@ __device__ __forceinline__ void stage_and_store(uint8_t* buf, const uint32_t (&p
   }
 }
 
-__global__ void __launch_bounds__(64 + 32 * SmemG::kEpiWarps, 1)
+template <int STAGES_, int NBUF>
+__global__ void __launch_bounds__(64 + 32 * 8, 1)
 grouped_gemm2_kernel(const __grid_constant__ GArgs args) {
-  using L = SmemG;
+  using L = SmemG<STAGES_, NBUF>;
   constexpr int STAGES = L::kStages;
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
@@ -899,7 +905,7 @@ grouped_gemm2_kernel(const __grid_constant__ GArgs args) {
     // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
     const int half = (warp - 2) >> 2;       // which 128 of the tile's 256 columns
-    uint8_t* bufs = epi_base + (warp - 2) * 8192;
+    uint8_t* bufs = epi_base + (warp - 2) * (NBUF * 4096);
     int tcount = 0, nstore = 0;
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tcount) {
       const GTile tc = gtile(args, tile);
@@ -951,9 +957,8 @@ grouped_gemm2_kernel(const __grid_constant__ GArgs args) {
               pk[j] = __float_as_uint(__uint_as_float(r[j]) * wv);
             }
           }
-          stage_and_store(bufs + (nstore & 1) * 4096, pk, lane, &p.tmOut, nb, row0, nb < p.NN && row0 < p.MM,
-                          epi == kGEpiScoreGrad && p.reduce_out);
-          ++nstore;
+          stage_and_store<NBUF>(bufs, nstore, pk, lane, &p.tmOut, nb, row0, nb < p.NN && row0 < p.MM,
+                                epi == kGEpiScoreGrad && p.reduce_out);
         }
       } else {
         // ---- bf16 out: 64 columns per 128-byte staging row
@@ -1007,8 +1012,7 @@ grouped_gemm2_kernel(const __grid_constant__ GArgs args) {
                 pk[16 + j] = pack2_bf16(__uint_as_float(r2[2 * j]) * g[2], __uint_as_float(r2[2 * j + 1]) * g[3]);
               }
             }
-            stage_and_store(bufs + (nstore & 1) * 4096, pk, lane, &p.tmOut, nb, row0, nb < p.NN && row0 < p.MM, false);
-            ++nstore;
+            stage_and_store<NBUF>(bufs, nstore, pk, lane, &p.tmOut, nb, row0, nb < p.NN && row0 < p.MM, false);
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -1020,13 +1024,11 @@ grouped_gemm2_kernel(const __grid_constant__ GArgs args) {
             if (epi == kGEpiGelu) {
               // the pre-activation goes out as it is (bf16), then the same registers become gelu(u) -- computed
               // from the ROUNDED u, which is what the backward multiplies gelu'() of
-              stage_and_store(bufs + (nstore & 1) * 4096, pk, lane, &p.tmAux, nb, row0, nb < p.NN && row0 < p.MM, false);
-              ++nstore;
+              stage_and_store<NBUF>(bufs, nstore, pk, lane, &p.tmAux, nb, row0, nb < p.NN && row0 < p.MM, false);
 #pragma unroll
               for (int j = 0; j < 32; ++j) pk[j] = pack2_bf16(gelu_f(bf16_lo(pk[j])), gelu_f(bf16_hi(pk[j])));
             }
-            stage_and_store(bufs + (nstore & 1) * 4096, pk, lane, &p.tmOut, nb, row0, nb < p.NN && row0 < p.MM, false);
-            ++nstore;
+            stage_and_store<NBUF>(bufs, nstore, pk, lane, &p.tmOut, nb, row0, nb < p.NN && row0 < p.MM, false);
           }
         }
       }
@@ -1272,8 +1274,9 @@ extern "C" int crv_masked_linear_bwd_ds(const uint16_t* dy, const uint16_t* x, c
   p.kb_per_split = (num_kb + splits - 1) / splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.w = w;
-  p.reduce_out = (p.splits > 1 || accumulate) ? 1 : 0;
-  if (p.splits > 1 && !accumulate)
+  const bool add = accumulate != 0 && accumulate != CRV_DS_ZEROED;     // CRV_DS_ZEROED: dS already holds zeros
+  p.reduce_out = (p.splits > 1 || add) ? 1 : 0;
+  if (p.splits > 1 && accumulate == 0)
     CRV_CUDA(cudaMemsetAsync(dscores, 0, static_cast<size_t>(N) * K * sizeof(float), st));
   CUtensorMap tmA, tmB, tmO;
   int rc;
@@ -1325,12 +1328,12 @@ static int simulate_makespan(const GArgs& g, int pairs) {
   return mx;
 }
 
-static void set_split(GProblem& p, int splits, int accumulate) {
+static void set_split(GProblem& p, int splits, int must_reduce) {
   const int total_kb = (p.KK + BK - 1) / BK;
   if (splits < 1) splits = 1;
   p.kb_per_split = (total_kb + splits - 1) / splits;
   p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
-  p.reduce_out = (p.splits > 1 || accumulate) ? 1 : 0;
+  p.reduce_out = (p.splits > 1 || must_reduce) ? 1 : 0;
 }
 
 static void finish_tiles(GArgs& g) {
@@ -1342,7 +1345,7 @@ static void finish_tiles(GArgs& g) {
   g.total_tiles = t;
 }
 
-static void choose_splits(GArgs& g, const int* accumulate, int pairs) {
+static void choose_splits(GArgs& g, const int* must_reduce, int pairs) {
   static const int cand[] = {1, 2, 3, 4, 6, 8, 9, 12, 16, 18, 24};
   for (int i = 0; i < g.count; ++i) {
     GProblem& p = g.p[i];
@@ -1351,26 +1354,38 @@ static void choose_splits(GArgs& g, const int* accumulate, int pairs) {
     int best = 1, best_cost = 1 << 30;
     for (int c : cand) {
       if (c > 1 && total_kb / c < 8) break;   // keep >= 8 k-blocks per split
-      set_split(p, c, accumulate[i]);
+      set_split(p, c, must_reduce[i]);
       const int cost = simulate_makespan(g, pairs);
       if (cost < best_cost) { best_cost = cost; best = c; }
     }
-    set_split(p, best, accumulate[i]);
+    set_split(p, best, must_reduce[i]);
   }
 }
 
+template <int STAGES_, int NBUF>
+static int launch_group_t(GArgs& g, cudaStream_t stream);
+
 static int launch_group(GArgs& g, cudaStream_t stream) {
+  // CRVQA_GROUP_STAGES=5: five operand stages + double-buffered epilogue staging; default six + single staging
+  static const int stages = [] { const char* e = getenv("CRVQA_GROUP_STAGES"); return e ? atoi(e) : 6; }();
+  return stages == 5 ? launch_group_t<5, 2>(g, stream) : launch_group_t<6, 1>(g, stream);
+}
+
+template <int STAGES_, int NBUF>
+static int launch_group_t(GArgs& g, cudaStream_t stream) {
+  using L = SmemG<STAGES_, NBUF>;
+  auto kern = grouped_gemm2_kernel<STAGES_, NBUF>;
   static bool configured = false;
   if (!configured) {
-    CRV_CUDA(cudaFuncSetAttribute(grouped_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemG::kTotal));
+    CRV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = g.total_tiles < max_pairs ? g.total_tiles : max_pairs;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(64 + 32 * SmemG::kEpiWarps);
-  cfg.dynamicSmemBytes = SmemG::kTotal;
+  cfg.blockDim = dim3(64 + 32 * L::kEpiWarps);
+  cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1381,7 +1396,7 @@ static int launch_group(GArgs& g, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  CRV_CUDA(cudaLaunchKernelEx(&cfg, grouped_gemm2_kernel, g));
+  CRV_CUDA(cudaLaunchKernelEx(&cfg, kern, g));
   return launch_status();
 }
 
@@ -1421,7 +1436,8 @@ extern "C" int crv_masked_gemm_grouped(const crv_gemm_problem* pr, int count, vo
       continue;
     }
     GArgs g{};
-    int accumulate[kMaxGroup] = {0, 0, 0, 0};
+    int must_reduce[kMaxGroup] = {0, 0, 0, 0};   // add into dS whatever the split
+    int holds_junk[kMaxGroup] = {0, 0, 0, 0};    // dS must be cleared before a reduce-add
     int src[kMaxGroup];
     while (i < count && g.count < kMaxGroup && group_eligible(pr[i])) {
       const crv_gemm_problem& q = pr[i];
@@ -1456,33 +1472,33 @@ extern "C" int crv_masked_gemm_grouped(const crv_gemm_problem* pr, int count, vo
         if ((rc = make_out_map(&p.tmOut, q.out, false, q.N, q.K))) return rc;
         p.w = q.w_f32;
         p.epi = kGEpiScoreGrad;
-        accumulate[g.count] = q.accumulate;
+        must_reduce[g.count] = (q.accumulate != 0 && q.accumulate != CRV_DS_ZEROED) ? 1 : 0;
+        holds_junk[g.count] = q.accumulate == 0 ? 1 : 0;
       }
       p.num_m = (p.MM + 255) / 256;
       p.num_n = (p.NN + 255) / 256;
-      set_split(p, 1, accumulate[g.count]);
+      set_split(p, 1, must_reduce[g.count]);
       src[g.count] = i;
       ++g.count;
       ++i;
     }
     // two score-gradient problems of one group that write the same dS (a shared module applied to both modalities)
-    // run concurrently: both must reduce-add, into a buffer cleared once
+    // run concurrently: both must reduce-add, into a buffer that is cleared once if it holds junk
     bool dup[kMaxGroup] = {false, false, false, false};
     for (int a = 0; a < g.count; ++a)
       for (int b = a + 1; b < g.count; ++b)
         if (g.p[a].epi == kGEpiScoreGrad && g.p[b].epi == kGEpiScoreGrad && pr[src[a]].out == pr[src[b]].out) {
           dup[b] = true;
-          if (!accumulate[a]) { accumulate[a] = 2; }   // 2 = "clear first, then reduce"
-          accumulate[b] = 1;
+          must_reduce[a] = must_reduce[b] = 1;
         }
     finish_tiles(g);
-    choose_splits(g, accumulate, pairs);
+    choose_splits(g, must_reduce, pairs);
     finish_tiles(g);
     for (int a = 0; a < g.count; ++a) {
       if (g.p[a].epi != kGEpiScoreGrad || dup[a]) continue;
       const crv_gemm_problem& q = pr[src[a]];
-      const bool clear = (accumulate[a] == 2) || (accumulate[a] == 0 && g.p[a].splits > 1);
-      if (clear) CRV_CUDA(cudaMemsetAsync(q.out, 0, static_cast<size_t>(q.N) * q.K * sizeof(float), st));
+      if (holds_junk[a] && g.p[a].reduce_out)
+        CRV_CUDA(cudaMemsetAsync(q.out, 0, static_cast<size_t>(q.N) * q.K * sizeof(float), st));
     }
     int rc = launch_group(g, st);
     if (rc) return rc;

@@ -19,6 +19,7 @@ GradSync
     over NVLink / NVSwitch) while the remaining dS / dX GEMMs run.
 """
 import contextlib
+import os
 
 import torch
 import torch.distributed as dist
@@ -86,6 +87,7 @@ class ScoreArena:
             p.grad = self._view(self.grads, i)
             m._arena_grad = p.grad
             m._grad_dirty = False
+            m._grad_zero = True        # the gradient buffer starts as zeros
             m._arena = self
             self._index[id(p)] = i
         # thresholds of all modules in one device vector; module.threshold stays a 0-dim tensor (a view)
@@ -94,6 +96,10 @@ class ScoreArena:
             m.threshold = self.thr_vec[i]
         # mask cache (enable_mask_cache): bf16 weights and W (.) M, same element offsets as the scores
         self.cache_on = False
+        # CRVQA_KEEP_GRADS=1 (parity tests that read the gradients after a full step): the optimiser pass does not
+        # clear the gradient arena; split score-gradient GEMMs then clear their output with a memset per module
+        self.keep_grads = os.environ.get("CRVQA_KEEP_GRADS", "0") == "1"
+        self.step_chunks = None
         self.epoch = 0
         self.w16 = self.wm = self.w32 = self.chunks = None
 
@@ -158,13 +164,29 @@ class ScoreArena:
             for c0 in range(0, n, 8192):
                 rows.append(((off + c0) // 8, min(8192, n - c0), i, 0))
         self.chunks = torch.tensor(rows, dtype=torch.int32, device=dev).contiguous()
+        self.step_chunks = None
         self.cache_on = True
         self.refresh_masked()
+
+    def _step_chunk_table(self):
+        """{start / 8, length, segment, flags} rows covering EVERY module (flags bit 0: it has a bf16 operand)."""
+        if self.step_chunks is None:
+            rows = []
+            for i, m in enumerate(self.modules):
+                n, off = m.weight_mask.numel(), self.offsets[i]
+                flag = 1 if (self.cache_on and self._gemm_module(m)) else 0
+                for c0 in range(0, n, 8192):
+                    rows.append(((off + c0) // 8, min(8192, n - c0), i, flag))
+            self.step_chunks = torch.tensor(rows, dtype=torch.int32, device=self.scores.device).contiguous()
+        return self.step_chunks
 
     def refresh_masked(self):
         if not self.cache_on:
             return
         ops.apply_mask_segmented(self.w16, self.scores, self.thr_vec, self.chunks, self.wm)
+        self._mark_cache_valid()
+
+    def _mark_cache_valid(self):
         for m in self.modules:
             m._wm_epoch = self.epoch
             m._wm_sver = m.weight_mask._version
@@ -192,7 +214,8 @@ class ScoreArena:
         ops.ds_lane_join()
         for m in self.modules:
             if not m._grad_dirty:
-                m._arena_grad.zero_()
+                if not getattr(m, "_grad_zero", False):
+                    m._arena_grad.zero_()
                 m._grad_dirty = True
 
     def grad_sumsq_into(self, acc):
@@ -200,11 +223,20 @@ class ScoreArena:
 
     def adamw_step(self, lr, step, beta1, beta2, eps, weight_decay, correct_bias, clip_sumsq, max_norm,
                    with_sum=True, hyper=None):
+        """Clip + AdamW over the arena, the masked-operand refresh and (unless keep_grads) the gradient clearing of
+        the reference's model.zero_grad() -- ONE launch (crv_adamw_segmented)."""
         self._ensure_state()
-        ops.adamw_step_flat(self.scores, self.grads, self.exp_avg, self.exp_avg_sq, self.sum if with_sum else None,
-                            lr, step, beta1, beta2, eps, weight_decay, clip_sumsq, max_norm, correct_bias, hyper)
-        self.epoch += 1            # scores moved: the mask cache is stale until refresh_masked()
-        self.refresh_masked()
+        self.epoch += 1            # scores move: the mask cache follows in the same pass
+        zero = not self.keep_grads
+        ops.adamw_segmented(self.scores, self.grads, self.exp_avg, self.exp_avg_sq, self.sum if with_sum else None,
+                            self._step_chunk_table(), self.thr_vec, self.w16 if self.cache_on else None,
+                            self.wm if self.cache_on else None, lr, step, beta1, beta2, eps, weight_decay, clip_sumsq,
+                            max_norm, correct_bias, hyper, zero)
+        if self.cache_on:
+            self._mark_cache_valid()
+        if zero:
+            for m in self.modules:
+                m._grad_zero = True
 
     def release(self):
         """Give the parameters their own storage back (used when a trainer is torn down)."""

@@ -126,6 +126,10 @@ int crv_masked_linear_bwd_ds(const uint16_t* dy_bf16, const uint16_t* x_bf16, co
 #define CRV_GEMM_DS 2
 #define CRV_ACT_NONE 0
 #define CRV_ACT_GELU 1
+/* `accumulate` of a DS problem / crv_masked_linear_bwd_ds: 0 = overwrite dS, 1 = add to dS, CRV_DS_ZEROED = dS is known
+ * to hold zeros (cleared by crv_adamw_segmented): plain store when the reduction is not split, reduce-add without a
+ * clearing memset when it is. */
+#define CRV_DS_ZEROED 3
 typedef struct crv_gemm_problem {
   int kind, act, out_dtype, accumulate;
   int M, N, K, reserved;
@@ -251,6 +255,18 @@ int crv_sumsq(const float* x, int64_t n, float* out, void* stream);
 int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int64_t n, float lr,
                    float step_size, float beta1, float beta2, float eps, float weight_decay,
                    const float* total_sumsq, float max_norm, const float* hyper_dev, void* stream);
+
+/* The same step over a whole score arena in ONE launch that also (a) refreshes the masked bf16 operand of every
+ * segment, wm = w_bf16 (.) (p_new > thr_vec[segment]) -- the scores are in registers, so the separate
+ * crv_apply_mask_segmented pass and its re-read of p disappear -- and (b) with zero_grad != 0 clears g after
+ * consuming it (the reference loop's model.zero_grad(), hg_transformers/mask_trainer_VQA.py:659), which lets the next
+ * step's split score-gradient GEMMs reduce-add without a memset per module (accumulate = CRV_DS_ZEROED).
+ * chunks = nchunks x int4 {start / 8, length, segment, flags} (device; no chunk straddles a segment; flags bit 0:
+ * the segment has a bf16 operand); w_bf16 / wm_bf16 may both be NULL (no operand refresh). */
+int crv_adamw_segmented(float* p, float* g, float* m, float* v, float* sum, const int* chunks, int nchunks,
+                        const float* thr_vec, const uint16_t* w_bf16, uint16_t* wm_bf16, float lr, float step_size,
+                        float beta1, float beta2, float eps, float weight_decay, const float* total_sumsq,
+                        float max_norm, const float* hyper_dev, int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

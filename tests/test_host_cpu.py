@@ -286,6 +286,8 @@ def _sync_worker(rank, world, port, q):
 
     mods = [(f"m{i}", M(s)) for i, s in enumerate([(8, 16), (4, 4), (32, 8), (5, 3), (16, 16)])]
     arena = ScoreArena(mods)
+    for _, m in mods:
+        m._grad_zero = False                          # as after a step whose optimiser pass kept the gradients
     sync = GradSync(arena, bucket_bytes=512)          # several small buckets
     assert len(sync.bucket_ranges) >= 3
     loose = [torch.full((7,), float(rank + 1)), torch.full((2, 3), 10.0 * (rank + 1))]

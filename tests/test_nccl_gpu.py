@@ -84,7 +84,7 @@ def _worker(rank, world, port, tmp, out_path, graph):
         if p not in sys.path:
             sys.path.insert(0, p)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank), CRVQA_CUDA_GRAPH="1" if graph else "0")
+                      LOCAL_RANK=str(rank), CRVQA_CUDA_GRAPH="1" if graph else "0", CRVQA_KEEP_GRADS="1")
     import torch.distributed as dist
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -138,11 +138,13 @@ def test_two_gpu_nccl_matches_ddp_semantics(tmp_path, graph):
     assert num / den < 1e-4
     # 1 GPU on the same GLOBAL batch: same thresholds / masks up to bf16 tiling noise of the gradients
     os.environ["CRVQA_CUDA_GRAPH"] = "0"
+    os.environ["CRVQA_KEEP_GRADS"] = "1"
     try:
         trainer, model, opt, sched = _make_trainer(str(tmp_path / "single"), 0, 1)
         g1, s1, t1 = _run(trainer, model, opt, sched, 0, 1, False)
     finally:
         os.environ.pop("CRVQA_CUDA_GRAPH", None)
+        os.environ.pop("CRVQA_KEEP_GRADS", None)
     rel = float((g1 - r0["grads"]).double().norm() / g1.double().norm())
     print(f"[nccl graph={graph}] 1-GPU vs 2-GPU first-step gradient (same global batch): {rel:.3e}")
     assert rel < 3e-2
