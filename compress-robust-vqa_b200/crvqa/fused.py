@@ -175,6 +175,7 @@ class MultiLinearFn(torch.autograd.Function):
                 ret.append(u.view(*x.shape[:-1], group.N))
                 outs.append(ret[-1])
         ops.gemm_grouped(problems)
+        ctx.set_materialize_grads(False)     # a member nothing downstream reads gets None, and its GEMMs are skipped
         ctx.specs = specs
         ctx.shapes = [x.shape for x in xs]
         ctx.need_dx = [x.requires_grad for x in xs]
@@ -194,12 +195,14 @@ class MultiLinearFn(torch.autograd.Function):
         for i, (group, out_dtype, gelu_out, has_u) in enumerate(specs):
             dy = dys[k]
             k += 2 if gelu_out else 1
+            if has_u:
+                ui += 1
+            if dy is None:         # e.g. the vision side of the last cross layer: no gradient, no work
+                dxs.append(None)
+                continue
             dy2 = dy.reshape(-1, group.N)
             dy2 = ops.to_bf16(dy2) if dy2.dtype != torch.bfloat16 else (dy2 if dy2.is_contiguous() else dy2.contiguous())
-            u = None
-            if has_u:
-                u = us[ui].reshape(-1, group.K)
-                ui += 1
+            u = us[ui - 1].reshape(-1, group.K) if has_u else None
             dx = None
             if ctx.need_dx[i]:
                 dx = torch.empty((dy2.shape[0], group.K), dtype=torch.bfloat16, device=dy2.device)
@@ -214,7 +217,13 @@ class MultiLinearFn(torch.autograd.Function):
         # dX feeds the next layer's backward, dS only the end of the step.  Either everything shares one grouped launch
         # list, or (CRVQA_GROUP_DS_LANE=1) the dS group runs on the dS lane beside the dX chain and the small kernels
         # between the GEMMs (ops._DsLane).
-        lane = ops.ds_lane(dys[0].device) if (p_dx and os.environ.get("CRVQA_GROUP_DS_LANE", "0") == "1") else None
+        if not p_ds:
+            for group, _, _, _ in specs:
+                for m in group.modules:
+                    ops._sink_skipped(m)
+            return (None,) * (1 + 2 * n + ctx.n_extra)
+        lane = (ops.ds_lane(x2s[0].device)
+                if (p_dx and os.environ.get("CRVQA_GROUP_DS_LANE", "0") == "1") else None)
         if lane is not None:
             lane.fork()
             ops.gemm_grouped(p_dx)
@@ -223,9 +232,12 @@ class MultiLinearFn(torch.autograd.Function):
             lane.hold(*held)
         else:
             ops.gemm_grouped(p_dx + p_ds)
-        for group, _, _, _ in specs:
+        k = 0
+        for group, _, gelu_out, _ in specs:
+            live = dys[k] is not None
+            k += 2 if gelu_out else 1
             for m in group.modules:
-                ops._sink_done(m)
+                (ops._sink_done if live else ops._sink_skipped)(m)
         grads = [dx.view(shp) if dx is not None else None for dx, shp in zip(dxs, ctx.shapes)]
         return (None, *grads, *([None] * n), *([None] * ctx.n_extra))
 
@@ -417,6 +429,7 @@ class CrossPairAttentionFn(torch.autograd.Function):
         _attn_fwd_raw([(qkv_l, 0), (qkv_v, H), (qkv_v, 2 * H)], mv, out_l, B, heads, Sl, Sv, scale, p, state, site_l)
         _attn_fwd_raw([(qkv_v, 0), (qkv_l, H), (qkv_l, 2 * H)], ml, out_v, B, heads, Sv, Sl, scale, p, state, site_v)
         ctx.save_for_backward(qkv_l, qkv_v)
+        ctx.set_materialize_grads(False)
         ctx.cfg = (heads, ml, mv, float(p), int(site_l), int(site_v), state, scale)
         return out_l, out_v
 
@@ -426,13 +439,23 @@ class CrossPairAttentionFn(torch.autograd.Function):
         qkv_l, qkv_v = ctx.saved_tensors
         H = qkv_l.shape[-1] // 3
         B, Sl, Sv = qkv_l.shape[0], qkv_l.shape[1], qkv_v.shape[1]
+        if do_l is None and do_v is None:
+            return (None,) * 9
         d_l, d_v = torch.empty_like(qkv_l), torch.empty_like(qkv_v)
-        do_l = do_l if do_l.is_contiguous() else do_l.contiguous()
-        do_v = do_v if do_v.is_contiguous() else do_v.contiguous()
-        _attn_bwd_raw([(qkv_l, 0), (qkv_v, H), (qkv_v, 2 * H)], mv, do_l, [(d_l, 0), (d_v, H), (d_v, 2 * H)],
-                      B, heads, Sl, Sv, scale, p, state, site_l)
-        _attn_bwd_raw([(qkv_v, 0), (qkv_l, H), (qkv_l, 2 * H)], ml, do_v, [(d_v, 0), (d_l, H), (d_l, 2 * H)],
-                      B, heads, Sv, Sl, scale, p, state, site_v)
+        if do_l is not None:
+            do_l = do_l if do_l.is_contiguous() else do_l.contiguous()
+            _attn_bwd_raw([(qkv_l, 0), (qkv_v, H), (qkv_v, 2 * H)], mv, do_l, [(d_l, 0), (d_v, H), (d_v, 2 * H)],
+                          B, heads, Sl, Sv, scale, p, state, site_l)
+        else:                       # this direction feeds nothing: its slices of the two gradients are zero
+            d_l[..., :H].zero_()
+            d_v[..., H:].zero_()
+        if do_v is not None:
+            do_v = do_v if do_v.is_contiguous() else do_v.contiguous()
+            _attn_bwd_raw([(qkv_v, 0), (qkv_l, H), (qkv_l, 2 * H)], ml, do_v, [(d_v, 0), (d_l, H), (d_l, 2 * H)],
+                          B, heads, Sv, Sl, scale, p, state, site_v)
+        else:                       # the last cross layer: nothing reads the vision output
+            d_v[..., :H].zero_()
+            d_l[..., H:].zero_()
         return None, None, None, None, None, None, None, d_l, d_v
 
 

@@ -283,6 +283,14 @@ def ds_mode(*modules):
     return DS_ZEROED if zeroed else DS_OVERWRITE
 
 
+def _sink_skipped(sink):
+    """A forward invocation of `sink` whose output nothing read: its backward is owed no gradient, but the bucket
+    bookkeeping of the gradient exchange still has to see the invocation finish."""
+    sync = getattr(sink, "_sync", None)
+    if sync is not None:
+        sync.module_backward_done(sink)
+
+
 def _sink_done(sink):
     sink._grad_dirty = True
     sync = getattr(sink, "_sync", None)

@@ -782,6 +782,135 @@ __device__ __forceinline__ void stage_and_store(uint8_t* bufs, int& nstore, cons
   }
 }
 
+
+// One epilogue warp's share of a tile: 32 accumulator rows (lane = row) x 128 columns, in chunks of one 128-byte
+// staging row (32 fp32 or 64 bf16 columns).
+template <int EPI, int NBUF>
+__device__ __forceinline__ void epilogue_tile(const GProblem& p, int n0, int row0, uint32_t t_addr, int half, int lane,
+                                              uint8_t* bufs, int& nstore) {
+  const int MM = p.MM, NN = p.NN;
+  const int m = row0 + lane;
+  const bool row_ok = m < MM;
+  const CUtensorMap* tm_out = &p.tmOut;
+  if (EPI == kGEpiF32 || EPI == kGEpiScoreGrad) {
+    const float* bias = p.bias;
+    const float* wmul = p.w;
+    const bool reduce = EPI == kGEpiScoreGrad && p.reduce_out;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int col0 = half * 128 + c * 32;
+      const int nb = n0 + col0;
+      uint32_t r[32], pk[32];
+      float bias_v = 0.f;
+      float4 wq[8];
+      const bool fast = row_ok && nb + 32 <= NN;
+      if (EPI == kGEpiF32) {
+        if (bias != nullptr && nb + lane < NN) bias_v = __ldg(bias + nb + lane);
+      } else if (fast) {       // the fp32 multiplier row is fetched while the TMEM load is in flight
+        const float* wrow = wmul + static_cast<size_t>(m) * NN + nb;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wq[j] = __ldg(reinterpret_cast<const float4*>(wrow) + j);
+      }
+      tmem_ld_32x32(t_addr + col0, r);
+      tmem_ld_wait();
+      if (EPI == kGEpiF32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          pk[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_v, j));
+      } else if (fast) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          pk[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) * wq[j].x);
+          pk[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) * wq[j].y);
+          pk[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) * wq[j].z);
+          pk[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) * wq[j].w);
+        }
+      } else {
+        const float* wrow = wmul + static_cast<size_t>(row_ok ? m : 0) * NN + nb;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float wv = (row_ok && nb + j < NN) ? __ldg(wrow + j) : 0.f;
+          pk[j] = __float_as_uint(__uint_as_float(r[j]) * wv);
+        }
+      }
+      stage_and_store<NBUF>(bufs, nstore, pk, lane, tm_out, nb, row0, nb < NN && row0 < MM, reduce);
+    }
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int col0 = half * 128 + c * 64;
+      const int nb = n0 + col0;
+      uint32_t r[32], r2[32], pk[32];
+      const bool in_range = nb < NN && row0 < MM;
+      if (EPI == kGEpiGeluGrad) {
+        const bool fast = row_ok && nb + 64 <= NN;
+        uint4 uq[8];
+        if (fast) {
+          const uint16_t* urow = p.aux_in + static_cast<size_t>(m) * NN + nb;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) uq[j] = __ldg(reinterpret_cast<const uint4*>(urow) + j);
+        }
+        tmem_ld_32x32(t_addr + col0, r);
+        tmem_ld_32x32(t_addr + col0 + 32, r2);
+        tmem_ld_wait();
+        if (fast) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {        // uq[j]: u of columns 8j .. 8j+7 ; uq[4 + j]: columns 32 + 8j ..
+            const uint32_t ua[4] = {uq[j].x, uq[j].y, uq[j].z, uq[j].w};
+            const uint32_t ub[4] = {uq[4 + j].x, uq[4 + j].y, uq[4 + j].z, uq[4 + j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              pk[4 * j + e] = pack2_bf16(__uint_as_float(r[8 * j + 2 * e]) * gelu_grad_f(bf16_lo(ua[e])),
+                                         __uint_as_float(r[8 * j + 2 * e + 1]) * gelu_grad_f(bf16_hi(ua[e])));
+              pk[16 + 4 * j + e] = pack2_bf16(__uint_as_float(r2[8 * j + 2 * e]) * gelu_grad_f(bf16_lo(ub[e])),
+                                              __uint_as_float(r2[8 * j + 2 * e + 1]) * gelu_grad_f(bf16_hi(ub[e])));
+            }
+          }
+        } else {
+          const uint16_t* urow = p.aux_in + static_cast<size_t>(row_ok ? m : 0) * NN + nb;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float g[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = (e < 2 ? 2 * j + e : 32 + 2 * j + (e - 2));
+              const bool ok = row_ok && nb + col < NN;
+              g[e] = ok ? gelu_grad_f(__uint_as_float(static_cast<uint32_t>(__ldg(urow + col)) << 16)) : 0.f;
+            }
+            pk[j] = pack2_bf16(__uint_as_float(r[2 * j]) * g[0], __uint_as_float(r[2 * j + 1]) * g[1]);
+            pk[16 + j] = pack2_bf16(__uint_as_float(r2[2 * j]) * g[2], __uint_as_float(r2[2 * j + 1]) * g[3]);
+          }
+        }
+        stage_and_store<NBUF>(bufs, nstore, pk, lane, tm_out, nb, row0, in_range, false);
+      } else {
+        float bias_lo = 0.f, bias_hi = 0.f;
+        if (p.bias != nullptr) {
+          if (nb + lane < NN) bias_lo = __ldg(p.bias + nb + lane);
+          if (nb + 32 + lane < NN) bias_hi = __ldg(p.bias + nb + 32 + lane);
+        }
+        tmem_ld_32x32(t_addr + col0, r);
+        tmem_ld_32x32(t_addr + col0 + 32, r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          pk[j] = pack2_bf16(__uint_as_float(r[2 * j]) + __shfl_sync(0xffffffffu, bias_lo, 2 * j),
+                             __uint_as_float(r[2 * j + 1]) + __shfl_sync(0xffffffffu, bias_lo, 2 * j + 1));
+          pk[16 + j] = pack2_bf16(__uint_as_float(r2[2 * j]) + __shfl_sync(0xffffffffu, bias_hi, 2 * j),
+                                  __uint_as_float(r2[2 * j + 1]) + __shfl_sync(0xffffffffu, bias_hi, 2 * j + 1));
+        }
+        if (EPI == kGEpiGelu) {
+          // the pre-activation goes out as it is (bf16), then the same registers become gelu(u) -- computed from
+          // the ROUNDED u, which is what the backward multiplies gelu'() of
+          stage_and_store<NBUF>(bufs, nstore, pk, lane, &p.tmAux, nb, row0, in_range, false);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pk[j] = pack2_bf16(gelu_f(bf16_lo(pk[j])), gelu_f(bf16_hi(pk[j])));
+        }
+        stage_and_store<NBUF>(bufs, nstore, pk, lane, tm_out, nb, row0, in_range, false);
+      }
+    }
+  }
+}
+
 template <int STAGES_, int NBUF>
 __global__ void __launch_bounds__(64 + 32 * 8, 1)
 grouped_gemm2_kernel(const __grid_constant__ GArgs args) {
@@ -913,124 +1042,15 @@ grouped_gemm2_kernel(const __grid_constant__ GArgs args) {
       const int epi = p.epi;
       const int acc = tcount & 1;
       const int row0 = tc.m0 + rank * BM + q * 32;
-      const int m = row0 + lane;
-      const bool row_ok = m < p.MM;
       mbar_wait(&tmem_full_bar[acc], (tcount >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-      if (epi == kGEpiF32 || epi == kGEpiScoreGrad) {
-        // ---- fp32 out: 32 columns per 128-byte staging row
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int col0 = half * 128 + c * 32;
-          const int nb = tc.n0 + col0;
-          uint32_t r[32], pk[32];
-          float bias_v = 0.f;
-          float4 wq[8];
-          const bool fast = row_ok && nb + 32 <= p.NN;
-          if (epi == kGEpiF32) {
-            if (p.bias != nullptr && nb + lane < p.NN) bias_v = __ldg(p.bias + nb + lane);
-          } else if (fast) {
-            const float* wrow = p.w + static_cast<size_t>(m) * p.NN + nb;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) wq[j] = __ldg(reinterpret_cast<const float4*>(wrow) + j);
-          }
-          tmem_ld_32x32(t_addr + col0, r);
-          tmem_ld_wait();
-          if (epi == kGEpiF32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              pk[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_v, j));
-          } else if (fast) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              pk[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) * wq[j].x);
-              pk[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) * wq[j].y);
-              pk[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) * wq[j].z);
-              pk[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) * wq[j].w);
-            }
-          } else {
-            const float* wrow = p.w + static_cast<size_t>(row_ok ? m : 0) * p.NN + nb;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float wv = (row_ok && nb + j < p.NN) ? __ldg(wrow + j) : 0.f;
-              pk[j] = __float_as_uint(__uint_as_float(r[j]) * wv);
-            }
-          }
-          stage_and_store<NBUF>(bufs, nstore, pk, lane, &p.tmOut, nb, row0, nb < p.NN && row0 < p.MM,
-                                epi == kGEpiScoreGrad && p.reduce_out);
-        }
-      } else {
-        // ---- bf16 out: 64 columns per 128-byte staging row
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const int col0 = half * 128 + c * 64;
-          const int nb = tc.n0 + col0;
-          uint32_t r[32], r2[32], pk[32];
-          float bias_lo = 0.f, bias_hi = 0.f;
-          uint4 uq[8];
-          const bool fast = row_ok && nb + 64 <= p.NN;
-          if (epi == kGEpiGeluGrad) {
-            if (fast) {
-              const uint16_t* urow = p.aux_in + static_cast<size_t>(m) * p.NN + nb;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) uq[j] = __ldg(reinterpret_cast<const uint4*>(urow) + j);
-            }
-          } else if (p.bias != nullptr) {
-            if (nb + lane < p.NN) bias_lo = __ldg(p.bias + nb + lane);
-            if (nb + 32 + lane < p.NN) bias_hi = __ldg(p.bias + nb + 32 + lane);
-          }
-          tmem_ld_32x32(t_addr + col0, r);
-          tmem_ld_32x32(t_addr + col0 + 32, r2);
-          tmem_ld_wait();
-          if (epi == kGEpiGeluGrad) {
-            if (fast) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {        // uq[j]: u of columns 8j .. 8j+7 ; uq[4 + j]: columns 32 + 8j ..
-                const uint32_t ua[4] = {uq[j].x, uq[j].y, uq[j].z, uq[j].w};
-                const uint32_t ub[4] = {uq[4 + j].x, uq[4 + j].y, uq[4 + j].z, uq[4 + j].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  pk[4 * j + e] = pack2_bf16(__uint_as_float(r[8 * j + 2 * e]) * gelu_grad_f(bf16_lo(ua[e])),
-                                             __uint_as_float(r[8 * j + 2 * e + 1]) * gelu_grad_f(bf16_hi(ua[e])));
-                  pk[16 + 4 * j + e] = pack2_bf16(__uint_as_float(r2[8 * j + 2 * e]) * gelu_grad_f(bf16_lo(ub[e])),
-                                                  __uint_as_float(r2[8 * j + 2 * e + 1]) * gelu_grad_f(bf16_hi(ub[e])));
-                }
-              }
-            } else {
-              const uint16_t* urow = p.aux_in + static_cast<size_t>(row_ok ? m : 0) * p.NN + nb;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float g[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int col = (e < 2 ? 2 * j + e : 32 + 2 * j + (e - 2));
-                  const bool ok = row_ok && nb + col < p.NN;
-                  g[e] = ok ? gelu_grad_f(__uint_as_float(static_cast<uint32_t>(__ldg(urow + col)) << 16)) : 0.f;
-                }
-                pk[j] = pack2_bf16(__uint_as_float(r[2 * j]) * g[0], __uint_as_float(r[2 * j + 1]) * g[1]);
-                pk[16 + j] = pack2_bf16(__uint_as_float(r2[2 * j]) * g[2], __uint_as_float(r2[2 * j + 1]) * g[3]);
-              }
-            }
-            stage_and_store<NBUF>(bufs, nstore, pk, lane, &p.tmOut, nb, row0, nb < p.NN && row0 < p.MM, false);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              pk[j] = pack2_bf16(__uint_as_float(r[2 * j]) + __shfl_sync(0xffffffffu, bias_lo, 2 * j),
-                                 __uint_as_float(r[2 * j + 1]) + __shfl_sync(0xffffffffu, bias_lo, 2 * j + 1));
-              pk[16 + j] = pack2_bf16(__uint_as_float(r2[2 * j]) + __shfl_sync(0xffffffffu, bias_hi, 2 * j),
-                                      __uint_as_float(r2[2 * j + 1]) + __shfl_sync(0xffffffffu, bias_hi, 2 * j + 1));
-            }
-            if (epi == kGEpiGelu) {
-              // the pre-activation goes out as it is (bf16), then the same registers become gelu(u) -- computed
-              // from the ROUNDED u, which is what the backward multiplies gelu'() of
-              stage_and_store<NBUF>(bufs, nstore, pk, lane, &p.tmAux, nb, row0, nb < p.NN && row0 < p.MM, false);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) pk[j] = pack2_bf16(gelu_f(bf16_lo(pk[j])), gelu_f(bf16_hi(pk[j])));
-            }
-            stage_and_store<NBUF>(bufs, nstore, pk, lane, &p.tmOut, nb, row0, nb < p.NN && row0 < p.MM, false);
-          }
-        }
+      switch (epi) {     // one specialised loop per epilogue kind: no kind test, no dead registers inside the loops
+        case kGEpiF32: epilogue_tile<kGEpiF32, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore); break;
+        case kGEpiBf16: epilogue_tile<kGEpiBf16, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore); break;
+        case kGEpiScoreGrad: epilogue_tile<kGEpiScoreGrad, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore); break;
+        case kGEpiGelu: epilogue_tile<kGEpiGelu, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore); break;
+        default: epilogue_tile<kGEpiGeluGrad, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore); break;
       }
       tc_fence_before();
       __syncwarp();
@@ -1366,9 +1386,9 @@ template <int STAGES_, int NBUF>
 static int launch_group_t(GArgs& g, cudaStream_t stream);
 
 static int launch_group(GArgs& g, cudaStream_t stream) {
-  // CRVQA_GROUP_STAGES=5: five operand stages + double-buffered epilogue staging; default six + single staging
-  static const int stages = [] { const char* e = getenv("CRVQA_GROUP_STAGES"); return e ? atoi(e) : 6; }();
-  return stages == 5 ? launch_group_t<5, 2>(g, stream) : launch_group_t<6, 1>(g, stream);
+  // five operand stages + double-buffered epilogue staging (measured faster); CRVQA_GROUP_STAGES=6: six + single staging
+  static const int stages = [] { const char* e = getenv("CRVQA_GROUP_STAGES"); return e ? atoi(e) : 5; }();
+  return stages == 6 ? launch_group_t<6, 1>(g, stream) : launch_group_t<5, 2>(g, stream);
 }
 
 template <int STAGES_, int NBUF>

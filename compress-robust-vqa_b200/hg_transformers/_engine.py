@@ -102,6 +102,8 @@ class ScoreArena:
         self.step_chunks = None
         self.epoch = 0
         self.w16 = self.wm = self.w32 = self.chunks = None
+        if self.scores.is_cuda:
+            self._step_chunk_table()
 
     def _view(self, flat, i):
         p = self.modules[i].weight_mask
@@ -164,8 +166,9 @@ class ScoreArena:
             for c0 in range(0, n, 8192):
                 rows.append(((off + c0) // 8, min(8192, n - c0), i, 0))
         self.chunks = torch.tensor(rows, dtype=torch.int32, device=dev).contiguous()
-        self.step_chunks = None
         self.cache_on = True
+        self.step_chunks = None
+        self._step_chunk_table()    # built now: a CUDA-graph capture of the step must not create it
         self.refresh_masked()
 
     def _step_chunk_table(self):
