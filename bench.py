@@ -291,6 +291,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     record, ops.RECORD = ops.RECORD, None
+    if os.environ.get("CRVQA_BENCH_DUMP_GEMMS") and rank == 0:      # debugging aid: the GEMM list of one step
+        with open(os.environ["CRVQA_BENCH_DUMP_GEMMS"], "w") as f:
+            json.dump([[k, m, n, kk] for k, m, n, kk, _ in record], f)
     if graphed is not None:
         launches = (lib.crv_launch_count() - c0) * args.steps  # replays launch from the graph, not from Python
     side = torch.cuda.Stream(device=dev)

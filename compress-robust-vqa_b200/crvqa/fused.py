@@ -638,3 +638,17 @@ def cross_attention_pair(plan, lang32, lang16, visn32, visn16, lang_mask, visn_m
     ln, pd = plan.out.LayerNorm, plan.out.dropout.p
     return (drop_add_layernorm(ao_l, lang32, ln, pd, site_l, training),
             drop_add_layernorm(ao_v, visn32, ln, pd, site_v, training))
+
+
+def cross_attention_lang_only(plan, lang32, lang16, visn16, visn_mask, training, site_l):
+    """The language direction of a cross layer alone (q from language, k | v from vision): what is left of the last
+    cross layer when nothing reads its vision output."""
+    a = plan.att
+    Sl, Sv = lang16.shape[1], visn16.shape[1]
+    if plan.kv is None or not plan._small(Sl, Sv):
+        return plan.cross_attention(lang32, lang16, visn16, visn_mask, training, site_l)
+    q, kv = multi_linear([(plan.q, lang16, torch.bfloat16, False, None), (plan.kv, visn16, torch.bfloat16, False, None)])
+    m = None if visn_mask is None else visn_mask.reshape(visn_mask.shape[0], -1)
+    ctx = small_attention(1, a.num_attention_heads, m, a.dropout.p, site_l + 1, training, q, kv)
+    (ao,) = multi_linear([(plan.ao, ctx, torch.bfloat16, False, None)])
+    return drop_add_layernorm(ao, lang32, plan.out.LayerNorm, plan.out.dropout.p, site_l, training)

@@ -784,109 +784,84 @@ __device__ __forceinline__ void stage_and_store(uint8_t* bufs, int& nstore, cons
 
 
 // One epilogue warp's share of a tile: 32 accumulator rows (lane = row) x 128 columns, in chunks of one 128-byte
-// staging row (32 fp32 or 64 bf16 columns).
+// staging row (32 fp32 or 64 bf16 columns).  The grouped kernel only takes problems whose output width is a multiple
+// of 256, so every chunk has all its columns; rows past MM exist only in the last row tile: their loads are clamped
+// to row MM - 1 and their results never leave the SM (the TMA store clips them).  No per-element guards: the kernel
+// has to stay small -- past ~40 KB of code the single MMA-issuing thread starts to wait on instruction fetches.
 template <int EPI, int NBUF>
 __device__ __forceinline__ void epilogue_tile(const GProblem& p, int n0, int row0, uint32_t t_addr, int half, int lane,
                                               uint8_t* bufs, int& nstore) {
   const int MM = p.MM, NN = p.NN;
-  const int m = row0 + lane;
-  const bool row_ok = m < MM;
+  const int m_ld = min(row0 + lane, MM - 1);
+  const bool in_range = row0 < MM;
   const CUtensorMap* tm_out = &p.tmOut;
   if (EPI == kGEpiF32 || EPI == kGEpiScoreGrad) {
     const float* bias = p.bias;
-    const float* wmul = p.w;
+    const float* wrow0 = EPI == kGEpiScoreGrad ? p.w + static_cast<size_t>(m_ld) * NN : nullptr;
     const bool reduce = EPI == kGEpiScoreGrad && p.reduce_out;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       const int col0 = half * 128 + c * 32;
       const int nb = n0 + col0;
-      uint32_t r[32], pk[32];
+      uint32_t r[32];
       float bias_v = 0.f;
       float4 wq[8];
-      const bool fast = row_ok && nb + 32 <= NN;
       if (EPI == kGEpiF32) {
-        if (bias != nullptr && nb + lane < NN) bias_v = __ldg(bias + nb + lane);
-      } else if (fast) {       // the fp32 multiplier row is fetched while the TMEM load is in flight
-        const float* wrow = wmul + static_cast<size_t>(m) * NN + nb;
+        if (bias != nullptr) bias_v = __ldg(bias + nb + lane);
+      } else {                 // the fp32 multiplier row is fetched while the TMEM load is in flight
 #pragma unroll
-        for (int j = 0; j < 8; ++j) wq[j] = __ldg(reinterpret_cast<const float4*>(wrow) + j);
+        for (int j = 0; j < 8; ++j) wq[j] = __ldg(reinterpret_cast<const float4*>(wrow0 + nb) + j);
       }
       tmem_ld_32x32(t_addr + col0, r);
       tmem_ld_wait();
       if (EPI == kGEpiF32) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          pk[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_v, j));
-      } else if (fast) {
+          r[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_v, j));
+      } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          pk[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) * wq[j].x);
-          pk[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) * wq[j].y);
-          pk[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) * wq[j].z);
-          pk[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) * wq[j].w);
-        }
-      } else {
-        const float* wrow = wmul + static_cast<size_t>(row_ok ? m : 0) * NN + nb;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float wv = (row_ok && nb + j < NN) ? __ldg(wrow + j) : 0.f;
-          pk[j] = __float_as_uint(__uint_as_float(r[j]) * wv);
+          r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) * wq[j].x);
+          r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) * wq[j].y);
+          r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) * wq[j].z);
+          r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) * wq[j].w);
         }
       }
-      stage_and_store<NBUF>(bufs, nstore, pk, lane, tm_out, nb, row0, nb < NN && row0 < MM, reduce);
+      stage_and_store<NBUF>(bufs, nstore, r, lane, tm_out, nb, row0, in_range, reduce);
     }
   } else {
+    const uint16_t* urow0 = EPI == kGEpiGeluGrad ? p.aux_in + static_cast<size_t>(m_ld) * NN : nullptr;
+    const float* bias = p.bias;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       const int col0 = half * 128 + c * 64;
       const int nb = n0 + col0;
       uint32_t r[32], r2[32], pk[32];
-      const bool in_range = nb < NN && row0 < MM;
       if (EPI == kGEpiGeluGrad) {
-        const bool fast = row_ok && nb + 64 <= NN;
         uint4 uq[8];
-        if (fast) {
-          const uint16_t* urow = p.aux_in + static_cast<size_t>(m) * NN + nb;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) uq[j] = __ldg(reinterpret_cast<const uint4*>(urow) + j);
-        }
+        for (int j = 0; j < 8; ++j) uq[j] = __ldg(reinterpret_cast<const uint4*>(urow0 + nb) + j);
         tmem_ld_32x32(t_addr + col0, r);
         tmem_ld_32x32(t_addr + col0 + 32, r2);
         tmem_ld_wait();
-        if (fast) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {        // uq[j]: u of columns 8j .. 8j+7 ; uq[4 + j]: columns 32 + 8j ..
-            const uint32_t ua[4] = {uq[j].x, uq[j].y, uq[j].z, uq[j].w};
-            const uint32_t ub[4] = {uq[4 + j].x, uq[4 + j].y, uq[4 + j].z, uq[4 + j].w};
+        for (int j = 0; j < 4; ++j) {        // uq[j]: u of columns 8j .. 8j+7 ; uq[4 + j]: columns 32 + 8j ..
+          const uint32_t ua[4] = {uq[j].x, uq[j].y, uq[j].z, uq[j].w};
+          const uint32_t ub[4] = {uq[4 + j].x, uq[4 + j].y, uq[4 + j].z, uq[4 + j].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              pk[4 * j + e] = pack2_bf16(__uint_as_float(r[8 * j + 2 * e]) * gelu_grad_f(bf16_lo(ua[e])),
-                                         __uint_as_float(r[8 * j + 2 * e + 1]) * gelu_grad_f(bf16_hi(ua[e])));
-              pk[16 + 4 * j + e] = pack2_bf16(__uint_as_float(r2[8 * j + 2 * e]) * gelu_grad_f(bf16_lo(ub[e])),
-                                              __uint_as_float(r2[8 * j + 2 * e + 1]) * gelu_grad_f(bf16_hi(ub[e])));
-            }
-          }
-        } else {
-          const uint16_t* urow = p.aux_in + static_cast<size_t>(row_ok ? m : 0) * NN + nb;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float g[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int col = (e < 2 ? 2 * j + e : 32 + 2 * j + (e - 2));
-              const bool ok = row_ok && nb + col < NN;
-              g[e] = ok ? gelu_grad_f(__uint_as_float(static_cast<uint32_t>(__ldg(urow + col)) << 16)) : 0.f;
-            }
-            pk[j] = pack2_bf16(__uint_as_float(r[2 * j]) * g[0], __uint_as_float(r[2 * j + 1]) * g[1]);
-            pk[16 + j] = pack2_bf16(__uint_as_float(r2[2 * j]) * g[2], __uint_as_float(r2[2 * j + 1]) * g[3]);
+          for (int e = 0; e < 4; ++e) {
+            pk[4 * j + e] = pack2_bf16(__uint_as_float(r[8 * j + 2 * e]) * gelu_grad_f(bf16_lo(ua[e])),
+                                       __uint_as_float(r[8 * j + 2 * e + 1]) * gelu_grad_f(bf16_hi(ua[e])));
+            pk[16 + 4 * j + e] = pack2_bf16(__uint_as_float(r2[8 * j + 2 * e]) * gelu_grad_f(bf16_lo(ub[e])),
+                                            __uint_as_float(r2[8 * j + 2 * e + 1]) * gelu_grad_f(bf16_hi(ub[e])));
           }
         }
         stage_and_store<NBUF>(bufs, nstore, pk, lane, tm_out, nb, row0, in_range, false);
       } else {
         float bias_lo = 0.f, bias_hi = 0.f;
-        if (p.bias != nullptr) {
-          if (nb + lane < NN) bias_lo = __ldg(p.bias + nb + lane);
-          if (nb + 32 + lane < NN) bias_hi = __ldg(p.bias + nb + 32 + lane);
+        if (bias != nullptr) {
+          bias_lo = __ldg(bias + nb + lane);
+          bias_hi = __ldg(bias + nb + 32 + lane);
         }
         tmem_ld_32x32(t_addr + col0, r);
         tmem_ld_32x32(t_addr + col0 + 32, r2);
@@ -911,7 +886,8 @@ __device__ __forceinline__ void epilogue_tile(const GProblem& p, int n0, int row
   }
 }
 
-template <int STAGES_, int NBUF>
+// EPIMASK: bit k set = the group may contain epilogue kind k (only those loops are compiled in)
+template <int STAGES_, int NBUF, int EPIMASK>
 __global__ void __launch_bounds__(64 + 32 * 8, 1)
 grouped_gemm2_kernel(const __grid_constant__ GArgs args) {
   using L = SmemG<STAGES_, NBUF>;
@@ -1045,13 +1021,17 @@ grouped_gemm2_kernel(const __grid_constant__ GArgs args) {
       mbar_wait(&tmem_full_bar[acc], (tcount >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-      switch (epi) {     // one specialised loop per epilogue kind: no kind test, no dead registers inside the loops
-        case kGEpiF32: epilogue_tile<kGEpiF32, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore); break;
-        case kGEpiBf16: epilogue_tile<kGEpiBf16, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore); break;
-        case kGEpiScoreGrad: epilogue_tile<kGEpiScoreGrad, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore); break;
-        case kGEpiGelu: epilogue_tile<kGEpiGelu, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore); break;
-        default: epilogue_tile<kGEpiGeluGrad, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore); break;
-      }
+      // one specialised loop per epilogue kind the instantiation admits
+      if (((EPIMASK >> kGEpiF32) & 1) && epi == kGEpiF32)
+        epilogue_tile<kGEpiF32, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore);
+      if (((EPIMASK >> kGEpiBf16) & 1) && epi == kGEpiBf16)
+        epilogue_tile<kGEpiBf16, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore);
+      if (((EPIMASK >> kGEpiScoreGrad) & 1) && epi == kGEpiScoreGrad)
+        epilogue_tile<kGEpiScoreGrad, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore);
+      if (((EPIMASK >> kGEpiGelu) & 1) && epi == kGEpiGelu)
+        epilogue_tile<kGEpiGelu, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore);
+      if (((EPIMASK >> kGEpiGeluGrad) & 1) && epi == kGEpiGeluGrad)
+        epilogue_tile<kGEpiGeluGrad, NBUF>(p, tc.n0, row0, t_addr, half, lane, bufs, nstore);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0);
@@ -1382,19 +1362,10 @@ static void choose_splits(GArgs& g, const int* must_reduce, int pairs) {
   }
 }
 
-template <int STAGES_, int NBUF>
-static int launch_group_t(GArgs& g, cudaStream_t stream);
-
-static int launch_group(GArgs& g, cudaStream_t stream) {
-  // five operand stages + double-buffered epilogue staging (measured faster); CRVQA_GROUP_STAGES=6: six + single staging
-  static const int stages = [] { const char* e = getenv("CRVQA_GROUP_STAGES"); return e ? atoi(e) : 5; }();
-  return stages == 6 ? launch_group_t<6, 1>(g, stream) : launch_group_t<5, 2>(g, stream);
-}
-
-template <int STAGES_, int NBUF>
+template <int EPIMASK>
 static int launch_group_t(GArgs& g, cudaStream_t stream) {
-  using L = SmemG<STAGES_, NBUF>;
-  auto kern = grouped_gemm2_kernel<STAGES_, NBUF>;
+  using L = SmemG<5, 2>;
+  auto kern = grouped_gemm2_kernel<5, 2, EPIMASK>;
   static bool configured = false;
   if (!configured) {
     CRV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -1418,6 +1389,19 @@ static int launch_group_t(GArgs& g, cudaStream_t stream) {
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   CRV_CUDA(cudaLaunchKernelEx(&cfg, kern, g));
   return launch_status();
+}
+
+// Instantiations by what a group can hold: forward (bf16 / fp32 stores), forward with GELU, backward (dX stores +
+// score gradients), backward with gelu'.  The smallest one that covers the group's epilogue kinds is launched.
+static int launch_group(GArgs& g, cudaStream_t stream) {
+  constexpr int F = 1 << kGEpiF32, B = 1 << kGEpiBf16, S = 1 << kGEpiScoreGrad, G = 1 << kGEpiGelu, D = 1 << kGEpiGeluGrad;
+  int mask = 0;
+  for (int i = 0; i < g.count; ++i) mask |= 1 << g.p[i].epi;
+  if ((mask & ~(F | B)) == 0) return launch_group_t<F | B>(g, stream);
+  if ((mask & ~(B | G)) == 0) return launch_group_t<B | G>(g, stream);
+  if ((mask & ~(F | B | S)) == 0) return launch_group_t<F | B | S>(g, stream);
+  if ((mask & ~(B | S | D)) == 0) return launch_group_t<B | S | D>(g, stream);
+  return launch_group_t<F | B | S | G | D>(g, stream);
 }
 
 static int single_launch(const crv_gemm_problem& q, void* stream) {

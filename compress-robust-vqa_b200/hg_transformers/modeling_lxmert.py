@@ -188,7 +188,7 @@ class LxmertEncoder(nn.Module):
         self.x_layers = nn.ModuleList([LxmertXLayer(config) for _ in range(config.x_layers)])
         self.r_layers = nn.ModuleList([LxmertLayer(config) for _ in range(config.r_layers)])
 
-    def forward(self, lang, lang_mask, visual_feats, visual_pos, visn_mask=None):
+    def forward(self, lang, lang_mask, visual_feats, visual_pos, visn_mask=None, need_visn_output=True):
         """`lang` is the language embedding output or a callable producing it.  LxmertModel passes a callable so the
         fast path can create the embedding node AFTER the vision stack: autograd runs later-created nodes first,
         which puts the 94 MB word-embedding gradient before the vision stack in the backward pass instead of at
@@ -196,7 +196,7 @@ class LxmertEncoder(nn.Module):
         visn = self.visn_fc(visual_feats, visual_pos)
         fast = self._fast_plans() if visn.is_cuda else None
         if fast is not None:
-            return self._forward_fast(fast, lang, lang_mask, visn, visn_mask)
+            return self._forward_fast(fast, lang, lang_mask, visn, visn_mask, need_visn_output)
         if callable(lang):
             lang = lang()
         for blk in self.layer:
@@ -242,11 +242,13 @@ class LxmertEncoder(nn.Module):
             return None
         return plans
 
-    def _forward_fast(self, plans, lang32, lang_mask, visn32, visn_mask):
+    def _forward_fast(self, plans, lang32, lang_mask, visn32, visn_mask, need_visn_output=True):
         """Language and vision stacks run in LOCKSTEP (layer i of both, then the remaining language layers): the two
         are independent until the cross layers, so their GEMMs of one phase share a grouped launch
         (crvqa.fused.self_attention_multi / ffn_multi); inside a cross layer the two modalities are grouped the same
-        way.  CRVQA_GROUPED=0 issues every GEMM on its own."""
+        way.  CRVQA_GROUPED=0 issues every GEMM on its own.  With need_visn_output=False (the VQA head reads the
+        pooled LANGUAGE output only, reference :256-360) the vision half of the LAST cross layer is dead code -- the
+        reference computes it and throws it away -- and is not executed."""
         from crvqa import fused
         tr = self.training
         visn16 = visn32.to(torch.bfloat16)
@@ -268,7 +270,13 @@ class LxmertEncoder(nn.Module):
                     lang32, lang16 = o32, o16
                 else:
                     visn32, visn16 = o32, o16
-        for cross, site_l, site_v, ls, vs, lf, vf in plans["cross"]:
+        for li, (cross, site_l, site_v, ls, vs, lf, vf) in enumerate(plans["cross"]):
+            if not need_visn_output and li == len(plans["cross"]) - 1 and fused._grouped_on():
+                lx32, lx16 = fused.cross_attention_lang_only(cross, lang32, lang16, visn16, visn_mask, tr, site_l)
+                ((ls32, ls16),) = fused.self_attention_multi([(ls, lx32, lx16, lang_mask)], tr)
+                ((lang32, lang16),) = fused.ffn_multi([(lf, ls32, ls16)], tr)
+                visn32 = None
+                break
             (lx32, lx16), (vx32, vx16) = fused.cross_attention_pair(cross, lang32, lang16, visn32, visn16, lang_mask,
                                                                     visn_mask, tr, site_l, site_v)
             (ls32, ls16), (vs32, vs16) = fused.self_attention_multi([(ls, lx32, lx16, lang_mask),
@@ -332,7 +340,7 @@ class LxmertModel(LxmertPreTrainedModel):
         self.init_weights()
 
     def forward(self, input_ids=None, visual_feats=None, visual_pos=None, attention_mask=None,
-                visual_attention_mask=None, token_type_ids=None, **unused):
+                visual_attention_mask=None, token_type_ids=None, need_visn_output=True, **unused):
         if input_ids is None:
             raise ValueError("You have to specify input_ids")
         if visual_feats is None:
@@ -346,7 +354,7 @@ class LxmertModel(LxmertPreTrainedModel):
         if visual_attention_mask is not None:
             visn_mask = (1.0 - visual_attention_mask[:, None, None, :].to(visual_feats.dtype)) * -10000.0
         lang, visn = self.encoder(lambda: self.embeddings(input_ids, token_type_ids), lang_mask, visual_feats,
-                                  visual_pos, visn_mask)
+                                  visual_pos, visn_mask, need_visn_output)
         return lang, visn, self.pooler(lang)
 
 
@@ -373,7 +381,7 @@ class LxmertForMultipleChoice(LxmertPreTrainedModel):
                 visual_attention_mask=None, token_type_ids=None, labels=None, **unused):
         _, _, pooled = self.lxmert(input_ids=input_ids, visual_feats=visual_feats, visual_pos=visual_pos,
                                    attention_mask=attention_mask, visual_attention_mask=visual_attention_mask,
-                                   token_type_ids=token_type_ids)
+                                   token_type_ids=token_type_ids, need_visn_output=False)
         logits = self.classifier(pooled)
         loss = self.instance_bce_with_logits(logits, labels) if labels is not None else None
         return loss, logits, pooled
