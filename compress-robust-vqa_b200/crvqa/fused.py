@@ -89,6 +89,7 @@ class ProjectionGroup:
         return all(a.cached_masked_weight(m) is not None for m in self.modules)
 
     def note_forward(self):
+        self.arena.wait_ready(self.modules[-1])       # sharded optimiser: this bucket's operand all-gather has landed
         if torch.is_grad_enabled():
             for m in self.modules:
                 if getattr(m, "_sync", None) is not None:

@@ -631,6 +631,11 @@ def sumsq_into(x, acc):
     check(lib.crv_sumsq(_p(x), x.numel(), _p(acc), _stream()), "crv_sumsq")
 
 
+def sumsq_segmented_into(x, chunks, acc):
+    if chunks.shape[0]:
+        check(lib.crv_sumsq_segmented(_p(x), _p(chunks), chunks.shape[0], _p(acc), _stream()), "crv_sumsq_segmented")
+
+
 def adam_step_size(lr, step, beta1, beta2, correct_bias=True):
     if not correct_bias:
         return lr

@@ -180,6 +180,31 @@ __global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __re
   }
 }
 
+// sum of squares over the chunks of a table (the gradient shard a rank owns under the sharded optimiser)
+__global__ void sumsq_segmented_kernel(const float* __restrict__ x, const int4* __restrict__ chunks, int nchunks,
+                                       float* __restrict__ out) {
+  float acc = 0.f;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int4 ch = __ldg(chunks + c);
+    const int64_t base = static_cast<int64_t>(ch.x) * 8;
+    const int nvec = ch.y >> 2;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + base) + i);
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    for (int i = (nvec << 2) + threadIdx.x; i < ch.y; i += blockDim.x) acc += x[base + i] * x[base + i];
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float wsum[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) t += wsum[w];
+    atomicAdd(out, t);
+  }
+}
+
 struct AdamArgs {
   float lr, step_size, beta1, beta2, eps, weight_decay, max_norm;
 };
@@ -489,6 +514,16 @@ extern "C" int crv_sumsq(const float* x, int64_t n, float* out, void* stream) {
   if (n == 0) return CRV_OK;
   if (!aligned16(x)) return CRV_E_ALIGN;
   sumsq_kernel<<<stream_grid(n >> 2, 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out);
+  return launch_status();
+}
+
+extern "C" int crv_sumsq_segmented(const float* x, const int* chunks, int nchunks, float* out, void* stream) {
+  if (!x || !chunks || !out || nchunks < 0) return CRV_E_BADARG;
+  if (nchunks == 0) return CRV_OK;
+  if (!aligned16(x) || !aligned16(chunks)) return CRV_E_ALIGN;
+  const int grid = nchunks < num_sms() * 4 ? nchunks : num_sms() * 4;
+  sumsq_segmented_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<const int4*>(chunks), nchunks, out);
   return launch_status();
 }
 

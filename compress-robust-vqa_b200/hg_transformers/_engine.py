@@ -100,6 +100,7 @@ class ScoreArena:
         # clear the gradient arena; split score-gradient GEMMs then clear their output with a memset per module
         self.keep_grads = os.environ.get("CRVQA_KEEP_GRADS", "0") == "1"
         self.step_chunks = None
+        self.shard = None
         self.epoch = 0
         self.w16 = self.wm = self.w32 = self.chunks = None
         if self.scores.is_cuda:
@@ -171,23 +172,59 @@ class ScoreArena:
         self._step_chunk_table()    # built now: a CUDA-graph capture of the step must not create it
         self.refresh_masked()
 
+    def _chunk_rows(self, ranges=None, modules=None):
+        """{start / 8, length, segment, flags} rows (flags bit 0: the segment has a bf16 operand) over whole modules
+        (`modules`: indices, default all) or over the parts of the modules inside `ranges` (element intervals whose
+        bounds are multiples of 8)."""
+        rows = []
+        for i, m in enumerate(self.modules):
+            if modules is not None and i not in modules:
+                continue
+            n, off = m.weight_mask.numel(), self.offsets[i]
+            flag = 1 if (self.cache_on and self._gemm_module(m)) else 0
+            spans = [(off, off + n)] if ranges is None else [(max(off, lo), min(off + n, hi)) for lo, hi in ranges]
+            for lo, hi in spans:
+                for c0 in range(lo, hi, 8192):
+                    rows.append((c0 // 8, min(8192, hi - c0), i, flag))
+        if not rows:
+            return torch.zeros((0, 4), dtype=torch.int32, device=self.scores.device)
+        return torch.tensor(rows, dtype=torch.int32, device=self.scores.device).contiguous()
+
     def _step_chunk_table(self):
-        """{start / 8, length, segment, flags} rows covering EVERY module (flags bit 0: it has a bf16 operand)."""
+        """Rows the optimiser pass of THIS rank covers: every module, or (sharded optimiser, GradSync) the element
+        ranges this rank owns plus the replicated modules."""
         if self.step_chunks is None:
-            rows = []
-            for i, m in enumerate(self.modules):
-                n, off = m.weight_mask.numel(), self.offsets[i]
-                flag = 1 if (self.cache_on and self._gemm_module(m)) else 0
-                for c0 in range(0, n, 8192):
-                    rows.append(((off + c0) // 8, min(8192, n - c0), i, flag))
-            self.step_chunks = torch.tensor(rows, dtype=torch.int32, device=self.scores.device).contiguous()
+            if self.shard is None:
+                self.step_chunks = self._chunk_rows()
+            else:
+                own = self._chunk_rows(ranges=self.shard["own"], modules=self.shard["sharded_modules"])
+                rep = self._chunk_rows(modules=self.shard["replicated_modules"])
+                self.shard["own_chunks"], self.shard["rep_chunks"] = own, rep
+                self.step_chunks = torch.cat([own, rep]).contiguous()
         return self.step_chunks
+
+    def install_shard(self, own_ranges, sharded_modules, replicated_modules, sync):
+        """GradSync (sharded mode): this rank updates only `own_ranges` of the sharded modules; their masked operands
+        reach the other ranks by all-gather before first use (wait_ready), their scores on demand (sync.sync_scores)."""
+        self.shard = {"own": own_ranges, "sharded_modules": set(sharded_modules),
+                      "replicated_modules": set(replicated_modules), "sync": sync}
+        self.step_chunks = None
+        self._step_chunk_table()
+
+    def wait_ready(self, m):
+        """Make the current stream wait until module `m`'s masked operand is complete on this rank."""
+        if self.shard is not None:
+            self.shard["sync"].wait_operand(m)
 
     def refresh_masked(self):
         if not self.cache_on:
             return
+        if self.shard is not None:
+            self.shard["sync"].sync_scores()          # the whole arena is re-masked here: every score must be current
         ops.apply_mask_segmented(self.w16, self.scores, self.thr_vec, self.chunks, self.wm)
         self._mark_cache_valid()
+        if self.shard is not None:
+            self.shard["sync"].operands_are_current()
 
     def _mark_cache_valid(self):
         for m in self.modules:
@@ -199,6 +236,7 @@ class ScoreArena:
         """The module's W (.) M if it is valid for the current scores and threshold, else None."""
         if (self.cache_on and getattr(m, "_wm_epoch", -1) == self.epoch and m.weight_mask._version == m._wm_sver
                 and torch.is_tensor(m.threshold) and m.threshold.data_ptr() == m._wm_thr_ptr):
+            self.wait_ready(m)
             return m._wm
         return None
 
@@ -240,6 +278,8 @@ class ScoreArena:
         if zero:
             for m in self.modules:
                 m._grad_zero = True
+        if self.shard is not None:
+            self.shard["sync"].after_optimizer_step()
 
     def release(self):
         """Give the parameters their own storage back (used when a trainer is torn down)."""
@@ -254,27 +294,52 @@ class ScoreArena:
 
 
 class GradSync:
-    """Bucketed asynchronous all-reduce(mean) of an arena's gradient buffer + a few loose tensors."""
+    """Data-parallel exchange of an arena's gradients (+ a few loose tensors), bucketed and asynchronous.
 
-    def __init__(self, arena, bucket_bytes=32 << 20, group=None):
+    Buckets are runs of consecutive modules in arena (= execution) order; as soon as the backward pass has produced
+    every module of a bucket, its collective is issued on a side stream while the remaining GEMMs run.
+
+    Two modes (CRVQA_DP=sharded | allreduce; sharded needs NCCL and 2, 4 or 8 ranks):
+
+    allreduce  every bucket is all-reduced (mean) and every rank runs the whole optimiser pass (the reference's DDP
+               semantics, hg_transformers/mask_trainer_VQA.py:537-543, literally).
+    sharded    same result, less traffic and less HBM work: a bucket of GEMM modules is REDUCE-SCATTERED, rank r keeps
+               the mean gradient of slice r only, runs clip + AdamW + masked-operand refresh on that slice (1/N of the
+               44 B per score), and the bf16 masked operands W (.) M -- all the forward / dX GEMMs read -- are
+               ALL-GATHERED at the start of the next step, bucket by bucket in execution order, overlapping the forward
+               pass (a module's first use waits for its bucket only).  Per step and score that is 4 B (fp32 reduce-
+               scatter) + 2 B (bf16 all-gather) on the wire instead of 4 B + 4 B.  Modules whose scores are read
+               directly by a kernel (word embeddings, box_fc) stay replicated: all-reduce + full update.  The fp32
+               scores of non-owned slices go stale between threshold refreshes; sync_scores() all-gathers them
+               (reset_threshold, save_model_mask, evaluation, end of training call it)."""
+
+    def __init__(self, arena, bucket_bytes=32 << 20, group=None, mode=None):
         self.arena = arena
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        active = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if active else 1
+        self.rank = dist.get_rank(group) if active else 0
         self.enabled = self.world > 1
+        mode = mode or os.environ.get("CRVQA_DP", "sharded")
+        self.sharded = (self.enabled and mode == "sharded" and self.world in (2, 4, 8) and arena.scores.is_cuda
+                        and arena.cache_on and dist.get_backend(group) == "nccl")
         # buckets = runs of consecutive modules (arena order == execution order).  The FIRST buckets of the arena are
-        # the last ones the backward pass completes, and only their all-reduce is exposed at the end of the step, so
-        # they start small (bucket_bytes / 4, / 2, then bucket_bytes).
-        self.bucket_of, self.bucket_ranges, self.bucket_members = [], [], []
-        start_mod, start_off, cur = 0, 0, 0
+        # the last ones the backward pass completes, and only their exchange is exposed at the end of the step, so
+        # they start small (bucket_bytes / 4, / 2, then bucket_bytes).  Sharded mode: a bucket holds either GEMM
+        # modules only (reduce-scatter) or replicated modules only (all-reduce).
         n = len(arena.modules)
+        shardable = [self.sharded and arena._gemm_module(m) for m in arena.modules]
+        self.bucket_of, self.bucket_ranges, self.bucket_members, self.bucket_sharded = [], [], [], []
+        start_mod, start_off = 0, 0
         for i in range(n):
             end = arena.offsets[i + 1] if i + 1 < n else arena.total
-            cur = end - start_off
             self.bucket_of.append(len(self.bucket_ranges))
             limit = (bucket_bytes >> max(0, 2 - len(self.bucket_ranges))) // 4
-            if cur >= limit or i == n - 1:
+            last = i == n - 1
+            if end - start_off >= limit or last or shardable[i + 1] != shardable[i]:
                 self.bucket_ranges.append((start_off, end))
                 self.bucket_members.append(list(range(start_mod, i + 1)))
+                self.bucket_sharded.append(shardable[i])
                 start_mod, start_off = i + 1, end
         self._pending = None
         self._handles = []
@@ -284,11 +349,28 @@ class GradSync:
             m._sync = self
             m._sync_index = i
             m._calls_outstanding = 0
+        self._wm_stale = False        # non-owned slices of the masked operands are out of date (sharded mode)
+        self._scores_stale = False
+        self._gather = None           # per-bucket handles of the running operand all-gather
+        if self.sharded:
+            own = []
+            for (lo, hi), sh in zip(self.bucket_ranges, self.bucket_sharded):
+                if sh:
+                    assert (hi - lo) % (8 * self.world) == 0, "bucket does not split into 8-element aligned shards"
+                    s = (hi - lo) // self.world
+                    own.append((lo + self.rank * s, lo + (self.rank + 1) * s))
+            arena.install_shard(own, [i for i in range(n) if shardable[i]], [i for i in range(n) if not shardable[i]],
+                                self)
 
     # called by MaskedLinear1.forward in training mode: one more backward invocation is owed
     @staticmethod
     def note_forward(module):
         module._calls_outstanding = getattr(module, "_calls_outstanding", 0) + 1
+
+    def _own(self, b):
+        lo, hi = self.bucket_ranges[b]
+        s = (hi - lo) // self.world
+        return lo + self.rank * s, lo + (self.rank + 1) * s
 
     def begin_step(self):
         self._pending = [len(b) for b in self.bucket_members]
@@ -296,7 +378,100 @@ class GradSync:
         self._handles = []
         for m in self.arena.modules:
             m._calls_outstanding = 0
+        # a captured step graph must always contain the gather (replays follow optimiser passes), whatever the
+        # Python-side flag says at capture time
+        if self.sharded and self._gather is None and (self._wm_stale or torch.cuda.is_current_stream_capturing()):
+            self._start_operand_gather()
 
+    # -- sharded mode: masked operands ---------------------------------------------------------------------
+    def after_optimizer_step(self):
+        self._wm_stale = True
+        self._scores_stale = True
+
+    def operands_are_current(self):
+        """The whole masked-operand arena was just recomputed locally from current scores (refresh_masked)."""
+        self._wm_stale = False
+        self._gather = None
+
+    def _side_stream(self, device):
+        lane = ops.ds_lane(device)
+        if lane is None:
+            return None
+        lane.stream.wait_stream(torch.cuda.current_stream(device))
+        lane.open = True
+        return lane.stream
+
+    def _start_operand_gather(self):
+        """All-gather W (.) M of every sharded bucket, in execution order, on the side stream: the forward pass that
+        follows waits bucket by bucket (wait_operand)."""
+        wm = self.arena.wm
+        side = self._side_stream(wm.device)
+        ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+        self._gather = {}
+        with ctx:
+            for b, sh in enumerate(self.bucket_sharded):
+                if not sh:
+                    continue
+                lo, hi = self.bucket_ranges[b]
+                olo, ohi = self._own(b)
+                self._gather[b] = dist.all_gather_into_tensor(wm[lo:hi], wm[olo:ohi], group=self.group, async_op=True)
+
+    def wait_operand(self, module):
+        if self._gather is None:
+            if self._wm_stale:         # a forward outside the step protocol (evaluation): gather now
+                self._start_operand_gather()
+            else:
+                return
+        b = self.bucket_of[module._sync_index]
+        pending = [k for k in self._gather if k <= b]
+        for k in pending:              # handles complete in issue order; waiting marks the dependency on this stream
+            self._gather.pop(k).wait()
+        if not self._gather:
+            self._gather = None
+            self._wm_stale = False
+
+    def finish_operand_gather(self):
+        if self._gather is not None:
+            for k in sorted(self._gather):
+                self._gather.pop(k).wait()
+            self._gather = None
+            self._wm_stale = False
+
+    def sync_scores(self):
+        """All-gather the fp32 scores of the sharded buckets so that every rank holds every current score."""
+        if not (self.sharded and self._scores_stale):
+            return
+        sc = self.arena.scores
+        for b, sh in enumerate(self.bucket_sharded):
+            if sh:
+                lo, hi = self.bucket_ranges[b]
+                olo, ohi = self._own(b)
+                dist.all_gather_into_tensor(sc[lo:hi], sc[olo:ohi], group=self.group)
+        self._scores_stale = False
+
+    def make_consistent(self):
+        """Everything another consumer (evaluation, checkpoint, mask export) may read is current on this rank."""
+        if self.sharded:
+            if self._wm_stale and self._gather is None:
+                self._start_operand_gather()
+            self.finish_operand_gather()
+            self.sync_scores()
+
+    def global_sumsq(self, loose_grads):
+        """Sum of squares of the full mean gradient (clip_grad_norm_): own slices summed over ranks + replicated
+        modules + loose tensors (identical on every rank)."""
+        a = self.arena
+        acc = torch.zeros((), dtype=torch.float32, device=a.grads.device)
+        a._step_chunk_table()
+        ops.sumsq_segmented_into(a.grads, a.shard["own_chunks"], acc)
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+        ops.sumsq_segmented_into(a.grads, a.shard["rep_chunks"], acc)
+        for g in loose_grads:
+            if g is not None:
+                ops.sumsq_into(g.contiguous(), acc)
+        return acc
+
+    # -- gradient exchange -------------------------------------------------------------------------------------
     def _launch(self, b):
         if self._sent[b]:
             return
@@ -305,9 +480,9 @@ class GradSync:
             return
         lo, hi = self.bucket_ranges[b]
         view = self.arena.grads[lo:hi]
-        # The bucket's dS GEMMs run on the dS lane.  Issue the collective FROM the lane (ordered after the current
-        # stream as well, for the few gradients written there): NCCL then waits for exactly the work that
-        # produced the bucket, and the dX chain on the current stream is not held up at bucket boundaries.
+        # The bucket's dS GEMMs may run on the dS lane.  Issue the collective FROM the lane (ordered after the current
+        # stream as well): NCCL then waits for exactly the work that produced the bucket, and the dX chain on the
+        # current stream is not held up at bucket boundaries.
         lane = ops.ds_lane(view.device) if view.is_cuda else None
         if lane is not None:
             lane.stream.wait_stream(torch.cuda.current_stream(view.device))
@@ -315,7 +490,11 @@ class GradSync:
         else:
             ctx = contextlib.nullcontext()
         with ctx:
-            if dist.get_backend(self.group) == "nccl":
+            if self.sharded and self.bucket_sharded[b]:
+                olo, ohi = self._own(b)
+                self._handles.append(dist.reduce_scatter_tensor(self.arena.grads[olo:ohi], view, op=dist.ReduceOp.AVG,
+                                                                group=self.group, async_op=True))
+            elif dist.get_backend(self.group) == "nccl":
                 self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
             else:
                 h = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -338,6 +517,7 @@ class GradSync:
     def finish(self, loose=()):
         """After backward: zero-fill untouched modules, send what is left, all-reduce the loose
         (classifier) gradients as one flat message, and wait for everything."""
+        self.finish_operand_gather()     # a forward that skipped modules leaves their buckets' gathers un-awaited
         self.arena.finalize_grads()
         if self._sent is None:
             self.begin_step()
@@ -359,6 +539,17 @@ class GradSync:
                     h[1].div_(self.world)
                 else:
                     h.wait()
+            if self.sharded and not self.arena.keep_grads:
+                # the reduce-scatter left partial sums in the slices this rank does not own; the optimiser pass clears
+                # only what it updates, and next step's split score-gradient GEMMs reduce-add into zeros
+                for b, sh in enumerate(self.bucket_sharded):
+                    if sh:
+                        lo, hi = self.bucket_ranges[b]
+                        olo, ohi = self._own(b)
+                        if olo > lo:
+                            self.arena.grads[lo:olo].zero_()
+                        if hi > ohi:
+                            self.arena.grads[ohi:hi].zero_()
         self._handles = []
         self._pending = None
 

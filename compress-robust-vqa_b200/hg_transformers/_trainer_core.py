@@ -220,6 +220,8 @@ class TrainerCore:
         mods = masked_modules_of(model)
         if not mods:
             return float("nan")
+        if getattr(self, "grad_sync", None) is not None:
+            self.grad_sync.sync_scores()          # sharded optimiser: every rank selects over every current score
         if self.threshold_mode == "union":
             return self._reset_threshold_union(mods, init_sparsity)
         ks = []
@@ -287,6 +289,8 @@ class TrainerCore:
     def save_model_mask(self, output_dir: Optional[str] = None):
         """mask.pt = {module_name + '.weight': BoolTensor(cpu)}; returns the overall zero rate in percent
         (reference mask_trainer_VQA.py:930-949; per-modality logging of mask_trainer_Robust_VQA.py:943-991)."""
+        if getattr(self, "grad_sync", None) is not None:
+            self.grad_sync.make_consistent()
         mask_dict = {}
         zeros = {"all": 0, "Lang": 0, "Vis": 0, "Fus": 0, "P": 0}
         elems = dict(zeros)
@@ -377,7 +381,9 @@ class TrainerCore:
     def _clip_and_optimizer_step(self, model, optimizer):
         """clip_grad_norm_(max_grad_norm) + optimizer.step() (reference :646-653): device work only."""
         max_norm = self.args.max_grad_norm
-        if self.arena is not None and hasattr(optimizer, "set_clip"):
+        if self.grad_sync is not None and self.grad_sync.sharded and hasattr(optimizer, "set_clip"):
+            optimizer.set_clip(self.grad_sync.global_sumsq([p.grad for p in self._loose_params()]), max_norm)
+        elif self.arena is not None and hasattr(optimizer, "set_clip"):
             sumsq = torch.zeros((), dtype=torch.float32, device=self.args.device)
             self.arena.grad_sumsq_into(sumsq)
             for p in self._loose_params():
@@ -504,6 +510,8 @@ class TrainerCore:
                 break
         if self.tb_writer:
             self.tb_writer.close()
+        if self.grad_sync is not None:
+            self.grad_sync.make_consistent()      # sharded optimiser: leave every rank with the full final state
         logger.info("\n\nTraining completed.\n\n")
         return (TrainOutput(self.global_step, float(tr_loss) / max(1, self.global_step)), best_eval_loss, best_score,
                 results_at_best_score)
@@ -607,6 +615,8 @@ class TrainerCore:
     def _prediction_loop(self, dataloader: DataLoader, description: str,
                          prediction_loss_only: Optional[bool] = None) -> PredictionOutput:
         prediction_loss_only = prediction_loss_only if prediction_loss_only is not None else self.prediction_loss_only
+        if getattr(self, "grad_sync", None) is not None:
+            self.grad_sync.make_consistent()
         model = self.model
         logger.info("***** Running %s *****", description)
         logger.info("  Num examples = %d", self.num_examples(dataloader))

@@ -245,6 +245,9 @@ int crv_rng_advance(unsigned long long* rng_state, void* stream);
 /* Optimiser ("next" row f1; hg_transformers/mask_trainer_VQA.py:646-659 + optimization.py:66-129) */
 /* sum of squares of n floats accumulated into *out (device, fp32; caller zeroes it) */
 int crv_sumsq(const float* x, int64_t n, float* out, void* stream);
+/* the same over the chunks {start / 8, length, -, -} of a table: the gradient shard one rank owns when the optimiser
+ * state is sharded across data-parallel ranks */
+int crv_sumsq_segmented(const float* x, const int* chunks, int nchunks, float* out, void* stream);
 /* One AdamW step of the reference optimiser on a flat fp32 segment, with the clip coefficient of
  * torch.nn.utils.clip_grad_norm_ folded in:  g' = g * min(1, max_norm / (sqrt(*total_sumsq) + 1e-6));
  * sum += |g'|; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= step_size * m / (sqrt(v) + eps);

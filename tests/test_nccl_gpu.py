@@ -71,11 +71,28 @@ def _run(trainer, model, opt, sched, rank, world, graph):
             sched.step()
         if step == 0:
             torch.cuda.synchronize()
-            first_grads = trainer.arena.grads.detach().cpu().clone()
+            first_grads = _assembled_grads(trainer)
     trainer.reset_threshold(model, 0.7)
+    if trainer.grad_sync is not None:
+        trainer.grad_sync.make_consistent()
     torch.cuda.synchronize()
     arena = trainer.arena
     return first_grads, arena.scores.detach().cpu().clone(), arena.thr_vec.detach().cpu().clone()
+
+
+def _assembled_grads(trainer):
+    """The exchanged (mean) gradient of the whole arena on this rank.  Sharded optimiser: a rank holds the mean only
+    for the slices it owns (reduce-scatter), so the owned slices are all-gathered into a copy."""
+    import torch.distributed as dist
+    g = trainer.arena.grads.detach().clone()
+    sync = trainer.grad_sync
+    if sync is not None and sync.sharded:
+        for b, sh in enumerate(sync.bucket_sharded):
+            if sh:
+                lo, hi = sync.bucket_ranges[b]
+                olo, ohi = sync._own(b)
+                dist.all_gather_into_tensor(g[lo:hi], g[olo:ohi].clone())
+    return g.cpu()
 
 
 def _worker(rank, world, port, tmp, out_path, graph):
@@ -112,11 +129,12 @@ def _worker(rank, world, port, tmp, out_path, graph):
         os._exit(0) if graph else dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_two_gpu_nccl_matches_ddp_semantics(tmp_path, graph):
+@pytest.mark.parametrize("graph,mode", [(False, "sharded"), (True, "sharded"), (False, "allreduce")])
+def test_two_gpu_nccl_matches_ddp_semantics(tmp_path, graph, mode, monkeypatch):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
+    monkeypatch.setenv("CRVQA_DP", mode)          # inherited by the spawned ranks
     out = str(tmp_path / "res")
     ctx = mp.get_context("spawn")
     port = _free_port()
@@ -134,7 +152,7 @@ def test_two_gpu_nccl_matches_ddp_semantics(tmp_path, graph):
     # exchanged gradient == mean of the per-rank gradients (split-K reduce order differs run to run: 1e-5 norm-wise)
     num = float((r0["grads"] - r0["mean_local"]).double().norm())
     den = float(r0["mean_local"].double().norm())
-    print(f"[nccl graph={graph}] exchanged vs mean-of-local gradient: {num / den:.3e}")
+    print(f"[nccl graph={graph} {mode}] exchanged vs mean-of-local gradient: {num / den:.3e}")
     assert num / den < 1e-4
     # 1 GPU on the same GLOBAL batch: same thresholds / masks up to bf16 tiling noise of the gradients
     os.environ["CRVQA_CUDA_GRAPH"] = "0"
