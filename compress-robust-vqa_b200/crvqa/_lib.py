@@ -58,10 +58,11 @@ _PROTOS = {
     "crv_gelu_fwd": (c_int, [_P, _P, c_int64, _P]),
     "crv_gelu_bwd": (c_int, [_P, _P, _P, c_int64, _P]),
     "crv_rng_advance": (c_int, [_P, _P]),
-    "crv_sumsq": (c_int, [_P, c_int64, _P, _P]),
+    "crv_sumsq_workspace_bytes": (c_size_t, []),
+    "crv_sumsq": (c_int, [_P, c_int64, _P, _P, _P]),
     "crv_adamw_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float,
                                c_float, _P, c_float, _P, _P]),
-    "crv_sumsq_segmented": (c_int, [_P, _P, c_int, _P, _P]),
+    "crv_sumsq_segmented": (c_int, [_P, _P, c_int, _P, _P, _P]),
     "crv_adamw_segmented": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_float, c_float, c_float, c_float, c_float,
                                     c_float, _P, c_float, _P, c_int, _P]),
 }

@@ -627,13 +627,26 @@ def vqa_loss_lmh(logits, bias, labels, factor_pre, smooth, w):
 
 
 # ----------------------------------------------------------------------------- optimiser pieces
+_sumsq_ws = {}
+
+
+def _sumsq_workspace(device):
+    """Per-device scratch of the deterministic sum of squares (zeroed once; the kernels leave it zeroed)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _sumsq_ws.get(key)
+    if ws is None:
+        ws = _sumsq_ws[key] = torch.zeros(lib.crv_sumsq_workspace_bytes() // 4, dtype=torch.float32, device=device)
+    return ws
+
+
 def sumsq_into(x, acc):
-    check(lib.crv_sumsq(_p(x), x.numel(), _p(acc), _stream()), "crv_sumsq")
+    check(lib.crv_sumsq(_p(x), x.numel(), _p(acc), _p(_sumsq_workspace(x.device)), _stream()), "crv_sumsq")
 
 
 def sumsq_segmented_into(x, chunks, acc):
     if chunks.shape[0]:
-        check(lib.crv_sumsq_segmented(_p(x), _p(chunks), chunks.shape[0], _p(acc), _stream()), "crv_sumsq_segmented")
+        check(lib.crv_sumsq_segmented(_p(x), _p(chunks), chunks.shape[0], _p(acc), _p(_sumsq_workspace(x.device)),
+                                      _stream()), "crv_sumsq_segmented")
 
 
 def adam_step_size(lr, step, beta1, beta2, correct_bias=True):

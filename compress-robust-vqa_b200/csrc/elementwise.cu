@@ -157,7 +157,42 @@ __global__ void magnitude_init_kernel(const float* __restrict__ w, const float* 
   }
 }
 
-__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+// Block partials -> *out in a FIXED order: every rank of a data-parallel job must get the same bits (the clip
+// coefficient feeds every update; a float atomicAdd per block would make it depend on block scheduling).  Each block
+// publishes its partial in `ws`; the block that arrives last (ticket in ws[0]) adds them up in index order.
+__device__ __forceinline__ void sumsq_finish(float acc, float* __restrict__ ws, float* __restrict__ out) {
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float wsum[kThreads / 32];
+  __shared__ bool last;
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) t += wsum[w];
+    ws[1 + blockIdx.x] = t;
+    __threadfence();
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(ws), 1u);
+    last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    // fixed-shape tree over the partials: thread i sums i, i + 256, ... ; then the block tree above
+    float t = 0.f;
+    for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += __ldcg(ws + 1 + i);
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float total = 0.f;
+      for (int w = 0; w < kThreads / 32; ++w) total += wsum[w];
+      *out += total;
+      *reinterpret_cast<unsigned*>(ws) = 0u;      // ready for the next launch
+    }
+  }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out, float* __restrict__ ws) {
   const int64_t nvec = n >> 2;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   float acc = 0.f;
@@ -169,20 +204,12 @@ __global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __re
     const float v = x[(nvec << 2) + threadIdx.x];
     acc += v * v;
   }
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  __shared__ float wsum[kThreads / 32];
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < kThreads / 32; ++w) t += wsum[w];
-    atomicAdd(out, t);
-  }
+  sumsq_finish(acc, ws, out);
 }
 
 // sum of squares over the chunks of a table (the gradient shard a rank owns under the sharded optimiser)
 __global__ void sumsq_segmented_kernel(const float* __restrict__ x, const int4* __restrict__ chunks, int nchunks,
-                                       float* __restrict__ out) {
+                                       float* __restrict__ out, float* __restrict__ ws) {
   float acc = 0.f;
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const int4 ch = __ldg(chunks + c);
@@ -194,15 +221,7 @@ __global__ void sumsq_segmented_kernel(const float* __restrict__ x, const int4* 
     }
     for (int i = (nvec << 2) + threadIdx.x; i < ch.y; i += blockDim.x) acc += x[base + i] * x[base + i];
   }
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  __shared__ float wsum[kThreads / 32];
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < kThreads / 32; ++w) t += wsum[w];
-    atomicAdd(out, t);
-  }
+  sumsq_finish(acc, ws, out);
 }
 
 struct AdamArgs {
@@ -509,21 +528,25 @@ extern "C" int crv_magnitude_init(const float* w, const float* w_thr, float hi, 
   return launch_status();
 }
 
-extern "C" int crv_sumsq(const float* x, int64_t n, float* out, void* stream) {
-  if (!x || !out || n < 0) return CRV_E_BADARG;
+extern "C" size_t crv_sumsq_workspace_bytes(void) { return (1 + 8 * 148 * 2) * sizeof(float); }
+
+extern "C" int crv_sumsq(const float* x, int64_t n, float* out, void* workspace, void* stream) {
+  if (!x || !out || !workspace || n < 0) return CRV_E_BADARG;
   if (n == 0) return CRV_OK;
   if (!aligned16(x)) return CRV_E_ALIGN;
-  sumsq_kernel<<<stream_grid(n >> 2, 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out);
+  sumsq_kernel<<<stream_grid(n >> 2, 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, n, out, static_cast<float*>(workspace));
   return launch_status();
 }
 
-extern "C" int crv_sumsq_segmented(const float* x, const int* chunks, int nchunks, float* out, void* stream) {
-  if (!x || !chunks || !out || nchunks < 0) return CRV_E_BADARG;
+extern "C" int crv_sumsq_segmented(const float* x, const int* chunks, int nchunks, float* out, void* workspace,
+                                   void* stream) {
+  if (!x || !chunks || !out || !workspace || nchunks < 0) return CRV_E_BADARG;
   if (nchunks == 0) return CRV_OK;
   if (!aligned16(x) || !aligned16(chunks)) return CRV_E_ALIGN;
   const int grid = nchunks < num_sms() * 4 ? nchunks : num_sms() * 4;
   sumsq_segmented_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, reinterpret_cast<const int4*>(chunks), nchunks, out);
+      x, reinterpret_cast<const int4*>(chunks), nchunks, out, static_cast<float*>(workspace));
   return launch_status();
 }
 

@@ -629,6 +629,7 @@ class GraphedStep:
                 self.optimizer.ensure_state()
             from crvqa.fused import RngState
             RngState.get(dev)
+            ops._sumsq_workspace(torch.device(dev))
             self.shapes = self._shape_key(inputs)
             self.static_inputs = list(inputs)
             for i in self.TENSOR_SLOTS:

@@ -243,11 +243,15 @@ int crv_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du, int64_t n,
 int crv_rng_advance(unsigned long long* rng_state, void* stream);
 
 /* Optimiser ("next" row f1; hg_transformers/mask_trainer_VQA.py:646-659 + optimization.py:66-129) */
-/* sum of squares of n floats accumulated into *out (device, fp32; caller zeroes it) */
-int crv_sumsq(const float* x, int64_t n, float* out, void* stream);
+/* sum of squares of n floats accumulated into *out (device, fp32; caller zeroes it).  DETERMINISTIC: block partials
+ * are added in a fixed order (the last-arriving block sums them by index), so every data-parallel rank derives the
+ * same clip coefficient bit for bit.  workspace: crv_sumsq_workspace_bytes() bytes, ZEROED ONCE by the caller before
+ * its first use and then owned by these calls (launches sharing a workspace must be stream-ordered). */
+size_t crv_sumsq_workspace_bytes(void);
+int crv_sumsq(const float* x, int64_t n, float* out, void* workspace, void* stream);
 /* the same over the chunks {start / 8, length, -, -} of a table: the gradient shard one rank owns when the optimiser
  * state is sharded across data-parallel ranks */
-int crv_sumsq_segmented(const float* x, const int* chunks, int nchunks, float* out, void* stream);
+int crv_sumsq_segmented(const float* x, const int* chunks, int nchunks, float* out, void* workspace, void* stream);
 /* One AdamW step of the reference optimiser on a flat fp32 segment, with the clip coefficient of
  * torch.nn.utils.clip_grad_norm_ folded in:  g' = g * min(1, max_norm / (sqrt(*total_sumsq) + 1e-6));
  * sum += |g'|; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= step_size * m / (sqrt(v) + eps);
