@@ -281,7 +281,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 // and, optionally, clears the gradient after consuming it (model.zero_grad() of the reference loop,
 // hg_transformers/mask_trainer_VQA.py:659) so that next step's split-K score-gradient GEMMs reduce-add into zeros
 // without a memset per module.  chunks = {start / 8, length, segment, flags}; flags bit 0 = segment has a bf16
-// operand to refresh.  40 B per score: p, g, m, v, sum read; p, m, v, sum (+ g) written; W16 read, Wm written.
+// operand to refresh, bit 1 = clear-only chunk (a slice owned by another data-parallel rank).  40 B per score: p, g, m, v, sum read; p, m, v, sum (+ g) written; W16 read, Wm written.
 __global__ void __launch_bounds__(kThreads)
 adamw_segmented_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                        float* __restrict__ sum, const int4* __restrict__ chunks, int nchunks,
@@ -303,6 +303,14 @@ adamw_segmented_kernel(float* __restrict__ p, float* __restrict__ g, float* __re
     const bool has_wm = (ch.w & 1) != 0;
     const int64_t base = static_cast<int64_t>(ch.x) * 8;
     const int nvec = ch.y >> 3;
+    if (ch.w & 2) {      // a slice another rank owns (sharded optimiser): nothing to update, only the gradient to clear
+      if (zero_grad) {
+        for (int i = threadIdx.x; i < 2 * nvec; i += blockDim.x)
+          reinterpret_cast<float4*>(g + base)[i] = make_float4(0, 0, 0, 0);
+        for (int i = (nvec << 3) + threadIdx.x; i < ch.y; i += blockDim.x) g[base + i] = 0.f;
+      }
+      continue;
+    }
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
       const int64_t e = base + static_cast<int64_t>(i) * 8;
       float4 pp[2], gg[2], mm[2], vv[2], ss[2];

@@ -172,7 +172,7 @@ class ScoreArena:
         self._step_chunk_table()    # built now: a CUDA-graph capture of the step must not create it
         self.refresh_masked()
 
-    def _chunk_rows(self, ranges=None, modules=None):
+    def _chunk_rows(self, ranges=None, modules=None, extra_flags=0):
         """{start / 8, length, segment, flags} rows (flags bit 0: the segment has a bf16 operand) over whole modules
         (`modules`: indices, default all) or over the parts of the modules inside `ranges` (element intervals whose
         bounds are multiples of 8)."""
@@ -185,7 +185,7 @@ class ScoreArena:
             spans = [(off, off + n)] if ranges is None else [(max(off, lo), min(off + n, hi)) for lo, hi in ranges]
             for lo, hi in spans:
                 for c0 in range(lo, hi, 8192):
-                    rows.append((c0 // 8, min(8192, hi - c0), i, flag))
+                    rows.append((c0 // 8, min(8192, hi - c0), i, flag | extra_flags))
         if not rows:
             return torch.zeros((0, 4), dtype=torch.int32, device=self.scores.device)
         return torch.tensor(rows, dtype=torch.int32, device=self.scores.device).contiguous()
@@ -200,13 +200,15 @@ class ScoreArena:
                 own = self._chunk_rows(ranges=self.shard["own"], modules=self.shard["sharded_modules"])
                 rep = self._chunk_rows(modules=self.shard["replicated_modules"])
                 self.shard["own_chunks"], self.shard["rep_chunks"] = own, rep
-                self.step_chunks = torch.cat([own, rep]).contiguous()
+                # slices other ranks own: clear-only rows (their gradient holds reduce-scatter leftovers)
+                other = self._chunk_rows(ranges=self.shard["other"], modules=self.shard["sharded_modules"], extra_flags=2)
+                self.step_chunks = torch.cat([own, rep, other]).contiguous()
         return self.step_chunks
 
-    def install_shard(self, own_ranges, sharded_modules, replicated_modules, sync):
+    def install_shard(self, own_ranges, other_ranges, sharded_modules, replicated_modules, sync):
         """GradSync (sharded mode): this rank updates only `own_ranges` of the sharded modules; their masked operands
         reach the other ranks by all-gather before first use (wait_ready), their scores on demand (sync.sync_scores)."""
-        self.shard = {"own": own_ranges, "sharded_modules": set(sharded_modules),
+        self.shard = {"own": own_ranges, "other": other_ranges, "sharded_modules": set(sharded_modules),
                       "replicated_modules": set(replicated_modules), "sync": sync}
         self.step_chunks = None
         self._step_chunk_table()
@@ -236,8 +238,7 @@ class ScoreArena:
         """The module's W (.) M if it is valid for the current scores and threshold, else None."""
         if (self.cache_on and getattr(m, "_wm_epoch", -1) == self.epoch and m.weight_mask._version == m._wm_sver
                 and torch.is_tensor(m.threshold) and m.threshold.data_ptr() == m._wm_thr_ptr):
-            self.wait_ready(m)
-            return m._wm
+            return m._wm          # callers that READ it on a stream call wait_ready(m) first (sharded optimiser)
         return None
 
     # -- per-step protocol ---------------------------------------------------------------------
@@ -353,14 +354,16 @@ class GradSync:
         self._scores_stale = False
         self._gather = None           # per-bucket handles of the running operand all-gather
         if self.sharded:
-            own = []
+            own, other = [], []
             for (lo, hi), sh in zip(self.bucket_ranges, self.bucket_sharded):
                 if sh:
                     assert (hi - lo) % (8 * self.world) == 0, "bucket does not split into 8-element aligned shards"
                     s = (hi - lo) // self.world
-                    own.append((lo + self.rank * s, lo + (self.rank + 1) * s))
-            arena.install_shard(own, [i for i in range(n) if shardable[i]], [i for i in range(n) if not shardable[i]],
-                                self)
+                    olo, ohi = lo + self.rank * s, lo + (self.rank + 1) * s
+                    own.append((olo, ohi))
+                    other += [r for r in ((lo, olo), (ohi, hi)) if r[1] > r[0]]
+            arena.install_shard(own, other, [i for i in range(n) if shardable[i]],
+                                [i for i in range(n) if not shardable[i]], self)
 
     # called by MaskedLinear1.forward in training mode: one more backward invocation is owed
     @staticmethod
@@ -539,17 +542,8 @@ class GradSync:
                     h[1].div_(self.world)
                 else:
                     h.wait()
-            if self.sharded and not self.arena.keep_grads:
-                # the reduce-scatter left partial sums in the slices this rank does not own; the optimiser pass clears
-                # only what it updates, and next step's split score-gradient GEMMs reduce-add into zeros
-                for b, sh in enumerate(self.bucket_sharded):
-                    if sh:
-                        lo, hi = self.bucket_ranges[b]
-                        olo, ohi = self._own(b)
-                        if olo > lo:
-                            self.arena.grads[lo:olo].zero_()
-                        if hi > ohi:
-                            self.arena.grads[ohi:hi].zero_()
+            # (the reduce-scatter leaves partial sums in the slices this rank does not own; the optimiser pass clears
+            # them through its clear-only chunk rows, ScoreArena._step_chunk_table)
         self._handles = []
         self._pending = None
 

@@ -409,6 +409,8 @@ class MaskedLinear1(MaskedLinearX):
             return ops.MaskedLinearSmallKFn.apply(x, self.weight_mask, self.weight, thr, self.bias, sink)
         arena = getattr(self, "_arena", None)
         wm = arena.cached_masked_weight(self) if arena is not None else self._held_masked_weight(thr)
+        if arena is not None and wm is not None:
+            arena.wait_ready(self)       # sharded optimiser: this module's operand all-gather has landed
         w32 = self.weight if self.weight.dtype == torch.float32 and self.weight.is_contiguous() else None
         return ops.MaskedLinearFn.apply(x, self.weight_mask, self._weight_bf16(), thr, self.bias, sink, wm, w32)
 

@@ -269,7 +269,8 @@ int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int
  * consuming it (the reference loop's model.zero_grad(), hg_transformers/mask_trainer_VQA.py:659), which lets the next
  * step's split score-gradient GEMMs reduce-add without a memset per module (accumulate = CRV_DS_ZEROED).
  * chunks = nchunks x int4 {start / 8, length, segment, flags} (device; no chunk straddles a segment; flags bit 0:
- * the segment has a bf16 operand); w_bf16 / wm_bf16 may both be NULL (no operand refresh). */
+ * the segment has a bf16 operand; bit 1: clear-only chunk -- under the sharded data-parallel optimiser a slice owned
+ * by another rank, whose gradient buffer holds reduce-scatter leftovers); w_bf16 / wm_bf16 may both be NULL. */
 int crv_adamw_segmented(float* p, float* g, float* m, float* v, float* sum, const int* chunks, int nchunks,
                         const float* thr_vec, const uint16_t* w_bf16, uint16_t* wm_bf16, float lr, float step_size,
                         float beta1, float beta2, float eps, float weight_decay, const float* total_sumsq,
