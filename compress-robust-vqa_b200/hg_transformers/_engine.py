@@ -353,6 +353,11 @@ class GradSync:
         self._wm_stale = False        # non-owned slices of the masked operands are out of date (sharded mode)
         self._scores_stale = False
         self._gather = None           # per-bucket handles of the running operand all-gather
+        # Replicated buckets (the 94 MB word-embedding gradient) and the loose tensors travel on a SECOND communicator:
+        # the embedding gradient is complete only when the backward pass is almost over, and on one communicator the
+        # small reduce-scatters of the first layers would queue behind its all-reduce at the very end of the step.
+        self.group_rep = dist.new_group(backend="nccl") if self.sharded else group
+        self._loose, self._loose_left, self._loose_work = [], 0, None
         if self.sharded:
             own, other = [], []
             for (lo, hi), sh in zip(self.bucket_ranges, self.bucket_sharded):
@@ -375,10 +380,39 @@ class GradSync:
         s = (hi - lo) // self.world
         return lo + self.rank * s, lo + (self.rank + 1) * s
 
+    def attach_loose(self, params):
+        """Loose trainable tensors (the answer head): their gradients are complete at the START of the backward pass,
+        so their all-reduce is issued from a post-accumulate hook and overlaps everything that follows."""
+        if not (self.sharded and hasattr(torch.Tensor, "register_post_accumulate_grad_hook")):
+            return
+        self._loose = [p for p in params]
+
+        def hook(_p):
+            if self._pending is None or self.defer:
+                return
+            self._loose_left -= 1
+            if self._loose_left == 0:
+                self._launch_loose()
+        for p in self._loose:
+            p.register_post_accumulate_grad_hook(hook)
+
+    def _launch_loose(self):
+        grads = [p.grad for p in self._loose if p.grad is not None]
+        if not grads:
+            return
+        dev = grads[0].device
+        side = self._side_stream(dev)
+        ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+        with ctx:
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group_rep, async_op=True)
+        self._loose_work = (work, flat, grads)
+
     def begin_step(self):
         self._pending = [len(b) for b in self.bucket_members]
         self._sent = [False] * len(self.bucket_ranges)
         self._handles = []
+        self._loose_left, self._loose_work = len(self._loose), None
         for m in self.arena.modules:
             m._calls_outstanding = 0
         # a captured step graph must always contain the gather (replays follow optimiser passes), whatever the
@@ -498,7 +532,7 @@ class GradSync:
                 self._handles.append(dist.reduce_scatter_tensor(self.arena.grads[olo:ohi], view, op=dist.ReduceOp.AVG,
                                                                 group=self.group, async_op=True))
             elif dist.get_backend(self.group) == "nccl":
-                self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+                self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group_rep, async_op=True))
             else:
                 h = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
                 self._handles.append((h, view))
@@ -528,7 +562,15 @@ class GradSync:
             self._launch(b)
         if self.enabled:
             loose = [g for g in loose if g is not None]
-            if loose:
+            if self._loose_work is not None:      # issued from the gradient hooks at the start of the backward pass
+                work, flat, grads = self._loose_work
+                work.wait()
+                off = 0
+                for g in grads:
+                    g.copy_(flat[off: off + g.numel()].view_as(g))
+                    off += g.numel()
+                self._loose_work = None
+            elif loose:
                 flat = torch.cat([g.reshape(-1) for g in loose])
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
                 flat.div_(self.world)

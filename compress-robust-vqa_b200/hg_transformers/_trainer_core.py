@@ -336,6 +336,7 @@ class TrainerCore:
             optimizer.attach_arena(self.arena)
         self.grad_sync = GradSync(self.arena)
         self.grad_sync.defer = self.args.gradient_accumulation_steps > 1
+        self.grad_sync.attach_loose(self._loose_params())
 
     def _prefetched(self, dataloader):
         """Yield batches whose host -> device copy was started one step ahead on a side stream."""
