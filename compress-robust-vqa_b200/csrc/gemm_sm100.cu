@@ -1069,6 +1069,20 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// SMs the persistent GEMM grids may occupy.  Default: all.  CRVQA_GEMM_SMS=n (even) leaves the rest to whatever runs
+// beside the GEMMs -- in data-parallel runs the NCCL kernels of the gradient exchange, whose CTAs cannot share an SM
+// with a 227 KB GEMM CTA and would otherwise delay the tiles statically assigned to the SMs they grab.
+static int gemm_sms() {
+  static const int n = [] {
+    const char* e = getenv("CRVQA_GEMM_SMS");
+    int v = e ? atoi(e) : 0;
+    const int all = num_sms();
+    if (v <= 0 || v > all) v = all;
+    return v & ~1;
+  }();
+  return n;
+}
+
 // 2-D row-major tensor [rows][cols] of elem_bytes elements; box = [box_rows][box_cols], 128B swizzle.
 static int make_map(CUtensorMap* map, const void* base, int elem_bytes, bool is_float, int64_t rows, int64_t cols,
                     int box_rows, int box_cols) {
@@ -1108,7 +1122,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   p.num_n = (p.NN + BN - 1) / BN;
   p.dbg = g_dbg;
   const int tiles = p.num_m * p.num_n * p.splits;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int grid = tiles < gemm_sms() ? tiles : gemm_sms();
   CRV_CUDA(launch_pdl(kern, dim3(grid), dim3(XFORM ? 320 : 192), L::kTotal, stream, tmA, tmB, tmS, tmOut, p));
   return launch_status();
 }
@@ -1127,7 +1141,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   p.num_n = (p.NN + 255) / 256;
   p.dbg = nullptr;
   const int tiles = p.num_m * p.num_n * p.splits;
-  const int max_pairs = num_sms() / 2;
+  const int max_pairs = gemm_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
@@ -1158,7 +1172,7 @@ static int pick_bn(int MM, int NN) {
   if (NN % 256) return 128;
   static const int forced = [] { const char* e = getenv("CRVQA_BN"); return e ? atoi(e) : 0; }();
   if (forced == 128 || forced == 256) return forced;
-  const int sms = num_sms();
+  const int sms = gemm_sms();
   const int mt = (MM + BM - 1) / BM;
   const int t256 = mt * (NN / 256), t128 = mt * ((NN + 127) / 128);
   const int c256 = ((t256 + sms - 1) / sms) * 256, c128 = ((t128 + sms - 1) / sms) * 128;
@@ -1265,7 +1279,7 @@ extern "C" int crv_masked_linear_bwd_ds(const uint16_t* dy, const uint16_t* x, c
   const bool two = use_2cta(N, K);
   const int bn = (K % 256 == 0) ? 256 : 128;
   const int tiles = two ? ((N + 255) / 256) * (K / 256) : ((N + BM - 1) / BM) * ((K + bn - 1) / bn);
-  int splits = (two ? num_sms() / 2 : num_sms()) / tiles;
+  int splits = (two ? gemm_sms() / 2 : gemm_sms()) / tiles;
   const int max_splits = (num_kb + 7) / 8;  // keep >= 8 k-blocks per split
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -1371,7 +1385,7 @@ static int launch_group_t(GArgs& g, cudaStream_t stream) {
     CRV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  const int max_pairs = num_sms() / 2;
+  const int max_pairs = gemm_sms() / 2;
   const int pairs = g.total_tiles < max_pairs ? g.total_tiles : max_pairs;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
@@ -1430,7 +1444,7 @@ extern "C" int crv_masked_gemm_grouped(const crv_gemm_problem* pr, int count, vo
         (q.w_f32 && !aligned16(q.w_f32)))
       return CRV_E_ALIGN;
   }
-  const int pairs = num_sms() / 2;
+  const int pairs = gemm_sms() / 2;
   int i = 0;
   while (i < count) {
     if (!group_eligible(pr[i])) {
