@@ -47,6 +47,7 @@ _PROTOS = {
     "crv_vqa_loss_workspace_bytes": (c_size_t, [c_int]),
     "crv_vqa_loss_bce": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P]),
     "crv_vqa_loss_lpf": (c_int, [_P, _P, _P, c_float, _P, _P, _P, c_int, c_int, _P, _P]),
+    "crv_vqa_loss_rubi": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P]),
     "crv_vqa_loss_lmh": (c_int, [_P, _P, _P, _P, c_float, c_float, _P, _P, _P, c_int, c_int, _P, _P]),
     "crv_ln_fwd": (c_int, [_P, c_int, _P, _P, _P, c_float, c_float, _P, c_int, _P, _P, _P, _P, c_int, c_int, _P]),
     "crv_ln_bwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P, c_float, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),

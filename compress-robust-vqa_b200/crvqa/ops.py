@@ -583,6 +583,11 @@ class _FusedLoss(torch.autograd.Function):
             check(lib.crv_vqa_loss_lpf(_p(lg), _p(bias.contiguous()), _p(max_label.contiguous()), float(gamma),
                                        _p(out), _p(labels.contiguous() if labels is not None else None), _p(dl),
                                        B, A, _p(ws), _stream()), "crv_vqa_loss_lpf")
+        elif kind == "rubi":
+            bias, max_label, labels = args
+            check(lib.crv_vqa_loss_rubi(_p(lg), _p(bias.contiguous()), _p(max_label.contiguous()), _p(out),
+                                        _p(labels.contiguous() if labels is not None else None), _p(dl), B, A, _p(ws),
+                                        _stream()), "crv_vqa_loss_rubi")
         elif kind == "lmh":
             bias, labels, factor_pre, smooth, w = args
             fp = factor_pre.detach().contiguous().float().view(-1)
@@ -619,6 +624,18 @@ def vqa_loss_bce(logits, labels):
 def vqa_loss_lpf(logits, bias, max_label, gamma, labels=None):
     """LPF_loss (mask_trainer_VQA.py:111-129) + VQA score (needs labels)."""
     return _FusedLoss.apply("lpf", logits, bias, max_label, gamma, labels)
+
+
+def vqa_loss_rubi(logits, bias, max_label, labels=None):
+    """RUBI_loss (mask_trainer_VQA.py:131-135) + VQA score (needs labels)."""
+    return _FusedLoss.apply("rubi", logits, bias, max_label, labels)
+
+
+def vqa_loss_bias_product(logits, bias, labels, smooth):
+    """BiasProduct (vqa_debias_loss_functions.py:83-122) = the LearnedMixin expression with factor 1 and no entropy
+    term: the LMH kernel with a constant pre-softplus factor log(e - 1)."""
+    fp = torch.full((logits.shape[0], 1), 0.5413248546129181, dtype=torch.float32, device=logits.device)
+    return _FusedLoss.apply("lmh", logits, bias, labels, fp, smooth, 0.0)
 
 
 def vqa_loss_lmh(logits, bias, labels, factor_pre, smooth, w):

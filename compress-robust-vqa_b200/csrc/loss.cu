@@ -135,6 +135,44 @@ lpf_kernel(const float* __restrict__ logits, const float* __restrict__ bias, con
   }
 }
 
+// RUBI_loss (hg_transformers/mask_trainer_VQA.py:131-135): cross entropy of the bias-gated logits
+// z = logits * sigmoid(bias) against the majority label y; d loss / d logits = (softmax(z) - onehot(y)) sigmoid(bias) / B.
+__global__ void __launch_bounds__(kLossThreads)
+rubi_kernel(const float* __restrict__ logits, const float* __restrict__ bias, const long long* __restrict__ max_label,
+            const float* __restrict__ labels, float* __restrict__ dlogits, float* __restrict__ ws, int B, int A) {
+  extern __shared__ float row[];
+  __shared__ float red[kLossThreads / 32];
+  __shared__ int redi[kLossThreads / 32];
+  const int b = blockIdx.x;
+  const float* x = logits + static_cast<size_t>(b) * A;
+  const float* bi = bias + static_cast<size_t>(b) * A;
+  float* dx = dlogits + static_cast<size_t>(b) * A;
+  float mx = -FLT_MAX, bestv = -FLT_MAX;
+  int besti = 0x7FFFFFFF;
+  for (int a = threadIdx.x; a < A; a += kLossThreads) {
+    const float xv = x[a];
+    const float z = xv * sigmoidf(bi[a]);
+    row[a] = z;
+    mx = fmaxf(mx, z);
+    if (xv > bestv) { bestv = xv; besti = a; }     // the VQA score is taken on the raw logits (reference :839-842)
+  }
+  mx = block_max(mx, red);
+  const int am = block_argmax(bestv, besti, red, redi);
+  float se = 0.f;
+  for (int a = threadIdx.x; a < A; a += kLossThreads) se += expf(row[a] - mx);
+  se = block_sum(se, red);
+  const long long yb = max_label[b];
+  const float lse = mx + logf(se);
+  const float invB = 1.f / B;
+  for (int a = threadIdx.x; a < A; a += kLossThreads)
+    dx[a] = (expf(row[a] - lse) - (a == yb ? 1.f : 0.f)) * sigmoidf(bi[a]) * invB;
+  if (threadIdx.x == 0) {
+    ws[b] = lse - row[yb];
+    ws[B + b] = labels ? labels[static_cast<size_t>(b) * A + am] : 0.f;
+    ws[2 * B + b] = 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(kLossThreads)
 lmh_kernel(const float* __restrict__ logits, const float* __restrict__ bias, const float* __restrict__ labels,
            const float* __restrict__ factor_pre, float smooth, float w_ent, float* __restrict__ dlogits,
@@ -224,6 +262,27 @@ extern "C" int crv_vqa_loss_lpf(const float* logits, const float* bias, const lo
     }
   }
   lpf_kernel<<<B, kLossThreads, smem, st>>>(logits, bias, max_label, labels, gamma, dlogits, ws, B, A);
+  int rc = launch_status();
+  if (rc) return rc;
+  loss_finalize_kernel<<<1, kLossThreads, 0, st>>>(ws, B, 1.f / B, 0.f, loss_out);
+  return launch_status();
+}
+
+extern "C" int crv_vqa_loss_rubi(const float* logits, const float* bias, const long long* max_label, float* loss_out,
+                                 const float* labels, float* dlogits, int B, int A, void* workspace, void* stream) {
+  if (!logits || !bias || !max_label || !loss_out || !dlogits || !workspace || B <= 0 || A <= 0) return CRV_E_BADARG;
+  if (static_cast<size_t>(A) * sizeof(float) > 200 * 1024) return CRV_E_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* ws = static_cast<float*>(workspace);
+  const size_t smem = static_cast<size_t>(A) * sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      CRV_CUDA(cudaFuncSetAttribute(rubi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+  }
+  rubi_kernel<<<B, kLossThreads, smem, st>>>(logits, bias, max_label, labels, dlogits, ws, B, A);
   int rc = launch_status();
   if (rc) return rc;
   loss_finalize_kernel<<<1, kLossThreads, 0, st>>>(ws, B, 1.f / B, 0.f, loss_out);

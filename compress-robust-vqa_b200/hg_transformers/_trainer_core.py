@@ -96,7 +96,9 @@ def LPF_loss(logits, bias, max_label, device, gamma):
 
 
 def RUBI_loss(logits, bias, max_label):
-    """CE(logits * sigmoid(bias), y) (reference :131-135); secondary, stays a torch graph."""
+    """CE(logits * sigmoid(bias), y) (reference :131-135): fused kernel on CUDA tensors, torch graph on CPU ones."""
+    if logits.is_cuda:
+        return ops.vqa_loss_rubi(logits, bias, max_label)[0]
     return F.cross_entropy(logits * torch.sigmoid(bias), max_label)
 
 
@@ -584,8 +586,8 @@ class TrainerCore:
             loss, score = ops.vqa_loss_lpf(logits, inputs[6].to(dev, non_blocking=True),
                                            inputs[7].to(dev, non_blocking=True), self.args.gamma, labels)
         else:  # rubi
-            loss = self.rubi_loss(logits, inputs[6].to(dev), inputs[7].to(dev))
-            score = labels.gather(1, logits.detach().max(1)[1].view(-1, 1)).sum()
+            loss, score = ops.vqa_loss_rubi(logits, inputs[6].to(dev, non_blocking=True),
+                                            inputs[7].to(dev, non_blocking=True), labels)
         return loss, score
 
     def _training_step(self, model: nn.Module, inputs, optimizer) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -1,8 +1,9 @@
 """Debias losses of the answer head (reference hg_transformers/vqa_debias_loss_functions.py).
 
-``LearnedMixin`` (LMH) and ``Plain`` run as ONE fused forward+backward CUDA kernel over [B, A]
-(libcrvqa: crv_vqa_loss_lmh / crv_vqa_loss_bce); ``BiasProduct`` / ``ReweightByInvBias`` are secondary
-losses no stage-2 script selects and stay as torch graphs."""
+``LearnedMixin`` (LMH), ``BiasProduct`` and ``Plain`` run as ONE fused forward+backward CUDA kernel over [B, A]
+(libcrvqa: crv_vqa_loss_lmh / crv_vqa_loss_bce; BiasProduct is the LMH expression with factor 1 and no entropy
+term) on CUDA tensors; ``ReweightByInvBias`` -- which no script selects -- stays a torch graph, and so does
+``BiasProduct`` on CPU tensors (host-logic tests)."""
 import numpy as np
 import torch
 from torch import nn
@@ -71,6 +72,8 @@ class BiasProduct(_Smoothed):
         super().__init__(smooth, smooth_init, constant_smooth)
 
     def forward(self, hidden, logits, bias, labels):
+        if logits.is_cuda:
+            return ops.vqa_loss_bias_product(logits, bias, labels, self.smooth_value())[0]
         smooth = self.constant_smooth
         if self.smooth:
             smooth = smooth + torch.sigmoid(self.smooth_param)

@@ -196,9 +196,14 @@ int crv_vqa_loss_bce(const float* logits, const float* labels, float* loss_out, 
 int crv_vqa_loss_lpf(const float* logits, const float* bias, const long long* max_label, float gamma,
                      float* loss_out, const float* labels /* for the score; may be NULL */, float* dlogits,
                      int B, int A, void* workspace, void* stream);
+/* RUBI_loss (hg_transformers/mask_trainer_VQA.py:131-135): mean_b CE(logits * sigmoid(bias), max_label). */
+int crv_vqa_loss_rubi(const float* logits, const float* bias, const long long* max_label, float* loss_out,
+                      const float* labels /* for the score; may be NULL */, float* dlogits, int B, int A,
+                      void* workspace, void* stream);
 /* LearnedMixin.forward (hg_transformers/vqa_debias_loss_functions.py:148-196) with entropy weight w:
  * factor_pre[B] = bias_lin(pooled) (pre-softplus), smooth = sigmoid(smooth_param) + constant_smooth.
- * Outputs dlogits[B,A] and dfactor_pre[B] (gradient w.r.t. the pre-softplus factor). */
+ * Outputs dlogits[B,A] and dfactor_pre[B] (gradient w.r.t. the pre-softplus factor).
+ * BiasProduct.forward (:83-122) is the same expression with factor = 1 and w = 0: pass factor_pre = log(e - 1). */
 int crv_vqa_loss_lmh(const float* logits, const float* bias, const float* labels, const float* factor_pre,
                      float smooth, float w, float* loss_out, float* dlogits, float* dfactor_pre, int B, int A,
                      void* workspace, void* stream);

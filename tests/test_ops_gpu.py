@@ -314,3 +314,28 @@ def test_apply_mask_segmented_bit_exact():
         assert torch.equal(wm[sl].view(torch.int16), want.view(torch.int16)), i
         pad = wm[offs[i] + n: (offs[i + 1] if i + 1 < len(sizes) else off)]
         assert bool((pad.float() == 7.0).all())      # alignment padding between modules is never written
+
+
+def test_secondary_debias_losses_on_gpu():
+    """RUBI_loss and BiasProduct through the fused CUDA kernels against the reference's own
+    values and logit gradients (tests/golden/secondary_losses.pt)."""
+    from crvqa import ops
+    from hg_transformers._trainer_core import RUBI_loss
+    from hg_transformers.vqa_debias_loss_functions import BiasProduct
+    g = torch.load(os.path.join(GOLD, "secondary_losses.pt"), weights_only=False)
+    lg = dev(g["logits"]).requires_grad_(True)
+    loss = RUBI_loss(lg, dev(g["bias"]), dev(g["max_label"]))
+    loss.backward()
+    assert abs(float(loss) - float(g["rubi"])) <= 1e-5 * abs(float(g["rubi"]))
+    torch.testing.assert_close(lg.grad.cpu(), g["rubi_dlogits"], rtol=1e-4, atol=1e-7)
+    l2, score = ops.vqa_loss_rubi(lg.detach(), dev(g["bias"]), dev(g["max_label"]), dev(g["labels"]))
+    want = g["labels"].gather(1, g["logits"].argmax(1, keepdim=True)).sum()
+    assert float(l2) == float(loss) and abs(float(score) - float(want)) < 1e-6
+    bp = BiasProduct().cuda()
+    if g["bp_smooth_param"] is not None:
+        bp.smooth_param.data.copy_(g["bp_smooth_param"])
+    lg2 = dev(g["logits"]).requires_grad_(True)
+    loss = bp(dev(g["hidden"]), lg2, dev(g["bias"]), dev(g["labels"]))
+    loss.backward()
+    assert abs(float(loss) - float(g["bp"])) <= 1e-5 * abs(float(g["bp"]))
+    torch.testing.assert_close(lg2.grad.cpu(), g["bp_dlogits"], rtol=1e-4, atol=1e-7)
