@@ -50,7 +50,11 @@ _PROTOS = {
     "crv_vqa_loss_rubi": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P]),
     "crv_vqa_loss_lmh": (c_int, [_P, _P, _P, _P, c_float, c_float, _P, _P, _P, c_int, c_int, _P, _P]),
     "crv_ln_fwd": (c_int, [_P, c_int, _P, _P, _P, c_float, c_float, _P, c_int, _P, _P, _P, _P, c_int, c_int, _P]),
-    "crv_ln_bwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P, c_float, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
+    "crv_ln_bwd_partials_bytes": (c_size_t, [c_int, c_int]),
+    "crv_ln_bwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P, c_float, _P, c_int, _P, c_int, _P, _P, c_int, c_int, _P]),
+    "crv_partial_reduce": (c_int, [_P, c_int, c_int, _P, c_int, _P]),
+    "crv_colsum_workspace_bytes": (c_size_t, [c_int]),
+    "crv_colsum_bf16": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P]),
     "crv_attention_fwd": (c_int, [_P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P,
                                   _P, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),
     "crv_attention_bwd": (c_int, [_P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P,
@@ -62,10 +66,10 @@ _PROTOS = {
     "crv_sumsq_workspace_bytes": (c_size_t, []),
     "crv_sumsq": (c_int, [_P, c_int64, _P, _P, _P]),
     "crv_adamw_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float,
-                               c_float, _P, c_float, _P, _P]),
+                               c_float, _P, c_float, _P, c_int, c_float, _P]),
     "crv_sumsq_segmented": (c_int, [_P, _P, c_int, _P, _P, _P]),
     "crv_adamw_segmented": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_float, c_float, c_float, c_float, c_float,
-                                    c_float, _P, c_float, _P, c_int, _P]),
+                                    c_float, _P, c_float, _P, c_int, c_int, c_float, _P]),
 }
 EXPORTED = tuple(_PROTOS)
 for _name, (_res, _args) in _PROTOS.items():

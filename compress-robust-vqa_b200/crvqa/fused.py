@@ -263,6 +263,10 @@ def multi_linear(items):
 
 # ----------------------------------------------------------------------------- dropout + residual + LayerNorm
 class DropAddLayerNormFn(torch.autograd.Function):
+    """(y fp32, y bf16) = LayerNorm(dropout(g) + res).  gamma / beta are frozen in stage 2; when they require a
+    gradient (stage-3 fine-tune) the backward kernel also emits per-CTA partial sums of dgamma / dbeta, which a second
+    launch adds up in index order."""
+
     @staticmethod
     def forward(ctx, g, res32, gamma, beta, eps, p, site, rng):
         H = g.shape[-1]
@@ -285,6 +289,7 @@ class DropAddLayerNormFn(torch.autograd.Function):
         ctx.save_for_backward(g2, r2, gamma, mean, rstd)
         ctx.p, ctx.site, ctx.state, ctx.shape = float(p), int(site), state, g.shape
         ctx.need_res = res32 is not None and res32.requires_grad
+        ctx.need_param = gamma.requires_grad or beta.requires_grad
         return y32.view(g.shape), y16.view(g.shape)
 
     @staticmethod
@@ -295,10 +300,19 @@ class DropAddLayerNormFn(torch.autograd.Function):
         d16 = dy16.reshape(M, H).contiguous() if dy16 is not None else None
         dg = torch.empty((M, H), dtype=torch.bfloat16, device=g2.device)
         dres = torch.empty((M, H), dtype=torch.float32, device=g2.device) if ctx.need_res else None
+        part = None
+        if ctx.need_param:
+            part = torch.empty((lib.crv_ln_bwd_partials_bytes(M, H) // (8 * H), 2 * H), dtype=torch.float32,
+                               device=g2.device)
         check(lib.crv_ln_bwd(_p(d32), _p(d16), _p(g2), ops.DT_BF16 if g2.dtype == torch.bfloat16 else ops.DT_F32,
                              _p(r2), _p(gamma), _p(mean), _p(rstd), ctx.p, _p(ctx.state), ctx.site, _p(dg),
-                             ops.DT_BF16, _p(dres), M, H, _stream()), "crv_ln_bwd")
-        return (dg.view(ctx.shape), dres.view(ctx.shape) if dres is not None else None, None, None, None, None, None,
+                             ops.DT_BF16, _p(dres), _p(part), M, H, _stream()), "crv_ln_bwd")
+        dgamma = dbeta = None
+        if part is not None:
+            both = torch.empty(2 * H, dtype=torch.float32, device=g2.device)
+            ops.partial_reduce(part, both)
+            dgamma, dbeta = both[:H], both[H:]
+        return (dg.view(ctx.shape), dres.view(ctx.shape) if dres is not None else None, dgamma, dbeta, None, None, None,
                 None)
 
 

@@ -672,20 +672,50 @@ def adam_step_size(lr, step, beta1, beta2, correct_bias=True):
     return lr * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
 
 
+ADAM_REFERENCE, ADAM_TORCH = 0, 1     # root optimization.AdamW (stage 2) | torch.optim.Adam (stage 3)
+
+
+def adam_hyper(mode, lr, step, beta1, beta2, correct_bias=True):
+    """(lr, step_size, inv_bc2_sqrt) of crv_adamw_step / crv_adamw_segmented for optimiser step `step` (1-based)."""
+    if mode == ADAM_REFERENCE:
+        return lr, adam_step_size(lr, step, beta1, beta2, correct_bias), 1.0
+    return lr, lr / (1.0 - beta1 ** step), 1.0 / math.sqrt(1.0 - beta2 ** step)
+
+
 def adamw_step_flat(p, g, m, v, s, lr, step, beta1, beta2, eps, weight_decay, total_sumsq=None, max_norm=1.0,
-                    correct_bias=True, hyper=None):
-    """hyper: optional device tensor {lr, step_size}; when given it overrides lr / step (CUDA-graph replay)."""
-    step_size = adam_step_size(lr, step, beta1, beta2, correct_bias)
+                    correct_bias=True, hyper=None, mode=ADAM_REFERENCE):
+    """hyper: optional device tensor {lr, step_size, inv_bc2_sqrt}; when given it overrides lr / step (graph replay)."""
+    lr, step_size, inv_bc2 = adam_hyper(mode, lr, step, beta1, beta2, correct_bias)
     check(lib.crv_adamw_step(_p(p), _p(g), _p(m), _p(v), _p(s), p.numel(), float(lr), float(step_size),
                              float(beta1), float(beta2), float(eps), float(weight_decay), _p(total_sumsq),
-                             float(max_norm), _p(hyper), _stream()), "crv_adamw_step")
+                             float(max_norm), _p(hyper), int(mode), float(inv_bc2), _stream()), "crv_adamw_step")
 
 
 def adamw_segmented(p, g, m, v, s, chunks, thr_vec, w16, wm, lr, step, beta1, beta2, eps, weight_decay,
-                    total_sumsq=None, max_norm=1.0, correct_bias=True, hyper=None, zero_grad=False):
-    """crv_adamw_segmented: clip + AdamW over a score arena + masked-operand refresh (+ gradient clearing)."""
-    step_size = adam_step_size(lr, step, beta1, beta2, correct_bias)
+                    total_sumsq=None, max_norm=1.0, correct_bias=True, hyper=None, zero_grad=False,
+                    mode=ADAM_REFERENCE):
+    """crv_adamw_segmented: clip + Adam over an arena + masked-operand refresh (+ gradient clearing)."""
+    lr, step_size, inv_bc2 = adam_hyper(mode, lr, step, beta1, beta2, correct_bias)
     check(lib.crv_adamw_segmented(_p(p), _p(g), _p(m), _p(v), _p(s), _p(chunks), chunks.shape[0], _p(thr_vec), _p(w16),
                                   _p(wm), float(lr), float(step_size), float(beta1), float(beta2), float(eps),
                                   float(weight_decay), _p(total_sumsq), float(max_norm), _p(hyper), int(bool(zero_grad)),
-                                  _stream()), "crv_adamw_segmented")
+                                  int(mode), float(inv_bc2), _stream()), "crv_adamw_segmented")
+
+
+_colsum_ws = {}
+
+
+def colsum_bf16(x, out, accumulate=False):
+    """out[n] (+)= sum_m x[m, n] for a bf16 [M, N] matrix (bias gradient of a linear layer), deterministic."""
+    M, N = x.shape
+    key = (x.device.index, N)
+    ws = _colsum_ws.get(key)
+    if ws is None:
+        ws = _colsum_ws[key] = torch.empty(lib.crv_colsum_workspace_bytes(N) // 4, dtype=torch.float32, device=x.device)
+    check(lib.crv_colsum_bf16(_p(x), M, N, _p(out), int(bool(accumulate)), _p(ws), _stream()), "crv_colsum_bf16")
+
+
+def partial_reduce(part, out, accumulate=False):
+    """out[j] (+)= sum_i part[i, j]."""
+    check(lib.crv_partial_reduce(_p(part), part.shape[0], part.shape[1], _p(out), int(bool(accumulate)), _stream()),
+          "crv_partial_reduce")

@@ -224,27 +224,41 @@ __global__ void sumsq_segmented_kernel(const float* __restrict__ x, const int4* 
   sumsq_finish(acc, ws, out);
 }
 
+// mode 0: the reference's root optimization.AdamW (stage 2): step_size = lr sqrt(1 - b2^t) / (1 - b1^t) computed by the
+//         caller, denom = sqrt(v) + eps, decoupled weight decay, running sum of |g|.
+// mode 1: torch.optim.Adam as the stage-3 driver builds it (run_vqa_stage3.py:577-598): L2 weight decay folded into g,
+//         step_size = lr / (1 - b1^t), denom = sqrt(v) / sqrt(1 - b2^t) + eps  (inv_bc2_sqrt = 1 / sqrt(1 - b2^t)).
 struct AdamArgs {
-  float lr, step_size, beta1, beta2, eps, weight_decay, max_norm;
+  float lr, step_size, beta1, beta2, eps, weight_decay, max_norm, inv_bc2_sqrt;
+  int mode;
 };
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float* sum, const AdamArgs& a,
                                          float clip) {
   g *= clip;
-  if (sum) *sum += fabsf(g);
-  m = m * a.beta1 + (1.0f - a.beta1) * g;
-  v = v * a.beta2 + (1.0f - a.beta2) * g * g;
-  const float denom = sqrtf(v) + a.eps;
-  p = p - a.step_size * (m / denom);
-  if (a.weight_decay > 0.f) p = p - a.lr * a.weight_decay * p;
+  if (a.mode == 0) {
+    if (sum) *sum += fabsf(g);
+    m = m * a.beta1 + (1.0f - a.beta1) * g;
+    v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+    const float denom = sqrtf(v) + a.eps;
+    p = p - a.step_size * (m / denom);
+    if (a.weight_decay > 0.f) p = p - a.lr * a.weight_decay * p;
+  } else {
+    if (a.weight_decay > 0.f) g = fmaf(a.weight_decay, p, g);
+    m = m + (g - m) * (1.0f - a.beta1);
+    v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+    const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
+    p = p - a.step_size * (m / denom);
+  }
 }
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, float* __restrict__ sum, int64_t n, AdamArgs a,
                              const float* __restrict__ total_sumsq, const float* __restrict__ hyper) {
-  if (hyper) {  // {lr, step_size} live in device memory so a captured CUDA graph follows the LR schedule
+  if (hyper) {  // {lr, step_size, 1/sqrt(1-b2^t)} live in device memory so a captured CUDA graph follows the schedule
     a.lr = __ldg(hyper);
     a.step_size = __ldg(hyper + 1);
+    a.inv_bc2_sqrt = __ldg(hyper + 2);
   }
   float clip = 1.0f;
   if (total_sumsq) {
@@ -291,6 +305,7 @@ adamw_segmented_kernel(float* __restrict__ p, float* __restrict__ g, float* __re
   if (hyper) {
     a.lr = __ldg(hyper);
     a.step_size = __ldg(hyper + 1);
+    a.inv_bc2_sqrt = __ldg(hyper + 2);
   }
   float clip = 1.0f;
   if (total_sumsq) {
@@ -299,7 +314,7 @@ adamw_segmented_kernel(float* __restrict__ p, float* __restrict__ g, float* __re
   }
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const int4 ch = __ldg(chunks + c);
-    const float thr = __ldg(thr_vec + ch.z);
+    const float thr = a.mode == 0 ? __ldg(thr_vec + ch.z) : 0.f;
     const bool has_wm = (ch.w & 1) != 0;
     const int64_t base = static_cast<int64_t>(ch.x) * 8;
     const int nvec = ch.y >> 3;
@@ -336,10 +351,17 @@ adamw_segmented_kernel(float* __restrict__ p, float* __restrict__ g, float* __re
         if (zero_grad) reinterpret_cast<float4*>(g + e)[h] = make_float4(0, 0, 0, 0);
       }
       if (has_wm) {
-        wv.x &= (pp[0].x > thr ? 0x0000FFFFu : 0u) | (pp[0].y > thr ? 0xFFFF0000u : 0u);
-        wv.y &= (pp[0].z > thr ? 0x0000FFFFu : 0u) | (pp[0].w > thr ? 0xFFFF0000u : 0u);
-        wv.z &= (pp[1].x > thr ? 0x0000FFFFu : 0u) | (pp[1].y > thr ? 0xFFFF0000u : 0u);
-        wv.w &= (pp[1].z > thr ? 0x0000FFFFu : 0u) | (pp[1].w > thr ? 0xFFFF0000u : 0u);
+        if (a.mode == 0) {       // stage 2: frozen bf16 weight AND (new score > threshold)
+          wv.x &= (pp[0].x > thr ? 0x0000FFFFu : 0u) | (pp[0].y > thr ? 0xFFFF0000u : 0u);
+          wv.y &= (pp[0].z > thr ? 0x0000FFFFu : 0u) | (pp[0].w > thr ? 0xFFFF0000u : 0u);
+          wv.z &= (pp[1].x > thr ? 0x0000FFFFu : 0u) | (pp[1].y > thr ? 0xFFFF0000u : 0u);
+          wv.w &= (pp[1].z > thr ? 0x0000FFFFu : 0u) | (pp[1].w > thr ? 0xFFFF0000u : 0u);
+        } else {                 // stage 3: bf16(new weight) where the frozen 0/1 mask (bf16 in `w16`) is set
+          wv.x = pack_bf16(pp[0].x, pp[0].y) & ((wv.x & 0xFFFFu ? 0x0000FFFFu : 0u) | (wv.x >> 16 ? 0xFFFF0000u : 0u));
+          wv.y = pack_bf16(pp[0].z, pp[0].w) & ((wv.y & 0xFFFFu ? 0x0000FFFFu : 0u) | (wv.y >> 16 ? 0xFFFF0000u : 0u));
+          wv.z = pack_bf16(pp[1].x, pp[1].y) & ((wv.z & 0xFFFFu ? 0x0000FFFFu : 0u) | (wv.z >> 16 ? 0xFFFF0000u : 0u));
+          wv.w = pack_bf16(pp[1].z, pp[1].w) & ((wv.w & 0xFFFFu ? 0x0000FFFFu : 0u) | (wv.w >> 16 ? 0xFFFF0000u : 0u));
+        }
         *reinterpret_cast<uint4*>(wm + e) = wv;
       }
     }
@@ -347,9 +369,61 @@ adamw_segmented_kernel(float* __restrict__ p, float* __restrict__ g, float* __re
       const int64_t e = base + i;
       adam_one(p[e], g[e], m[e], v[e], sum ? sum + e : nullptr, a, clip);
       if (zero_grad) g[e] = 0.f;
-      if (has_wm) wm[e] = p[e] > thr ? w16[e] : uint16_t(0);
+      if (has_wm) {
+        if (a.mode == 0) {
+          wm[e] = p[e] > thr ? w16[e] : uint16_t(0);
+        } else {
+          __nv_bfloat16 t = __float2bfloat16_rn(p[e]);
+          wm[e] = w16[e] ? *reinterpret_cast<uint16_t*>(&t) : uint16_t(0);
+        }
+      }
     }
   }
+}
+
+// ------------------------------------------------------------------ bias gradients: db[n] = sum_m dY[m, n]
+// Stage 3 trains the biases too (run_vqa_stage3.py:577-598).  dY is the bf16 [M, N] operand the GEMMs already read;
+// one more streaming pass: a CTA owns 256 columns x one slice of the rows (8 warps stride the rows, a lane holds 8
+// columns = one 16-byte load), row-slice partials go to a workspace and a second launch adds them in index order
+// (deterministic; gridDim.y <= 64 slices).
+__global__ void colsum_partial_kernel(const uint16_t* __restrict__ x, int M, int N, float* __restrict__ part) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r_begin = blockIdx.y * rows_per, r_end = min(M, r_begin + rows_per);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < N) {
+    for (int r = r_begin + warp; r < r_end; r += 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * N + c0));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += __uint_as_float(w[j] << 16);
+        acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    part[static_cast<size_t>(blockIdx.y) * N + c] = t;
+  }
+}
+
+// out[j] (+)= sum_i part[i][j], i in index order (also the second stage of the LayerNorm parameter gradients)
+__global__ void partial_reduce_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out,
+                                      int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float t = 0.f;
+  for (int i = 0; i < nparts; ++i) t += __ldg(part + static_cast<size_t>(i) * n + j);
+  out[j] = accumulate ? out[j] + t : t;
 }
 
 // ------------------------------------------------------------------ tiny-K masked linear (box_fc, K = 4)
@@ -560,13 +634,43 @@ extern "C" int crv_sumsq_segmented(const float* x, const int* chunks, int nchunk
 
 extern "C" int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int64_t n, float lr,
                               float step_size, float beta1, float beta2, float eps, float weight_decay,
-                              const float* total_sumsq, float max_norm, const float* hyper_dev, void* stream) {
+                              const float* total_sumsq, float max_norm, const float* hyper_dev, int mode,
+                              float inv_bc2_sqrt, void* stream) {
   if (!p || !g || !m || !v || n < 0) return CRV_E_BADARG;
   if (n == 0) return CRV_OK;
   if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (sum && !aligned16(sum))) return CRV_E_ALIGN;
-  AdamArgs a{lr, step_size, beta1, beta2, eps, weight_decay, max_norm};
+  if (mode != 0 && mode != 1) return CRV_E_BADARG;
+  AdamArgs a{lr, step_size, beta1, beta2, eps, weight_decay, max_norm, inv_bc2_sqrt, mode};
   adamw_kernel<<<stream_grid(n >> 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, sum, n, a,
                                                                                          total_sumsq, hyper_dev);
+  return launch_status();
+}
+
+extern "C" size_t crv_colsum_workspace_bytes(int N) { return N > 0 ? static_cast<size_t>(64) * N * sizeof(float) : 0; }
+
+extern "C" int crv_colsum_bf16(const uint16_t* x, int M, int N, float* out, int accumulate, void* workspace,
+                               void* stream) {
+  if (!x || !out || !workspace || M <= 0 || N <= 0) return CRV_E_BADARG;
+  if (N % 8) return CRV_E_SHAPE;
+  if (!aligned16(x)) return CRV_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int col_blocks = (N + 255) / 256;
+  int slices = (num_sms() * 4 + col_blocks - 1) / col_blocks;
+  if (slices > 64) slices = 64;
+  if (slices > (M + 63) / 64) slices = (M + 63) / 64;
+  if (slices < 1) slices = 1;
+  float* part = static_cast<float*>(workspace);
+  colsum_partial_kernel<<<dim3(col_blocks, slices), 256, 0, st>>>(x, M, N, part);
+  int rc = launch_status();
+  if (rc) return rc;
+  partial_reduce_kernel<<<(N + 255) / 256, 256, 0, st>>>(part, slices, N, out, accumulate);
+  return launch_status();
+}
+
+extern "C" int crv_partial_reduce(const float* part, int nparts, int n, float* out, int accumulate, void* stream) {
+  if (!part || !out || nparts <= 0 || n <= 0) return CRV_E_BADARG;
+  partial_reduce_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(part, nparts, n, out,
+                                                                                         accumulate);
   return launch_status();
 }
 
@@ -574,14 +678,15 @@ extern "C" int crv_adamw_segmented(float* p, float* g, float* m, float* v, float
                                    const float* thr_vec, const uint16_t* w_bf16, uint16_t* wm_bf16, float lr,
                                    float step_size, float beta1, float beta2, float eps, float weight_decay,
                                    const float* total_sumsq, float max_norm, const float* hyper_dev, int zero_grad,
-                                   void* stream) {
-  if (!p || !g || !m || !v || !chunks || !thr_vec || nchunks < 0) return CRV_E_BADARG;
+                                   int mode, float inv_bc2_sqrt, void* stream) {
+  if (!p || !g || !m || !v || !chunks || (!thr_vec && mode == 0) || nchunks < 0) return CRV_E_BADARG;
   if ((w_bf16 == nullptr) != (wm_bf16 == nullptr)) return CRV_E_BADARG;
   if (nchunks == 0) return CRV_OK;
   if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (sum && !aligned16(sum)) ||
       !aligned16(chunks) || (w_bf16 && (!aligned16(w_bf16) || !aligned16(wm_bf16))))
     return CRV_E_ALIGN;
-  AdamArgs a{lr, step_size, beta1, beta2, eps, weight_decay, max_norm};
+  if (mode != 0 && mode != 1) return CRV_E_BADARG;
+  AdamArgs a{lr, step_size, beta1, beta2, eps, weight_decay, max_norm, inv_bc2_sqrt, mode};
   const int grid = nchunks < num_sms() * 8 ? nchunks : num_sms() * 8;
   adamw_segmented_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, sum, reinterpret_cast<const int4*>(chunks), nchunks, thr_vec, w_bf16, wm_bf16, a, total_sumsq,

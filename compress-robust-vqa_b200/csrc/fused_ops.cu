@@ -130,23 +130,28 @@ ln_fwd_kernel(const void* __restrict__ g, int g_bf16, const float* __restrict__ 
   }
 }
 
-template <int VEC>
+// PGRAD: also emit this CTA's partial sums of the LayerNorm parameter gradients (stage-3 fine-tune: gamma / beta are
+// trained) -- part[blockIdx.x][0..H) = sum_rows d * xhat (dgamma), part[blockIdx.x][H..2H) = sum_rows d (dbeta), d =
+// dy32 + dy16 -- which crv_partial_reduce adds up in index order.
+template <int VEC, bool PGRAD>
 __global__ void __launch_bounds__(kRowsPerBlock * 32, 2)
 ln_bwd_kernel(const float* __restrict__ dy32, const uint16_t* __restrict__ dy16, const void* __restrict__ g, int g_bf16,
               const float* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, float p, const unsigned long long* __restrict__ rng_state, int site,
-              void* __restrict__ dg, int dg_bf16, float* __restrict__ dres, int M, int H) {
+              void* __restrict__ dg, int dg_bf16, float* __restrict__ dres, float* __restrict__ part, int M, int H) {
   pdl_wait();
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= M) return;
+  const bool valid = row < M;
+  if (!PGRAD && !valid) return;
+  const int rrow = valid ? row : M - 1;
   const Rng rng = make_rng(rng_state, site, p);
-  const float mean = mean_in[row], rstd = rstd_in[row];
+  const float mean = mean_in[rrow], rstd = rstd_in[rrow];
   // all loads first (see ln_fwd_kernel)
   float4 xh[VEC], dyg[VEC], rv[VEC], d2[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    const int64_t e = static_cast<int64_t>(row) * H + (i * 32 + lane) * 4;
+    const int64_t e = static_cast<int64_t>(rrow) * H + (i * 32 + lane) * 4;
     xh[i] = load4(g, g_bf16, e);
     rv[i] = res ? __ldg(reinterpret_cast<const float4*>(res + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
     dyg[i] = dy32 ? __ldg(reinterpret_cast<const float4*>(dy32 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -156,13 +161,14 @@ ln_bwd_kernel(const float* __restrict__ dy32, const uint16_t* __restrict__ dy16,
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const int col = (i * 32 + lane) * 4;
-    const int64_t e = static_cast<int64_t>(row) * H + col;
+    const int64_t e = static_cast<int64_t>(rrow) * H + col;
     float4 gv = xh[i];
     if (rng.thresh) rng.drop4(gv, e);
     gv.x += rv[i].x; gv.y += rv[i].y; gv.z += rv[i].z; gv.w += rv[i].w;
     xh[i] = make_float4((gv.x - mean) * rstd, (gv.y - mean) * rstd, (gv.z - mean) * rstd, (gv.w - mean) * rstd);
     float4 d = dyg[i];
     d.x += d2[i].x; d.y += d2[i].y; d.z += d2[i].z; d.w += d2[i].w;
+    if (PGRAD) d2[i] = valid ? d : make_float4(0.f, 0.f, 0.f, 0.f);      // the pre-gamma gradient, kept for dgamma / dbeta
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + col));
     d.x *= ga.x; d.y *= ga.y; d.z *= ga.z; d.w *= ga.w;
     dyg[i] = d;
@@ -171,20 +177,46 @@ ln_bwd_kernel(const float* __restrict__ dy32, const uint16_t* __restrict__ dy16,
   }
   pdl_launch_dependents();     // inputs are in registers
   const float m1 = warp_sum(s1) / H, m2 = warp_sum(s2) / H;
+  if (valid) {
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int col = (i * 32 + lane) * 4;
-    const int64_t e = static_cast<int64_t>(row) * H + col;
-    float4 dz;
-    dz.x = rstd * (dyg[i].x - m1 - xh[i].x * m2);
-    dz.y = rstd * (dyg[i].y - m1 - xh[i].y * m2);
-    dz.z = rstd * (dyg[i].z - m1 - xh[i].z * m2);
-    dz.w = rstd * (dyg[i].w - m1 - xh[i].w * m2);
-    if (dres) *reinterpret_cast<float4*>(dres + e) = dz;
-    if (dg) {
-      if (rng.thresh) rng.drop4(dz, e);
-      if (dg_bf16) *reinterpret_cast<uint2*>(static_cast<uint16_t*>(dg) + e) = pack4(dz);
-      else *reinterpret_cast<float4*>(static_cast<float*>(dg) + e) = dz;
+    for (int i = 0; i < VEC; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      const int64_t e = static_cast<int64_t>(row) * H + col;
+      float4 dz;
+      dz.x = rstd * (dyg[i].x - m1 - xh[i].x * m2);
+      dz.y = rstd * (dyg[i].y - m1 - xh[i].y * m2);
+      dz.z = rstd * (dyg[i].z - m1 - xh[i].z * m2);
+      dz.w = rstd * (dyg[i].w - m1 - xh[i].w * m2);
+      if (dres) *reinterpret_cast<float4*>(dres + e) = dz;
+      if (dg) {
+        if (rng.thresh) rng.drop4(dz, e);
+        if (dg_bf16) *reinterpret_cast<uint2*>(static_cast<uint16_t*>(dg) + e) = pack4(dz);
+        else *reinterpret_cast<float4*>(static_cast<float*>(dg) + e) = dz;
+      }
+    }
+  }
+  if (PGRAD) {
+    __shared__ float4 red[kRowsPerBlock][VEC * 32];
+    const int w = threadIdx.x >> 5;
+    float* out = part + static_cast<size_t>(blockIdx.x) * 2 * H;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        red[w][i * 32 + lane] = pass == 0 ? make_float4(d2[i].x * xh[i].x, d2[i].y * xh[i].y, d2[i].z * xh[i].z,
+                                                        d2[i].w * xh[i].w)
+                                          : d2[i];
+      __syncthreads();
+      for (int c = threadIdx.x; c < VEC * 32; c += kRowsPerBlock * 32) {
+        float4 t = red[0][c];
+#pragma unroll
+        for (int r = 1; r < kRowsPerBlock; ++r) {
+          const float4 o = red[r][c];
+          t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+        }
+        *reinterpret_cast<float4*>(out + pass * H + c * 4) = t;
+      }
+      __syncthreads();
     }
   }
 }
@@ -253,19 +285,28 @@ extern "C" int crv_ln_fwd(const void* g, int g_dtype, const float* res, const fl
   });
 }
 
+extern "C" size_t crv_ln_bwd_partials_bytes(int M, int H) {
+  return M > 0 && H > 0 ? static_cast<size_t>((M + kRowsPerBlock - 1) / kRowsPerBlock) * 2 * H * sizeof(float) : 0;
+}
+
 extern "C" int crv_ln_bwd(const float* dy_f32, const uint16_t* dy_bf16, const void* g, int g_dtype, const float* res,
                           const float* gamma, const float* mean, const float* rstd, float p_drop,
-                          const unsigned long long* rng_state, int site, void* dg, int dg_dtype, float* dres, int M,
-                          int H, void* stream) {
+                          const unsigned long long* rng_state, int site, void* dg, int dg_dtype, float* dres,
+                          float* param_partials, int M, int H, void* stream) {
   if ((!dy_f32 && !dy_bf16) || !g || !gamma || !mean || !rstd || M <= 0 || H <= 0) return CRV_E_BADARG;
   if (H % 128 || H > 1024) return CRV_E_SHAPE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = (M + kRowsPerBlock - 1) / kRowsPerBlock;
   return dispatch_vec(H, [&](auto v) {
     constexpr int VEC = decltype(v)::value;
-    CRV_CUDA(launch_pdl(ln_bwd_kernel<VEC>, dim3(grid), dim3(kRowsPerBlock * 32), 0, st, dy_f32, dy_bf16, g,
-                        static_cast<int>(g_dtype == CRV_DTYPE_BF16), res, gamma, mean, rstd, p_drop, rng_state, site, dg,
-                        static_cast<int>(dg_dtype == CRV_DTYPE_BF16), dres, M, H));
+    if (param_partials)
+      CRV_CUDA(launch_pdl(ln_bwd_kernel<VEC, true>, dim3(grid), dim3(kRowsPerBlock * 32), 0, st, dy_f32, dy_bf16, g,
+                          static_cast<int>(g_dtype == CRV_DTYPE_BF16), res, gamma, mean, rstd, p_drop, rng_state, site,
+                          dg, static_cast<int>(dg_dtype == CRV_DTYPE_BF16), dres, param_partials, M, H));
+    else
+      CRV_CUDA(launch_pdl(ln_bwd_kernel<VEC, false>, dim3(grid), dim3(kRowsPerBlock * 32), 0, st, dy_f32, dy_bf16, g,
+                          static_cast<int>(g_dtype == CRV_DTYPE_BF16), res, gamma, mean, rstd, p_drop, rng_state, site,
+                          dg, static_cast<int>(dg_dtype == CRV_DTYPE_BF16), dres, param_partials, M, H));
     return launch_status();
   });
 }

@@ -612,11 +612,11 @@ class GraphedStep:
         self.static_inputs = None
         self.static_out = None
         dev = trainer.args.device
-        self.hyper = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.hyper = torch.zeros(3, dtype=torch.float32, device=dev)    # {lr, step_size, 1 / sqrt(1 - b2^t)}
         # {lr, step_size} of step n travel through a RING of pinned buffers: the host runs many steps ahead of the GPU
         # (no sync between logging steps), so one reused buffer would be overwritten with step n+k's values while the
         # copy for step n is still queued.  A slot is rewritten only after the event behind its last copy completed.
-        self.hyper_ring = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(self.HYPER_SLOTS)]
+        self.hyper_ring = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(self.HYPER_SLOTS)]
         self.hyper_events = [None] * self.HYPER_SLOTS
         self.hyper_turn = 0
         self.shapes = None
@@ -629,13 +629,13 @@ class GraphedStep:
         return self.optimizer.state[p0]["step"] + 1
 
     def _upload_hyper(self):
-        lr, step_size = self.optimizer.hyper_values(self._next_step_index())
+        vals = self.optimizer.hyper_values(self._next_step_index())
         i = self.hyper_turn
         self.hyper_turn = (i + 1) % self.HYPER_SLOTS
         if self.hyper_events[i] is not None:
             self.hyper_events[i].synchronize()      # returns at once unless the GPU is HYPER_SLOTS steps behind
         buf = self.hyper_ring[i]
-        buf[0], buf[1] = lr, step_size
+        buf[0], buf[1], buf[2] = vals[0], vals[1], (vals[2] if len(vals) > 2 else 1.0)
         self.hyper.copy_(buf, non_blocking=True)
         ev = self.hyper_events[i] or torch.cuda.Event()
         ev.record(torch.cuda.current_stream())

@@ -218,12 +218,21 @@ int crv_ln_fwd(const void* g, int g_dtype, const float* res, const float* gamma,
                float p_drop, const unsigned long long* rng_state, int site, float* y_f32, uint16_t* y_bf16,
                float* mean, float* rstd, int M, int H, void* stream);
 /* backward: dz = LayerNorm'(dy_f32 + dy_bf16) (either may be NULL); d_res = dz (fp32, may be NULL);
- * d_g = dropout'(dz) in fp32 or bf16 (may be NULL).  gamma / beta are frozen in stage 2: no parameter
- * gradients.  The forward mask is regenerated from the same (rng_state, site). */
+ * d_g = dropout'(dz) in fp32 or bf16 (may be NULL).  The forward mask is regenerated from the same (rng_state, site).
+ * gamma / beta are frozen in stage 2 (param_partials = NULL).  Stage 3 trains them (run_vqa_stage3.py:577-598): pass
+ * crv_ln_bwd_partials_bytes(M, H) bytes; the kernel writes ceil(M / 8) rows of {dgamma[H] | dbeta[H]} partial sums
+ * and crv_partial_reduce adds them in index order (deterministic). */
+size_t crv_ln_bwd_partials_bytes(int M, int H);
 int crv_ln_bwd(const float* dy_f32, const uint16_t* dy_bf16, const void* g, int g_dtype, const float* res,
                const float* gamma, const float* mean, const float* rstd, float p_drop,
-               const unsigned long long* rng_state, int site, void* dg, int dg_dtype, float* dres, int M, int H,
-               void* stream);
+               const unsigned long long* rng_state, int site, void* dg, int dg_dtype, float* dres,
+               float* param_partials, int M, int H, void* stream);
+/* out[j] (+)= sum_i part[i][j], i = 0 .. nparts-1 in order (n columns). */
+int crv_partial_reduce(const float* part, int nparts, int n, float* out, int accumulate, void* stream);
+/* Bias gradient of a linear layer (stage 3): out[n] (+)= sum_m x[m, n], x bf16 [M, N] (N % 8 == 0), deterministic;
+ * workspace: crv_colsum_workspace_bytes(N). */
+size_t crv_colsum_workspace_bytes(int N);
+int crv_colsum_bf16(const uint16_t* x, int M, int N, float* out, int accumulate, void* workspace, void* stream);
 /* Small-sequence multi-head attention, head dim 64, Sq, Sk <= 64 (LxmertAttention.forward,
  * hg_transformers/modeling_lxmert.py:798-827): out = dropout(softmax(Q K^T * scale + mask)) V.
  * q / k / v are bf16 and addressed as base + b * bs + s * ss + head * 64 + d (element strides), so they can
@@ -266,7 +275,12 @@ int crv_sumsq_segmented(const float* x, const int* chunks, int nchunks, float* o
  * follows the learning-rate schedule). */
 int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int64_t n, float lr,
                    float step_size, float beta1, float beta2, float eps, float weight_decay,
-                   const float* total_sumsq, float max_norm, const float* hyper_dev, void* stream);
+                   const float* total_sumsq, float max_norm, const float* hyper_dev, int mode, float inv_bc2_sqrt,
+                   void* stream);
+/* mode: 0 = the rule above (the reference's root optimization.AdamW, stage 2).  1 = torch.optim.Adam as the stage-3
+ * driver builds it (run_vqa_stage3.py:577-598): g' += weight_decay * p; m, v as above; step_size = lr / (1 - b1^t)
+ * (caller); p -= step_size * m / (sqrt(v) * inv_bc2_sqrt + eps) with inv_bc2_sqrt = 1 / sqrt(1 - b2^t); `sum` unused.
+ * hyper_dev, when given, holds {lr, step_size, inv_bc2_sqrt}. */
 
 /* The same step over a whole score arena in ONE launch that also (a) refreshes the masked bf16 operand of every
  * segment, wm = w_bf16 (.) (p_new > thr_vec[segment]) -- the scores are in registers, so the separate
@@ -279,7 +293,10 @@ int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int
 int crv_adamw_segmented(float* p, float* g, float* m, float* v, float* sum, const int* chunks, int nchunks,
                         const float* thr_vec, const uint16_t* w_bf16, uint16_t* wm_bf16, float lr, float step_size,
                         float beta1, float beta2, float eps, float weight_decay, const float* total_sumsq,
-                        float max_norm, const float* hyper_dev, int zero_grad, void* stream);
+                        float max_norm, const float* hyper_dev, int zero_grad, int mode, float inv_bc2_sqrt,
+                        void* stream);
+/* mode 1 (stage 3): p are the trained weights themselves, w_bf16 holds the frozen 0/1 mask as bf16 and the refreshed
+ * operand is wm = bf16(p_new) where the mask is set, 0 elsewhere; thr_vec is not read and may be NULL. */
 
 #ifdef __cplusplus
 }
