@@ -65,24 +65,25 @@ class ProjectionGroup:
     def __init__(self, modules):
         self.modules = list(modules)
         arena = self.modules[0]._arena
-        idx = [arena._index[id(m.weight_mask)] for m in self.modules]
+        idx = [arena.index_of(m) for m in self.modules]
+        shapes = [arena.weight_shape(m) for m in self.modules]
         off0 = arena.offsets[idx[0]]
         off = off0
-        for i, m in zip(idx, self.modules):
-            if arena.offsets[i] != off or m.weight.shape[1] != self.modules[0].weight.shape[1]:
+        for i, shp in zip(idx, shapes):
+            if arena.offsets[i] != off or shp[1] != shapes[0][1]:
                 raise ValueError("modules are not adjacent in the arena")
-            off += m.weight_mask.numel()
+            off += shp[0] * shp[1]
         self.arena = arena
-        self.K = self.modules[0].weight.shape[1]
-        self.N = sum(m.weight.shape[0] for m in self.modules)
+        self.K = shapes[0][1]
+        self.N = sum(shp[0] for shp in shapes)
         n = self.N * self.K
         self.wm = arena.wm[off0: off0 + n].view(self.N, self.K)
         self.w16 = arena.w16[off0: off0 + n].view(self.N, self.K)
-        self.w32 = arena.w32[off0: off0 + n].view(self.N, self.K)
+        self.w32 = arena.w32[off0: off0 + n].view(self.N, self.K)      # the dS multiplier: fp32 W (stage 2) / fp32 mask
         self.grad = arena.grads[off0: off0 + n].view(self.N, self.K)
-        biases = [m.bias for m in self.modules]
-        self.bias = None if any(b is None for b in biases) else torch.cat([b.detach().float() for b in biases]).contiguous()
-        self.anchor = self.modules[0].weight_mask  # keeps the autograd node alive even if x needs no gradient
+        # stage 2: frozen biases (a private copy); stage 3: live views of the trained biases and of their gradients
+        self.bias, self.bias_grad = arena.group_bias(self.modules)
+        self.anchor = arena.anchor(self.modules[0])  # keeps the autograd node alive even if x needs no gradient
 
     def valid(self):
         a = self.arena
@@ -126,9 +127,13 @@ class GroupLinearFn(torch.autograd.Function):
         if lane is not None:
             with torch.cuda.stream(lane.stream):
                 ops.masked_linear_bwd_ds(dy2, x2, g.w32, out=g.grad, accumulate=dirty)
+                if g.bias_grad is not None:
+                    ops.colsum_bf16(dy2, g.bias_grad, accumulate=True)
             lane.hold(dy2, x2)
         else:
             ops.masked_linear_bwd_ds(dy2, x2, g.w32, out=g.grad, accumulate=dirty)
+            if g.bias_grad is not None:      # stage 3: db += column sums of dY (the optimiser pass cleared G)
+                ops.colsum_bf16(dy2, g.bias_grad, accumulate=True)
         for m in g.modules:
             ops._sink_done(m)
         return dx, None, None, None
@@ -192,7 +197,7 @@ class MultiLinearFn(torch.autograd.Function):
         specs, n = ctx.specs, len(ctx.specs)
         saved = list(ctx.saved_tensors)
         x2s, us = saved[:n], saved[n:]
-        p_dx, p_ds, dxs, seen, k, ui, held = [], [], [], set(), 0, 0, []
+        p_dx, p_ds, dxs, seen, k, ui, held, colsums = [], [], [], set(), 0, 0, [], []
         for i, (group, out_dtype, gelu_out, has_u) in enumerate(specs):
             dy = dys[k]
             k += 2 if gelu_out else 1
@@ -215,6 +220,8 @@ class MultiLinearFn(torch.autograd.Function):
             seen.add(key)
             p_ds.append(ops.gemm_problem(ops.GEMM_DS, dy2, x2s[i], group.grad, w_f32=group.w32, accumulate=acc))
             held += [dy2, x2s[i]]
+            if group.bias_grad is not None:
+                colsums.append((dy2, group.bias_grad))
         # dX feeds the next layer's backward, dS only the end of the step.  Either everything shares one grouped launch
         # list, or (CRVQA_GROUP_DS_LANE=1) the dS group runs on the dS lane beside the dX chain and the small kernels
         # between the GEMMs (ops._DsLane).
@@ -233,6 +240,8 @@ class MultiLinearFn(torch.autograd.Function):
             lane.hold(*held)
         else:
             ops.gemm_grouped(p_dx + p_ds)
+        for dy2, bg in colsums:              # stage 3: bias gradients (G is cleared by the optimiser pass)
+            ops.colsum_bf16(dy2, bg, accumulate=True)
         k = 0
         for group, _, gelu_out, _ in specs:
             live = dys[k] is not None
@@ -309,9 +318,13 @@ class DropAddLayerNormFn(torch.autograd.Function):
                              ops.DT_BF16, _p(dres), _p(part), M, H, _stream()), "crv_ln_bwd")
         dgamma = dbeta = None
         if part is not None:
-            both = torch.empty(2 * H, dtype=torch.float32, device=g2.device)
-            ops.partial_reduce(part, both)
-            dgamma, dbeta = both[:H], both[H:]
+            pair = getattr(gamma, "_arena_pair", None)
+            if pair is not None and gamma.grad is not None:     # [dgamma | dbeta] added straight into the arena
+                ops.partial_reduce(part, pair, accumulate=True)
+            else:
+                both = torch.empty(2 * H, dtype=torch.float32, device=g2.device)
+                ops.partial_reduce(part, both)
+                dgamma, dbeta = both[:H], both[H:]
         return (dg.view(ctx.shape), dres.view(ctx.shape) if dres is not None else None, dgamma, dbeta, None, None, None,
                 None)
 
@@ -484,7 +497,7 @@ def small_attention(kind, heads, mask, p, site, training, *srcs):
 def _arena_ready(*mods):
     for m in mods:
         a = getattr(m, "_arena", None)
-        if a is None or not a.cache_on or a.cached_masked_weight(m) is None or not m.weight_mask.is_cuda:
+        if a is None or not a.cache_on or not a.module_ready(m) or a.cached_masked_weight(m) is None:
             return False
     return True
 

@@ -73,14 +73,17 @@ def to_bf16(x):
     return out
 
 
-def mul_cast_bf16(w, mask):
+def mul_cast_bf16(w, mask, out=None):
     """bf16(w * mask), product in fp32 (stage-3 pruned operand, crv_mul_cast_bf16)."""
     _need_cuda(w)
     w = w.detach().contiguous()
     mask = mask.contiguous()
     if w.dtype != torch.float32 or mask.dtype != torch.float32 or w.shape != mask.shape:
         raise ValueError("mul_cast_bf16 needs fp32 weight and fp32 0/1 mask of the same shape")
-    out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    if out is None:
+        out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    elif out.dtype != torch.bfloat16 or out.numel() != w.numel() or not out.is_contiguous():
+        raise ValueError("mul_cast_bf16: out must be a contiguous bf16 tensor of the same size")
     check(lib.crv_mul_cast_bf16(_p(w), _p(mask), _p(out), w.numel(), _stream()), "crv_mul_cast_bf16")
     return out
 

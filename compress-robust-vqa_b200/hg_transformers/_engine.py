@@ -113,6 +113,29 @@ class ScoreArena:
     def owns(self, p):
         return id(p) in self._index
 
+    # -- what crvqa.fused.ProjectionGroup asks of an arena (hg_transformers._engine_ft.WeightArena answers the same) ----
+    def index_of(self, m):
+        return self._index[id(m.weight_mask)]
+
+    def weight_shape(self, m):
+        return tuple(m.weight.shape)
+
+    def anchor(self, m):
+        return m.weight_mask
+
+    def module_ready(self, m):
+        return m.weight_mask.is_cuda
+
+    def group_bias(self, modules):
+        """(bias, bias gradient): the biases are frozen in stage 2 -- one private fp32 copy, no gradient."""
+        biases = [m.bias for m in modules]
+        if any(b is None for b in biases):
+            return None, None
+        return torch.cat([b.detach().float() for b in biases]).contiguous(), None
+
+    def loose_grads(self):
+        return []
+
     def _ensure_state(self):
         if self.exp_avg is None:
             self.exp_avg = torch.zeros_like(self.scores)

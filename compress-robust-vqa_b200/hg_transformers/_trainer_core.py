@@ -327,6 +327,8 @@ class TrainerCore:
         """Move the scores into a flat arena and hook up the data-parallel gradient exchange."""
         if self.arena is not None:
             return
+        if self.masker is None and hasattr(optimizer, "attach_weight_arena"):
+            return self._setup_finetune_engine(optimizer)
         mods = [(n, m) for n, m in masked_modules_of(self.model)
                 if m.weight_mask.requires_grad and m.weight_mask.is_cuda and getattr(m, "unstructured_masked", False)]
         if not mods:
@@ -339,6 +341,23 @@ class TrainerCore:
         self.grad_sync = GradSync(self.arena)
         self.grad_sync.defer = self.args.gradient_accumulation_steps > 1
         self.grad_sync.attach_loose(self._loose_params())
+
+    def _setup_finetune_engine(self, optimizer):
+        """Stage 3 (FT_trainedMask / FT_randMask, run_vqa_stage3.py): every trainable tensor moves into a WeightArena,
+        the optimiser (run_vqa_stage3.ArenaAdam) steps it with one launch.  CRVQA_FT_ENGINE=0 keeps per-tensor Adam."""
+        if os.environ.get("CRVQA_FT_ENGINE", "1") == "0" or self.args.device.type != "cuda":
+            return
+        from ._engine_ft import WeightArena
+        owned = {id(p) for g in optimizer.param_groups for p in g["params"]}
+        if owned != {id(p) for p in self.model.parameters() if p.requires_grad}:
+            return          # a hand-made optimiser over a subset: leave it alone
+        try:
+            self.arena = WeightArena(self.model)
+        except ValueError:
+            return
+        optimizer.attach_weight_arena(self.arena)
+        self.grad_sync = GradSync(self.arena, mode="allreduce")
+        self.grad_sync.defer = self.args.gradient_accumulation_steps > 1
 
     def _prefetched(self, dataloader):
         """Yield batches whose host -> device copy was started one step ahead on a side stream."""
@@ -410,7 +429,7 @@ class TrainerCore:
             RngState.get(self.args.device).advance()   # fresh dropout masks for the fused kernels, graph-safe
         loss, score = self._training_step(model, inputs, optimizer)
         if self.grad_sync is not None:
-            self.grad_sync.finish([p.grad for p in self._loose_params()])
+            self.grad_sync.finish([p.grad for p in self._loose_params()] + self.arena.loose_grads())
         self._clip_and_optimizer_step(model, optimizer)
         self._zero_grad(optimizer)
         return loss, score
@@ -474,7 +493,7 @@ class TrainerCore:
                 if (step + 1) % accum == 0 or (n_batches <= accum and (step + 1) == n_batches):
                     if graphed is None:
                         if self.grad_sync is not None:
-                            self.grad_sync.finish([p.grad for p in self._loose_params()])
+                            self.grad_sync.finish([p.grad for p in self._loose_params()] + self.arena.loose_grads())
                         self._clip_and_step(model, optimizer, scheduler)
                         self._zero_grad(optimizer)
                     self.global_step += 1

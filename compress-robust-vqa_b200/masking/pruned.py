@@ -21,15 +21,20 @@ from crvqa import ops
 
 
 class PrunedLinearFn(torch.autograd.Function):
+    """`wm` / `sink`: under the stage-3 engine (hg_transformers._engine_ft.WeightArena) the bf16 operand is the arena's
+    (kept current by the optimiser pass) and dW_orig is written into the arena gradient by the GEMM epilogue."""
+
     @staticmethod
-    def forward(ctx, x, weight_orig, mask, bias):
+    def forward(ctx, x, weight_orig, mask, bias, wm=None, sink=None):
         shp = x.shape
         x2 = ops.to_bf16(x.reshape(-1, shp[-1]))
-        wm = ops.mul_cast_bf16(weight_orig, mask)
+        if wm is None:
+            wm = ops.mul_cast_bf16(weight_orig, mask)
         y = ops.masked_linear_fwd(x2, wm, None, None, bias, torch.float32)
         ctx.save_for_backward(x2, wm, mask)
         ctx.x_shape = shp
         ctx.has_bias = bias is not None
+        ctx.sink = sink
         return y.view(*shp[:-1], wm.shape[0])
 
     @staticmethod
@@ -41,10 +46,15 @@ class PrunedLinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = ops.masked_linear_bwd_dx(dy2, wm, None, None, torch.float32).view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            dw = ops.masked_linear_bwd_ds(dy2, x2, mask)        # (dY^T X) (.) M: the multiplier is the 0/1 mask
+            sink = ctx.sink
+            if sink is not None and ops._sink_grad(sink) is not None:
+                ops.masked_linear_bwd_ds(dy2, x2, mask, out=ops._sink_grad(sink), accumulate=ops.ds_mode(sink))
+                ops._sink_done(sink)
+            else:
+                dw = ops.masked_linear_bwd_ds(dy2, x2, mask)    # (dY^T X) (.) M: the multiplier is the 0/1 mask
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = d.sum(0)
-        return dx, dw, None, db
+        return dx, dw, None, db, None, None
 
 
 class PrunedLinear(nn.Module):
@@ -65,7 +75,13 @@ class PrunedLinear(nn.Module):
         if self.in_features % 8 != 0:
             # box_fc (K = 4) cannot be a TMA operand; 3 K-element rows of torch math on the device
             return F.linear(x, self.weight_orig * self.weight_mask, self.bias)
-        return PrunedLinearFn.apply(x, self.weight_orig, self.weight_mask.contiguous(), self.bias)
+        arena = getattr(self, "_arena", None)
+        wm = sink = None
+        if arena is not None and x.is_cuda:
+            wm, sink = arena.cached_masked_weight(self), self
+            if torch.is_grad_enabled() and getattr(self, "_sync", None) is not None:
+                self._sync.note_forward(self)
+        return PrunedLinearFn.apply(x, self.weight_orig, self.weight_mask.contiguous(), self.bias, wm, sink)
 
     def extra_repr(self):
         return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}"

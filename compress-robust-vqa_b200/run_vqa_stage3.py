@@ -14,6 +14,7 @@ reference driver is out of scope.
 import torch
 from torch.optim._functional import adam as _adam_functional
 
+from crvqa import ops
 from hg_transformers.optimization import get_linear_schedule_with_warmup
 from masking.pruned import PrunedEmbedding, PrunedLinear, custom_from_mask, l1_unstructured_mask  # noqa: F401 (re-exported)
 
@@ -98,6 +99,86 @@ class GroupedAdam(torch.optim.Adam):
         return loss
 
 
+class ArenaAdam(GroupedAdam):
+    """GroupedAdam that, once a hg_transformers._engine_ft.WeightArena is attached (Trainer._setup_engine), performs
+    the whole step -- global-norm clip, Adam on every trainable tensor, refresh of the bf16 GEMM operands, gradient
+    clearing -- as ONE launch over the arena (crv_adamw_segmented, torch.optim.Adam rule).  `param_groups`, the
+    per-parameter state (`step`, `exp_avg`, `exp_avg_sq`: views of the arena's flat buffers) and the LambdaLR
+    scheduler contract are torch.optim.Adam's; without an arena it IS GroupedAdam."""
+
+    def __init__(self, params, **kw):
+        super().__init__(params, **kw)
+        self._arena = None
+        self._clip = None
+        self._hyper = None
+
+    def attach_weight_arena(self, arena):
+        for group in self.param_groups:
+            if group["amsgrad"] or group["maximize"]:
+                raise ValueError("the arena optimiser pass implements plain Adam (no amsgrad / maximize)")
+            for p in group["params"]:
+                views = arena.state_views(p)
+                if views is None:
+                    raise ValueError("every parameter of the optimiser must live in the arena")
+                st = self.state[p]
+                for k in ("exp_avg", "exp_avg_sq"):
+                    if k in st:
+                        views[k].copy_(st[k])
+                    st[k] = views[k]
+                if "step" not in st:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+        self._arena = arena
+
+    # -- engine hooks (same contract as optimization.AdamW) ----------------------------------------------------
+    def set_clip(self, total_sumsq, max_norm):
+        self._clip = (total_sumsq, float(max_norm))
+
+    def use_device_hyper(self, hyper):
+        self._hyper = hyper
+
+    def ensure_state(self):
+        pass
+
+    def _steps(self):
+        return [self.state[p]["step"] for g in self.param_groups for p in g["params"]]
+
+    def advance_steps(self, n=1):
+        n = int(n)
+        if n:
+            torch._foreach_add_(self._steps(), float(n))
+
+    def _shared(self):
+        g = self.param_groups[0]
+        key = (g["lr"], g["betas"], g["eps"], g["weight_decay"])
+        for other in self.param_groups[1:]:
+            if (other["lr"], other["betas"], other["eps"], other["weight_decay"]) != key:
+                raise RuntimeError("the arena optimiser pass needs one lr / betas / eps / weight_decay for all groups "
+                                   "(true of init_optimizer + LambdaLR); set CRVQA_FT_ENGINE=0 otherwise")
+        return g
+
+    def hyper_values(self, next_step):
+        g = self._shared()
+        return ops.adam_hyper(ops.ADAM_TORCH, g["lr"], int(next_step), g["betas"][0], g["betas"][1])
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if self._arena is None:
+            return super().step(closure)
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        g = self._shared()
+        p0 = g["params"][0]
+        t = int(self.state[p0]["step"]) + 1
+        clip_sumsq, max_norm = self._clip if self._clip is not None else (None, 1.0)
+        self._clip = None
+        self._arena.adam_step(g["lr"], t, g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], clip_sumsq,
+                              max_norm, self._hyper)
+        self.advance_steps(1)
+        return loss
+
+
 def init_optimizer(model, training_args, num_train_data):
     """torch.optim.Adam with one param group per tensor + linear schedule (:577-598)."""
     params = [{"params": [value], "name": key, "weight_decay": training_args.weight_decay,
@@ -106,8 +187,8 @@ def init_optimizer(model, training_args, num_train_data):
     # same update rule as the reference's torch.optim.Adam(params, lr, betas, eps): fused implementation on CUDA, and
     # all groups stepped by one multi-tensor call (GroupedAdam)
     on_cuda = all(g["params"][0].is_cuda for g in params) and len(params) > 0
-    optimizer = GroupedAdam(params, lr=training_args.learning_rate, betas=(0.9, 0.999),
-                            eps=training_args.adam_epsilon, **({"fused": True} if on_cuda else {}))
+    optimizer = ArenaAdam(params, lr=training_args.learning_rate, betas=(0.9, 0.999),
+                          eps=training_args.adam_epsilon, **({"fused": True} if on_cuda else {}))
     num_training_steps = int(int(num_train_data / (max(1, training_args.n_gpu) * training_args.per_gpu_train_batch_size) + 1)
                              * training_args.num_train_epochs)
     scheduler = get_linear_schedule_with_warmup(optimizer, num_warmup_steps=training_args.warmup_steps,
@@ -115,5 +196,5 @@ def init_optimizer(model, training_args, num_train_data):
     return optimizer, scheduler
 
 
-__all__ = ["GroupedAdam", "PrunedLinear", "PrunedEmbedding", "pruning_model_with_mask", "mag_pruning", "see_weight_rate",
+__all__ = ["ArenaAdam", "GroupedAdam", "PrunedLinear", "PrunedEmbedding", "pruning_model_with_mask", "mag_pruning", "see_weight_rate",
            "init_optimizer", "trained_mask_module_names"]
