@@ -186,16 +186,98 @@ def run_torch_gpu(args):
           "last_loss": last, "gpu_launches": 0})
 
 
+# --------------------------------------------------------------------------- workloads of the GPU arm
+# --config lxmert (default) is BASELINE configs[1], the line the driver records.  The other two put BASELINE configs[2]
+# (VisualBERT stage 2) and configs[3] (LXMERT stage-3 fine-tune of the pruned model) through the same timing code so
+# that their numbers are reproducible with one command; they print the same JSON line with their own metric name.
+WORKLOADS = {
+    "lxmert": {"metric": METRIC, "gflop_per_sample": GFLOP_PER_SAMPLE},
+    "visualbert": {"metric": "VisualBERT stage-2 mask-train samples/s", "gflop_per_sample": 28.54},
+    "stage3": {"metric": "LXMERT stage-3 pruned fine-tune samples/s", "gflop_per_sample": GFLOP_PER_SAMPLE},
+}
+
+
+def build_workload(args, dev, world, local_rank, rank):
+    """-> dict(trainer, model, optimizer, scheduler, refresh (callable or None), host (8-tuple of CPU tensors),
+    workload (str), logging_steps)."""
+    import logging
+    import types
+
+    import torch
+    from hg_transformers.data.data_collator import TrimCollator
+    from hg_transformers.data.metrics import vqa_compute_metrics
+    from hg_transformers.training_args import TrainingArguments
+    from prune_debias_VQA import batch_tuple, synthetic_batch
+    B, A = args.batch, args.ans_num
+    out_dir = os.path.join(ROOT, "gpurun_out", "bench_out")
+    common = dict(output_dir=out_dir, per_gpu_train_batch_size=B, logging_steps=100, seed=49, save_steps=0,
+                  local_rank=local_rank if world > 1 else -1, dataloader_num_workers=0)
+    host = batch_tuple(synthetic_batch(B, A, seed=49 + rank))
+    if args.config == "lxmert":
+        from hg_transformers.mask_trainer_Robust_VQA import Trainer
+        from prune_debias_VQA import build_stage2, init_optimizer
+        targs = TrainingArguments(Masker_type=args.loss, training_type="Masker", **common)
+        model, masker, margs = build_stage2(A, device=dev, seed=49)
+        optimizer, scheduler = init_optimizer(model, targs, num_train_data=B * world * 10000)
+        trainer = Trainer(model=model, args=targs, model_args=margs, data_collator=TrimCollator(), train_dataset=None,
+                          compute_metrics=vqa_compute_metrics, optimizers=(optimizer, scheduler), masker=masker)
+        name = workload_name(B, A, args.loss)
+    elif args.config == "visualbert":
+        # BASELINE configs[2]: 74 masked modules, 109 M scores, one uniform zero rate 0.7, lr 5e-5, 20 + 36 = 56 tokens,
+        # BCE (the visualBERT trainer's `normal` loss; hg_transformers/mask_trainer_visualBERT_VQA.py:815-830)
+        from hg_transformers.mask_trainer_visualBERT_VQA import Trainer
+        from prune_debias_VQA import init_optimizer
+        from prune_debias_VQA_visualBERT import build_stage2
+        targs = TrainingArguments(Masker_type="normal", training_type="Masker", learning_rate=5e-5, **common)
+        model, masker, margs = build_stage2(A, device=dev, seed=49, config_kwargs={"visual_embedding_dim": 2048})
+        optimizer, scheduler = init_optimizer(model, targs, num_train_data=B * world * 10000)
+        trainer = Trainer(model=model, args=targs, model_args=margs, data_collator=TrimCollator(), train_dataset=None,
+                          compute_metrics=vqa_compute_metrics, optimizers=(optimizer, scheduler), masker=masker)
+        host[0] = host[0].clamp_min(1)                 # VisualBERT's padding id is 1 (configuration_visualbert.py:125)
+        name = (f"VisualBERT 12L h=768 stage-2 mask train (BCE), batch {B}/GPU, 20 tokens + 36x2048 regions, A={A}, uniform "
+                f"zero-rate 0.7, lr 5e-5, seed 49, random init, dropout on, bf16 MMA / fp32 accumulate")
+    else:
+        # BASELINE configs[3]: stage-3 fine-tune of the pruned model: frozen magnitude masks at zero rate 0.7 on the 168
+        # stage-2 modules, EVERY tensor trained by torch.optim.Adam semantics, LMH loss (run_vqa_stage3.py:577-598,773-799)
+        import run_vqa_stage3 as s3
+        from crvqa import ops
+        from hg_transformers.mask_trainer_VQA import Trainer
+        from hg_transformers.modeling_lxmert import LxmertConfig, LxmertForMultipleChoice
+        from prune_debias_VQA import ModelArguments
+        torch.manual_seed(49)
+        model = LxmertForMultipleChoice(LxmertConfig(ans_num=A)).to(dev)
+        mods = dict(model.lxmert.named_modules())
+        names = s3.trained_mask_module_names()
+        ws = [mods[n].weight.detach() for n in names]
+        thr = ops.kth_value_batched(ws, [max(1, int(w.numel() * 0.7)) for w in ws], use_abs=True)
+        s3.pruning_model_with_mask(model.lxmert, {f"lxmert.{n}.weight_mask": (w.abs() > thr[i])
+                                                  for i, (n, w) in enumerate(zip(names, ws))}, "lxmert")
+        targs = TrainingArguments(training_type="FT_trainedMask", FT_type="lmh", **common)
+        optimizer, scheduler = s3.init_optimizer(model, targs, B * world * 10000)
+        trainer = Trainer(model=model, args=targs, model_args=ModelArguments(), data_collator=TrimCollator(),
+                          train_dataset=None, compute_metrics=vqa_compute_metrics, optimizers=(optimizer, scheduler),
+                          masker=None)
+        masker = None
+        name = (f"LXMERT 9L/5R/5X h=768 stage-3 fine-tune of the pruned model (frozen masks, zero-rate 0.7, every tensor "
+                f"trained, Adam, LMH loss), batch {B}/GPU, 20 tokens + 36x2048 regions, A={A}, seed 49, random init, "
+                f"dropout on, bf16 MMA / fp32 accumulate")
+    trainer._setup_engine(optimizer)
+    if trainer.arena is None:
+        raise SystemExit(f"bench.py --config {args.config}: the arena engine did not engage")
+    trainer.global_step = 0
+    refresh = None
+    if masker is not None:
+        def refresh():
+            trainer.reset_threshold(model, masker.masker_scheduler.init_sparsity)
+    return {"trainer": trainer, "model": model, "optimizer": optimizer, "scheduler": scheduler, "refresh": refresh,
+            "host": host, "workload": name, "logging_steps": targs.logging_steps}
+
+
 # --------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from crvqa import lib, ops
-    from hg_transformers.data.data_collator import TrimCollator
-    from hg_transformers.data.metrics import vqa_compute_metrics
-    from hg_transformers.mask_trainer_Robust_VQA import Trainer
-    from hg_transformers.training_args import TrainingArguments
-    from prune_debias_VQA import batch_tuple, build_stage2, init_optimizer, synthetic_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,18 +290,10 @@ def run_ours(args):
         dist.init_process_group(backend="nccl", device_id=dev)
 
     B, A = args.batch, args.ans_num
-    targs = TrainingArguments(output_dir=os.path.join(ROOT, "gpurun_out", "bench_out"), per_gpu_train_batch_size=B,
-                              logging_steps=100, seed=49, Masker_type=args.loss, training_type="Masker",
-                              save_steps=0, local_rank=local_rank if world > 1 else -1, dataloader_num_workers=0)
-    model, masker, margs = build_stage2(A, device=dev, seed=49)
-    optimizer, scheduler = init_optimizer(model, targs, num_train_data=B * world * 10000)
-    trainer = Trainer(model=model, args=targs, model_args=margs, data_collator=TrimCollator(), train_dataset=None,
-                      compute_metrics=vqa_compute_metrics, optimizers=(optimizer, scheduler), masker=masker)
-    trainer._setup_engine(optimizer)
-    trainer.global_step = 0
-
-    host = synthetic_batch(B, A, seed=49 + rank)
-    host_inputs = [t.pin_memory() for t in batch_tuple(host)]
+    wl = build_workload(args, dev, world, local_rank, rank)
+    trainer, model, optimizer, scheduler = wl["trainer"], wl["model"], wl["optimizer"], wl["scheduler"]
+    logging_steps = wl["logging_steps"]
+    host_inputs = [t.pin_memory() for t in wl["host"]]
     dev_inputs = [t.to(dev) for t in host_inputs]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_inputs)
 
@@ -236,8 +310,7 @@ def run_ours(args):
         trainer.global_step += 1
         return loss
 
-    def refresh():
-        trainer.reset_threshold(model, masker.masker_scheduler.init_sparsity)
+    refresh = wl["refresh"]           # None for stage 3: the masks are frozen, there is no threshold to refresh
 
     def barrier():
         if world > 1:
@@ -270,15 +343,17 @@ def run_ours(args):
     # ---- threshold refresh (reset_threshold: 168 exact selects + mask-cache refresh), every `logging_steps` = 100
     # steps in the recipe: a K-step region cannot hold 1/100 of one, so it is timed here (CUDA events, host enqueue
     # included) and its amortised share is ADDED to ms_per_step / value below
-    refresh()
-    torch.cuda.synchronize()
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r0.record()
-    for _ in range(3):
+    refresh_ms = 0.0
+    if refresh is not None:
         refresh()
-    r1.record()
-    torch.cuda.synchronize()
-    refresh_ms = r0.elapsed_time(r1) / 3
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(3):
+            refresh()
+        r1.record()
+        torch.cuda.synchronize()
+        refresh_ms = r0.elapsed_time(r1) / 3
     # ---- masked-GEMM family alone: record every GEMM launch of one eager step of the same workload (same
     # operands, same order), re-issue them back to back as one CUDA graph and time the replays with CUDA events
     c0 = lib.crv_launch_count()
@@ -322,7 +397,7 @@ def run_ours(args):
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms) + args.steps * refresh_ms / targs.logging_steps
+    ms_total = float(ms) + args.steps * refresh_ms / logging_steps
     clock_info = clocks.stop() if rank == 0 else None
 
     # ---- timed region 2: end to end (pinned host inputs -> H2D every step, loss read back every step)
@@ -354,7 +429,7 @@ def run_ours(args):
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    ms_e2e = float(ms2) + args.steps * refresh_ms / targs.logging_steps
+    ms_e2e = float(ms2) + args.steps * refresh_ms / logging_steps
 
     def finish():
         """Multi-rank teardown: NCCL communicators referenced by a live CUDA graph can block in
@@ -404,21 +479,22 @@ def run_ours(args):
                        "graph, CUDA events around 5 replays",
                 "by_kernel": {k: {"launches": v[0], "gflop": v[1] / 1e9} for k, v in by_kind.items()}}
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.config == "lxmert":
         cpu = cpu_baseline_subprocess(A, args.loss)
     value = world * B * args.steps / (ms_total * 1e-3)
-    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": WORKLOADS[args.config]["metric"], "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(B, A, args.loss), "global_batch": B * world,
+            "config": {"workload": wl["workload"], "global_batch": B * world,
                        "parallelism": f"dp{world}",
-                       "threshold_refresh": {"every_steps": targs.logging_steps, "refresh_ms": refresh_ms,
-                                             "amortised_ms_per_step": refresh_ms / targs.logging_steps,
-                                             "included_in_value_and_e2e": True},
+                       "threshold_refresh": ({"every_steps": logging_steps, "refresh_ms": refresh_ms,
+                                              "amortised_ms_per_step": refresh_ms / logging_steps,
+                                              "included_in_value_and_e2e": True} if refresh is not None else
+                                             "none (stage 3: frozen masks)"),
                        "step_execution": "eager" if graphed is None else "cuda-graph replay of the whole step",
                        "mask_mode": os.environ.get("CRVQA_MASK_MODE", "cached"),
                        "l2": "per-step working set (weights 0.4 GB + scores/grads/Adam 4 GB) far exceeds the 126 MB L2",
-                       "gflop_per_sample_masked_gemm": GFLOP_PER_SAMPLE},
+                       "gflop_per_sample_masked_gemm": WORKLOADS[args.config]["gflop_per_sample"]},
             "clocks": clock_info,
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
@@ -467,6 +543,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
+    ap.add_argument("--config", default="lxmert", choices=sorted(WORKLOADS),
+                    help="lxmert = BASELINE configs[1] (the recorded line); visualbert = configs[2]; stage3 = configs[3]")
     ap.add_argument("--precision", default="bf16-autocast", choices=["fp32", "tf32", "bf16-autocast"],
                     help="--impl torch-gpu only")
     ap.add_argument("--cpu-batch", type=int, default=32, help="--impl reference: batch of one bounded CPU step")

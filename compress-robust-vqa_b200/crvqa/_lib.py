@@ -1,7 +1,7 @@
 """Loader and prototypes for the C ABI declared in include/crvqa.h."""
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_size_t, c_void_p
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcrvqa.so")
 
@@ -65,10 +65,10 @@ _PROTOS = {
     "crv_rng_advance": (c_int, [_P, _P]),
     "crv_sumsq_workspace_bytes": (c_size_t, []),
     "crv_sumsq": (c_int, [_P, c_int64, _P, _P, _P]),
-    "crv_adamw_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float,
+    "crv_adamw_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_double, c_double, c_float,
                                c_float, _P, c_float, _P, c_int, c_float, _P]),
     "crv_sumsq_segmented": (c_int, [_P, _P, c_int, _P, _P, _P]),
-    "crv_adamw_segmented": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_float, c_float, c_float, c_float, c_float,
+    "crv_adamw_segmented": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_float, c_float, c_double, c_double, c_float,
                                     c_float, _P, c_float, _P, c_int, c_int, c_float, _P]),
 }
 EXPORTED = tuple(_PROTOS)

@@ -231,22 +231,30 @@ __global__ void sumsq_segmented_kernel(const float* __restrict__ x, const int4* 
 struct AdamArgs {
   float lr, step_size, beta1, beta2, eps, weight_decay, max_norm, inv_bc2_sqrt;
   int mode;
+  // 1 - beta rounded ONCE from double, as torch rounds the Python scalars `1.0 - beta` of add_(alpha=) / lerp_ /
+  // addcmul_(value=): float(1 - 0.999) = 0.001f, whereas 1.0f - 0.999f = 0.00100005f (4.7e-5 off in exp_avg_sq)
+  float omb1, omb2;
 };
+static AdamArgs make_adam_args(float lr, float step_size, double beta1, double beta2, float eps, float weight_decay,
+                               float max_norm, float inv_bc2_sqrt, int mode) {
+  return AdamArgs{lr, step_size, static_cast<float>(beta1), static_cast<float>(beta2), eps, weight_decay, max_norm,
+                  inv_bc2_sqrt, mode, static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2)};
+}
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float* sum, const AdamArgs& a,
                                          float clip) {
   g *= clip;
   if (a.mode == 0) {
     if (sum) *sum += fabsf(g);
-    m = m * a.beta1 + (1.0f - a.beta1) * g;
-    v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+    m = m * a.beta1 + a.omb1 * g;
+    v = v * a.beta2 + a.omb2 * g * g;
     const float denom = sqrtf(v) + a.eps;
     p = p - a.step_size * (m / denom);
     if (a.weight_decay > 0.f) p = p - a.lr * a.weight_decay * p;
   } else {
     if (a.weight_decay > 0.f) g = fmaf(a.weight_decay, p, g);
-    m = m + (g - m) * (1.0f - a.beta1);
-    v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+    m = m + (g - m) * a.omb1;
+    v = v * a.beta2 + a.omb2 * g * g;
     const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
     p = p - a.step_size * (m / denom);
   }
@@ -633,14 +641,14 @@ extern "C" int crv_sumsq_segmented(const float* x, const int* chunks, int nchunk
 }
 
 extern "C" int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int64_t n, float lr,
-                              float step_size, float beta1, float beta2, float eps, float weight_decay,
+                              float step_size, double beta1, double beta2, float eps, float weight_decay,
                               const float* total_sumsq, float max_norm, const float* hyper_dev, int mode,
                               float inv_bc2_sqrt, void* stream) {
   if (!p || !g || !m || !v || n < 0) return CRV_E_BADARG;
   if (n == 0) return CRV_OK;
   if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (sum && !aligned16(sum))) return CRV_E_ALIGN;
   if (mode != 0 && mode != 1) return CRV_E_BADARG;
-  AdamArgs a{lr, step_size, beta1, beta2, eps, weight_decay, max_norm, inv_bc2_sqrt, mode};
+  const AdamArgs a = make_adam_args(lr, step_size, beta1, beta2, eps, weight_decay, max_norm, inv_bc2_sqrt, mode);
   adamw_kernel<<<stream_grid(n >> 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, sum, n, a,
                                                                                          total_sumsq, hyper_dev);
   return launch_status();
@@ -676,7 +684,7 @@ extern "C" int crv_partial_reduce(const float* part, int nparts, int n, float* o
 
 extern "C" int crv_adamw_segmented(float* p, float* g, float* m, float* v, float* sum, const int* chunks, int nchunks,
                                    const float* thr_vec, const uint16_t* w_bf16, uint16_t* wm_bf16, float lr,
-                                   float step_size, float beta1, float beta2, float eps, float weight_decay,
+                                   float step_size, double beta1, double beta2, float eps, float weight_decay,
                                    const float* total_sumsq, float max_norm, const float* hyper_dev, int zero_grad,
                                    int mode, float inv_bc2_sqrt, void* stream) {
   if (!p || !g || !m || !v || !chunks || (!thr_vec && mode == 0) || nchunks < 0) return CRV_E_BADARG;
@@ -686,7 +694,7 @@ extern "C" int crv_adamw_segmented(float* p, float* g, float* m, float* v, float
       !aligned16(chunks) || (w_bf16 && (!aligned16(w_bf16) || !aligned16(wm_bf16))))
     return CRV_E_ALIGN;
   if (mode != 0 && mode != 1) return CRV_E_BADARG;
-  AdamArgs a{lr, step_size, beta1, beta2, eps, weight_decay, max_norm, inv_bc2_sqrt, mode};
+  const AdamArgs a = make_adam_args(lr, step_size, beta1, beta2, eps, weight_decay, max_norm, inv_bc2_sqrt, mode);
   const int grid = nchunks < num_sms() * 8 ? nchunks : num_sms() * 8;
   adamw_segmented_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, sum, reinterpret_cast<const int4*>(chunks), nchunks, thr_vec, w_bf16, wm_bf16, a, total_sumsq,

@@ -274,7 +274,7 @@ int crv_sumsq_segmented(const float* x, const int* chunks, int nchunks, float* o
  * read from that device array instead of the by-value arguments (so a captured CUDA graph of the step
  * follows the learning-rate schedule). */
 int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int64_t n, float lr,
-                   float step_size, float beta1, float beta2, float eps, float weight_decay,
+                   float step_size, double beta1, double beta2, float eps, float weight_decay,
                    const float* total_sumsq, float max_norm, const float* hyper_dev, int mode, float inv_bc2_sqrt,
                    void* stream);
 /* mode: 0 = the rule above (the reference's root optimization.AdamW, stage 2).  1 = torch.optim.Adam as the stage-3
@@ -292,7 +292,7 @@ int crv_adamw_step(float* p, const float* g, float* m, float* v, float* sum, int
  * by another rank, whose gradient buffer holds reduce-scatter leftovers); w_bf16 / wm_bf16 may both be NULL. */
 int crv_adamw_segmented(float* p, float* g, float* m, float* v, float* sum, const int* chunks, int nchunks,
                         const float* thr_vec, const uint16_t* w_bf16, uint16_t* wm_bf16, float lr, float step_size,
-                        float beta1, float beta2, float eps, float weight_decay, const float* total_sumsq,
+                        double beta1, double beta2, float eps, float weight_decay, const float* total_sumsq,
                         float max_norm, const float* hyper_dev, int zero_grad, int mode, float inv_bc2_sqrt,
                         void* stream);
 /* mode 1 (stage 3): p are the trained weights themselves, w_bf16 holds the frozen 0/1 mask as bf16 and the refreshed
