@@ -23,6 +23,9 @@
 // transform thread reads one 16-byte chunk of W (8 bf16) plus the two matching 16-byte chunks of S
 // without bank conflicts, then fences its generic-proxy writes towards the async proxy.
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 #include "gelu.cuh"
@@ -45,6 +48,8 @@ struct GemmParams {
   const float* w;          // [MM, NN] fp32 multiplier (score-grad epilogue): the reference's dS = dM * W is fp32
   int reduce_out;          // score-grad: 1 = TMA reduce-add into out, 0 = plain TMA store
   long long* dbg;          // optional per-CTA timestamps (crv_gemm_debug_timestamps), else null
+  const uint8_t* bits;     // 2-CTA mask transform: tile-contiguous mask bits (binarize_bits_tiled_kernel), 1 KB per half tile
+  int bits_pitch;          // tiles per tile-row of that layout
 };
 
 template <int BN, bool XFORM>
@@ -69,6 +74,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// contiguous global -> shared bulk copy (16-byte aligned, size a multiple of 16) completing on an mbarrier of this CTA
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -444,23 +456,40 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                : "memory");
 }
 
-struct Smem2 {
+// XFORM = the in-kernel mask transform (north-star kernel 1) at 2-CTA speed.  The scores are binarised ONCE per call
+// into a bit mask (binarize_bits_kernel: 1 bit per weight, [rows][cols / 8] bytes -- 32 x less than the fp32 score tile
+// the 1-CTA transform stages, which made that kernel shared-memory / L2-ingest bound at ~290 TFLOP/s).  Per k-block
+// each CTA's producer TMA-loads its half of the W tile AND the matching 1-2 KB of mask bits onto a CTA-local barrier;
+// four transform warps (one thread per 128-byte swizzled W row) AND the bf16 lanes with the expanded bits in place,
+// fence towards the async proxy and arrive (cluster scope) on the leader's full barrier, which the MMA thread waits on.
+template <bool XFORM>
+struct Smem2T {
   static constexpr int kA = BM * BK * 2;        // 16 KB: this CTA's 128 rows of A
   static constexpr int kB = 128 * BK * 2;       // 16 KB: this CTA's half of the 256 B columns
-  static constexpr int kStage = kA + kB;
-  static constexpr int kStages = 6;
+  static constexpr int kBits = XFORM ? 1024 : 0;  // mask bits of the half tile: [128 rows][8 B] or [64 rows][16 B]
+  static constexpr int kStage = kA + kB + kBits;
+  static constexpr int kStages = XFORM ? 5 : 6;
   static constexpr int kEpiWarps = 8;            // two per TMEM lane quadrant: each drains 32 rows x 128 columns
+  static constexpr int kXformWarps = XFORM ? 4 : 0;
+  static constexpr int kThreads = 64 + 32 * (kEpiWarps + kXformWarps);
   static constexpr int kEpi = kEpiWarps * 4096;  // one 4 KB staging buffer per epilogue warp
   static constexpr int kTotal = kStages * kStage + kEpi + 256 + 1024;
 };
+using Smem2 = Smem2T<false>;
 
-template <bool A_MN, bool B_MN, int EPI, bool OUT_BF16>
-__global__ void __launch_bounds__(64 + 32 * Smem2::kEpiWarps, 1)
+// expand two mask bits into the lane mask of a packed bf16 pair
+__device__ __forceinline__ uint32_t bits2_to_lanes(uint32_t t) {
+  return ((t & 1u) ? 0x0000FFFFu : 0u) | ((t & 2u) ? 0xFFFF0000u : 0u);
+}
+
+template <bool A_MN, bool B_MN, int EPI, bool OUT_BF16, bool XFORM = false>
+__global__ void __launch_bounds__(Smem2T<XFORM>::kThreads, 1)
 masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const GemmParams p) {
-  using L = Smem2;
+  using L = Smem2T<XFORM>;
   constexpr int STAGES = L::kStages;
   constexpr int BN = 256;
+  constexpr uint32_t kBitsBox = 1024;   // mask bits of one half tile (128 x 64 weights), one contiguous bulk copy
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_base = smem + STAGES * L::kStage;
@@ -468,7 +497,8 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* bfull_bar = tmem_empty_bar + 2;       // [STAGES] XFORM: this CTA's W half + mask bits have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull_bar + STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -483,8 +513,10 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 2);
+      // XFORM: + one arrival per transform warp of both CTAs (the operands are complete only once masked)
+      mbar_init(&full_bar[s], 2 + 2 * L::kXformWarps);
       mbar_init(&empty_bar[s], 1);
+      if (XFORM) mbar_init(&bfull_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
@@ -512,7 +544,8 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          if (leader) mbar_expect_tx(&full_bar[s], 2 * L::kStage);
+          // XFORM: only A goes to the leader's barrier; B and its mask bits land on this CTA's own barrier
+          if (leader) mbar_expect_tx(&full_bar[s], XFORM ? 2 * L::kA : 2 * L::kStage);
           else mbar_arrive_remote(&full_bar[s], 0);
           uint8_t* sA = smem + s * L::kStage;
           uint8_t* sB = sA + L::kA;
@@ -523,7 +556,19 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sA + j * 8192, &tmA, &full_bar[s], m0 + 64 * j, kk0);
           }
-          if (!B_MN) {
+          if (XFORM) {
+            mbar_expect_tx(&bfull_bar[s], L::kB + kBitsBox);
+            uint8_t* sBits = sB + L::kB;
+            const int kbi = tc.kb_begin + kb;
+            if (!B_MN) {     // W rows nh .. nh+127, W columns kk0 .. kk0+63: bit tile (nh / 128, kbi)
+              tma_load_2d(sB, &tmB, &bfull_bar[s], kk0, nh);
+              bulk_load_1d(sBits, p.bits + (static_cast<size_t>(nh >> 7) * p.bits_pitch + kbi) * 1024, 1024, &bfull_bar[s]);
+            } else {         // W rows kk0 .. kk0+63, W columns nh .. nh+127: bit tile (kbi, nh / 128)
+#pragma unroll
+              for (int j = 0; j < 2; ++j) tma_load_2d(sB + j * 8192, &tmB, &bfull_bar[s], nh + 64 * j, kk0);
+              bulk_load_1d(sBits, p.bits + (static_cast<size_t>(kbi) * p.bits_pitch + (nh >> 7)) * 1024, 1024, &bfull_bar[s]);
+            }
+          } else if (!B_MN) {
             tma_load_2d_2sm(sB, &tmB, &full_bar[s], kk0, nh);
           } else {
 #pragma unroll
@@ -532,6 +577,44 @@ masked_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       pdl_launch_dependents();   // every load of this CTA is in flight: let the next grid be scheduled
+    }
+  } else if (XFORM && warp >= 2 + L::kEpiWarps) {
+    // ------------------------------------------------------------------ mask transform (both CTAs, 128 threads)
+    // thread r owns one 128-byte (64 bf16) swizzled row of this CTA's W half; its 64 mask bits sit in the bits box
+    const int r = threadIdx.x - 32 * (2 + L::kEpiWarps);
+    const int sw = r & 7;
+    const uint32_t row_off = B_MN ? (r >> 6) * 8192 + (r & 63) * 128 : r * 128;
+    const uint32_t bits_off = B_MN ? (r & 63) * 16 + (r >> 6) * 8 : r * 8;
+    int it = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      const TileCoord tc = tile_coord(p, tile, BN);
+      for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        uint8_t* sB = smem + s * L::kStage + L::kA;
+        mbar_wait(&bfull_bar[s], ph);
+        const uint2 bw = *reinterpret_cast<const uint2*>(sB + L::kB + bits_off);
+        uint4* row = reinterpret_cast<uint4*>(sB + row_off);
+        uint4 w[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w[c] = row[c ^ sw];      // logical 16-byte chunk c (elements 8c .. 8c+7)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t b = ((c < 4 ? bw.x : bw.y) >> (8 * (c & 3))) & 0xFFu;
+          w[c].x &= bits2_to_lanes(b);
+          w[c].y &= bits2_to_lanes(b >> 2);
+          w[c].z &= bits2_to_lanes(b >> 4);
+          w[c].w &= bits2_to_lanes(b >> 6);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) row[c ^ sw] = w[c];
+        // generic-proxy writes -> async proxy (the tensor core reads this tile), then tell the leader's MMA thread; same
+        // arrive as the epilogue's tmem-empty hand-off (a cluster-scope release compiles to MEMBAR.GPU per warp per
+        // stage and measured no different in results)
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&full_bar[s], 0);
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
@@ -1128,13 +1211,99 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
 }
 
 
-template <bool A_MN, bool B_MN, int EPI, bool OUT_BF16>
+static bool use_2cta(int MM, int NN) {
+  static const int mode = [] { const char* e = getenv("CRVQA_2CTA"); return e ? atoi(e) : 1; }();
+  return mode != 0 && NN % 256 == 0 && MM >= 256;
+}
+
+// ---- mask bits of the 2-CTA in-kernel transform ------------------------------------------------------------------
+// bit j of a byte = S[row][8 c + j] > thr, stored TILE-CONTIGUOUS so that the bits of one half tile (128 x 64 weights =
+// 1 KB) arrive with one bulk copy:
+//   layout 0 (forward, tile = 128 W rows x 64 W cols):  tile (row / 128, col / 64),  byte (row % 128) * 8  + (col % 64) / 8
+//   layout 1 (dX,      tile = 64 W rows x 128 W cols):  tile (row / 64,  col / 128), byte (row % 64)  * 16 + (col % 128) / 8
+// Rows / columns past the matrix get zero bits (the W tile is zero-filled there anyway).
+__global__ void binarize_bits_tiled_kernel(const float* __restrict__ s, const float* __restrict__ thr,
+                                           uint8_t* __restrict__ bits, int rows, int cols, int layout, int pitch,
+                                           int64_t nbytes) {
+  pdl_wait();
+  const float t = __ldg(thr);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nbytes; i += stride) {
+    const int64_t tile = i >> 10;
+    const int in = static_cast<int>(i & 1023);
+    const int tr = static_cast<int>(tile / pitch), tcn = static_cast<int>(tile % pitch);
+    int row, col;
+    if (layout == 0) { row = tr * 128 + (in >> 3); col = tcn * 64 + (in & 7) * 8; }
+    else { row = tr * 64 + (in >> 4); col = tcn * 128 + (in & 15) * 8; }
+    uint32_t v = 0;
+    if (row < rows && col < cols) {       // cols % 8 == 0: the eight scores of a byte are all inside
+      const float4* src = reinterpret_cast<const float4*>(s + static_cast<size_t>(row) * cols + col);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      v = (a.x > t ? 1u : 0u) | (a.y > t ? 2u : 0u) | (a.z > t ? 4u : 0u) | (a.w > t ? 8u : 0u) |
+          (b.x > t ? 16u : 0u) | (b.y > t ? 32u : 0u) | (b.z > t ? 64u : 0u) | (b.w > t ? 128u : 0u);
+    }
+    bits[i] = static_cast<uint8_t>(v);
+  }
+}
+
+// Scratch for the mask bits, one buffer per (device, stream): calls on one stream are ordered, so the next call's
+// pre-pass cannot overwrite bits a running GEMM still reads; another stream gets its own buffer.  Grown (never
+// shrunk) outside the data path; the allocation runs in relaxed capture mode so a first use during CUDA-graph
+// capture is legal (the buffer outlives the graph: it is never freed while the library is loaded).
+static uint8_t* xform_bits_scratch(cudaStream_t stream, size_t bytes) {
+  struct Buf { uint8_t* p; size_t n; };
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, Buf> bufs;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  Buf& b = bufs[{dev, stream}];
+  if (b.n < bytes) {
+    size_t want = bytes < (size_t(4) << 20) ? (size_t(4) << 20) : bytes;   // 4 MB covers every LXMERT / VisualBERT module
+    cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    uint8_t* np = nullptr;
+    const cudaError_t e = cudaMalloc(&np, want);
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    if (e != cudaSuccess) { g_last_cuda_error = static_cast<int>(e); return nullptr; }
+    // the old buffer (if any) may still be read by a kernel in flight: it is left allocated (a few MB, once)
+    b.p = np;
+    b.n = want;
+  }
+  return b.p;
+}
+
+// the 2-CTA transform needs whole 256-wide tiles; forward k-blocks must be whole too (w_cols % 64 == 0)
+static bool use_2cta_xform(int MM, int NN, int w_cols) {
+  static const int mode = [] { const char* e = getenv("CRVQA_XFORM_2CTA"); return e ? atoi(e) : 1; }();
+  return mode != 0 && use_2cta(MM, NN) && w_cols % 64 == 0;
+}
+
+// binarise `scores` [rows][cols] against *thr into the stream's scratch in tile layout `layout`; fills p.bits / p.bits_pitch
+static int prepare_mask_bits(const float* scores, const float* thr, int rows, int cols, int layout, GemmParams* p,
+                             cudaStream_t st) {
+  const int tile_rows = layout == 0 ? 128 : 64, tile_cols = layout == 0 ? 64 : 128;
+  const int tr = (rows + tile_rows - 1) / tile_rows, tcn = (cols + tile_cols - 1) / tile_cols;
+  const int64_t nbytes = static_cast<int64_t>(tr) * tcn * 1024;
+  uint8_t* bits = xform_bits_scratch(st, static_cast<size_t>(nbytes));
+  if (!bits) return CRV_E_DRIVER;
+  int64_t blocks = (nbytes + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  CRV_CUDA(launch_pdl(binarize_bits_tiled_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, scores, thr,
+                      bits, rows, cols, layout, tcn, nbytes));
+  p->bits = bits;
+  p->bits_pitch = tcn;
+  return launch_status();
+}
+
+template <bool A_MN, bool B_MN, int EPI, bool OUT_BF16, bool XFORM = false>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, GemmParams p,
                    cudaStream_t stream) {
-  auto kern = masked_gemm2_kernel<A_MN, B_MN, EPI, OUT_BF16>;
+  using L2 = Smem2T<XFORM>;
+  auto kern = masked_gemm2_kernel<A_MN, B_MN, EPI, OUT_BF16, XFORM>;
   static bool configured = false;
   if (!configured) {
-    CRV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::kTotal));
+    CRV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::kTotal));
     configured = true;
   }
   p.num_m = (p.MM + 255) / 256;
@@ -1145,8 +1314,8 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(64 + 32 * Smem2::kEpiWarps);
-  cfg.dynamicSmemBytes = Smem2::kTotal;
+  cfg.blockDim = dim3(L2::kThreads);
+  cfg.dynamicSmemBytes = L2::kTotal;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1159,11 +1328,6 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   CRV_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, p));
   return launch_status();
-}
-
-static bool use_2cta(int MM, int NN) {
-  static const int mode = [] { const char* e = getenv("CRVQA_2CTA"); return e ? atoi(e) : 1; }();
-  return mode != 0 && NN % 256 == 0 && MM >= 256;
 }
 
 static int pick_bn(int MM, int NN) {
@@ -1208,6 +1372,13 @@ extern "C" int crv_masked_linear_fwd(const uint16_t* x, const uint16_t* w, const
   int rc;
   if ((rc = make_map(&tmA, x, 2, false, M, K, BM, BK))) return rc;
   if ((rc = make_out_map(&tmO, y, obf, M, N))) return rc;
+  if (scores && use_2cta_xform(M, N, K)) {
+    // in-kernel mask at 2-CTA speed: bits pre-pass (one read of S) + transform warps between TMA and tcgen05.mma
+    if ((rc = prepare_mask_bits(scores, thr, N, K, 0, &p, st))) return rc;
+    if ((rc = make_map(&tmB, w, 2, false, N, K, 128, BK))) return rc;
+    return obf ? launch2<false, false, kEpiStore, true, true>(tmA, tmB, tmO, p, st)
+               : launch2<false, false, kEpiStore, false, true>(tmA, tmB, tmO, p, st);
+  }
   if (scores) {
     if ((rc = make_map(&tmB, w, 2, false, N, K, 128, BK))) return rc;
     if ((rc = make_map(&tmS, scores, 4, true, N, K, 128, 32))) return rc;
@@ -1250,6 +1421,11 @@ extern "C" int crv_masked_linear_bwd_dx(const uint16_t* dy, const uint16_t* w, c
   if ((rc = make_map(&tmA, dy, 2, false, M, N, BM, BK))) return rc;
   if ((rc = make_map(&tmB, w, 2, false, N, K, 64, 64))) return rc;
   if ((rc = make_out_map(&tmO, dx, obf, M, K))) return rc;
+  if (scores && use_2cta_xform(M, K, K)) {
+    if ((rc = prepare_mask_bits(scores, thr, N, K, 1, &p, st))) return rc;
+    return obf ? launch2<false, true, kEpiStore, true, true>(tmA, tmB, tmO, p, st)
+               : launch2<false, true, kEpiStore, false, true>(tmA, tmB, tmO, p, st);
+  }
   if (scores) {
     if ((rc = make_map(&tmS, scores, 4, true, N, K, 64, 32))) return rc;
     return obf ? launch<false, true, 128, true, kEpiStore, true>(tmA, tmB, tmS, tmO, p, st)

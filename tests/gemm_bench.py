@@ -30,6 +30,7 @@ for (M, N, K) in SHAPES:
     res['fwd plain f32'] = timeit(lambda: ops.masked_linear_fwd(x, w, None, thr, b))
     res['fwd plain bf16'] = timeit(lambda: ops.masked_linear_fwd(x, w, None, thr, b, torch.bfloat16))
     res['dx masked f32'] = timeit(lambda: ops.masked_linear_bwd_dx(dy, w, s, thr))
+    res['dx masked bf16'] = timeit(lambda: ops.masked_linear_bwd_dx(dy, w, s, thr, torch.bfloat16))
     res['dx plain f32'] = timeit(lambda: ops.masked_linear_bwd_dx(dy, w, None, thr))
     res['dx plain bf16'] = timeit(lambda: ops.masked_linear_bwd_dx(dy, w, None, thr, torch.bfloat16))
     res['ds store'] = timeit(lambda: ops.masked_linear_bwd_ds(dy, x, w32, out=ds, accumulate=False))

@@ -81,3 +81,35 @@ def test_ds(M, N, K):
     # accumulate: second invocation of a shared module adds
     ds2 = ops.masked_linear_bwd_ds(dyb, xb, w, out=ds.clone(), accumulate=True)
     assert _rel(ds2, 2 * ref) < 2e-3
+
+
+@pytest.mark.parametrize("N,K", [(768, 768), (3072, 768), (768, 3072), (768, 2048), (256, 128)])
+def test_in_kernel_mask_transform_is_bit_exact(N, K):
+    """North-star kernel (1) on its fast variant (2-CTA tcgen05 GEMM, scores binarised to a bit mask, transform warps AND
+    the W tile in shared memory before the MMA; csrc/gemm_sm100.cu Smem2T<true>): with identity activations the output
+    IS the masked weight, so every mask bit's position is checked exactly -- forward Y = I . (W (.) M)^T and
+    dX = I . (W (.) M), bf16 products with one non-zero term are exact.  Scores sit at, just below and just above the
+    threshold (strict `>`, reference masking/maskers.py:325-339)."""
+    from crvqa import ops
+    g = torch.Generator().manual_seed(N + K)
+    w = (torch.randn(N, K, generator=g) * 0.02).bfloat16().cuda()
+    thr = torch.tensor(0.01, device="cuda")
+    s = torch.rand(N, K, generator=g) * 0.02
+    pick = torch.rand(N, K, generator=g)
+    s[pick < 0.2] = 0.01                                    # ties: masked out
+    s[(pick >= 0.2) & (pick < 0.3)] = torch.nextafter(torch.tensor(0.01), torch.tensor(1.0))
+    s[(pick >= 0.3) & (pick < 0.4)] = torch.nextafter(torch.tensor(0.01), torch.tensor(0.0))
+    s = s.cuda()
+    wm = torch.where(s > thr, w.float(), torch.zeros((), device="cuda"))
+    eye_k = torch.eye(K, device="cuda").bfloat16()          # M = K rows (>= 256 where the 2-CTA variant applies)
+    y = ops.masked_linear_fwd(eye_k, w, s, thr, None)
+    assert torch.equal(y, wm.t())
+    eye_n = torch.eye(N, device="cuda").bfloat16()
+    dx = ops.masked_linear_bwd_dx(eye_n, w, s, thr)
+    assert torch.equal(dx, wm)
+    # ragged M (partial last tile) and a second call with other scores on the same stream (the bit scratch is reused)
+    s2 = torch.rand(N, K, generator=g).cuda() * 0.02
+    x = torch.randn(300, K, generator=g).bfloat16().cuda()
+    y2 = ops.masked_linear_fwd(x, w, s2, thr, None)
+    ref2 = x.float() @ torch.where(s2 > thr, w.float(), torch.zeros((), device="cuda")).t()
+    assert _rel(y2, ref2) < 2e-3
