@@ -363,6 +363,16 @@ def _off(t, elems):
     return ctypes.c_void_p(t.data_ptr() + 2 * elems)
 
 
+def _save_probs():
+    """Training keeps the (signed) softmax probabilities of the forward for the backward (crv_attention_fwd_p / _bwd_p);
+    CRVQA_ATTN_SAVE_P=0 selects the recomputing backward (crv_attention_bwd)."""
+    return os.environ.get("CRVQA_ATTN_SAVE_P", "1") != "0"
+
+
+def _probs_buffer(B, heads, Sq, Sk, device):
+    return torch.empty((B * heads, Sq, lib.crv_attention_probs_pitch(Sk)), dtype=torch.bfloat16, device=device)
+
+
 class SmallAttentionFn(torch.autograd.Function):
     """softmax(Q K^T / sqrt(d) + mask) V with dropout for S <= 64, d = 64 (crv_attention_fwd / _bwd).
     kind 0: srcs = (qkv [B,S,3H],)   kind 1: srcs = (q [B,Sq,H], kv [B,Sk,2H])   kind 2: srcs = (q, k, v)."""
@@ -392,10 +402,12 @@ class SmallAttentionFn(torch.autograd.Function):
         m2 = None
         if mask is not None:
             m2 = mask.reshape(B, Sk).float().contiguous()
-        check(lib.crv_attention_fwd(_off(qt, qo), qt.stride(0), qt.stride(1), _off(kt, ko), kt.stride(0), kt.stride(1),
-                                    _off(vt, vo), vt.stride(0), vt.stride(1), _p(m2), _p(out), B, heads, Sq, Sk,
-                                    scale, float(p), _p(state), int(site), _stream()), "crv_attention_fwd")
+        probs = None
+        if any(ctx.needs_input_grad[6:]) and _save_probs():
+            probs = _probs_buffer(B, heads, Sq, Sk, qt.device)
+        _attn_fwd_raw(views, m2, out, B, heads, Sq, Sk, scale, p, state, site, probs)
         ctx.save_for_backward(*srcs)
+        ctx.probs = probs
         ctx.cfg = (kind, heads, m2, float(p), int(site), state, scale)
         return out
 
@@ -410,24 +422,32 @@ class SmallAttentionFn(torch.autograd.Function):
         (dq, dqo), (dk, dko), (dv, dvo) = gviews
         B, Sq, Sk = qt.shape[0], qt.shape[1], kt.shape[1]
         dout = dout if dout.is_contiguous() else dout.contiguous()
-        check(lib.crv_attention_bwd(_off(qt, qo), qt.stride(0), qt.stride(1), _off(kt, ko), kt.stride(0), kt.stride(1),
-                                    _off(vt, vo), vt.stride(0), vt.stride(1), _p(m2), _p(dout),
-                                    _off(dq, dqo), dq.stride(0), dq.stride(1), _off(dk, dko), dk.stride(0), dk.stride(1),
-                                    _off(dv, dvo), dv.stride(0), dv.stride(1), B, heads, Sq, Sk, scale, p, _p(state),
-                                    site, _stream()), "crv_attention_bwd")
+        _attn_bwd_raw(views, m2, dout, gviews, B, heads, Sq, Sk, scale, p, state, site, ctx.probs)
         return (None, None, None, None, None, None) + grads
 
 
-def _attn_fwd_raw(views, m2, out, B, heads, Sq, Sk, scale, p, state, site):
+def _attn_fwd_raw(views, m2, out, B, heads, Sq, Sk, scale, p, state, site, probs=None):
     (qt, qo), (kt, ko), (vt, vo) = views
+    if probs is not None:
+        check(lib.crv_attention_fwd_p(_off(qt, qo), qt.stride(0), qt.stride(1), _off(kt, ko), kt.stride(0), kt.stride(1),
+                                      _off(vt, vo), vt.stride(0), vt.stride(1), _p(m2), _p(out), _p(probs), B, heads, Sq,
+                                      Sk, scale, float(p), _p(state), int(site), _stream()), "crv_attention_fwd_p")
+        return
     check(lib.crv_attention_fwd(_off(qt, qo), qt.stride(0), qt.stride(1), _off(kt, ko), kt.stride(0), kt.stride(1),
                                 _off(vt, vo), vt.stride(0), vt.stride(1), _p(m2), _p(out), B, heads, Sq, Sk,
                                 scale, float(p), _p(state), int(site), _stream()), "crv_attention_fwd")
 
 
-def _attn_bwd_raw(views, m2, dout, gviews, B, heads, Sq, Sk, scale, p, state, site):
+def _attn_bwd_raw(views, m2, dout, gviews, B, heads, Sq, Sk, scale, p, state, site, probs=None):
     (qt, qo), (kt, ko), (vt, vo) = views
     (dq, dqo), (dk, dko), (dv, dvo) = gviews
+    if probs is not None:
+        check(lib.crv_attention_bwd_p(_off(qt, qo), qt.stride(0), qt.stride(1), _off(kt, ko), kt.stride(0), kt.stride(1),
+                                      _off(vt, vo), vt.stride(0), vt.stride(1), _p(probs), _p(dout),
+                                      _off(dq, dqo), dq.stride(0), dq.stride(1), _off(dk, dko), dk.stride(0),
+                                      dk.stride(1), _off(dv, dvo), dv.stride(0), dv.stride(1), B, heads, Sq, Sk, scale,
+                                      float(p), _stream()), "crv_attention_bwd_p")
+        return
     check(lib.crv_attention_bwd(_off(qt, qo), qt.stride(0), qt.stride(1), _off(kt, ko), kt.stride(0), kt.stride(1),
                                 _off(vt, vo), vt.stride(0), vt.stride(1), _p(m2), _p(dout),
                                 _off(dq, dqo), dq.stride(0), dq.stride(1), _off(dk, dko), dk.stride(0), dk.stride(1),
@@ -454,9 +474,13 @@ class CrossPairAttentionFn(torch.autograd.Function):
         mv = mask_v.reshape(B, Sv).float().contiguous() if mask_v is not None else None
         out_l = torch.empty((B, Sl, H), dtype=torch.bfloat16, device=qkv_l.device)
         out_v = torch.empty((B, Sv, H), dtype=torch.bfloat16, device=qkv_l.device)
-        _attn_fwd_raw([(qkv_l, 0), (qkv_v, H), (qkv_v, 2 * H)], mv, out_l, B, heads, Sl, Sv, scale, p, state, site_l)
-        _attn_fwd_raw([(qkv_v, 0), (qkv_l, H), (qkv_l, 2 * H)], ml, out_v, B, heads, Sv, Sl, scale, p, state, site_v)
+        pl = pv = None
+        if any(ctx.needs_input_grad[7:]) and _save_probs():
+            pl, pv = _probs_buffer(B, heads, Sl, Sv, qkv_l.device), _probs_buffer(B, heads, Sv, Sl, qkv_l.device)
+        _attn_fwd_raw([(qkv_l, 0), (qkv_v, H), (qkv_v, 2 * H)], mv, out_l, B, heads, Sl, Sv, scale, p, state, site_l, pl)
+        _attn_fwd_raw([(qkv_v, 0), (qkv_l, H), (qkv_l, 2 * H)], ml, out_v, B, heads, Sv, Sl, scale, p, state, site_v, pv)
         ctx.save_for_backward(qkv_l, qkv_v)
+        ctx.probs = (pl, pv)
         ctx.set_materialize_grads(False)
         ctx.cfg = (heads, ml, mv, float(p), int(site_l), int(site_v), state, scale)
         return out_l, out_v
@@ -470,17 +494,18 @@ class CrossPairAttentionFn(torch.autograd.Function):
         if do_l is None and do_v is None:
             return (None,) * 9
         d_l, d_v = torch.empty_like(qkv_l), torch.empty_like(qkv_v)
+        pl, pv = ctx.probs
         if do_l is not None:
             do_l = do_l if do_l.is_contiguous() else do_l.contiguous()
             _attn_bwd_raw([(qkv_l, 0), (qkv_v, H), (qkv_v, 2 * H)], mv, do_l, [(d_l, 0), (d_v, H), (d_v, 2 * H)],
-                          B, heads, Sl, Sv, scale, p, state, site_l)
+                          B, heads, Sl, Sv, scale, p, state, site_l, pl)
         else:                       # this direction feeds nothing: its slices of the two gradients are zero
             d_l[..., :H].zero_()
             d_v[..., H:].zero_()
         if do_v is not None:
             do_v = do_v if do_v.is_contiguous() else do_v.contiguous()
             _attn_bwd_raw([(qkv_v, 0), (qkv_l, H), (qkv_l, 2 * H)], ml, do_v, [(d_v, 0), (d_l, H), (d_l, 2 * H)],
-                          B, heads, Sv, Sl, scale, p, state, site_v)
+                          B, heads, Sv, Sl, scale, p, state, site_v, pv)
         else:                       # the last cross layer: nothing reads the vision output
             d_v[..., :H].zero_()
             d_l[..., H:].zero_()

@@ -44,6 +44,11 @@ struct AttnParams {
   float scale, p_drop;
   const unsigned long long* rng_state;
   int site;
+  // saved-probability path (training): probs[pair][i][j] = +P_ij if the dropout kept (i, j), -P_ij if it dropped it
+  // (P = softmax probability BEFORE dropout, bf16; row pitch skp = Sk rounded up to 8, columns Sk .. skp-1 hold 0).
+  // The forward writes it, the backward reads it instead of recomputing Q K^T, the softmax and the dropout hash twice.
+  __nv_bfloat16* probs;
+  int skp;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -234,18 +239,32 @@ attn_fwd_kernel(const AttnParams p) {
     }
     const float i0 = 1.f / quad_sum(l0), i1 = 1.f / quad_sum(l1);
     uint32_t pa[KT2][4];
+    __nv_bfloat16* pr = p.probs ? p.probs + static_cast<size_t>(pair) * p.Sq * p.skp : nullptr;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       float v[4];
       const int jb = nt * 8 + 2 * t;
       const uint64_t h0 = dk.thresh ? dk.bits(r0, jb) : 0ull, h1 = dk.thresh ? dk.bits(r1, jb) : 0ull;
+      bool kp[4];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        v[e] = dk.keep(h0, r0, jb + e) ? s[nt][e] * i0 * dk.scale : 0.f;
-        v[2 + e] = dk.keep(h1, r1, jb + e) ? s[nt][2 + e] * i1 * dk.scale : 0.f;
+        kp[e] = dk.keep(h0, r0, jb + e);
+        kp[2 + e] = dk.keep(h1, r1, jb + e);
+        s[nt][e] *= i0;                      // P
+        s[nt][2 + e] *= i1;
+        v[e] = kp[e] ? s[nt][e] * dk.scale : 0.f;
+        v[2 + e] = kp[2 + e] ? s[nt][2 + e] * dk.scale : 0.f;
       }
       pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(v[0], v[1]);
       pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(v[2], v[3]);
+      if (pr != nullptr && jb < p.skp) {     // the sign carries the dropout decision (P >= 0)
+        if (r0 < p.Sq)
+          *reinterpret_cast<uint32_t*>(pr + r0 * p.skp + jb) =
+              pack_bf16x2(kp[0] ? s[nt][0] : -s[nt][0], kp[1] ? s[nt][1] : -s[nt][1]);
+        if (r1 < p.Sq)
+          *reinterpret_cast<uint32_t*>(pr + r1 * p.skp + jb) =
+              pack_bf16x2(kp[2] ? s[nt][2] : -s[nt][2], kp[3] ? s[nt][3] : -s[nt][3]);
+      }
     }
     __nv_bfloat16* ob = p.out + (static_cast<long long>(b) * p.Sq) * HD + h * kHeadDim;
 #pragma unroll
@@ -450,6 +469,188 @@ attn_bwd_kernel(const AttnParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Backward from the SAVED probabilities (the training path).  The recomputing kernel above spends ~3800 warp
+// instructions per 16-row block on Q K^T in both orientations, two softmaxes and two rounds of dropout hashing and is
+// issue-bound at 23 % of HBM bandwidth; with P (and the dropout decision in its sign) read back, what is left is
+//   pass A (query rows):  dPd = dO V^T,  D_i = sum_j dPd_ij Pd_ij,  dS = P (.) (keep dPd / (1-p) - D) scale  -> dQ = dS K,
+//                         dS also goes to shared memory (bf16)
+//   pass B (key rows):    P^T and dS^T arrive as MMA A fragments through transposing ldmatrix from the two [i][j]
+//                         tiles:  dV = Pd^T dO,  dK = dS^T Q
+// -- five small GEMMs instead of eight, no exp, no hash.
+template <int KT2>
+struct AttnSmemP {
+  static constexpr int SP = 16 * KT2;
+  static constexpr int SPP = SP + 8;                 // bf16 pitch of the P / dS tiles: (SP + 8) / 8 is odd -> ldmatrix rows spread over the banks
+  static constexpr int kTile = SP * kLdH * 2;
+  static constexpr int kP = SP * SPP * 2;
+  static constexpr int kTotal = 4 * kTile + 2 * kP;  // Q, K, V, dO, P, dS
+};
+
+// A fragment (rows r0 .. r0+15, k k0 .. k0+15) of the TRANSPOSE of a tile stored [k][row] with pitch `ld`
+__device__ __forceinline__ void ld_a_trans(uint32_t (&a)[4], const __nv_bfloat16* tile, int ld, int r0, int k0, int lane) {
+  const __nv_bfloat16* p = tile + (k0 + (lane & 7) + (lane >> 4) * 8) * ld + r0 + ((lane >> 3) & 1) * 8;
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(sptr(p)));
+}
+__device__ __forceinline__ float bf16_lo_f(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+template <int KT2>
+__global__ void __launch_bounds__(KT2 * 32)
+attn_bwd_p_kernel(const AttnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  using L = AttnSmemP<KT2>;
+  constexpr int SP = L::SP, SPP = L::SPP, NT = 2 * KT2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tile = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x;
+  const int b = pair / p.heads, h = pair % p.heads;
+  const int g = lane >> 2, t = lane & 3;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sK = sQ + SP * kLdH;
+  __nv_bfloat16* sV = sK + SP * kLdH;
+  __nv_bfloat16* sdO = sV + SP * kLdH;
+  __nv_bfloat16* sP = sdO + SP * kLdH;
+  __nv_bfloat16* sdS = sP + SP * SPP;
+  const long long HD = static_cast<long long>(p.heads) * kHeadDim;
+  {
+    const int tid = threadIdx.x;
+    load_tile<SP>(sQ, p.q + b * p.q_bs + h * kHeadDim, p.q_ss, p.Sq, tid, KT2 * 32);
+    load_tile<SP>(sK, p.k + b * p.k_bs + h * kHeadDim, p.k_ss, p.Sk, tid, KT2 * 32);
+    load_tile<SP>(sV, p.v + b * p.v_bs + h * kHeadDim, p.v_ss, p.Sk, tid, KT2 * 32);
+    load_tile<SP>(sdO, p.dout + static_cast<long long>(b) * p.Sq * HD + h * kHeadDim, HD, p.Sq, tid, KT2 * 32);
+    const __nv_bfloat16* pr = p.probs + static_cast<size_t>(pair) * p.Sq * p.skp;
+    for (int i = tid; i < SP * (SP / 8); i += KT2 * 32) {     // whole [SP][SP] tile: rows >= Sq, columns >= skp zero-filled
+      const int r = i / (SP / 8), c = i % (SP / 8);
+      const bool valid = r < p.Sq && c * 8 < p.skp;
+      cp_async16(sP + r * SPP + c * 8, pr + (valid ? r * p.skp + c * 8 : 0), valid);
+    }
+  }
+  const float dscale = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+  const int mt = tile;
+  if (mt * 16 >= p.Sq) {      // no query rows here: this block of dS^T columns must still read as zeros in pass B
+    for (int i = lane; i < 16 * (SP / 2); i += 32)
+      *reinterpret_cast<uint32_t*>(sdS + (mt * 16 + i / (SP / 2)) * SPP + (i % (SP / 2)) * 2) = 0u;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- pass A: this warp's query-row block
+  if (mt * 16 < p.Sq) {
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    uint32_t a[4][4];
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) ld_a(a[kt], sdO, mt * 16, kt * 16, lane);
+    float dp[NT][4];
+    scores_16<KT2>(dp, a, sV, lane);               // dPd = dO . V^T
+    float pv[NT][4];
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int jb = nt * 8 + 2 * t;
+      const uint32_t u0 = *reinterpret_cast<const uint32_t*>(sP + r0 * SPP + jb);
+      const uint32_t u1 = *reinterpret_cast<const uint32_t*>(sP + r1 * SPP + jb);
+      const float s0 = bf16_lo_f(u0), s1 = bf16_hi_f(u0), s2 = bf16_lo_f(u1), s3 = bf16_hi_f(u1);
+      pv[nt][0] = fabsf(s0); pv[nt][1] = fabsf(s1); pv[nt][2] = fabsf(s2); pv[nt][3] = fabsf(s3);
+      dp[nt][0] = (u0 & 0x8000u) ? 0.f : dp[nt][0] * dscale;          // dP = keep dPd / (1 - p)
+      dp[nt][1] = (u0 & 0x80000000u) ? 0.f : dp[nt][1] * dscale;
+      dp[nt][2] = (u1 & 0x8000u) ? 0.f : dp[nt][2] * dscale;
+      dp[nt][3] = (u1 & 0x80000000u) ? 0.f : dp[nt][3] * dscale;
+      d0 += dp[nt][0] * pv[nt][0] + dp[nt][1] * pv[nt][1];
+      d1 += dp[nt][2] * pv[nt][2] + dp[nt][3] * pv[nt][3];
+    }
+    d0 = quad_sum(d0);
+    d1 = quad_sum(d1);
+    uint32_t da[KT2][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int jb = nt * 8 + 2 * t;
+      const uint32_t w0 = pack_bf16x2(pv[nt][0] * (dp[nt][0] - d0) * p.scale, pv[nt][1] * (dp[nt][1] - d0) * p.scale);
+      const uint32_t w1 = pack_bf16x2(pv[nt][2] * (dp[nt][2] - d1) * p.scale, pv[nt][3] * (dp[nt][3] - d1) * p.scale);
+      da[nt >> 1][(nt & 1) * 2 + 0] = w0;
+      da[nt >> 1][(nt & 1) * 2 + 1] = w1;
+      *reinterpret_cast<uint32_t*>(sdS + r0 * SPP + jb) = w0;
+      *reinterpret_cast<uint32_t*>(sdS + r1 * SPP + jb) = w1;
+    }
+    __nv_bfloat16* qo = p.dq + b * p.dq_bs + h * kHeadDim;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kt = 0; kt < KT2; ++kt) {
+        uint32_t bk[2];
+        ld_b_kn(bk, sK, dt * 8, kt * 16, lane);   // B[k = j][n = d] = K[j][d]
+        mma16816(o, da[kt], bk);
+      }
+      const int c = dt * 8 + 2 * t;
+      if (r0 < p.Sq) *reinterpret_cast<uint32_t*>(qo + r0 * p.dq_ss + c) = pack_bf16x2(o[0], o[1]);
+      if (r1 < p.Sq) *reinterpret_cast<uint32_t*>(qo + r1 * p.dq_ss + c) = pack_bf16x2(o[2], o[3]);
+    }
+  }
+  __syncthreads();   // dS of every row block is in shared memory
+
+  // ---- pass B: this warp's key-row block: dV = Pd^T dO, dK = dS^T Q
+  const int jt = tile;
+  if (jt * 16 < p.Sk) {
+    const int j0 = jt * 16 + g, j1 = j0 + 8;
+    uint32_t pa[KT2][4], da[KT2][4];
+    const __nv_bfloat162 ds2 = __floats2bfloat162_rn(dscale, dscale);
+#pragma unroll
+    for (int kt = 0; kt < KT2; ++kt) {
+      ld_a_trans(pa[kt], sP, SPP, jt * 16, kt * 16, lane);
+      ld_a_trans(da[kt], sdS, SPP, jt * 16, kt * 16, lane);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {      // signed P -> Pd: dropped entries (sign set) to +0, kept ones times 1 / (1 - p)
+        uint32_t x = pa[kt][e];
+        x &= ((x & 0x8000u) ? 0u : 0x0000FFFFu) | ((x & 0x80000000u) ? 0u : 0xFFFF0000u);
+        if (p.p_drop > 0.f) {
+          __nv_bfloat162 v = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&x), ds2);
+          x = *reinterpret_cast<uint32_t*>(&v);
+        }
+        pa[kt][e] = x;
+      }
+    }
+    __nv_bfloat16* vo = p.dv + b * p.dv_bs + h * kHeadDim;
+    __nv_bfloat16* ko = p.dk + b * p.dk_bs + h * kHeadDim;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      float ov[4] = {0.f, 0.f, 0.f, 0.f}, ok[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kt = 0; kt < KT2; ++kt) {
+        uint32_t bo[2], bq[2];
+        ld_b_kn(bo, sdO, dt * 8, kt * 16, lane);   // B[k = i][n = d] = dO[i][d]
+        ld_b_kn(bq, sQ, dt * 8, kt * 16, lane);    // B[k = i][n = d] = Q[i][d]
+        mma16816(ov, pa[kt], bo);
+        mma16816(ok, da[kt], bq);
+      }
+      const int c = dt * 8 + 2 * t;
+      if (j0 < p.Sk) {
+        *reinterpret_cast<uint32_t*>(vo + j0 * p.dv_ss + c) = pack_bf16x2(ov[0], ov[1]);
+        *reinterpret_cast<uint32_t*>(ko + j0 * p.dk_ss + c) = pack_bf16x2(ok[0], ok[1]);
+      }
+      if (j1 < p.Sk) {
+        *reinterpret_cast<uint32_t*>(vo + j1 * p.dv_ss + c) = pack_bf16x2(ov[2], ov[3]);
+        *reinterpret_cast<uint32_t*>(ko + j1 * p.dk_ss + c) = pack_bf16x2(ok[2], ok[3]);
+      }
+    }
+  }
+}
+
+template <int KT2>
+static int launch_attn_bwd_p(const AttnParams& p, cudaStream_t st) {
+  using L = AttnSmemP<KT2>;
+  auto kern = attn_bwd_p_kernel<KT2>;
+  static bool configured = false;
+  if (!configured) {
+    CRV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  CRV_CUDA(launch_pdl(kern, dim3(p.B * p.heads), dim3(KT2 * 32), L::kTotal, st, p));
+  return launch_status();
+}
+
 template <int KT2, int PAIRS, bool BWD>
 static int launch_attn(const AttnParams& p, cudaStream_t st) {
   using L = AttnSmem<KT2>;
@@ -521,4 +722,60 @@ extern "C" int crv_attention_bwd(const uint16_t* q, long long q_bs, long long q_
   if (S <= 32) return launch_attn<2, 1, true>(p, st);
   if (S <= 48) return launch_attn<3, 1, true>(p, st);
   return launch_attn<4, 1, true>(p, st);
+}
+
+
+// Training pair: the forward also writes the signed probabilities (probs [B * heads][Sq][skp] bf16, skp = Sk rounded up
+// to a multiple of 8), the backward consumes them.  crv_attention_probs_pitch() gives skp.
+extern "C" int crv_attention_probs_pitch(int Sk) { return (Sk + 7) / 8 * 8; }
+
+extern "C" int crv_attention_fwd_p(const uint16_t* q, long long q_bs, long long q_ss, const uint16_t* k, long long k_bs,
+                                   long long k_ss, const uint16_t* v, long long v_bs, long long v_ss, const float* mask,
+                                   uint16_t* out, uint16_t* probs, int B, int heads, int Sq, int Sk, float scale,
+                                   float p_drop, const unsigned long long* rng_state, int site, void* stream) {
+  AttnParams p{};
+  p.q = reinterpret_cast<const __nv_bfloat16*>(q); p.k = reinterpret_cast<const __nv_bfloat16*>(k);
+  p.v = reinterpret_cast<const __nv_bfloat16*>(v);
+  p.q_bs = q_bs; p.q_ss = q_ss; p.k_bs = k_bs; p.k_ss = k_ss; p.v_bs = v_bs; p.v_ss = v_ss;
+  p.mask = mask; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.B = B; p.heads = heads; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.p_drop = p_drop; p.rng_state = rng_state; p.site = site;
+  p.probs = reinterpret_cast<__nv_bfloat16*>(probs);
+  p.skp = crv_attention_probs_pitch(Sk);
+  int rc = check_attn(p);
+  if (rc) return rc;
+  if (!out || !aligned16(out) || !probs || !aligned16(probs)) return CRV_E_BADARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int S = Sq > Sk ? Sq : Sk;
+  if (S <= 32) return launch_attn<2, 4, false>(p, st);
+  if (S <= 48) return launch_attn<3, 2, false>(p, st);
+  return launch_attn<4, 2, false>(p, st);
+}
+
+extern "C" int crv_attention_bwd_p(const uint16_t* q, long long q_bs, long long q_ss, const uint16_t* k, long long k_bs,
+                                   long long k_ss, const uint16_t* v, long long v_bs, long long v_ss,
+                                   const uint16_t* probs, const uint16_t* dout, uint16_t* dq, long long dq_bs,
+                                   long long dq_ss, uint16_t* dk, long long dk_bs, long long dk_ss, uint16_t* dv,
+                                   long long dv_bs, long long dv_ss, int B, int heads, int Sq, int Sk, float scale,
+                                   float p_drop, void* stream) {
+  AttnParams p{};
+  p.q = reinterpret_cast<const __nv_bfloat16*>(q); p.k = reinterpret_cast<const __nv_bfloat16*>(k);
+  p.v = reinterpret_cast<const __nv_bfloat16*>(v);
+  p.q_bs = q_bs; p.q_ss = q_ss; p.k_bs = k_bs; p.k_ss = k_ss; p.v_bs = v_bs; p.v_ss = v_ss;
+  p.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
+  p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dk = reinterpret_cast<__nv_bfloat16*>(dk);
+  p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
+  p.dq_bs = dq_bs; p.dq_ss = dq_ss; p.dk_bs = dk_bs; p.dk_ss = dk_ss; p.dv_bs = dv_bs; p.dv_ss = dv_ss;
+  p.B = B; p.heads = heads; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.p_drop = p_drop;
+  p.probs = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(probs));
+  p.skp = crv_attention_probs_pitch(Sk);
+  int rc = check_attn(p);
+  if (rc) return rc;
+  if (!dout || !dq || !dk || !dv || !probs || !aligned16(probs)) return CRV_E_BADARG;
+  if (p_drop < 0.f || p_drop >= 1.f) return CRV_E_BADARG;
+  if ((dq_ss | dk_ss | dv_ss | dq_bs | dk_bs | dv_bs) & 7) return CRV_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int S = Sq > Sk ? Sq : Sk;
+  if (S <= 32) return launch_attn_bwd_p<2>(p, st);
+  if (S <= 48) return launch_attn_bwd_p<3>(p, st);
+  return launch_attn_bwd_p<4>(p, st);
 }

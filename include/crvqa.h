@@ -250,6 +250,22 @@ int crv_attention_bwd(const uint16_t* q, long long q_bs, long long q_ss, const u
                       int heads, int Sq, int Sk, float scale, float p_drop, const unsigned long long* rng_state,
                       int site, void* stream);
 
+/* Training pair of the same attention (hg_transformers/modeling_lxmert.py:798-827 and its autograd): the forward also
+ * writes probs [B * heads][Sq][skp] bf16, skp = crv_attention_probs_pitch(Sk) = Sk rounded up to 8: +P_ij where the
+ * dropout kept (i, j), -P_ij where it dropped it (P = softmax probability before dropout).  The backward reads probs
+ * instead of recomputing Q K^T, the softmax and the dropout decisions: dQ, dK, dV from five small tensor-core GEMMs per
+ * (batch, head).  No mask / rng arguments in the backward: both are folded into probs. */
+int crv_attention_probs_pitch(int Sk);
+int crv_attention_fwd_p(const uint16_t* q, long long q_bs, long long q_ss, const uint16_t* k, long long k_bs,
+                        long long k_ss, const uint16_t* v, long long v_bs, long long v_ss, const float* mask,
+                        uint16_t* out, uint16_t* probs, int B, int heads, int Sq, int Sk, float scale, float p_drop,
+                        const unsigned long long* rng_state, int site, void* stream);
+int crv_attention_bwd_p(const uint16_t* q, long long q_bs, long long q_ss, const uint16_t* k, long long k_bs,
+                        long long k_ss, const uint16_t* v, long long v_bs, long long v_ss, const uint16_t* probs,
+                        const uint16_t* dout, uint16_t* dq, long long dq_bs, long long dq_ss, uint16_t* dk,
+                        long long dk_bs, long long dk_ss, uint16_t* dv, long long dv_bs, long long dv_ss, int B,
+                        int heads, int Sq, int Sk, float scale, float p_drop, void* stream);
+
 /* erf GELU on bf16 (LxmertIntermediate): y = gelu(u);  du = dy * gelu'(u).  n % 8 == 0. */
 int crv_gelu_fwd(const uint16_t* u, uint16_t* y, int64_t n, void* stream);
 int crv_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du, int64_t n, void* stream);

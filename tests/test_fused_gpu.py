@@ -239,6 +239,35 @@ def test_small_attention_dropout_forward_and_backward_use_one_mask(Sq, Sk):
         assert rel < 2e-2, rel
 
 
+@pytest.mark.parametrize("Sq,Sk,p", [(36, 36, 0.1), (20, 36, 0.1), (36, 20, 0.0), (20, 20, 0.1), (56, 56, 0.1), (7, 64, 0.1),
+                                     (33, 17, 0.1)])
+def test_saved_probability_backward_matches_recomputing_backward(Sq, Sk, p, monkeypatch):
+    """The training path keeps the signed softmax probabilities of the forward (crv_attention_fwd_p) and its backward
+    (crv_attention_bwd_p) never recomputes them; the recomputing backward (crv_attention_bwd) regenerates the same
+    dropout decisions from the hash.  Same inputs, same step, same site: identical forward output, and gradients that
+    differ only by the bf16 rounding of the stored probabilities (1e-2 norm-wise; measured ~3e-3)."""
+    from crvqa import fused
+    torch.manual_seed(Sq * 64 + Sk)
+    B, heads, H = 6, 12, 768
+    mask = torch.zeros(B, Sk, device="cuda")
+    mask[:, Sk - 2:] = -10000.0
+    base = [(torch.randn(B, s, H, device="cuda") * 0.7).bfloat16() for s in (Sq, Sk, Sk)]
+    do = torch.randn(B, Sq, H, device="cuda").bfloat16()
+    rng = fused.RngState.get(do.device)
+    rng.advance()
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CRVQA_ATTN_SAVE_P", mode)
+        srcs = tuple(t.clone().requires_grad_(True) for t in base)
+        out = fused.small_attention(2, heads, mask, p, 11, True, *srcs)
+        out.backward(do)
+        res[mode] = (out.detach().clone(), [t.grad.float() for t in srcs])
+    assert torch.equal(res["1"][0], res["0"][0])
+    for a, b in zip(res["1"][1], res["0"][1]):
+        assert bool(torch.isfinite(a).all())
+        assert float((a - b).norm() / b.norm()) < 1e-2
+
+
 def test_visualbert_fast_path_matches_generic_path():
     """VisualBERT (BASELINE config 3 in miniature, 20 + 36 = 56 tokens): fused fast path vs generic per-module path on
     the same scores, dropout off -- logits, loss and every score gradient."""

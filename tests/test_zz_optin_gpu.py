@@ -72,4 +72,4 @@ def test_mplug_training_trajectory_follows_reference():
             got_thr, got_kept = thr_record(model), kept(model)
             for n, (value, dtype) in want["thresholds"].items():
                 assert got_thr[n][1] == dtype and got_thr[n][0] == pytest.approx(value, rel=1e-2, abs=1e-4), (step, n)
-                assert abs(got_kept[n] - want["kept"][n]) <= max(2, 0.01 * want["kept"][n]), (step, n)
+                assert abs(got_kept[n] - want["kept"][n]) <= max(2, 0.02 * want["kept"][n]), (step, n)
