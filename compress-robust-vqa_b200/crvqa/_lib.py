@@ -57,6 +57,8 @@ _PROTOS = {
     "crv_colsum_bf16": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P]),
     "crv_attention_fwd": (c_int, [_P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P,
                                   _P, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),
+    "crv_ln_avg_drop_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_float, _P, c_int, _P, _P, _P, c_int, c_int, _P]),
+    "crv_ln_avg_drop_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_float, _P, c_int, _P, _P, c_int, c_int, _P]),
     "crv_attention_probs_pitch": (c_int, [c_int]),
     "crv_attention_fwd_p": (c_int, [_P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P, c_longlong, c_longlong, _P,
                                     _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),

@@ -191,24 +191,27 @@ attn_fwd_kernel(const AttnParams p) {
     load_tile<SP>(sK, p.k + b * p.k_bs + h * kHeadDim, p.k_ss, p.Sk, tile * 32 + lane, KT2 * 32);
     load_tile<SP>(sV, p.v + b * p.v_bs + h * kHeadDim, p.v_ss, p.Sk, tile * 32 + lane, KT2 * 32);
   }
+  // this warp's Q fragments straight from global memory, issued BEFORE waiting for the K / V tiles: one global round
+  // trip instead of two in a row
+  const __nv_bfloat16* qb = p.q + b * p.q_bs + h * kHeadDim;
+  const int mt = tile;
+  const bool active = valid && mt * 16 < p.Sq;
+  const int r0 = mt * 16 + g, r1 = r0 + 8;
+  uint32_t a[4][4];
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    const int c = kt * 16 + 2 * t;
+    a[kt][0] = (active && r0 < p.Sq) ? __ldg(reinterpret_cast<const uint32_t*>(qb + r0 * p.q_ss + c)) : 0u;
+    a[kt][1] = (active && r1 < p.Sq) ? __ldg(reinterpret_cast<const uint32_t*>(qb + r1 * p.q_ss + c)) : 0u;
+    a[kt][2] = (active && r0 < p.Sq) ? __ldg(reinterpret_cast<const uint32_t*>(qb + r0 * p.q_ss + c + 8)) : 0u;
+    a[kt][3] = (active && r1 < p.Sq) ? __ldg(reinterpret_cast<const uint32_t*>(qb + r1 * p.q_ss + c + 8)) : 0u;
+  }
   cp_async_wait_all();
   __syncthreads();
   const DropKey dk = make_key(p.rng_state, p.site, p.p_drop, pair, p.Sq, p.Sk);
-  const __nv_bfloat16* qb = p.q + b * p.q_bs + h * kHeadDim;
   const float* mrow = p.mask ? p.mask + static_cast<long long>(b) * p.Sk : nullptr;
   const long long HD = static_cast<long long>(p.heads) * kHeadDim;
-  const int mt = tile;
-  if (valid && mt * 16 < p.Sq) {
-    const int r0 = mt * 16 + g, r1 = r0 + 8;
-    uint32_t a[4][4];
-#pragma unroll
-    for (int kt = 0; kt < 4; ++kt) {
-      const int c = kt * 16 + 2 * t;
-      a[kt][0] = r0 < p.Sq ? __ldg(reinterpret_cast<const uint32_t*>(qb + r0 * p.q_ss + c)) : 0u;
-      a[kt][1] = r1 < p.Sq ? __ldg(reinterpret_cast<const uint32_t*>(qb + r1 * p.q_ss + c)) : 0u;
-      a[kt][2] = r0 < p.Sq ? __ldg(reinterpret_cast<const uint32_t*>(qb + r0 * p.q_ss + c + 8)) : 0u;
-      a[kt][3] = r1 < p.Sq ? __ldg(reinterpret_cast<const uint32_t*>(qb + r1 * p.q_ss + c + 8)) : 0u;
-    }
+  if (active) {
     float s[NT][4];
     scores_16<KT2>(s, a, sK, lane);
     float m0 = -INFINITY, m1 = -INFINITY;

@@ -221,6 +221,145 @@ ln_bwd_kernel(const float* __restrict__ dy32, const uint16_t* __restrict__ dy16,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// LayerNorm -> (average of two) -> dropout: the entry blocks of LXMERT, which normalise FIRST and drop after
+//   visual feature encoder  y = dropout((LN_a(visn_fc(feats)) + LN_b(box_fc(pos))) / 2)   (modeling_lxmert.py:576-592)
+//   embeddings              y = dropout(LN_a(word + position + token_type))               (modeling_lxmert.py:744-770)
+// PyTorch runs them as 6 - 8 launches over the [M, H] activations; here one pass reads a (and b), writes y as fp32
+// (residual stream) and bf16 (next GEMM operand) plus the row statistics; the backward regenerates the dropout mask
+// and returns da (and db).  gamma / beta are frozen in stage 2, so there are no parameter gradients (stage 3 keeps
+// the PyTorch path).  One warp per row, as ln_fwd / ln_bwd.
+template <int VEC, bool DUAL>
+__global__ void __launch_bounds__(kRowsPerBlock * 32, 2)
+ln_avg_drop_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gamma_a,
+                       const float* __restrict__ beta_a, const float* __restrict__ gamma_b,
+                       const float* __restrict__ beta_b, float eps, float p,
+                       const unsigned long long* __restrict__ rng_state, int site, float* __restrict__ y32,
+                       uint16_t* __restrict__ y16, float* __restrict__ stats, int M, int H) {
+  pdl_wait();
+  const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const Rng rng = make_rng(rng_state, site, p);
+  float4 av[VEC], bv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int64_t e = static_cast<int64_t>(row) * H + (i * 32 + lane) * 4;
+    av[i] = __ldg(reinterpret_cast<const float4*>(a + e));
+    if (DUAL) bv[i] = __ldg(reinterpret_cast<const float4*>(b + e));
+  }
+  pdl_launch_dependents();
+  float sa = 0.f, sb = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    sa += av[i].x + av[i].y + av[i].z + av[i].w;
+    if (DUAL) sb += bv[i].x + bv[i].y + bv[i].z + bv[i].w;
+  }
+  const float ma = warp_sum(sa) / H, mb = DUAL ? warp_sum(sb) / H : 0.f;
+  float va = 0.f, vb = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    float x = av[i].x - ma, y = av[i].y - ma, z = av[i].z - ma, w = av[i].w - ma;
+    va += x * x + y * y + z * z + w * w;
+    if (DUAL) {
+      x = bv[i].x - mb; y = bv[i].y - mb; z = bv[i].z - mb; w = bv[i].w - mb;
+      vb += x * x + y * y + z * z + w * w;
+    }
+  }
+  const float ra = rsqrtf(warp_sum(va) / H + eps), rb = DUAL ? rsqrtf(warp_sum(vb) / H + eps) : 0.f;
+  if (lane == 0) *reinterpret_cast<float4*>(stats + static_cast<size_t>(row) * 4) = make_float4(ma, ra, mb, rb);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const int64_t e = static_cast<int64_t>(row) * H + col;
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma_a + col));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta_a + col));
+    float4 o;
+    o.x = (av[i].x - ma) * ra * ga.x + be.x;
+    o.y = (av[i].y - ma) * ra * ga.y + be.y;
+    o.z = (av[i].z - ma) * ra * ga.z + be.z;
+    o.w = (av[i].w - ma) * ra * ga.w + be.w;
+    if (DUAL) {
+      const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma_b + col));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(beta_b + col));
+      o.x = (o.x + (bv[i].x - mb) * rb * gb.x + bb.x) * 0.5f;     // (x + y) / 2 as the reference writes it
+      o.y = (o.y + (bv[i].y - mb) * rb * gb.y + bb.y) * 0.5f;
+      o.z = (o.z + (bv[i].z - mb) * rb * gb.z + bb.z) * 0.5f;
+      o.w = (o.w + (bv[i].w - mb) * rb * gb.w + bb.w) * 0.5f;
+    }
+    if (rng.thresh) rng.drop4(o, e);
+    *reinterpret_cast<float4*>(y32 + e) = o;
+    *reinterpret_cast<uint2*>(y16 + e) = pack4(o);
+  }
+}
+
+template <int VEC, bool DUAL>
+__global__ void __launch_bounds__(kRowsPerBlock * 32, 2)
+ln_avg_drop_bwd_kernel(const float* __restrict__ dy32, const uint16_t* __restrict__ dy16, const float* __restrict__ a,
+                       const float* __restrict__ b, const float* __restrict__ gamma_a, const float* __restrict__ gamma_b,
+                       const float* __restrict__ stats, float p, const unsigned long long* __restrict__ rng_state,
+                       int site, float* __restrict__ da, float* __restrict__ db, int M, int H) {
+  pdl_wait();
+  const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const Rng rng = make_rng(rng_state, site, p);
+  const float4 st = __ldg(reinterpret_cast<const float4*>(stats + static_cast<size_t>(row) * 4));
+  float4 d[VEC], xa[VEC], xb[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int64_t e = static_cast<int64_t>(row) * H + (i * 32 + lane) * 4;
+    d[i] = dy32 ? __ldg(reinterpret_cast<const float4*>(dy32 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dy16) {
+      const float4 t = load4(dy16, 1, e);
+      d[i].x += t.x; d[i].y += t.y; d[i].z += t.z; d[i].w += t.w;
+    }
+    xa[i] = __ldg(reinterpret_cast<const float4*>(a + e));
+    if (DUAL) xb[i] = __ldg(reinterpret_cast<const float4*>(b + e));
+  }
+  pdl_launch_dependents();
+  float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const int64_t e = static_cast<int64_t>(row) * H + col;
+    if (rng.thresh) rng.drop4(d[i], e);          // dropout' = the same keep / scale pattern
+    if (DUAL) { d[i].x *= 0.5f; d[i].y *= 0.5f; d[i].z *= 0.5f; d[i].w *= 0.5f; }
+    xa[i] = make_float4((xa[i].x - st.x) * st.y, (xa[i].y - st.x) * st.y, (xa[i].z - st.x) * st.y, (xa[i].w - st.x) * st.y);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma_a + col));
+    s1a += d[i].x * ga.x + d[i].y * ga.y + d[i].z * ga.z + d[i].w * ga.w;
+    s2a += d[i].x * ga.x * xa[i].x + d[i].y * ga.y * xa[i].y + d[i].z * ga.z * xa[i].z + d[i].w * ga.w * xa[i].w;
+    if (DUAL) {
+      xb[i] = make_float4((xb[i].x - st.z) * st.w, (xb[i].y - st.z) * st.w, (xb[i].z - st.z) * st.w, (xb[i].w - st.z) * st.w);
+      const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma_b + col));
+      s1b += d[i].x * gb.x + d[i].y * gb.y + d[i].z * gb.z + d[i].w * gb.w;
+      s2b += d[i].x * gb.x * xb[i].x + d[i].y * gb.y * xb[i].y + d[i].z * gb.z * xb[i].z + d[i].w * gb.w * xb[i].w;
+    }
+  }
+  const float m1a = warp_sum(s1a) / H, m2a = warp_sum(s2a) / H;
+  const float m1b = DUAL ? warp_sum(s1b) / H : 0.f, m2b = DUAL ? warp_sum(s2b) / H : 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const int64_t e = static_cast<int64_t>(row) * H + col;
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma_a + col));
+    float4 o;
+    o.x = st.y * (d[i].x * ga.x - m1a - xa[i].x * m2a);
+    o.y = st.y * (d[i].y * ga.y - m1a - xa[i].y * m2a);
+    o.z = st.y * (d[i].z * ga.z - m1a - xa[i].z * m2a);
+    o.w = st.y * (d[i].w * ga.w - m1a - xa[i].w * m2a);
+    if (da) *reinterpret_cast<float4*>(da + e) = o;
+    if (DUAL && db) {
+      const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma_b + col));
+      o.x = st.w * (d[i].x * gb.x - m1b - xb[i].x * m2b);
+      o.y = st.w * (d[i].y * gb.y - m1b - xb[i].y * m2b);
+      o.z = st.w * (d[i].z * gb.z - m1b - xb[i].z * m2b);
+      o.w = st.w * (d[i].w * gb.w - m1b - xb[i].w * m2b);
+      *reinterpret_cast<float4*>(db + e) = o;
+    }
+  }
+}
+
 __global__ void gelu_fwd_kernel(const uint16_t* __restrict__ u, uint16_t* __restrict__ y, int64_t n) {
   pdl_wait();
   const int64_t nvec = n >> 3;
@@ -335,4 +474,52 @@ extern "C" int crv_rng_advance(unsigned long long* rng_state, void* stream) {
   if (!rng_state) return CRV_E_BADARG;
   counter_inc_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(rng_state);
   return launch_status();
+}
+
+
+extern "C" int crv_ln_avg_drop_fwd(const float* a, const float* b, const float* gamma_a, const float* beta_a,
+                                   const float* gamma_b, const float* beta_b, float eps, float p_drop,
+                                   const unsigned long long* rng_state, int site, float* y_f32, uint16_t* y_bf16,
+                                   float* stats, int M, int H, void* stream) {
+  if (!a || !gamma_a || !beta_a || !y_f32 || !y_bf16 || !stats || M <= 0 || H <= 0) return CRV_E_BADARG;
+  if (b && (!gamma_b || !beta_b)) return CRV_E_BADARG;
+  if (H % 128 || H > 1024) return CRV_E_SHAPE;
+  if (!aligned16(a) || (b && !aligned16(b)) || !aligned16(y_f32) || !aligned16(y_bf16) || !aligned16(stats))
+    return CRV_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (M + kRowsPerBlock - 1) / kRowsPerBlock;
+  return dispatch_vec(H, [&](auto v) {
+    constexpr int VEC = decltype(v)::value;
+    if (b)
+      CRV_CUDA(launch_pdl(ln_avg_drop_fwd_kernel<VEC, true>, dim3(grid), dim3(kRowsPerBlock * 32), 0, st, a, b, gamma_a,
+                          beta_a, gamma_b, beta_b, eps, p_drop, rng_state, site, y_f32, y_bf16, stats, M, H));
+    else
+      CRV_CUDA(launch_pdl(ln_avg_drop_fwd_kernel<VEC, false>, dim3(grid), dim3(kRowsPerBlock * 32), 0, st, a, b, gamma_a,
+                          beta_a, gamma_b, beta_b, eps, p_drop, rng_state, site, y_f32, y_bf16, stats, M, H));
+    return launch_status();
+  });
+}
+
+extern "C" int crv_ln_avg_drop_bwd(const float* dy_f32, const uint16_t* dy_bf16, const float* a, const float* b,
+                                   const float* gamma_a, const float* gamma_b, const float* stats, float p_drop,
+                                   const unsigned long long* rng_state, int site, float* da, float* db, int M, int H,
+                                   void* stream) {
+  if ((!dy_f32 && !dy_bf16) || !a || !gamma_a || !stats || (!da && !db) || M <= 0 || H <= 0) return CRV_E_BADARG;
+  if (b && !gamma_b) return CRV_E_BADARG;
+  if (db && !b) return CRV_E_BADARG;
+  if (H % 128 || H > 1024) return CRV_E_SHAPE;
+  if (!aligned16(a) || (b && !aligned16(b)) || (da && !aligned16(da)) || (db && !aligned16(db)) || !aligned16(stats))
+    return CRV_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (M + kRowsPerBlock - 1) / kRowsPerBlock;
+  return dispatch_vec(H, [&](auto v) {
+    constexpr int VEC = decltype(v)::value;
+    if (b)
+      CRV_CUDA(launch_pdl(ln_avg_drop_bwd_kernel<VEC, true>, dim3(grid), dim3(kRowsPerBlock * 32), 0, st, dy_f32, dy_bf16,
+                          a, b, gamma_a, gamma_b, stats, p_drop, rng_state, site, da, db, M, H));
+    else
+      CRV_CUDA(launch_pdl(ln_avg_drop_bwd_kernel<VEC, false>, dim3(grid), dim3(kRowsPerBlock * 32), 0, st, dy_f32, dy_bf16,
+                          a, b, gamma_a, gamma_b, stats, p_drop, rng_state, site, da, db, M, H));
+    return launch_status();
+  });
 }

@@ -18,6 +18,8 @@ operand ``W (.) M`` between steps (one streaming pass per module and step) and f
 instead of re-deriving the mask inside every GEMM call.  Code that edits scores behind the engine's back must call
 ``invalidate_masks()``.
 """
+import os
+
 import torch
 import torch.distributed as dist
 from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors
@@ -39,6 +41,12 @@ class MaskTrainEngine:
         self.global_steps = 0
         self.last_grad_norm = None
         maskers.set_score_dtype(module, torch.bfloat16 if bf16 else torch.float32)
+        # bf16=True is the reference's DeepSpeed configuration (mPLUG/configs/ds_config.json): there the WHOLE forward
+        # runs in bf16.  The engine therefore switches the model to bf16 activations between the masked GEMMs (autocast;
+        # LayerNorm / softmax / loss stay fp32) unless CRVQA_MPLUG_BF16_ACTIVATIONS=0 asks for fp32 activations.
+        # Masks, thresholds and kept counts do not depend on the activation dtype (tests/test_zz_optin_gpu.py).
+        if bf16 and hasattr(module, "bf16_activations") and os.environ.get("CRVQA_MPLUG_BF16_ACTIVATIONS", "1") != "0":
+            module.bf16_activations = True
         self._masked = [m for m in module.modules() if hasattr(m, "hold_masked_weight")]
         for m in self._masked:
             m.hold_masked_weight(hold_masks)

@@ -266,6 +266,18 @@ int crv_attention_bwd_p(const uint16_t* q, long long q_bs, long long q_ss, const
                         long long dk_bs, long long dk_ss, uint16_t* dv, long long dv_bs, long long dv_ss, int B,
                         int heads, int Sq, int Sk, float scale, float p_drop, void* stream);
 
+/* LayerNorm -> (average of two) -> dropout, the entry blocks of LXMERT (hg_transformers/modeling_lxmert.py:576-592
+ * LxmertVisualFeatureEncoder: y = dropout((LN_a(a) + LN_b(b)) / 2); :744-770 LxmertEmbeddings: y = dropout(LN_a(a)),
+ * b = NULL).  a, b fp32 [M, H]; y as fp32 and bf16; stats [M][4] = {mean_a, rstd_a, mean_b, rstd_b}.  The backward
+ * regenerates the dropout mask (same rng_state / site) and writes da (and db); either may be NULL when its input
+ * needs no gradient.  No gamma / beta gradients (frozen in stage 2).  H % 128 == 0, H <= 1024. */
+int crv_ln_avg_drop_fwd(const float* a, const float* b, const float* gamma_a, const float* beta_a, const float* gamma_b,
+                        const float* beta_b, float eps, float p_drop, const unsigned long long* rng_state, int site,
+                        float* y_f32, uint16_t* y_bf16, float* stats, int M, int H, void* stream);
+int crv_ln_avg_drop_bwd(const float* dy_f32, const uint16_t* dy_bf16, const float* a, const float* b,
+                        const float* gamma_a, const float* gamma_b, const float* stats, float p_drop,
+                        const unsigned long long* rng_state, int site, float* da, float* db, int M, int H, void* stream);
+
 /* erf GELU on bf16 (LxmertIntermediate): y = gelu(u);  du = dy * gelu'(u).  n % 8 == 0. */
 int crv_gelu_fwd(const uint16_t* u, uint16_t* y, int64_t n, void* stream);
 int crv_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du, int64_t n, void* stream);
