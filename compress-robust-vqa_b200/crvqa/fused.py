@@ -336,6 +336,83 @@ def drop_add_layernorm(g, res32, ln, p, site, training):
     return DropAddLayerNormFn.apply(g, res32, ln.weight, ln.bias, ln.eps, p, site, rng)
 
 
+class LnAvgDropFn(torch.autograd.Function):
+    """(y fp32, y bf16) = dropout((LN_a(a) + LN_b(b)) / 2), or dropout(LN_a(a)) when b is None: the entry blocks of LXMERT
+    (LxmertVisualFeatureEncoder / LxmertEmbeddings, hg_transformers/modeling_lxmert.py:576-592, 744-770) in one pass each
+    way (crv_ln_avg_drop_fwd / _bwd).  LayerNorm parameters are constants here (frozen in stage 2)."""
+
+    @staticmethod
+    def forward(ctx, a, b, ga, ba, gb, bb, eps, p, site, rng):
+        H = a.shape[-1]
+        a2 = a.reshape(-1, H)
+        a2 = a2 if a2.is_contiguous() else a2.contiguous()
+        b2 = None
+        if b is not None:
+            b2 = b.reshape(-1, H)
+            b2 = b2 if b2.is_contiguous() else b2.contiguous()
+        M = a2.shape[0]
+        dev = a.device
+        y32 = torch.empty((M, H), dtype=torch.float32, device=dev)
+        y16 = torch.empty((M, H), dtype=torch.bfloat16, device=dev)
+        stats = torch.empty((M, 4), dtype=torch.float32, device=dev)
+        state = rng.state if (rng is not None and p > 0) else None
+        check(lib.crv_ln_avg_drop_fwd(_p(a2), _p(b2), _p(ga), _p(ba), _p(gb), _p(bb), float(eps), float(p), _p(state),
+                                      int(site), _p(y32), _p(y16), _p(stats), M, H, _stream()), "crv_ln_avg_drop_fwd")
+        ctx.save_for_backward(a2, b2, ga, gb, stats)
+        ctx.p, ctx.site, ctx.state, ctx.shape = float(p), int(site), state, a.shape
+        ctx.need = (ctx.needs_input_grad[0], b is not None and ctx.needs_input_grad[1])
+        ctx.set_materialize_grads(False)
+        return y32.view(a.shape), y16.view(a.shape)
+
+    @staticmethod
+    def backward(ctx, dy32, dy16):
+        a2, b2, ga, gb, stats = ctx.saved_tensors
+        if (dy32 is None and dy16 is None) or not any(ctx.need):
+            return (None,) * 10
+        M, H = a2.shape
+        d32 = dy32.reshape(M, H).contiguous() if dy32 is not None else None
+        d16 = dy16.reshape(M, H).contiguous() if dy16 is not None else None
+        da = torch.empty((M, H), dtype=torch.float32, device=a2.device) if ctx.need[0] else None
+        db = torch.empty((M, H), dtype=torch.float32, device=a2.device) if ctx.need[1] else None
+        check(lib.crv_ln_avg_drop_bwd(_p(d32), _p(d16), _p(a2), _p(b2), _p(ga), _p(gb), _p(stats), ctx.p, _p(ctx.state),
+                                      ctx.site, _p(da), _p(db), M, H, _stream()), "crv_ln_avg_drop_bwd")
+        return (da.view(ctx.shape) if da is not None else None, db.view(ctx.shape) if db is not None else None,
+                None, None, None, None, None, None, None, None)
+
+
+def ln_avg_drop_usable(a, b, ln_a, ln_b):
+    """The fused entry block applies on CUDA, fp32 inputs, H % 128 == 0, H <= 1024 and FROZEN LayerNorm parameters (stage
+    2); anything else (stage 3 trains them, CPU) keeps the PyTorch ops.  CRVQA_FUSED_ENTRY=0 turns it off."""
+    if os.environ.get("CRVQA_FUSED_ENTRY", "1") == "0" or os.environ.get("CRVQA_FUSED", "1") == "0":
+        return False
+    H = a.shape[-1]
+    if not a.is_cuda or a.dtype != torch.float32 or H % 128 or H > 1024:
+        return False
+    if b is not None and (b.dtype != torch.float32 or b.shape != a.shape):
+        return False
+    for ln in (ln_a, ln_b):
+        if ln is None:
+            continue
+        if ln.weight is None or ln.bias is None or ln.weight.requires_grad or ln.bias.requires_grad:
+            return False
+        if tuple(ln.normalized_shape) != (H,):
+            return False
+    if ln_b is not None and ln_b.eps != ln_a.eps:
+        return False
+    return True
+
+
+def ln_avg_drop(a, b, ln_a, ln_b, p, site, training):
+    """y fp32 of the entry block, with the bf16 copy the first GEMM reads attached as ``y._crv_bf16`` (an output of the
+    same autograd node, so gradients reaching either copy flow back)."""
+    p = float(p) if training else 0.0
+    rng = RngState.get(a.device) if p > 0 else None
+    y32, y16 = LnAvgDropFn.apply(a, b, ln_a.weight, ln_a.bias, ln_b.weight if ln_b is not None else None,
+                                 ln_b.bias if ln_b is not None else None, ln_a.eps, p, site, rng)
+    y32._crv_bf16 = y16
+    return y32
+
+
 class GeluFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u):

@@ -730,7 +730,7 @@ extern "C" int crv_attention_bwd(const uint16_t* q, long long q_bs, long long q_
 
 // Training pair: the forward also writes the signed probabilities (probs [B * heads][Sq][skp] bf16, skp = Sk rounded up
 // to a multiple of 8), the backward consumes them.  crv_attention_probs_pitch() gives skp.
-extern "C" int crv_attention_probs_pitch(int Sk) { return (Sk + 7) / 8 * 8; }
+extern "C" int crv_attention_probs_pitch(int Sk) { return Sk > 0 ? (Sk + 7) / 8 * 8 : CRV_E_BADARG; }
 
 extern "C" int crv_attention_fwd_p(const uint16_t* q, long long q_bs, long long q_ss, const uint16_t* k, long long k_bs,
                                    long long k_ss, const uint16_t* v, long long v_bs, long long v_ss, const float* mask,

@@ -42,6 +42,12 @@ class LxmertEmbeddings(nn.Module):
         if token_type_ids is None:
             token_type_ids = torch.zeros_like(input_ids)
         e = self.word_embeddings(input_ids) + self.position_embeddings(pos) + self.token_type_embeddings(token_type_ids)
+        if e.is_cuda:
+            from crvqa import fused
+            if fused.ln_avg_drop_usable(e, None, self.LayerNorm, None):      # LayerNorm + dropout in one pass
+                if not hasattr(self, "_site"):
+                    self._site = fused.RngState.new_site()
+                return fused.ln_avg_drop(e, None, self.LayerNorm, None, self.dropout.p, self._site, self.training)
         return self.dropout(self.LayerNorm(e))
 
 
@@ -173,8 +179,17 @@ class LxmertVisualFeatureEncoder(nn.Module):
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
 
     def forward(self, visual_feats, visual_pos):
-        x = self.visn_layer_norm(self.visn_fc(visual_feats))
-        y = self.box_layer_norm(self.box_fc(visual_pos))
+        a, b = self.visn_fc(visual_feats), self.box_fc(visual_pos)
+        if a.is_cuda:
+            from crvqa import fused
+            if fused.ln_avg_drop_usable(a, b, self.visn_layer_norm, self.box_layer_norm):
+                # both LayerNorms, the average and the dropout in one pass (crv_ln_avg_drop_fwd)
+                if not hasattr(self, "_site"):
+                    self._site = fused.RngState.new_site()
+                return fused.ln_avg_drop(a, b, self.visn_layer_norm, self.box_layer_norm, self.dropout.p, self._site,
+                                         self.training)
+        x = self.visn_layer_norm(a)
+        y = self.box_layer_norm(b)
         return self.dropout((x + y) / 2)
 
 
@@ -251,10 +266,14 @@ class LxmertEncoder(nn.Module):
         reference computes it and throws it away -- and is not executed."""
         from crvqa import fused
         tr = self.training
-        visn16 = visn32.to(torch.bfloat16)
+        visn16 = getattr(visn32, "_crv_bf16", None)       # the fused entry block already produced the bf16 copy
+        if visn16 is None:
+            visn16 = visn32.to(torch.bfloat16)
         if callable(lang32):
             lang32 = lang32()
-        lang16 = lang32.to(torch.bfloat16)
+        lang16 = getattr(lang32, "_crv_bf16", None)
+        if lang16 is None:
+            lang16 = lang32.to(torch.bfloat16)
         nl, nv = len(plans["lang"]), len(plans["visn"])
         for i in range(max(nl, nv)):
             items = []

@@ -268,6 +268,56 @@ def test_saved_probability_backward_matches_recomputing_backward(Sq, Sk, p, monk
         assert float((a - b).norm() / b.norm()) < 1e-2
 
 
+@pytest.mark.parametrize("dual", [True, False])
+@pytest.mark.parametrize("M,H", [(9216, 768), (5120, 768), (37, 256), (515, 1024)])
+def test_entry_block_layernorm_average_dropout(dual, M, H):
+    """crv_ln_avg_drop_fwd / _bwd against the PyTorch ops of LxmertVisualFeatureEncoder / LxmertEmbeddings
+    (hg_transformers/modeling_lxmert.py:576-592, 744-770): without dropout value and gradients to 1e-5 of the output /
+    gradient scale; with dropout the kept pattern is read from the output, the torch graph with THAT mask is the
+    reference, and the backward must have regenerated the same pattern."""
+    import types
+    from crvqa import fused
+    torch.manual_seed(M + H + dual)
+    mk = lambda: types.SimpleNamespace(weight=(torch.rand(H, device="cuda") + 0.5), bias=torch.randn(H, device="cuda") * 0.1,
+                                       eps=1e-12, normalized_shape=(H,))
+    ln_a, ln_b = mk(), (mk() if dual else None)
+    a = torch.randn(M, H, device="cuda", requires_grad=True)
+    b = (torch.randn(M, H, device="cuda") * 2 + 0.3).requires_grad_(True) if dual else None
+    assert fused.ln_avg_drop_usable(a, b, ln_a, ln_b)
+
+    def ref(a_, b_, keep, scale):
+        y = F.layer_norm(a_, (H,), ln_a.weight, ln_a.bias, 1e-12)
+        if dual:
+            y = (y + F.layer_norm(b_, (H,), ln_b.weight, ln_b.bias, 1e-12)) / 2
+        return y * keep * scale
+
+    fused.RngState.get(a.device).advance()
+    for p in (0.0, 0.1):
+        y32 = fused.ln_avg_drop(a, b, ln_a, ln_b, p, 77, True)
+        y16 = y32._crv_bf16
+        keep = torch.ones_like(y32)
+        if p > 0:
+            dense = ref(a.detach(), b.detach() if dual else None, 1.0, 1.0)
+            keep = ((y32.detach() != 0) | (dense == 0)).float()
+            assert abs(1.0 - float(keep.mean()) - p) < 0.01
+        a2 = a.detach().clone().requires_grad_(True)
+        b2 = b.detach().clone().requires_grad_(True) if dual else None
+        want = ref(a2, b2, keep, 1.0 / (1.0 - p))
+        scale = float(want.abs().max())
+        assert float((y32.detach() - want.detach()).abs().max()) <= 1e-5 * scale
+        assert torch.equal(y16.detach(), y32.detach().bfloat16())
+        d32, d16 = torch.randn_like(y32), torch.randn(M, H, device="cuda").bfloat16()
+        grads = torch.autograd.grad((y32, y16), (a, b) if dual else (a,), (d32, d16))
+        want_g = torch.autograd.grad(want, (a2, b2) if dual else (a2,), d32 + d16.float())
+        for g, w in zip(grads, want_g):
+            assert float((g - w).abs().max()) <= 2e-5 * float(w.abs().max()), float((g - w).abs().max() / w.abs().max())
+    # only one branch needs a gradient (box_fc's input never does, but its weight scores do; the embeddings' ids do not)
+    if dual:
+        y32 = fused.ln_avg_drop(a.detach(), b, ln_a, ln_b, 0.0, 77, True)
+        (gb,) = torch.autograd.grad(y32.sum(), (b,))
+        assert bool(torch.isfinite(gb).all())
+
+
 def test_visualbert_fast_path_matches_generic_path():
     """VisualBERT (BASELINE config 3 in miniature, 20 + 36 = 56 tokens): fused fast path vs generic per-module path on
     the same scores, dropout off -- logits, loss and every score gradient."""
