@@ -12,6 +12,8 @@
 // with (seed, counter) read from device memory so a captured CUDA graph draws a fresh mask every replay
 // and the backward pass regenerates the forward mask instead of storing it.
 // One warp per row (H <= 1024, H % 128 == 0), 16-byte accesses, fp32 math.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gelu.cuh"
 
@@ -75,7 +77,7 @@ __device__ __forceinline__ uint2 pack4(float4 v) {
 }
 
 template <int VEC>  // VEC = H / 128 float4 chunks per lane
-__global__ void __launch_bounds__(kRowsPerBlock * 32, 2)
+__global__ void __launch_bounds__(kRowsPerBlock * 32, VEC <= 6 ? 3 : 2)
 ln_fwd_kernel(const void* __restrict__ g, int g_bf16, const float* __restrict__ res, const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, float p, const unsigned long long* __restrict__ rng_state,
               int site, float* __restrict__ y32, uint16_t* __restrict__ y16, float* __restrict__ mean_out,
