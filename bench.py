@@ -407,6 +407,13 @@ def run_ours(args):
     from hg_transformers._engine import InputPrefetcher
     pre = InputPrefetcher(dev)
 
+    # Every step's loss is read back to the host inside the timed region: a 4-byte device -> pinned-host copy enqueued
+    # right behind the step, consumed (event wait + float()) after the NEXT step has been enqueued -- the way the
+    # trainer's own loop keeps the loss on the device between logging steps, so the GPU never idles behind a blocking
+    # .item() while the host (and, at N > 1, the slowest rank's host) catches up.
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+
     def e2e_steps(n):
         last = None
         handle = pre.stage(host_inputs)
@@ -416,7 +423,13 @@ def run_ours(args):
             handle = pre.stage(host_inputs) if i + 1 < n else None
             loss = one_step(batch)
             pre.release(cur)
-            last = float(loss)                   # .item(): device -> host read of the step's loss
+            loss_host[i & 1].copy_(loss.detach().reshape(()), non_blocking=True)
+            loss_ev[i & 1].record()
+            if i > 0:                            # read step i-1's loss now that step i is in the queue
+                loss_ev[(i - 1) & 1].synchronize()
+                last = float(loss_host[(i - 1) & 1])
+        loss_ev[(n - 1) & 1].synchronize()
+        last = float(loss_host[(n - 1) & 1])     # the last step's loss: inside the timed region as well
         return last
 
     e2e_steps(2)
@@ -498,6 +511,7 @@ def run_ours(args):
             "clocks": clock_info,
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                    "loss_readback": "every step: async copy to pinned host memory behind the step, read one step later",
                     "last_loss": last},
             "gpu_launches": int(launches), "roofline": roofline}
     if cpu is not None:

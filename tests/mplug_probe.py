@@ -86,7 +86,7 @@ def main():
         upd = time.time() - t1
     print(json.dumps({"workload": "mPLUG-base masked training, 384 px (577 image tokens), 16 question / 6 answer "
                                   "tokens, 2 answers per question, distill twins updated, zero rate 0.7",
-                      "batch": B, "steps": steps, "ms_per_step": ms, "hold_masks": hold, "bf16_activations": bool(MPLUG.bf16_activations),
+                      "batch": B, "steps": steps, "ms_per_step": ms, "hold_masks": hold, "bf16_activations": bool(model.bf16_activations),
                       "gpu_busy_ms_per_step": busy, "samples_per_s": B / ms * 1e3,
                       "masked_modules": len([1 for _, m in model.named_modules() if hasattr(m, "threshold")]),
                       "trainable_scores": n_scores, "loss": float(loss), "setup_s": setup_s,
