@@ -3,6 +3,11 @@
 on CPU fp32:
 
     python tests/golden/make_golden_visualbert.py        # writes tests/golden/visualbert_tiny.pt
+    python tests/golden/make_golden_visualbert.py --full # writes tests/golden/visualbert_full.pt (BASELINE config 3 at
+                                                         # full size: 12 layers, h = 768, 2048-d regions, A = 3129, 56
+                                                         # tokens, batch 32; statistics and samples only -- the
+                                                         # seed-49 init is reproduced bit for bit by the drop-in model,
+                                                         # pinned by the SHA-256 of the state_dict stored here)
 
 Model: 2 layers, hidden 128 (2 heads of 64), 20 tokens + 36 regions, A = 50; masker: uniform zero rate 0.7 over
 K,Q,V,AO,I,O x layers + pooler + word embeddings.  Stored: the reference's random init (state_dict), the batch seed,
@@ -34,14 +39,33 @@ def batch(B=8, T=20, R=36, seed=49):
     return {"ids": ids, "feats": feats, "target": target}
 
 
+def _sha(sd):
+    import hashlib
+    h = hashlib.sha256()
+    for k, v in sorted(sd.items()):
+        h.update(k.encode())
+        h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
 def main():
+    full = "--full" in sys.argv
+    if full:
+        CFG.clear()
+        CFG.update(visual_embedding_dim=2048, ans_num=3129)
     R = mg.load_reference()
     VB = importlib.import_module("hg_transformers.modeling_visualbert")
     VC = importlib.import_module("hg_transformers.configuration_visualbert")
     VT = importlib.import_module("hg_transformers.mask_trainer_visualBERT_VQA")
     torch.manual_seed(49)
-    model = VB.VisualBertForMultipleChoice(VC.visualBERTConfig(**CFG))
-    out = {"config": dict(CFG), "state_dict": {k: v.clone() for k, v in model.state_dict().items()}}
+    cfg_obj = VC.visualBERTConfig(**CFG)
+    model = VB.VisualBertForMultipleChoice(cfg_obj)
+    if full:
+        CFG["vocab_size"] = cfg_obj.vocab_size
+        out = {"config": dict(visual_embedding_dim=2048, ans_num=3129), "state_sha": _sha(model.state_dict()),
+               "vocab_size": cfg_obj.vocab_size, "B": 32}
+    else:
+        out = {"config": dict(CFG), "state_dict": {k: v.clone() for k, v in model.state_dict().items()}}
     conf = types.SimpleNamespace(
         masking_scheduler_conf_={"lambdas_lr": 0.0, "sparsity_warmup": "automated_gradual_sparsity",
                                  "sparsity_warmup_interval_epoch": 0.1, "init_epoch": 0.0, "final_epoch": 1.0,
@@ -58,7 +82,7 @@ def main():
     out["module_names"] = [n for n, _ in mods]
     out["kept_init"] = {n: int((m.weight_mask.detach() > 1e-2).sum()) for n, m in mods}
     out["trainable"] = sorted(n for n, p in model.named_parameters() if p.requires_grad)
-    b = batch()
+    b = batch(B=32) if full else batch()
     model.eval()
     model.zero_grad()
     o = model(input_ids=b["ids"], visual_embeds=b["feats"], labels=b["target"])
@@ -68,7 +92,7 @@ def main():
     def stat(g):
         flat = g.reshape(-1)
         return {"l2": float(g.double().norm()), "nnz": int((g != 0).sum()),
-                "sample": flat[:: max(1, flat.numel() // 2048)][:2048].clone()}
+                "sample": flat[:: max(1, flat.numel() // (512 if full else 2048))][:(512 if full else 2048)].clone()}
     out["grad_stats"] = {n: stat(m.weight_mask.grad.detach()) for n, m in mods if m.weight_mask.grad is not None}
     out["nograd"] = [n for n, m in mods if m.weight_mask.grad is None]
     out["cls_grad_stats"] = {n: stat(p.grad.detach()) for n, p in model.named_parameters()
@@ -81,7 +105,9 @@ def main():
     out["mean_threshold"] = float(VT.Trainer.reset_threshold(dummy, model, 0.7))
     out["thresholds_after"] = {n: m.threshold.detach().clone() for n, m in mods}
     out["kept_after"] = {n: int((m.weight_mask.detach() > m.threshold).sum()) for n, m in mods}
-    torch.save(out, os.path.join(HERE, "visualbert_tiny.pt"))
+    if full:                     # thresholds as Python floats keep the file small
+        out["thresholds_after"] = {n: float(t) for n, t in out["thresholds_after"].items()}
+    torch.save(out, os.path.join(HERE, "visualbert_full.pt" if full else "visualbert_tiny.pt"))
     print({k: (v if isinstance(v, (int, float, str)) else type(v).__name__) for k, v in out.items()})
     print("loss", float(loss), "modules", len(mods), "nograd", out["nograd"])
 
