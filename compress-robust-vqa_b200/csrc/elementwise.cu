@@ -702,11 +702,93 @@ extern "C" int crv_adamw_segmented(float* p, float* g, float* m, float* v, float
   return launch_status();
 }
 
+// K <= 8 (box_fc: K = 4) variants with the lanes along N: coalesced 16-byte stores of Y / coalesced reads of dY.
+// The general kernels above walk dY with a stride of N floats (one 32-byte sector per 4 useful bytes: 49 us for the
+// 28 MB of the box_fc dY) and recompute the masked weight per output element.
+namespace crv {
+__global__ void small_k8_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                    const float* __restrict__ s, const float* __restrict__ thr_p,
+                                    const float* __restrict__ bias, float* __restrict__ y, int M, int N, int K) {
+  // thread = 4 consecutive columns n of a row block; its masked weights (4 x K) and biases stay in registers
+  const float thr = s ? __ldg(thr_p) : 0.f;
+  const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (n0 >= N) return;
+  float wm[4][8], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + j;
+    b[j] = (bias && n < N) ? bias[n] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const bool ok = n < N && k < K;
+      const int64_t o = static_cast<int64_t>(n) * K + k;
+      wm[j][k] = (ok && (!s || s[o] > thr)) ? w[o] : 0.f;
+    }
+  }
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m_end = min(M, static_cast<int>((blockIdx.y + 1) * rows_per));
+  for (int m = blockIdx.y * rows_per; m < m_end; ++m) {
+    float xv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xv[k] = k < K ? __ldg(x + static_cast<int64_t>(m) * K + k) : 0.f;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = fmaf(xv[k], wm[j][k], acc);      // k ascending, as the general kernel
+      o[j] = acc + b[j];
+    }
+    float* yr = y + static_cast<int64_t>(m) * N + n0;
+    if (n0 + 3 < N && (N & 3) == 0) *reinterpret_cast<float4*>(yr) = make_float4(o[0], o[1], o[2], o[3]);
+    else
+      for (int j = 0; j < 4 && n0 + j < N; ++j) yr[j] = o[j];
+  }
+}
+
+// dS[n][k] += w[n][k] * sum_m dy[m][n] x[m][k]: lane = column n (coalesced dY), warps and blockIdx.y split the rows,
+// CTA partials go out with one atomicAdd per (n, k) (ds pre-zeroed by the caller unless accumulating)
+__global__ void small_k8_bwd_ds_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                       const float* __restrict__ w, float* __restrict__ ds, int M, int N, int K) {
+  __shared__ float red[8][8][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m_end = min(M, static_cast<int>((blockIdx.y + 1) * rows_per));
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int m = blockIdx.y * rows_per + wid; m < m_end; m += 8) {
+    const float d = n < N ? __ldg(dy + static_cast<int64_t>(m) * N + n) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < K) acc[k] = fmaf(d, __ldg(x + static_cast<int64_t>(m) * K + k), acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[wid][k][lane] = acc[k];
+  __syncthreads();
+  const int k = wid;                       // warp k finishes column block x score column k
+  if (k < K && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][k][lane];
+    const int64_t o = static_cast<int64_t>(n) * K + k;
+    atomicAdd(ds + o, t * w[o]);
+  }
+}
+}  // namespace crv
+
 extern "C" int crv_masked_linear_small_k_fwd(const float* x, const float* w, const float* scores, const float* thr,
                                              const float* bias, float* y, int M, int N, int K, void* stream) {
   if (!x || !w || !y || M <= 0 || N <= 0 || K <= 0) return CRV_E_BADARG;
   if (scores && !thr) return CRV_E_BADARG;
   if (K > 64) return CRV_E_SHAPE;
+  if (K <= 8 && aligned16(y)) {
+    const int col_blocks = (N + 4 * 64 - 1) / (4 * 64);            // 64 threads x 4 columns
+    int slices = (num_sms() * 8 + col_blocks - 1) / col_blocks;
+    if (slices > M) slices = M;
+    small_k8_fwd_kernel<<<dim3(col_blocks, slices), 64, 0, static_cast<cudaStream_t>(stream)>>>(x, w, scores, thr, bias,
+                                                                                               y, M, N, K);
+    return launch_status();
+  }
   const int64_t total = static_cast<int64_t>(M) * N;
   small_k_fwd_kernel<<<stream_grid(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, w, scores, thr, bias,
                                                                                               y, M, N, K);
@@ -720,8 +802,19 @@ extern "C" int crv_masked_linear_small_k_bwd(const float* dy, const float* x, co
   if (scores && !thr) return CRV_E_BADARG;
   if (K > 64) return CRV_E_SHAPE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  small_k_bwd_ds_kernel<<<N, 256, (256 / 32) * 8 * sizeof(float), st>>>(dy, x, w, dscores, accumulate, M, N, K);
-  int rc = launch_status();
+  int rc;
+  if (K <= 8) {
+    if (!accumulate) CRV_CUDA(cudaMemsetAsync(dscores, 0, static_cast<size_t>(N) * K * sizeof(float), st));
+    const int col_blocks = (N + 31) / 32;
+    int slices = (num_sms() * 4 + col_blocks - 1) / col_blocks;
+    if (slices > (M + 63) / 64) slices = (M + 63) / 64;
+    if (slices < 1) slices = 1;
+    small_k8_bwd_ds_kernel<<<dim3(col_blocks, slices), 256, 0, st>>>(dy, x, w, dscores, M, N, K);
+    rc = launch_status();
+  } else {
+    small_k_bwd_ds_kernel<<<N, 256, (256 / 32) * 8 * sizeof(float), st>>>(dy, x, w, dscores, accumulate, M, N, K);
+    rc = launch_status();
+  }
   if (rc) return rc;
   if (dx) {
     const int64_t total = static_cast<int64_t>(M) * K;

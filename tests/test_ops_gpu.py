@@ -339,3 +339,29 @@ def test_secondary_debias_losses_on_gpu():
     loss.backward()
     assert abs(float(loss) - float(g["bp"])) <= 1e-5 * abs(float(g["bp"]))
     torch.testing.assert_close(lg2.grad.cpu(), g["bp_dlogits"], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("M,N,K", [(9216, 768, 4), (300, 770, 3), (77, 768, 8), (129, 64, 12), (5, 9, 1)])
+def test_masked_linear_small_k(M, N, K):
+    """The fp32 SIMT masked linear for inner dimensions TMA cannot take (LXMERT's box_fc: K = 4; reference
+    masking/maskers.py:359-366 with a 4-wide input): K <= 8 runs the coalesced kernels (lanes along N, atomic row-slice
+    partials for dS), larger K the general ones.  Forward / dX / dS against fp32 torch math on the same mask."""
+    from crvqa import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(N, K, generator=g) * 0.3).cuda()
+    s = torch.rand(N, K, generator=g).cuda()
+    s[0, 0] = 0.5                                        # a tie: strict > masks it out
+    thr = torch.tensor(0.5, device="cuda")
+    b = torch.randn(N, generator=g).cuda()
+    scores = s.clone().requires_grad_(True)
+    y = ops.MaskedLinearSmallKFn.apply(x, scores, w, thr, b)
+    wm = w * (s > thr).float()
+    ref = x.detach() @ wm.t() + b
+    assert float((y - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    dy = torch.randn(M, N, generator=g).cuda()
+    y.backward(dy)
+    ref_dx = dy @ wm
+    ref_ds = (dy.t() @ x.detach()) * w
+    assert float((x.grad - ref_dx).abs().max()) <= 1e-5 * float(ref_dx.abs().max())
+    assert float((scores.grad - ref_ds).abs().max()) <= 2e-5 * float(ref_ds.abs().max())
