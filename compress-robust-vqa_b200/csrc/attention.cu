@@ -484,10 +484,10 @@ attn_bwd_kernel(const AttnParams p) {
 template <int KT2>
 struct AttnSmemP {
   static constexpr int SP = 16 * KT2;
-  static constexpr int SPP = SP + 8;                 // bf16 pitch of the P / dS tiles: (SP + 8) / 8 is odd -> ldmatrix rows spread over the banks
+  static constexpr int SPP = SP + 8;                 // bf16 pitch of the P / dS tile: (SP + 8) / 8 is odd -> ldmatrix rows spread over the banks
   static constexpr int kTile = SP * kLdH * 2;
   static constexpr int kP = SP * SPP * 2;
-  static constexpr int kTotal = 4 * kTile + 2 * kP;  // Q, K, V, dO, P, dS
+  static constexpr int kTotal = 4 * kTile + kP;      // Q, K, V, dO, and ONE [i][j] tile that holds P, then dS in place
 };
 
 // A fragment (rows r0 .. r0+15, k k0 .. k0+15) of the TRANSPOSE of a tile stored [k][row] with pitch `ld`
@@ -499,6 +499,10 @@ __device__ __forceinline__ void ld_a_trans(uint32_t (&a)[4], const __nv_bfloat16
 __device__ __forceinline__ float bf16_lo_f(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi_f(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
+// Order of work (three block barriers): tiles land -> dV = Pd^T dO for this warp's key rows (reads ALL rows of P)
+// -> barrier -> pass A for this warp's query rows: dS overwrites P in place (a lane rewrites exactly the elements it
+// read), dQ = dS K -> barrier -> dK = dS^T Q.  One shared [i][j] tile instead of two: 33 KB per (batch, head) at
+// S = 36, six CTAs per SM instead of five.
 template <int KT2>
 __global__ void __launch_bounds__(KT2 * 32)
 attn_bwd_p_kernel(const AttnParams p) {
@@ -515,8 +519,7 @@ attn_bwd_p_kernel(const AttnParams p) {
   __nv_bfloat16* sK = sQ + SP * kLdH;
   __nv_bfloat16* sV = sK + SP * kLdH;
   __nv_bfloat16* sdO = sV + SP * kLdH;
-  __nv_bfloat16* sP = sdO + SP * kLdH;
-  __nv_bfloat16* sdS = sP + SP * SPP;
+  __nv_bfloat16* sP = sdO + SP * kLdH;       // P (signed), later dS
   const long long HD = static_cast<long long>(p.heads) * kHeadDim;
   {
     const int tid = threadIdx.x;
@@ -532,15 +535,49 @@ attn_bwd_p_kernel(const AttnParams p) {
     }
   }
   const float dscale = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-  const int mt = tile;
-  if (mt * 16 >= p.Sq) {      // no query rows here: this block of dS^T columns must still read as zeros in pass B
-    for (int i = lane; i < 16 * (SP / 2); i += 32)
-      *reinterpret_cast<uint32_t*>(sdS + (mt * 16 + i / (SP / 2)) * SPP + (i % (SP / 2)) * 2) = 0u;
-  }
   cp_async_wait_all();
   __syncthreads();
 
-  // ---- pass A: this warp's query-row block
+  // ---- dV = Pd^T dO for this warp's key rows (P^T arrives as MMA A fragments through a transposing ldmatrix)
+  const int jt = tile;
+  const bool keys = jt * 16 < p.Sk;
+  const int j0 = jt * 16 + g, j1 = j0 + 8;
+  if (keys) {
+    uint32_t pa[KT2][4];
+    const __nv_bfloat162 ds2 = __floats2bfloat162_rn(dscale, dscale);
+#pragma unroll
+    for (int kt = 0; kt < KT2; ++kt) {
+      ld_a_trans(pa[kt], sP, SPP, jt * 16, kt * 16, lane);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {      // signed P -> Pd: dropped entries (sign set) to +0, kept ones times 1 / (1 - p)
+        uint32_t x = pa[kt][e];
+        x &= ((x & 0x8000u) ? 0u : 0x0000FFFFu) | ((x & 0x80000000u) ? 0u : 0xFFFF0000u);
+        if (p.p_drop > 0.f) {
+          __nv_bfloat162 v = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&x), ds2);
+          x = *reinterpret_cast<uint32_t*>(&v);
+        }
+        pa[kt][e] = x;
+      }
+    }
+    __nv_bfloat16* vo = p.dv + b * p.dv_bs + h * kHeadDim;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      float ov[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kt = 0; kt < KT2; ++kt) {
+        uint32_t bo[2];
+        ld_b_kn(bo, sdO, dt * 8, kt * 16, lane);   // B[k = i][n = d] = dO[i][d]
+        mma16816(ov, pa[kt], bo);
+      }
+      const int c = dt * 8 + 2 * t;
+      if (j0 < p.Sk) *reinterpret_cast<uint32_t*>(vo + j0 * p.dv_ss + c) = pack_bf16x2(ov[0], ov[1]);
+      if (j1 < p.Sk) *reinterpret_cast<uint32_t*>(vo + j1 * p.dv_ss + c) = pack_bf16x2(ov[2], ov[3]);
+    }
+  }
+  __syncthreads();   // every warp has read P^T: the tile may now turn into dS
+
+  // ---- pass A: this warp's query-row block: dPd = dO V^T, D, dS (in place over P), dQ = dS K
+  const int mt = tile;
   if (mt * 16 < p.Sq) {
     const int r0 = mt * 16 + g, r1 = r0 + 8;
     uint32_t a[4][4];
@@ -574,8 +611,8 @@ attn_bwd_p_kernel(const AttnParams p) {
       const uint32_t w1 = pack_bf16x2(pv[nt][2] * (dp[nt][2] - d1) * p.scale, pv[nt][3] * (dp[nt][3] - d1) * p.scale);
       da[nt >> 1][(nt & 1) * 2 + 0] = w0;
       da[nt >> 1][(nt & 1) * 2 + 1] = w1;
-      *reinterpret_cast<uint32_t*>(sdS + r0 * SPP + jb) = w0;
-      *reinterpret_cast<uint32_t*>(sdS + r1 * SPP + jb) = w1;
+      *reinterpret_cast<uint32_t*>(sP + r0 * SPP + jb) = w0;        // dS over P: same lane, same elements
+      *reinterpret_cast<uint32_t*>(sP + r1 * SPP + jb) = w1;
     }
     __nv_bfloat16* qo = p.dq + b * p.dq_bs + h * kHeadDim;
 #pragma unroll
@@ -592,51 +629,27 @@ attn_bwd_p_kernel(const AttnParams p) {
       if (r1 < p.Sq) *reinterpret_cast<uint32_t*>(qo + r1 * p.dq_ss + c) = pack_bf16x2(o[2], o[3]);
     }
   }
+  // row blocks without query rows keep their zero-filled P rows, which read as dS = 0 below
   __syncthreads();   // dS of every row block is in shared memory
 
-  // ---- pass B: this warp's key-row block: dV = Pd^T dO, dK = dS^T Q
-  const int jt = tile;
-  if (jt * 16 < p.Sk) {
-    const int j0 = jt * 16 + g, j1 = j0 + 8;
-    uint32_t pa[KT2][4], da[KT2][4];
-    const __nv_bfloat162 ds2 = __floats2bfloat162_rn(dscale, dscale);
+  // ---- dK = dS^T Q for this warp's key rows
+  if (keys) {
+    uint32_t da[KT2][4];
 #pragma unroll
-    for (int kt = 0; kt < KT2; ++kt) {
-      ld_a_trans(pa[kt], sP, SPP, jt * 16, kt * 16, lane);
-      ld_a_trans(da[kt], sdS, SPP, jt * 16, kt * 16, lane);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {      // signed P -> Pd: dropped entries (sign set) to +0, kept ones times 1 / (1 - p)
-        uint32_t x = pa[kt][e];
-        x &= ((x & 0x8000u) ? 0u : 0x0000FFFFu) | ((x & 0x80000000u) ? 0u : 0xFFFF0000u);
-        if (p.p_drop > 0.f) {
-          __nv_bfloat162 v = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&x), ds2);
-          x = *reinterpret_cast<uint32_t*>(&v);
-        }
-        pa[kt][e] = x;
-      }
-    }
-    __nv_bfloat16* vo = p.dv + b * p.dv_bs + h * kHeadDim;
+    for (int kt = 0; kt < KT2; ++kt) ld_a_trans(da[kt], sP, SPP, jt * 16, kt * 16, lane);
     __nv_bfloat16* ko = p.dk + b * p.dk_bs + h * kHeadDim;
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) {
-      float ov[4] = {0.f, 0.f, 0.f, 0.f}, ok[4] = {0.f, 0.f, 0.f, 0.f};
+      float ok[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int kt = 0; kt < KT2; ++kt) {
-        uint32_t bo[2], bq[2];
-        ld_b_kn(bo, sdO, dt * 8, kt * 16, lane);   // B[k = i][n = d] = dO[i][d]
+        uint32_t bq[2];
         ld_b_kn(bq, sQ, dt * 8, kt * 16, lane);    // B[k = i][n = d] = Q[i][d]
-        mma16816(ov, pa[kt], bo);
         mma16816(ok, da[kt], bq);
       }
       const int c = dt * 8 + 2 * t;
-      if (j0 < p.Sk) {
-        *reinterpret_cast<uint32_t*>(vo + j0 * p.dv_ss + c) = pack_bf16x2(ov[0], ov[1]);
-        *reinterpret_cast<uint32_t*>(ko + j0 * p.dk_ss + c) = pack_bf16x2(ok[0], ok[1]);
-      }
-      if (j1 < p.Sk) {
-        *reinterpret_cast<uint32_t*>(vo + j1 * p.dv_ss + c) = pack_bf16x2(ov[2], ov[3]);
-        *reinterpret_cast<uint32_t*>(ko + j1 * p.dk_ss + c) = pack_bf16x2(ok[2], ok[3]);
-      }
+      if (j0 < p.Sk) *reinterpret_cast<uint32_t*>(ko + j0 * p.dk_ss + c) = pack_bf16x2(ok[0], ok[1]);
+      if (j1 < p.Sk) *reinterpret_cast<uint32_t*>(ko + j1 * p.dk_ss + c) = pack_bf16x2(ok[2], ok[3]);
     }
   }
 }
