@@ -435,3 +435,43 @@ def test_reference_arm_prints_the_contract_line():
     assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0 and line["dtype"] == "f32"
+
+
+def test_answer_head_padded_path_is_the_same_function():
+    """SimpleClassifier pads its last weight-normed Linear to an aligned width on CUDA (hg_transformers/classifier.py;
+    reference classifier.py:5-22 has 3129 / 2274 answers).  The padded computation, run here on the CPU, returns exactly
+    the module's own output and the same parameter gradients."""
+    import torch.nn.functional as F
+    from hg_transformers.classifier import SimpleClassifier
+    torch.manual_seed(3)
+    head = SimpleClassifier(64, 96, 37).eval()
+    x = torch.randn(5, 64)
+    want = head(x)
+    want.sum().backward()
+    gw = {n: p.grad.clone() for n, p in head.named_parameters()}
+    head.zero_grad()
+    last = head.main[3]
+    h = head.main[2](head.main[1](head.main[0](x)))
+    for hook in last._forward_pre_hooks.values():
+        hook(last, (h,))
+    pad = (-37) % 16
+    got = F.linear(h, F.pad(last.weight, (0, 0, 0, pad)), F.pad(last.bias, (0, pad)))[:, :37]
+    assert torch.equal(got, want)
+    got.sum().backward()
+    for n, p in head.named_parameters():
+        torch.testing.assert_close(p.grad, gw[n], rtol=1e-6, atol=1e-7)
+    assert sorted(head.state_dict()) == ["main.0.bias", "main.0.weight_g", "main.0.weight_v", "main.3.bias",
+                                         "main.3.weight_g", "main.3.weight_v"]
+
+
+def test_bench_workloads_cover_the_baseline_configs():
+    """bench.py --config names: lxmert (BASELINE configs[1], the recorded line), visualbert (configs[2]), stage3
+    (configs[3]); every workload carries its own metric name and the algorithmic GFLOP per sample."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert sorted(bench.WORKLOADS) == ["lxmert", "stage3", "visualbert"]
+    assert bench.WORKLOADS["lxmert"]["metric"] == bench.METRIC == "LXMERT stage-2 mask-train samples/s"
+    assert bench.WORKLOADS["lxmert"]["gflop_per_sample"] == pytest.approx(10.4955 * 2 + 10.3821, abs=1e-3)
+    assert bench.WORKLOADS["visualbert"]["gflop_per_sample"] == pytest.approx(28.54)
