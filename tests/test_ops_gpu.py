@@ -356,12 +356,13 @@ def test_masked_linear_small_k(M, N, K):
     b = torch.randn(N, generator=g).cuda()
     scores = s.clone().requires_grad_(True)
     y = ops.MaskedLinearSmallKFn.apply(x, scores, w, thr, b)
-    wm = w * (s > thr).float()
-    ref = x.detach() @ wm.t() + b
+    # references in float64: other tests of the suite switch torch's fp32 matmuls to TF32 for the whole process
+    wm = (w * (s > thr).float()).double()
+    ref = x.detach().double() @ wm.t() + b.double()
     assert float((y - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
     dy = torch.randn(M, N, generator=g).cuda()
     y.backward(dy)
-    ref_dx = dy @ wm
-    ref_ds = (dy.t() @ x.detach()) * w
+    ref_dx = dy.double() @ wm
+    ref_ds = (dy.double().t() @ x.detach().double()) * w.double()
     assert float((x.grad - ref_dx).abs().max()) <= 1e-5 * float(ref_dx.abs().max())
     assert float((scores.grad - ref_ds).abs().max()) <= 2e-5 * float(ref_ds.abs().max())
