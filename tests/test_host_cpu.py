@@ -419,6 +419,37 @@ def test_recorded_bench_lines_follow_the_contract():
     assert ref[8]["value"] / ref[1]["value"] > 7.0          # the north_star's scaling target, as recorded
 
 
+def test_recorded_round2_bench_lines_follow_the_contract():
+    """The round-2 lines (profiles/r02_final_bench_{1,2,4,8}gpu.json): same contract; the reference arm of the GPU line
+    is the reference's OWN modules now (kind "reference"), the roofline fraction is against the BURST peak with the
+    sustained one beside it, the DRAM traffic per GEMM launch is measured, and 8 GPUs give more than 7.6x."""
+    lines = {}
+    for n in (1, 2, 4, 8):
+        with open(os.path.join(ROOT, "profiles", f"r02_final_bench_{n}gpu.json")) as f:
+            line = lines[n] = json.loads(f.read().strip().splitlines()[-1])
+        assert _LINE_KEYS - {"cpu_baseline"} <= set(line), n
+        assert line["n_gpus"] == n and line["higher_is_better"] is True and line["scaling"] == "weak"
+        assert line["metric"] == "LXMERT stage-2 mask-train samples/s" and line["unit"] == "samples/s"
+        assert line["vs_baseline"] is None and line["data"] == "synthetic" and line["dtype"] == "bf16"
+        assert line["config"]["global_batch"] == 256 * n and line["config"]["threshold_refresh"]["every_steps"] == 100
+        assert line["value"] == pytest.approx(256 * n / line["ms_per_step"] * 1e3, rel=1e-6)
+        assert line["warmup"] >= 3 and line["gpu_launches"] > 0
+        e2e = line["e2e"]
+        assert e2e["h2d_bytes_per_step"] == 82100224 and e2e["d2h_bytes_per_step"] == 4
+        assert e2e["value"] <= line["value"] * 1.02
+        assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        r = line["roofline"]
+        assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["launches_per_step"] <= 150
+        assert r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-9) and r["frac"] >= 0.60
+        assert r["peak"] > r["peak_sustained"] and r["frac_sustained"] > r["frac"]
+        if n == 1:
+            assert r["traffic"] is not None and r["traffic"] < r["traffic_algorithmic"]
+            c = line["cpu_baseline"]
+            assert c["kind"] == "reference" and c["cores"] >= 1 and c["value"] > 0 and "batch 32" in c["sample"]
+    assert lines[8]["value"] / lines[1]["value"] > 7.6
+    assert lines[2]["value"] / lines[1]["value"] > 1.9
+
+
 def test_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` runs the reference's own stage-2 modules (oracle/_ref, or /root/reference where it
     exists; the oracle port only when neither does) on the host cores and prints one JSON line with impl = reference,
