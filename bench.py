@@ -200,9 +200,6 @@ WORKLOADS = {
 def build_workload(args, dev, world, local_rank, rank):
     """-> dict(trainer, model, optimizer, scheduler, refresh (callable or None), host (8-tuple of CPU tensors),
     workload (str), logging_steps)."""
-    import logging
-    import types
-
     import torch
     from hg_transformers.data.data_collator import TrimCollator
     from hg_transformers.data.metrics import vqa_compute_metrics
