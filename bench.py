@@ -409,7 +409,7 @@ def run_ours(args):
     # trainer's own loop keeps the loss on the device between logging steps, so the GPU never idles behind a blocking
     # .item() while the host (and, at N > 1, the slowest rank's host) catches up.
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    loss_ev = [torch.cuda.Event(blocking=True) for _ in range(2)]   # sleep, do not spin: N ranks share the host cores
 
     def e2e_steps(n):
         last = None

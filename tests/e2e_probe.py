@@ -44,7 +44,7 @@ def main():
         graphed.step(resident)
     pre = InputPrefetcher(dev)
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    loss_ev = [torch.cuda.Event(blocking=True) for _ in range(2)]   # sleep, do not spin: N ranks share the host cores
 
     def loop(n, h2d, readback):
         handle = pre.stage(host) if h2d else None
