@@ -389,7 +389,13 @@ class MaskedLinearFn(torch.autograd.Function):
         ctx.split = operand_mode() == "split" and x.dtype == torch.float32
         if ctx.split:
             return MaskedLinearFn._forward_split(ctx, x, scores, w_bf16, thr_t, bias, sink, wm_bf16, w_f32)
-        x2 = to_bf16(x.reshape(-1, shp[-1]))
+        # a producer that already wrote the bf16 copy of x in the same launch (crvqa.fused.drop_add_layernorm /
+        # ln_avg_drop attach it as x._crv_bf16) saves the cast here; gradients still flow through x
+        x16 = getattr(x, "_crv_bf16", None)
+        if x16 is not None and x16.shape == shp and x16.dtype == torch.bfloat16 and x16.is_contiguous():
+            x2 = x16.reshape(-1, shp[-1])
+        else:
+            x2 = to_bf16(x.reshape(-1, shp[-1]))
         # bf16 activations (a bf16 input, or a caller running under bf16 autocast, where nn.Linear would answer in bf16
         # too) -> bf16 out; dX always comes back in the input's own dtype: no fp32 round trips between bf16 layers
         autocast16 = (x.is_cuda and torch.is_autocast_enabled("cuda")

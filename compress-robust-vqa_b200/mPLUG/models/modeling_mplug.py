@@ -46,6 +46,26 @@ class BertConfig:
         return dict(self.__dict__)
 
 
+def _fused_tail(dense_out, input_tensor, ln, dropout, owner):
+    """LayerNorm(dropout(dense_out) + input_tensor) of BertSelfOutput / BertOutput in ONE pass (crv_ln_fwd / crv_ln_bwd,
+    the kernels of the LXMERT layer path) when the dense output is bf16 on a GPU -- the engine's bf16-activation mode --
+    and the LayerNorm is frozen (mPLUG's masker freezes everything but the scores and the LM head).  Returns None when
+    the PyTorch ops have to run (CPU, fp32 activations, trainable LayerNorm, odd widths; CRVQA_MPLUG_FUSED=0)."""
+    if (not dense_out.is_cuda or dense_out.dtype != torch.bfloat16 or os.environ.get("CRVQA_MPLUG_FUSED", "1") == "0"
+            or ln.weight.requires_grad or ln.bias.requires_grad):
+        return None
+    H = dense_out.shape[-1]
+    if H % 128 or H > 1024 or tuple(ln.normalized_shape) != (H,):
+        return None
+    from crvqa import fused
+    if not hasattr(owner, "_site"):
+        owner._site = fused.RngState.new_site()
+    res = input_tensor if input_tensor.dtype == torch.float32 else input_tensor.float()
+    y32, y16 = fused.drop_add_layernorm(dense_out, res, ln, dropout.p, owner._site, owner.training)
+    y32._crv_bf16 = y16          # the next masked GEMM reads this copy instead of casting y32 again
+    return y32
+
+
 def _act(name):
     if callable(name):
         return name
@@ -109,7 +129,9 @@ class BertSelfOutput(nn.Module):
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
 
     def forward(self, hidden_states, input_tensor):
-        return self.LayerNorm(self.dropout(self.dense(hidden_states)) + input_tensor)
+        g = self.dense(hidden_states)
+        out = _fused_tail(g, input_tensor, self.LayerNorm, self.dropout, self)
+        return out if out is not None else self.LayerNorm(self.dropout(g) + input_tensor)
 
 
 class BertAttention(nn.Module):
@@ -130,7 +152,12 @@ class BertIntermediate(nn.Module):
         self.intermediate_act_fn = _act(config.hidden_act)
 
     def forward(self, hidden_states):
-        return self.intermediate_act_fn(self.dense(hidden_states))
+        u = self.dense(hidden_states)
+        if (u.is_cuda and u.dtype == torch.bfloat16 and self.intermediate_act_fn is F.gelu and u.numel() % 8 == 0
+                and os.environ.get("CRVQA_MPLUG_FUSED", "1") != "0"):
+            from crvqa import fused
+            return fused.gelu_bf16(u)            # erf GELU on bf16, one pass each way (crv_gelu_fwd / crv_gelu_bwd)
+        return self.intermediate_act_fn(u)
 
 
 class BertOutput(nn.Module):
@@ -141,7 +168,9 @@ class BertOutput(nn.Module):
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
 
     def forward(self, hidden_states, input_tensor):
-        return self.LayerNorm(self.dropout(self.dense(hidden_states)) + input_tensor)
+        g = self.dense(hidden_states)
+        out = _fused_tail(g, input_tensor, self.LayerNorm, self.dropout, self)
+        return out if out is not None else self.LayerNorm(self.dropout(g) + input_tensor)
 
 
 class BertLayer(nn.Module):
