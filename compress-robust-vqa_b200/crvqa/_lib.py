@@ -70,6 +70,8 @@ _PROTOS = {
                                   c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),
     "crv_gelu_fwd": (c_int, [_P, _P, c_int64, _P]),
     "crv_gelu_bwd": (c_int, [_P, _P, _P, c_int64, _P]),
+    "crv_quick_gelu_fwd": (c_int, [_P, _P, c_int64, _P]),
+    "crv_quick_gelu_bwd": (c_int, [_P, _P, _P, c_int64, _P]),
     "crv_rng_advance": (c_int, [_P, _P]),
     "crv_sumsq_workspace_bytes": (c_size_t, []),
     "crv_sumsq": (c_int, [_P, c_int64, _P, _P, _P]),

@@ -435,6 +435,30 @@ def gelu_bf16(u):
     return GeluFn.apply(u)
 
 
+class QuickGeluFn(torch.autograd.Function):
+    """x sigmoid(1.702 x) on bf16 (the CLIP vision tower of mPLUG, mPLUG/models/clip/model.py:25-27): one pass each way."""
+
+    @staticmethod
+    def forward(ctx, u):
+        u = u if u.is_contiguous() else u.contiguous()
+        y = torch.empty_like(u)
+        check(lib.crv_quick_gelu_fwd(_p(u), _p(y), u.numel(), _stream()), "crv_quick_gelu_fwd")
+        ctx.save_for_backward(u)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (u,) = ctx.saved_tensors
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        du = torch.empty_like(u)
+        check(lib.crv_quick_gelu_bwd(_p(u), _p(dy), _p(du), u.numel(), _stream()), "crv_quick_gelu_bwd")
+        return du
+
+
+def quick_gelu_bf16(u):
+    return QuickGeluFn.apply(u)
+
+
 # ----------------------------------------------------------------------------- small-sequence attention
 def _off(t, elems):
     return ctypes.c_void_p(t.data_ptr() + 2 * elems)

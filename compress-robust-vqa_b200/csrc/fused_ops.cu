@@ -390,6 +390,44 @@ __global__ void gelu_bwd_kernel(const uint16_t* __restrict__ u, const uint16_t* 
   }
 }
 
+// QuickGELU of the CLIP vision tower (mPLUG/models/clip/model.py:25-27): y = x sigmoid(1.702 x) on bf16, and
+// dx = dy * s (1 + 1.702 x (1 - s)), s = sigmoid(1.702 x).  PyTorch runs it as three elementwise kernels forward and
+// five backward over the [tokens, 3072] MLP activation; one pass each way here.  exp through ex2 / rcp on the SFU.
+__device__ __forceinline__ float sigmoid1702(float x) {
+  return sfu_rcp(1.f + sfu_ex2(x * (-1.702f * 1.4426950408889634f)));
+}
+__device__ __forceinline__ float qgelu_f(float x) { return x * sigmoid1702(x); }
+__device__ __forceinline__ float qgelu_grad_f(float x) {
+  const float s = sigmoid1702(x);
+  return s * fmaf(1.702f * x, 1.f - s, 1.f);
+}
+__global__ void qgelu_fwd_kernel(const uint16_t* __restrict__ u, uint16_t* __restrict__ y, int64_t n) {
+  pdl_wait();
+  const int64_t nvec = n >> 3;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    const float4 a = load4(u, 1, i * 8), b = load4(u, 1, i * 8 + 4);
+    const uint2 p0 = pack4(make_float4(qgelu_f(a.x), qgelu_f(a.y), qgelu_f(a.z), qgelu_f(a.w)));
+    const uint2 p1 = pack4(make_float4(qgelu_f(b.x), qgelu_f(b.y), qgelu_f(b.z), qgelu_f(b.w)));
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(p0.x, p0.y, p1.x, p1.y);
+  }
+}
+__global__ void qgelu_bwd_kernel(const uint16_t* __restrict__ u, const uint16_t* __restrict__ dy,
+                                 uint16_t* __restrict__ du, int64_t n) {
+  pdl_wait();
+  const int64_t nvec = n >> 3;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    const float4 a = load4(u, 1, i * 8), b = load4(u, 1, i * 8 + 4);
+    const float4 c = load4(dy, 1, i * 8), d = load4(dy, 1, i * 8 + 4);
+    const uint2 p0 = pack4(make_float4(c.x * qgelu_grad_f(a.x), c.y * qgelu_grad_f(a.y), c.z * qgelu_grad_f(a.z),
+                                       c.w * qgelu_grad_f(a.w)));
+    const uint2 p1 = pack4(make_float4(d.x * qgelu_grad_f(b.x), d.y * qgelu_grad_f(b.y), d.z * qgelu_grad_f(b.z),
+                                       d.w * qgelu_grad_f(b.w)));
+    reinterpret_cast<uint4*>(du)[i] = make_uint4(p0.x, p0.y, p1.x, p1.y);
+  }
+}
+
 __global__ void counter_inc_kernel(unsigned long long* state) { state[1] += 1ull; }
 
 template <typename F>
@@ -469,6 +507,26 @@ extern "C" int crv_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du,
   int64_t blocks = ((n >> 3) + 255) / 256;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   CRV_CUDA(launch_pdl(gelu_bwd_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), u, dy, du, n));
+  return launch_status();
+}
+
+extern "C" int crv_quick_gelu_fwd(const uint16_t* u, uint16_t* y, int64_t n, void* stream) {
+  if (!u || !y || n < 0) return CRV_E_BADARG;
+  if (n % 8) return CRV_E_SHAPE;
+  if (n == 0) return CRV_OK;
+  int64_t blocks = ((n >> 3) + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  CRV_CUDA(launch_pdl(qgelu_fwd_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), u, y, n));
+  return launch_status();
+}
+
+extern "C" int crv_quick_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du, int64_t n, void* stream) {
+  if (!u || !dy || !du || n < 0) return CRV_E_BADARG;
+  if (n % 8) return CRV_E_SHAPE;
+  if (n == 0) return CRV_OK;
+  int64_t blocks = ((n >> 3) + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  CRV_CUDA(launch_pdl(qgelu_bwd_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), u, dy, du, n));
   return launch_status();
 }
 

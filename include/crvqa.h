@@ -281,6 +281,10 @@ int crv_ln_avg_drop_bwd(const float* dy_f32, const uint16_t* dy_bf16, const floa
 /* erf GELU on bf16 (LxmertIntermediate): y = gelu(u);  du = dy * gelu'(u).  n % 8 == 0. */
 int crv_gelu_fwd(const uint16_t* u, uint16_t* y, int64_t n, void* stream);
 int crv_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du, int64_t n, void* stream);
+/* QuickGELU of mPLUG's CLIP vision tower (mPLUG/models/clip/model.py:25-27) on bf16: y = u sigmoid(1.702 u);
+ * du = dy * s (1 + 1.702 u (1 - s)), s = sigmoid(1.702 u).  n % 8 == 0. */
+int crv_quick_gelu_fwd(const uint16_t* u, uint16_t* y, int64_t n, void* stream);
+int crv_quick_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du, int64_t n, void* stream);
 /* rng_state[1] += 1 on the device (once per training step, inside the captured graph). */
 int crv_rng_advance(unsigned long long* rng_state, void* stream);
 

@@ -379,3 +379,19 @@ def test_visualbert_fast_path_matches_generic_path():
         assert model.visual_bert.encoder._fast_plans() is None
     finally:
         os.environ.pop("CRVQA_FUSED")
+
+
+def test_quick_gelu_bf16_matches_torch():
+    """crv_quick_gelu_fwd / _bwd (mPLUG's CLIP tower, mPLUG/models/clip/model.py:25-27) against torch on the same bf16
+    input: bf16 rounding of the result only."""
+    from crvqa import fused
+    torch.manual_seed(9)
+    u = (torch.randn(1000, 3072, device="cuda") * 2).bfloat16().requires_grad_(True)
+    y = fused.quick_gelu_bf16(u)
+    uf = u.detach().float().requires_grad_(True)
+    ref = uf * torch.sigmoid(1.702 * uf)
+    assert float((y.float() - ref).abs().max()) <= 2 ** -8 * float(ref.abs().max())
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    ref.backward(dy.float())
+    assert float((u.grad.float() - uf.grad).abs().max()) <= 2 ** -7 * float(uf.grad.abs().max())
