@@ -728,3 +728,35 @@ def partial_reduce(part, out, accumulate=False):
     """out[j] (+)= sum_i part[i, j]."""
     check(lib.crv_partial_reduce(_p(part), part.shape[0], part.shape[1], _p(out), int(bool(accumulate)), _stream()),
           "crv_partial_reduce")
+
+
+class MomentumPlan:
+    """Pointer / chunk tables of a fixed list of (online, twin) fp32 tensor pairs for crv_momentum_update: built once
+    (the pairs of mPLUG's towers never change), rebuilt when a tensor was re-allocated (its data_ptr moved)."""
+    CHUNK = 16384       # elements per row
+
+    def __init__(self, online, twins):
+        dev = twins[0].device
+        self.key = tuple(t.data_ptr() for t in online) + tuple(t.data_ptr() for t in twins)
+        rows = []
+        for i, (a, b) in enumerate(zip(online, twins)):
+            if (a.dtype != torch.float32 or b.dtype != torch.float32 or a.numel() != b.numel() or not a.is_contiguous()
+                    or not b.is_contiguous() or a.data_ptr() % 16 or b.data_ptr() % 16 or a.device != dev or b.device != dev):
+                raise ValueError("momentum pairs must be contiguous, 16-byte aligned fp32 tensors of equal size on one device")
+            n = a.numel()
+            for c0 in range(0, n, self.CHUNK):
+                ln = min(self.CHUNK, n - c0)
+                rows.append((i, c0 // 4, ln // 4, ln % 4))
+        self.online = torch.tensor([t.data_ptr() for t in online], dtype=torch.int64, device=dev)
+        self.twins = torch.tensor([t.data_ptr() for t in twins], dtype=torch.int64, device=dev)
+        self.rows = torch.tensor(rows, dtype=torch.int32, device=dev).contiguous()
+
+    @staticmethod
+    def key_of(online, twins):
+        return tuple(t.data_ptr() for t in online) + tuple(t.data_ptr() for t in twins)
+
+    def run(self, momentum):
+        m = float(torch.tensor(momentum, dtype=torch.float32))
+        om = float(torch.tensor(1.0 - momentum, dtype=torch.float32))      # torch rounds the Python scalar 1 - m to fp32
+        check(lib.crv_momentum_update(_p(self.online), _p(self.twins), _p(self.rows), self.rows.shape[0], m, om,
+                                      _stream()), "crv_momentum_update")

@@ -846,3 +846,42 @@ extern "C" int crv_masked_embedding_bwd(const long long* ids, const float* dout,
                                                                              padding_idx);
   return launch_status();
 }
+
+// Momentum (EMA) update of mPLUG's distillation twins over MANY separately allocated tensors in one launch
+// (mPLUG/models/model_vqa_mplug.py:152-156: param_m = param_m * m + param * (1 - m) for every paired parameter).
+// PyTorch needs three multi-tensor passes (28 B per element); here 12 B.  Same arithmetic: two rounded products, one
+// rounded sum (no FMA contraction), so the result is bit-identical to the reference expression.
+// rows = {tensor index, first element / 4, number of float4 (0: scalar tail of < 4 elements follows in .w), tail count}
+namespace crv {
+__global__ void momentum_update_kernel(const float* const* __restrict__ online, float* const* __restrict__ twins,
+                                       const int4* __restrict__ rows, int nrows, float m, float one_minus_m) {
+  for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+    const int4 row = __ldg(rows + r);
+    const float* p = online[row.x] + static_cast<int64_t>(row.y) * 4;
+    float* q = twins[row.x] + static_cast<int64_t>(row.y) * 4;
+    for (int i = threadIdx.x; i < row.z; i += blockDim.x) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p) + i);
+      float4 b = reinterpret_cast<float4*>(q)[i];
+      b.x = __fadd_rn(__fmul_rn(b.x, m), __fmul_rn(a.x, one_minus_m));
+      b.y = __fadd_rn(__fmul_rn(b.y, m), __fmul_rn(a.y, one_minus_m));
+      b.z = __fadd_rn(__fmul_rn(b.z, m), __fmul_rn(a.z, one_minus_m));
+      b.w = __fadd_rn(__fmul_rn(b.w, m), __fmul_rn(a.w, one_minus_m));
+      reinterpret_cast<float4*>(q)[i] = b;
+    }
+    const int64_t t0 = static_cast<int64_t>(row.z) * 4;
+    for (int i = threadIdx.x; i < row.w; i += blockDim.x)
+      q[t0 + i] = __fadd_rn(__fmul_rn(q[t0 + i], m), __fmul_rn(p[t0 + i], one_minus_m));
+  }
+}
+}  // namespace crv
+
+extern "C" int crv_momentum_update(const float* const* online_dev, float* const* twins_dev, const int* rows_dev,
+                                   int nrows, float m, float one_minus_m, void* stream) {
+  if (!online_dev || !twins_dev || !rows_dev || nrows < 0) return CRV_E_BADARG;
+  if (nrows == 0) return CRV_OK;
+  if (!aligned16(rows_dev)) return CRV_E_ALIGN;
+  const int grid = nrows < num_sms() * 8 ? nrows : num_sms() * 8;
+  momentum_update_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      online_dev, twins_dev, reinterpret_cast<const int4*>(rows_dev), nrows, m, one_minus_m);
+  return launch_status();
+}

@@ -108,9 +108,25 @@ class MPLUG(nn.Module):
                 twins.append(p_m.data)
         if not twins:
             return
+        if twins[0].is_cuda and os.environ.get("CRVQA_MPLUG_FUSED", "1") != "0":
+            # one launch over every pair (crv_momentum_update: 12 B per element, the same two products and one sum)
+            from crvqa import ops
+            plan = getattr(self, "_momentum_plan", None)
+            try:
+                if plan is None or plan.key != ops.MomentumPlan.key_of(online, twins):
+                    plan = self._momentum_plan = ops.MomentumPlan(online, twins)
+            except ValueError:
+                plan = None
+            if plan is not None:
+                plan.run(self.momentum)
+                self._drop_twin_caches()
+                return
         fresh = torch._foreach_mul(online, 1.0 - self.momentum)
         torch._foreach_mul_(twins, self.momentum)
         torch._foreach_add_(twins, fresh)
+        self._drop_twin_caches()
+
+    def _drop_twin_caches(self):
         # the twins' frozen weights and scores just moved underneath their masked modules (through .data, which does not
         # bump the version counters those modules key their bf16 operand caches on): drop the caches
         for _, twin in self.model_pairs:

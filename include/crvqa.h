@@ -285,6 +285,13 @@ int crv_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du, int64_t n,
  * du = dy * s (1 + 1.702 u (1 - s)), s = sigmoid(1.702 u).  n % 8 == 0. */
 int crv_quick_gelu_fwd(const uint16_t* u, uint16_t* y, int64_t n, void* stream);
 int crv_quick_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du, int64_t n, void* stream);
+/* Momentum update of mPLUG's distillation twins (mPLUG/models/model_vqa_mplug.py:152-156) over many separately
+ * allocated fp32 tensors in ONE launch: twins[t][e] = twins[t][e] * m + online[t][e] * one_minus_m (two rounded
+ * products, one rounded sum: bit-identical to the PyTorch expression).  online_dev / twins_dev: device arrays of
+ * tensor pointers (16-byte aligned tensors); rows_dev: device int4 rows {tensor, first element / 4, float4 count,
+ * scalar tail count} cutting the tensors into chunks. */
+int crv_momentum_update(const float* const* online_dev, float* const* twins_dev, const int* rows_dev, int nrows,
+                        float m, float one_minus_m, void* stream);
 /* rng_state[1] += 1 on the device (once per training step, inside the captured graph). */
 int crv_rng_advance(unsigned long long* rng_state, void* stream);
 

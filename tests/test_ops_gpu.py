@@ -366,3 +366,26 @@ def test_masked_linear_small_k(M, N, K):
     ref_ds = (dy.double().t() @ x.detach().double()) * w.double()
     assert float((x.grad - ref_dx).abs().max()) <= 1e-5 * float(ref_dx.abs().max())
     assert float((scores.grad - ref_ds).abs().max()) <= 2e-5 * float(ref_ds.abs().max())
+
+
+def test_momentum_update_is_bit_identical_to_the_torch_expression():
+    """crv_momentum_update over many separately allocated tensors against param_m = param_m * m + param * (1 - m)
+    (mPLUG/models/model_vqa_mplug.py:152-156; the three foreach passes of the PyTorch path): same two rounded products,
+    same rounded sum -- bit for bit, including sizes that are not multiples of 4 and tensors larger than one chunk."""
+    from crvqa import ops
+    g = torch.Generator().manual_seed(12)
+    shapes = [(768, 768), (3,), (1,), (30522, 32), (17, 5), (16384,), (16385,), (4, 4, 4, 3)]
+    online = [torch.randn(*sh, generator=g).cuda() for sh in shapes]
+    twins = [(t + 0.01 * torch.randn(*t.shape, generator=g).cuda()).contiguous() for t in online]
+    want = [b.clone() for b in twins]
+    m = 0.995
+    for _ in range(3):
+        fresh = torch._foreach_mul(online, 1.0 - m)
+        torch._foreach_mul_(want, m)
+        torch._foreach_add_(want, fresh)
+    plan = ops.MomentumPlan(online, twins)
+    assert plan.key == ops.MomentumPlan.key_of(online, twins)
+    for _ in range(3):
+        plan.run(m)
+    for a, b in zip(twins, want):
+        assert torch.equal(a, b)
