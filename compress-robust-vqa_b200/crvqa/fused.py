@@ -336,6 +336,53 @@ def drop_add_layernorm(g, res32, ln, p, site, training):
     return DropAddLayerNormFn.apply(g, res32, ln.weight, ln.bias, ln.eps, p, site, rng)
 
 
+class LayerNormBf16Fn(torch.autograd.Function):
+    """y (bf16) = LayerNorm(x) for a bf16 x with frozen gamma / beta: crv_ln_fwd / crv_ln_bwd without residual, dropout
+    or fp32 copy -- 4 B per element each way.  Under bf16 autocast torch runs the same fp32 arithmetic as three passes
+    (cast to fp32, LayerNorm, cast back: 20 B per element) and three more in the backward."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        H = x.shape[-1]
+        x2 = x.reshape(-1, H)
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        M = x2.shape[0]
+        y16 = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
+        mean = torch.empty(M, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+        check(lib.crv_ln_fwd(_p(x2), ops.DT_BF16, None, _p(gamma), _p(beta), float(eps), 0.0, None, 0, None, _p(y16),
+                             _p(mean), _p(rstd), M, H, _stream()), "crv_ln_fwd")
+        ctx.save_for_backward(x2, gamma, mean, rstd)
+        ctx.shape = x.shape
+        return y16.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, gamma, mean, rstd = ctx.saved_tensors
+        M, H = x2.shape
+        d = dy.reshape(M, H)
+        if d.dtype not in (torch.bfloat16, torch.float32):
+            d = d.float()
+        d = d if d.is_contiguous() else d.contiguous()
+        d32, d16 = (d, None) if d.dtype == torch.float32 else (None, d)
+        dx = torch.empty((M, H), dtype=torch.bfloat16, device=x2.device)
+        check(lib.crv_ln_bwd(_p(d32), _p(d16), _p(x2), ops.DT_BF16, None, _p(gamma), _p(mean), _p(rstd), 0.0, None, 0,
+                             _p(dx), ops.DT_BF16, None, None, M, H, _stream()), "crv_ln_bwd")
+        return dx.view(ctx.shape), None, None, None
+
+
+def layernorm_bf16_usable(x, ln):
+    H = x.shape[-1]
+    return (x.is_cuda and x.dtype == torch.bfloat16 and H % 128 == 0 and H <= 1024 and x.numel() > 0
+            and tuple(ln.normalized_shape) == (H,) and ln.weight is not None and ln.bias is not None
+            and ln.weight.dtype == torch.float32 and not ln.weight.requires_grad and not ln.bias.requires_grad)
+
+
+def layernorm_bf16(x, ln):
+    """bf16 LayerNorm(x) of a frozen nn.LayerNorm on a bf16 activation (check layernorm_bf16_usable first)."""
+    return LayerNormBf16Fn.apply(x, ln.weight, ln.bias, ln.eps)
+
+
 class LnAvgDropFn(torch.autograd.Function):
     """(y fp32, y bf16) = dropout((LN_a(a) + LN_b(b)) / 2), or dropout(LN_a(a)) when b is None: the entry blocks of LXMERT
     (LxmertVisualFeatureEncoder / LxmertEmbeddings, hg_transformers/modeling_lxmert.py:576-592, 744-770) in one pass each

@@ -760,3 +760,44 @@ class MomentumPlan:
         om = float(torch.tensor(1.0 - momentum, dtype=torch.float32))      # torch rounds the Python scalar 1 - m to fp32
         check(lib.crv_momentum_update(_p(self.online), _p(self.twins), _p(self.rows), self.rows.shape[0], m, om,
                                       _stream()), "crv_momentum_update")
+
+
+# ----------------------------------------------------------------------------- multi-tensor optimiser pieces (mPLUG engine)
+MULTI_CHUNK = 16384      # elements per row of the multi-tensor kernels (a multiple of 8: rows start 16-byte aligned)
+
+
+def multi_rows(numels, flags=None, chunk=MULTI_CHUNK):
+    """Host row table {tensor, first element / 8, elements, flags} cutting tensor i (numels[i] elements) into chunks."""
+    rows = []
+    for i, n in enumerate(numels):
+        f = int(flags[i]) if flags is not None else 0
+        for c0 in range(0, int(n), chunk):
+            rows.append((i, c0 // 8, min(chunk, int(n) - c0), f))
+    return rows
+
+
+def upload(values, dtype, device, out=None):
+    """Host list -> device tensor without a host-side wait: staged in pinned memory the caching host allocator keeps
+    alive until the copy has run (a reused pinned buffer could be overwritten while its copy is still queued)."""
+    host = torch.tensor(values, dtype=dtype).pin_memory()
+    if out is None:
+        out = torch.empty(host.shape, dtype=dtype, device=device)
+    out.copy_(host, non_blocking=True)
+    return out
+
+
+def sumsq_multi(ptrs, rows, acc):
+    """acc += sum of squares over the rows of the tensors whose addresses `ptrs` (device int64) lists."""
+    if rows.shape[0]:
+        check(lib.crv_sumsq_multi(_p(ptrs), _p(rows), rows.shape[0], _p(acc), _p(_sumsq_workspace(acc.device)),
+                                  _stream()), "crv_sumsq_multi")
+
+
+def adamw_multi(p, g, m, v, w16, wm, thr, rows, lr, step, beta1, beta2, eps, weight_decay, total_sumsq=None,
+                max_norm=1.0):
+    """crv_adamw_multi: clip + torch.optim.AdamW step `step` (1-based) over the rows of many tensors (device int64
+    address tables), refreshing W (.) (S_new > thr) for the tensors whose rows carry flag 1."""
+    if rows.shape[0]:
+        check(lib.crv_adamw_multi(_p(p), _p(g), _p(m), _p(v), _p(w16), _p(wm), _p(thr), _p(rows), rows.shape[0],
+                                  float(lr), int(step), float(beta1), float(beta2), float(eps), float(weight_decay),
+                                  _p(total_sumsq), float(max_norm), _stream()), "crv_adamw_multi")

@@ -1,6 +1,8 @@
 // Streaming (HBM-bound) kernels: operand casts, binariser, mask application, magnitude init,
 // gradient-norm partial sums and the fused clip+AdamW update.  All are grid-stride loops over
 // 16-byte vectors, launched with a multiple of the SM count.
+#include <cmath>
+
 #include "common.cuh"
 
 namespace crv {
@@ -228,9 +230,12 @@ __global__ void sumsq_segmented_kernel(const float* __restrict__ x, const int4* 
 //         caller, denom = sqrt(v) + eps, decoupled weight decay, running sum of |g|.
 // mode 1: torch.optim.Adam as the stage-3 driver builds it (run_vqa_stage3.py:577-598): L2 weight decay folded into g,
 //         step_size = lr / (1 - b1^t), denom = sqrt(v) / sqrt(1 - b2^t) + eps  (inv_bc2_sqrt = 1 / sqrt(1 - b2^t)).
+// mode 2: torch.optim.AdamW as mPLUG's driver builds it (mPLUG/optim/optim_factory.py:60-89): p *= 1 - lr * wd first
+//         (`decay`, rounded once from double as torch rounds the Python scalar), then mode 1's moments and step.
 struct AdamArgs {
   float lr, step_size, beta1, beta2, eps, weight_decay, max_norm, inv_bc2_sqrt;
   int mode;
+  float decay;
   // 1 - beta rounded ONCE from double, as torch rounds the Python scalars `1.0 - beta` of add_(alpha=) / lerp_ /
   // addcmul_(value=): float(1 - 0.999) = 0.001f, whereas 1.0f - 0.999f = 0.00100005f (4.7e-5 off in exp_avg_sq)
   float omb1, omb2;
@@ -238,7 +243,7 @@ struct AdamArgs {
 static AdamArgs make_adam_args(float lr, float step_size, double beta1, double beta2, float eps, float weight_decay,
                                float max_norm, float inv_bc2_sqrt, int mode) {
   return AdamArgs{lr, step_size, static_cast<float>(beta1), static_cast<float>(beta2), eps, weight_decay, max_norm,
-                  inv_bc2_sqrt, mode, static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2)};
+                  inv_bc2_sqrt, mode, 1.0f, static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2)};
 }
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float* sum, const AdamArgs& a,
@@ -252,7 +257,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
     p = p - a.step_size * (m / denom);
     if (a.weight_decay > 0.f) p = p - a.lr * a.weight_decay * p;
   } else {
-    if (a.weight_decay > 0.f) g = fmaf(a.weight_decay, p, g);
+    if (a.mode == 2) p = p * a.decay;
+    else if (a.weight_decay > 0.f) g = fmaf(a.weight_decay, p, g);
     m = m + (g - m) * a.omb1;
     v = v * a.beta2 + a.omb2 * g * g;
     const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
@@ -883,5 +889,128 @@ extern "C" int crv_momentum_update(const float* const* online_dev, float* const*
   const int grid = nrows < num_sms() * 8 ? nrows : num_sms() * 8;
   momentum_update_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       online_dev, twins_dev, reinterpret_cast<const int4*>(rows_dev), nrows, m, one_minus_m);
+  return launch_status();
+}
+
+// Global-norm clip + torch.optim.AdamW over MANY separately allocated tensors in two launches (mPLUG keeps its scores
+// as the module parameters the reference's checkpoints name; there is no arena).  What the engine does per step with
+// PyTorch -- clip_grad_norm_ (norms, scale pass) + the foreach AdamW passes + one apply-mask launch per module on the
+// next forward -- is ~88 B per score; here 4 B (norm) + 28 B (p, g, m, v read; p, m, v written) + 4 B (bf16 W read,
+// W (.) M written: the new score is in registers).
+// rows = {tensor, first element / 8, elements in this row, flags (bit 0: refresh the tensor's masked bf16 operand)}
+namespace crv {
+__global__ void sumsq_multi_kernel(const float* const* __restrict__ xs, const int4* __restrict__ rows, int nrows,
+                                   float* __restrict__ out, float* __restrict__ ws) {
+  float acc = 0.f;
+  for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+    const int4 row = __ldg(rows + r);
+    const float* x = xs[row.x] + static_cast<int64_t>(row.y) * 8;
+    const int nvec = row.z >> 2;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    for (int i = (nvec << 2) + threadIdx.x; i < row.z; i += blockDim.x) acc += x[i] * x[i];
+  }
+  sumsq_finish(acc, ws, out);
+}
+
+struct MultiAdamTables {
+  float* const* p;
+  const float* const* g;
+  float* const* m;
+  float* const* v;
+  const uint16_t* const* w16;
+  uint16_t* const* wm;
+  const float* const* thr;
+};
+
+__global__ void __launch_bounds__(kThreads)
+adamw_multi_kernel(MultiAdamTables t, const int4* __restrict__ rows, int nrows, AdamArgs a,
+                   const float* __restrict__ total_sumsq) {
+  float clip = 1.0f;
+  if (total_sumsq) {
+    const float c = a.max_norm / (sqrtf(__ldg(total_sumsq)) + 1e-6f);
+    clip = c < 1.0f ? c : 1.0f;
+  }
+  for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+    const int4 row = __ldg(rows + r);
+    const int64_t base = static_cast<int64_t>(row.y) * 8;
+    float* p = t.p[row.x] + base;
+    const float* g = t.g[row.x] + base;
+    float* m = t.m[row.x] + base;
+    float* v = t.v[row.x] + base;
+    const bool has_wm = (row.w & 1) != 0;
+    const uint16_t* w16 = has_wm ? t.w16[row.x] + base : nullptr;
+    uint16_t* wm = has_wm ? t.wm[row.x] + base : nullptr;
+    const float thr = has_wm ? __ldg(t.thr[row.x]) : 0.f;
+    const int nvec = row.z >> 3;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const int e = i * 8;
+      float4 pp[2], gg[2], mm[2], vv[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        pp[h] = reinterpret_cast<const float4*>(p + e)[h];
+        gg[h] = __ldg(reinterpret_cast<const float4*>(g + e) + h);
+        mm[h] = reinterpret_cast<const float4*>(m + e)[h];
+        vv[h] = reinterpret_cast<const float4*>(v + e)[h];
+      }
+      uint4 wv = has_wm ? __ldg(reinterpret_cast<const uint4*>(w16 + e)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        adam_one(pp[h].x, gg[h].x, mm[h].x, vv[h].x, nullptr, a, clip);
+        adam_one(pp[h].y, gg[h].y, mm[h].y, vv[h].y, nullptr, a, clip);
+        adam_one(pp[h].z, gg[h].z, mm[h].z, vv[h].z, nullptr, a, clip);
+        adam_one(pp[h].w, gg[h].w, mm[h].w, vv[h].w, nullptr, a, clip);
+        reinterpret_cast<float4*>(p + e)[h] = pp[h];
+        reinterpret_cast<float4*>(m + e)[h] = mm[h];
+        reinterpret_cast<float4*>(v + e)[h] = vv[h];
+      }
+      if (has_wm) {
+        wv.x &= (pp[0].x > thr ? 0x0000FFFFu : 0u) | (pp[0].y > thr ? 0xFFFF0000u : 0u);
+        wv.y &= (pp[0].z > thr ? 0x0000FFFFu : 0u) | (pp[0].w > thr ? 0xFFFF0000u : 0u);
+        wv.z &= (pp[1].x > thr ? 0x0000FFFFu : 0u) | (pp[1].y > thr ? 0xFFFF0000u : 0u);
+        wv.w &= (pp[1].z > thr ? 0x0000FFFFu : 0u) | (pp[1].w > thr ? 0xFFFF0000u : 0u);
+        *reinterpret_cast<uint4*>(wm + e) = wv;
+      }
+    }
+    for (int e = (nvec << 3) + threadIdx.x; e < row.z; e += blockDim.x) {
+      adam_one(p[e], g[e], m[e], v[e], nullptr, a, clip);
+      if (has_wm) wm[e] = p[e] > thr ? w16[e] : uint16_t(0);
+    }
+  }
+}
+}  // namespace crv
+
+extern "C" int crv_sumsq_multi(const float* const* xs_dev, const int* rows_dev, int nrows, float* out, void* workspace,
+                               void* stream) {
+  if (!xs_dev || !rows_dev || !out || !workspace || nrows < 0) return CRV_E_BADARG;
+  if (nrows == 0) return CRV_OK;
+  if (!aligned16(rows_dev)) return CRV_E_ALIGN;
+  const int grid = nrows < num_sms() * 8 ? nrows : num_sms() * 8;
+  sumsq_multi_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      xs_dev, reinterpret_cast<const int4*>(rows_dev), nrows, out, static_cast<float*>(workspace));
+  return launch_status();
+}
+
+extern "C" int crv_adamw_multi(float* const* p_dev, const float* const* g_dev, float* const* m_dev, float* const* v_dev,
+                               const uint16_t* const* w16_dev, uint16_t* const* wm_dev, const float* const* thr_dev,
+                               const int* rows_dev, int nrows, double lr, int step, double beta1, double beta2,
+                               double eps, double weight_decay, const float* total_sumsq, float max_norm,
+                               void* stream) {
+  if (!p_dev || !g_dev || !m_dev || !v_dev || !rows_dev || nrows < 0 || step < 1) return CRV_E_BADARG;
+  if ((w16_dev == nullptr) != (wm_dev == nullptr) || (w16_dev == nullptr) != (thr_dev == nullptr)) return CRV_E_BADARG;
+  if (nrows == 0) return CRV_OK;
+  if (!aligned16(rows_dev)) return CRV_E_ALIGN;
+  // torch.optim.AdamW (single-tensor / foreach paths): step_size = lr / (1 - b1^t), denom = sqrt(v) / sqrt(1 - b2^t) + eps
+  const double bc1 = 1.0 - std::pow(beta1, step), bc2 = 1.0 - std::pow(beta2, step);
+  AdamArgs a = make_adam_args(static_cast<float>(lr), static_cast<float>(lr / bc1), beta1, beta2,
+                              static_cast<float>(eps), static_cast<float>(weight_decay), max_norm,
+                              static_cast<float>(1.0 / std::sqrt(bc2)), 2);
+  a.decay = static_cast<float>(1.0 - lr * weight_decay);
+  const MultiAdamTables t{p_dev, g_dev, m_dev, v_dev, w16_dev, wm_dev, thr_dev};
+  const int grid = nrows < num_sms() * 8 ? nrows : num_sms() * 8;
+  adamw_multi_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      t, reinterpret_cast<const int4*>(rows_dev), nrows, a, total_sumsq);
   return launch_status();
 }

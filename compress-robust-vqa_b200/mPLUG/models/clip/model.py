@@ -8,6 +8,7 @@ import os
 from collections import OrderedDict
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 # see modeling_mplug.BF16_ATTENTION: the attention sub-block (in_proj, softmax(QK^T)V, out_proj) runs under bf16 autocast
@@ -19,6 +20,10 @@ class LayerNorm(nn.LayerNorm):
     """LayerNorm that returns its input's dtype (half-precision inputs are normalised by torch in fp32 anyway)."""
 
     def forward(self, x):
+        if x.is_cuda and x.dtype == torch.bfloat16 and os.environ.get("CRVQA_MPLUG_FUSED", "1") != "0":
+            from crvqa import fused
+            if fused.layernorm_bf16_usable(x, self):
+                return fused.layernorm_bf16(x, self)     # one bf16 -> bf16 pass (fp32 statistics) instead of three
         return super().forward(x).type(x.dtype)
 
 
@@ -41,16 +46,40 @@ class ResidualAttentionBlock(nn.Module):
         self.ln_2 = LayerNorm(d_model)
         self.attn_mask = attn_mask
 
-    def attention(self, x, text_mask=None):
+    def attention(self, x, text_mask=None, batch_first=False):
         if text_mask is None and self.attn_mask is not None:
             text_mask = self.attn_mask.to(dtype=x.dtype, device=x.device)
         bf16 = (torch.autocast("cuda", dtype=torch.bfloat16) if BF16_ATTENTION and x.is_cuda
                 else contextlib.nullcontext())
         with bf16:
+            if batch_first:
+                assert text_mask is None
+                return self._self_attention_batch_first(x).to(x.dtype)
             return self.attn(x, x, x, need_weights=False, attn_mask=text_mask)[0].to(x.dtype)
 
-    def forward(self, x, text_mask=None):
-        x = x + self.attention(self.ln_1(x), text_mask=text_mask)
+    def _self_attention_batch_first(self, x):
+        """What ``self.attn(x, x, x)`` computes (torch.nn.functional.multi_head_attention_forward: packed in-projection,
+        softmax(Q K^T / sqrt(d)) V with dropout on the probabilities, out-projection read through ``out_proj.weight`` /
+        ``.bias`` -- NOT ``out_proj.forward``, so a masked replacement of ``out_proj`` stays unmasked exactly as under
+        the reference's nn.MultiheadAttention) on a [batch, tokens, width] input.  The heads are strided views of the
+        packed projection and of the attention output: none of the four [tokens x batch x width]-sized layout copies
+        per block and direction that the sequence-first module makes (its ``.contiguous()`` after the packed
+        projection, the head merge after attention, and their backward copies / zero-filled select gradients)."""
+        a = self.attn
+        B, L, D = x.shape
+        H = a.num_heads
+        qkv = F.linear(x, a.in_proj_weight, a.in_proj_bias).view(B, L, 3, H, D // H)
+        q, k, v = (t.transpose(1, 2) for t in qkv.unbind(2))         # [B, H, L, d] views; unbind's backward is one stack
+        ctx = F.scaled_dot_product_attention(q, k, v, dropout_p=a.dropout if a.training else 0.0)
+        return F.linear(ctx.transpose(1, 2).reshape(B, L, D), a.out_proj.weight, a.out_proj.bias)
+
+    def batch_first_ok(self, text_mask=None):
+        a = self.attn
+        return (text_mask is None and self.attn_mask is None and a._qkv_same_embed_dim and a.bias_k is None
+                and a.bias_v is None and not a.add_zero_attn and a.in_proj_bias is not None)
+
+    def forward(self, x, text_mask=None, batch_first=False):
+        x = x + self.attention(self.ln_1(x), text_mask=text_mask, batch_first=batch_first)
         return x + self.mlp(self.ln_2(x))
 
 
@@ -60,13 +89,18 @@ class Transformer(nn.Module):
         self.width, self.layers = width, layers
         self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads, attn_mask) for _ in range(layers)])
 
-    def forward(self, x, text_mask=None, use_checkpoint=False):
+    def forward(self, x, text_mask=None, use_checkpoint=False, batch_first=False):
+        """x: [tokens, batch, width] as in the reference, or [batch, tokens, width] with ``batch_first``."""
         for block in self.resblocks:
             if use_checkpoint:
-                x = torch.utils.checkpoint.checkpoint(block, x, text_mask, use_reentrant=False)
+                x = torch.utils.checkpoint.checkpoint(block, x, text_mask, batch_first, use_reentrant=False)
             else:
-                x = block(x, text_mask=text_mask)
+                x = block(x, text_mask=text_mask, batch_first=batch_first)
         return x
+
+    def batch_first_ok(self, text_mask=None):
+        return (os.environ.get("CRVQA_MPLUG_FUSED", "1") != "0"
+                and all(block.batch_first_ok(text_mask) for block in self.resblocks))
 
 
 class VisualTransformer(nn.Module):
@@ -87,5 +121,9 @@ class VisualTransformer(nn.Module):
         cls = self.class_embedding.to(x.dtype).expand(x.shape[0], 1, -1)
         x = torch.cat([cls, x], dim=1)
         x = self.ln_pre(x + self.positional_embedding.to(x.dtype)[:x.size(1)])
-        x = self.transformer(x.permute(1, 0, 2), use_checkpoint=use_checkpoint).permute(1, 0, 2)
+        if self.transformer.batch_first_ok(text_mask):
+            # same arithmetic, batch-major: the attention blocks split heads as views (no layout copies)
+            x = self.transformer(x, use_checkpoint=use_checkpoint, batch_first=True)
+        else:
+            x = self.transformer(x.permute(1, 0, 2), use_checkpoint=use_checkpoint).permute(1, 0, 2)
         return self.ln_post(x) if skip_last_layer else x @ self.proj

@@ -426,16 +426,31 @@ class MaskedLinear1(MaskedLinearX):
         self._wm = None
         self._wm_key = None
 
+    def _wm_key_now(self, thr):
+        t = self.threshold               # the source object: alive as long as it is current, so its id is not reused
+        return (id(t), t._version if torch.is_tensor(t) else t, getattr(self, "score_dtype", None),
+                self.weight_mask.data_ptr(), self.weight_mask._version, thr.device)   # optimisers bump _version
+
     def _held_masked_weight(self, thr):
         if not getattr(self, "_hold_wm", False):
             return None
-        t = self.threshold               # the source object: alive as long as it is current, so its id is not reused
-        key = (id(t), t._version if torch.is_tensor(t) else t, getattr(self, "score_dtype", None),
-               self.weight_mask.data_ptr(), self.weight_mask._version, thr.device)   # optimisers bump _version
+        key = self._wm_key_now(thr)
         if self._wm is None or self._wm_key != key:
             self._wm = ops.apply_mask_bf16(self._weight_bf16(), self.weight_mask.detach(), thr)
             self._wm_key = key
         return self._wm
+
+    def holds_masked_operand(self):
+        """True when forward() takes its operand from _held_masked_weight (the tensor-core path of a held module)."""
+        return (getattr(self, "_hold_wm", False) and not (self.structured_masked or self.mask_biases)
+                and "embedding" not in self.name and self.weight.shape[1] % 8 == 0
+                and getattr(self, "_arena", None) is None)
+
+    def adopt_masked_weight(self, wm, thr):
+        """An engine whose optimiser pass wrote W (.) (S_new > thr) into `wm` (crv_adamw_multi) hands it over: valid for
+        the current scores / threshold, exactly as if _held_masked_weight had just built it."""
+        self._wm = wm
+        self._wm_key = self._wm_key_now(thr)
 
 
 class MaskedLinear2(MaskedLinearX):

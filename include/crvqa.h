@@ -292,6 +292,23 @@ int crv_quick_gelu_bwd(const uint16_t* u, const uint16_t* dy, uint16_t* du, int6
  * scalar tail count} cutting the tensors into chunks. */
 int crv_momentum_update(const float* const* online_dev, float* const* twins_dev, const int* rows_dev, int nrows,
                         float m, float one_minus_m, void* stream);
+/* Global-norm clip + optimiser step of mPLUG's engine over many separately allocated fp32 tensors (the step DeepSpeed
+ * runs for the reference: mPLUG/vqa_mplug.py:171-204 with mPLUG/configs/ds_config.json gradient_clipping 1.0 and the
+ * torch AdamW of mPLUG/optim/optim_factory.py:60-89).  rows_dev: device int4 rows {tensor, first element / 8, elements
+ * in the row, flags}; every *_dev argument is a device array of tensor pointers (16-byte aligned tensors).
+ * crv_sumsq_multi: *out += sum of squares over all rows (deterministic, same workspace contract as crv_sumsq).
+ * crv_adamw_multi: g' = g * min(1, max_norm / (sqrt(*total_sumsq) + 1e-6)) (total_sumsq NULL: no clip);
+ * p *= 1 - lr * weight_decay; m += (g' - m)(1 - b1); v = b2 v + (1 - b2) g'^2;
+ * p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)   (torch.optim.AdamW, step 1-based).
+ * Rows with flags bit 0 also refresh the tensor's masked bf16 operand from the new scores in registers:
+ * wm[t] = w16[t] (.) (p_new > *thr[t])  (masking/maskers.py:342-358; thr[t] points at one device float).
+ * w16_dev / wm_dev / thr_dev: all NULL or all given (entries of tensors without the flag are not read). */
+int crv_sumsq_multi(const float* const* xs_dev, const int* rows_dev, int nrows, float* out, void* workspace,
+                    void* stream);
+int crv_adamw_multi(float* const* p_dev, const float* const* g_dev, float* const* m_dev, float* const* v_dev,
+                    const uint16_t* const* w16_dev, uint16_t* const* wm_dev, const float* const* thr_dev,
+                    const int* rows_dev, int nrows, double lr, int step, double beta1, double beta2, double eps,
+                    double weight_decay, const float* total_sumsq, float max_norm, void* stream);
 /* rng_state[1] += 1 on the device (once per training step, inside the captured graph). */
 int crv_rng_advance(unsigned long long* rng_state, void* stream);
 

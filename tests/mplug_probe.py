@@ -50,6 +50,16 @@ def main():
     w = torch.rand(2 * B, device="cuda", generator=g)
     setup_s = time.time() - t0
 
+    # CRVQA_PROBE_SDPA=flash|cudnn|efficient|math pins torch's scaled_dot_product_attention backend for the probe
+    # (default: torch's own choice); a measurement aid, the model code does not read it
+    pin = os.environ.get("CRVQA_PROBE_SDPA")
+    if pin:
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        backend = {"flash": SDPBackend.FLASH_ATTENTION, "cudnn": SDPBackend.CUDNN_ATTENTION,
+                   "efficient": SDPBackend.EFFICIENT_ATTENTION, "math": SDPBackend.MATH}[pin]
+        ctx = sdpa_kernel([backend])
+        ctx.__enter__()
+
     def step():
         loss = eng(image, q, a, train=True, alpha=0.4, k=k, weights=w)
         eng.backward(loss)
@@ -88,6 +98,9 @@ def main():
                                   "tokens, 2 answers per question, distill twins updated, zero rate 0.7",
                       "batch": B, "steps": steps, "ms_per_step": ms, "hold_masks": hold, "bf16_activations": bool(model.bf16_activations),
                       "gpu_busy_ms_per_step": busy, "samples_per_s": B / ms * 1e3,
+                      "fused_optimizer_step": bool(eng._fused and eng._fused.plan is not None
+                                                   and eng._fused.plan.uniform_steps),
+                      "fused_env": os.environ.get("CRVQA_MPLUG_FUSED", "1"), "sdpa_backend": pin or "torch default",
                       "masked_modules": len([1 for _, m in model.named_modules() if hasattr(m, "threshold")]),
                       "trainable_scores": n_scores, "loss": float(loss), "setup_s": setup_s,
                       "mask_update_s": upd, "max_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))

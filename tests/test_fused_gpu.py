@@ -395,3 +395,39 @@ def test_quick_gelu_bf16_matches_torch():
     y.backward(dy)
     ref.backward(dy.float())
     assert float((u.grad.float() - uf.grad).abs().max()) <= 2 ** -7 * float(uf.grad.abs().max())
+
+
+def test_layernorm_bf16_matches_torch():
+    """fused.layernorm_bf16 (the LayerNorms of mPLUG's CLIP tower on bf16 activations, mPLUG/models/clip/model.py:12-19:
+    fp32 statistics, result in the input's dtype) against torch's fp32 LayerNorm of the same bf16 input: the result
+    differs by its bf16 rounding only, the input gradient by bf16 rounding of the output gradient; rows that do not
+    fill the last CTA, CLIP's LayerNorm module takes the path by itself and falls back when it may not."""
+    from crvqa import fused
+    from mPLUG.models.clip.model import LayerNorm
+    torch.manual_seed(4)
+    M, H = 4 * 577 + 3, 768
+    ln = LayerNorm(H).cuda()
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.1 * torch.randn(H))
+        ln.bias.copy_(0.1 * torch.randn(H))
+    x = (torch.randn(M, H, device="cuda") * 1.5 + 0.3).bfloat16().requires_grad_(True)
+    assert not fused.layernorm_bf16_usable(x, ln)            # trainable gamma / beta: the PyTorch ops
+    with torch.autocast("cuda", dtype=torch.bfloat16):       # as the tower runs: torch normalises in fp32, casts back
+        assert ln(x).dtype == torch.bfloat16
+    ln.weight.requires_grad = ln.bias.requires_grad = False
+    assert fused.layernorm_bf16_usable(x, ln)
+    y3 = ln(x.view(M, 1, H))                                 # through the module, any leading shape
+    assert y3.dtype == torch.bfloat16 and y3.shape == (M, 1, H)
+    assert "LayerNormBf16" in type(y3.grad_fn).__name__, type(y3.grad_fn).__name__
+    y = y3.view(M, H)
+    xf = x.detach().float().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xf, (H,), ln.weight, ln.bias, ln.eps)
+    err = float((y.detach().float() - ref.detach()).abs().max()) / float(ref.detach().abs().max())
+    assert err <= 2 ** -8, err
+    dy = torch.randn(M, H, device="cuda").bfloat16()
+    y.backward(dy)
+    ref.backward(dy.float())
+    gerr = float((x.grad.float() - xf.grad).abs().max()) / float(xf.grad.abs().max())
+    assert gerr <= 2 ** -7, gerr
+    assert not fused.layernorm_bf16_usable(x.float(), ln)
+    assert not fused.layernorm_bf16_usable(x[:, :700], torch.nn.LayerNorm(700).cuda().requires_grad_(False))

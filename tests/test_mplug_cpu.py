@@ -475,6 +475,185 @@ def test_held_masked_operand_is_rebuilt_exactly_when_it_must(gold, oracle_backen
     assert mod._wm is None
 
 
+# ----------------------------------------------------------------------------- engine: fused clip + AdamW step, host logic
+def _at(addr, n, ctype, dtype):
+    """numpy view of n elements at a raw host address (the tensors the address tables name live on the CPU here)."""
+    import ctypes
+    return np.frombuffer((ctype * n).from_address(int(addr)), dtype=dtype)
+
+
+def _emulated_multi_kernels(monkeypatch, ops):
+    """crv_sumsq_multi / crv_adamw_multi restated in numpy over the SAME address and row tables the engine hands to the
+    CUDA kernels (include/crvqa.h; csrc/elementwise.cu sumsq_multi_kernel / adamw_multi_kernel), so the engine's host
+    logic -- tables, groups, step counters, plan rebuilds, operand hand-over -- runs on a box without a GPU."""
+    import ctypes
+    f32 = np.float32
+    calls = {"sumsq": 0, "adamw": 0, "upload": 0}
+
+    def upload(values, dtype, device, out=None):
+        calls["upload"] += 1
+        t = torch.tensor(values, dtype=dtype)
+        if out is None:
+            return t
+        out.copy_(t)
+        return out
+
+    def sumsq_multi(ptrs, rows, acc):
+        calls["sumsq"] += 1
+        tot = 0.0
+        for t, first8, n, _ in rows.tolist():
+            x = _at(int(ptrs[t]) + first8 * 32, n, ctypes.c_float, f32)
+            tot += float(np.sum(x.astype(np.float64) ** 2))
+        acc += tot
+
+    def adamw_multi(p, g, m, v, w16, wm, thr, rows, lr, step, b1, b2, eps, wd, total_sumsq=None, max_norm=1.0):
+        calls["adamw"] += 1
+        clip = f32(1.0)
+        if total_sumsq is not None:
+            clip = min(f32(1.0), f32(max_norm) / (np.sqrt(f32(total_sumsq.item())) + f32(1e-6)))
+        decay, omb1, omb2 = f32(1.0 - lr * wd), f32(1.0 - b1), f32(1.0 - b2)
+        step_size, inv_bc2 = f32(lr / (1.0 - b1 ** step)), f32(1.0 / np.sqrt(1.0 - b2 ** step))
+        for t, first8, n, flags in rows.tolist():
+            off = first8 * 8
+            P, G, M, V = (_at(int(tab[t]) + off * 4, n, ctypes.c_float, f32) for tab in (p, g, m, v))
+            gc = G * clip
+            P *= decay
+            M += (gc - M) * omb1
+            V[:] = V * f32(b2) + omb2 * gc * gc
+            P -= step_size * (M / (np.sqrt(V) * inv_bc2 + f32(eps)))
+            if flags & 1:
+                T = _at(int(thr[t]), 1, ctypes.c_float, f32)[0]
+                W = _at(int(w16[t]) + off * 2, n, ctypes.c_uint16, np.uint16)
+                _at(int(wm[t]) + off * 2, n, ctypes.c_uint16, np.uint16)[:] = np.where(P > T, W, np.uint16(0))
+
+    monkeypatch.setattr(ops, "upload", upload)
+    monkeypatch.setattr(ops, "sumsq_multi", sumsq_multi)
+    monkeypatch.setattr(ops, "adamw_multi", adamw_multi)
+    return calls
+
+
+def test_fused_engine_step_host_logic_follows_clip_plus_torch_adamw(gold, oracle_backend, monkeypatch):
+    """MaskTrainEngine.step() with a stock torch AdamW: address / row tables per parameter group, torch-compatible
+    optimiser state, plan rebuilds (new threshold objects, parameters that start receiving gradients), the refreshed
+    masked operand handed to the modules -- against clip_grad_norm_ + torch.optim.AdamW.step on cloned tensors fed the
+    same gradients.  The two kernels are emulated in numpy over the engine's own tables (no GPU here)."""
+    from mPLUG import engine as eng_mod
+    from mPLUG import optim as mplug_optim
+    from mPLUG.masking import maskers
+    ops = oracle_backend
+    applied = []
+
+    def fake_apply(w16, scores, thr):
+        applied.append(1)
+        return (w16.float() * (scores > thr).float()).to(torch.bfloat16)
+
+    monkeypatch.setattr(ops, "apply_mask_bf16", fake_apply)
+    monkeypatch.setattr(ops, "to_bf16", lambda x: x.to(torch.bfloat16))
+    calls = _emulated_multi_kernels(monkeypatch, ops)
+    monkeypatch.setattr(eng_mod._FusedAdamW, "device_types", ("cpu", "cuda"))
+    model = fresh(gold)
+    _init(model, zero_rate=0.6, init_sparsity=0.2, final_sparsity_epoch=2)
+    args = types.SimpleNamespace(opt="adamW", lr=2e-3, weight_decay=0.02)
+    opt = mplug_optim.create_optimizer(args, model)
+    eng = eng_mod.MaskTrainEngine(model, opt, gradient_clipping=0.05, bf16=True)
+    trainable = [p for g in opt.param_groups for p in g["params"]]
+    twin = [[p.detach().clone().requires_grad_(True) for p in g["params"]] for g in opt.param_groups]
+    ref = torch.optim.AdamW([{"params": twin[0], "weight_decay": 0.0}, {"params": twin[1], "weight_decay": 0.02}],
+                            lr=2e-3)
+    flat_twin = [q for grp in twin for q in grp]
+    held = [m for _, m in masked(model) if m.holds_masked_operand()]
+    assert len(held) >= 20
+    late = {id(held[0].weight_mask), id(held[3].weight_mask)}       # these get no gradient in the first two steps
+    gen = torch.Generator().manual_seed(7)
+    plans = []
+    for it in range(5):
+        for g, h in zip(opt.param_groups, ref.param_groups):
+            g["lr"] = h["lr"] = 2e-3 * (1.0 - 0.1 * it)
+        for p, q in zip(trainable, flat_twin):
+            if it < 2 and id(p) in late:
+                p.grad = q.grad = None
+                continue
+            p.grad = torch.randn(p.shape, generator=gen) * 0.01
+            q.grad = p.grad.clone()
+        if it == 3:
+            maskers.reset_threshold(model, 0.5)                       # new threshold objects: the plan must follow
+        for m in held:                                               # a forward would fetch the operand here
+            m._held_masked_weight(m._threshold_on(torch.device("cpu")))
+        n_applied = len(applied)
+        before = dict(calls)
+        eng.step()
+        plans.append(eng._fused.plan)
+        if it == 2:
+            # two scores join with step counters behind the others' in their group: the kernels take one step number
+            # per launch, so this step (and every later one) must go through the PyTorch path -- still correct
+            assert not eng._fused.plan.uniform_steps and calls["adamw"] == before["adamw"]
+        want_norm = torch.nn.utils.clip_grad_norm_([q for q in flat_twin if q.grad is not None], 0.05)
+        ref.step()
+        assert float(eng.last_grad_norm) == pytest.approx(float(want_norm), rel=1e-5) and float(want_norm) > 0.05
+        for p, q in zip(trainable, flat_twin):
+            assert p.grad is None
+            assert torch.allclose(p.detach(), q.detach(), rtol=2e-6, atol=2e-8), float((p - q).abs().max())
+            if len(opt.state[p]):
+                assert float(opt.state[p]["step"]) == float(ref.state[q]["step"])
+                assert torch.allclose(opt.state[p]["exp_avg_sq"], ref.state[q]["exp_avg_sq"], rtol=1e-5, atol=1e-30)
+        if it < 2:
+            assert calls["sumsq"] == before["sumsq"] + 1 and calls["adamw"] == before["adamw"] + 2
+            refreshed = [m for m in eng._fused.plan.mods if m is not None]
+            assert len(refreshed) == len(held) - 2
+            for m in refreshed:
+                thr = m._threshold_on(torch.device("cpu"))
+                assert m._wm_key == m._wm_key_now(thr)
+                assert torch.equal(m._wm.float(), m.weight.bfloat16().float() * m.get_masks()[0])
+                assert m._held_masked_weight(thr) is m._wm            # no rebuild on the next forward
+            assert len(applied) == n_applied
+            assert held[0]._wm is None                                # outside the pass: dropped, rebuilt on demand
+    assert plans[0] is plans[1] and plans[1] is not plans[2]
+    sd = opt.state_dict()
+    assert len(sd["state"]) == len(trainable)
+
+
+def test_fused_engine_step_uniform_run_rebuilds_plan_on_new_thresholds(gold, oracle_backend, monkeypatch):
+    """Every trainable tensor has a gradient from the first step (the training loop's case): all steps take the fused
+    pass, a threshold refresh rebuilds the plan once, and the operand after it is the new mask's."""
+    from mPLUG import engine as eng_mod
+    from mPLUG.masking import maskers
+    ops = oracle_backend
+    monkeypatch.setattr(ops, "apply_mask_bf16", lambda w16, s, t: (w16.float() * (s > t).float()).to(torch.bfloat16))
+    monkeypatch.setattr(ops, "to_bf16", lambda x: x.to(torch.bfloat16))
+    calls = _emulated_multi_kernels(monkeypatch, ops)
+    monkeypatch.setattr(eng_mod._FusedAdamW, "device_types", ("cpu", "cuda"))
+    model = fresh(gold)
+    _init(model, zero_rate=0.6, init_sparsity=0.2, final_sparsity_epoch=2)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.0)
+    eng = eng_mod.MaskTrainEngine(model, opt, gradient_clipping=1.0, bf16=True)
+    twin = [p.detach().clone().requires_grad_(True) for p in params]
+    ref = torch.optim.AdamW(twin, lr=1e-3, weight_decay=0.0)
+    gen = torch.Generator().manual_seed(11)
+    plans = []
+    for it in range(4):
+        for p, q in zip(params, twin):
+            p.grad = torch.randn(p.shape, generator=gen) * 1e-3       # norm below 1: the clip stays off
+            q.grad = p.grad.clone()
+        if it == 2:
+            maskers.reset_threshold(model, 0.55)
+        eng.step()
+        plans.append(eng._fused.plan)
+        assert float(torch.nn.utils.clip_grad_norm_(twin, 1.0)) < 1.0
+        ref.step()
+        for p, q in zip(params, twin):
+            assert torch.allclose(p.detach(), q.detach(), rtol=2e-6, atol=2e-8)
+        for m in (m for m in plans[-1].mods if m is not None):
+            assert torch.equal(m._wm.float(), m.weight.bfloat16().float() * m.get_masks()[0])
+    assert calls["adamw"] == 4 and calls["sumsq"] == 4
+    assert plans[0] is plans[1] and plans[1] is not plans[2] and plans[2] is plans[3]
+    assert calls["upload"] == 2 * 2 + 4         # two tables per plan build + the gradient addresses of every step
+    # CRVQA_MPLUG_FUSED=0 keeps the PyTorch passes
+    monkeypatch.setenv("CRVQA_MPLUG_FUSED", "0")
+    assert not eng_mod._FusedAdamW.wanted(opt)
+    assert not eng_mod._FusedAdamW.wanted(torch.optim.SGD(params, lr=0.1))
+
+
 def test_optimizer_groups_and_cosine_schedule_match_reference():
     """mPLUG/optim + mPLUG/scheduler against the reference packages (tests/golden/mplug_host.json): same parameter
     groups (members, lr, weight decay) for create_optimizer / create_two_optimizer, same learning rate after every

@@ -182,3 +182,70 @@ def test_mplug_engine_trains_scores_and_head_only(gold):
             assert torch.equal(p, frozen[n]), n
     assert not torch.equal(model.text_decoder.cls.predictions.decoder.weight, head0)
     assert float(eng.last_grad_norm) > 0
+
+
+def test_fused_engine_step_matches_clip_plus_torch_adamw(gold):
+    """MaskTrainEngine.step() on a GPU runs clip + AdamW + the refresh of every held masked operand as multi-tensor
+    launches (crv_sumsq_multi, crv_adamw_multi) over the optimiser's own tensors.  Fed the SAME gradients, it must
+    follow torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step (what the PyTorch path of the engine runs) to fp32
+    rounding over several steps, with two parameter groups (decay / no decay) and a moving learning rate; the operand
+    it leaves behind is bit-exactly bf16(W) (.) bf16-mode mask of the NEW scores; optimizer.state stays torch's."""
+    from crvqa import lib
+    from mPLUG import optim as mplug_optim
+    from mPLUG.engine import MaskTrainEngine
+    import types
+    model = fresh(gold).cuda()
+    _init(model, zero_rate=0.6, init_sparsity=0.2, final_sparsity_epoch=2)
+    args = types.SimpleNamespace(opt="adamW", lr=2e-3, weight_decay=0.02)
+    opt = mplug_optim.create_optimizer(args, model)
+    assert len(opt.param_groups) == 2 and opt.param_groups[1]["weight_decay"] == 0.02
+    eng = MaskTrainEngine(model, opt, gradient_clipping=0.05, bf16=True)
+    trainable = [p for g in opt.param_groups for p in g["params"]]
+    twin = [[p.detach().clone().requires_grad_(True) for p in g["params"]] for g in opt.param_groups]
+    ref = torch.optim.AdamW([{"params": twin[0], "weight_decay": 0.0}, {"params": twin[1], "weight_decay": 0.02}],
+                            lr=2e-3)
+    flat_twin = [q for grp in twin for q in grp]
+    batch = tuple(t.cuda() for t in sk.batch())
+    model.train()
+    for it in range(5):
+        for g, h in zip(opt.param_groups, ref.param_groups):
+            g["lr"] = h["lr"] = 2e-3 * (1.0 - 0.1 * it)
+        loss = eng(*batch)
+        eng.backward(loss)
+        with_grad = 0
+        for p, q in zip(trainable, flat_twin):
+            q.grad = None if p.grad is None else p.grad.detach().clone()
+            with_grad += p.grad is not None
+        assert with_grad >= 40
+        groups_with_grads = sum(any(p.grad is not None for p in g["params"]) for g in opt.param_groups)
+        launches = lib.crv_launch_count()
+        eng.step()
+        assert eng._fused and eng._fused.plan is not None, "the fused step did not run"
+        assert groups_with_grads == 2
+        assert lib.crv_launch_count() - launches == 3            # norm + one AdamW launch per parameter group
+        want_norm = torch.nn.utils.clip_grad_norm_([q for q in flat_twin if q.grad is not None], 0.05)
+        ref.step()
+        assert float(eng.last_grad_norm) == pytest.approx(float(want_norm), rel=1e-5)
+        assert float(want_norm) > 0.05                           # the clip is active
+        for p, q in zip(trainable, flat_twin):
+            assert p.grad is None
+            # identical maths up to fp32 rounding (torch divides by sqrt(1 - b2^t), the kernel multiplies by its inverse)
+            assert torch.allclose(p.detach(), q.detach(), rtol=2e-6, atol=2e-8), float((p - q).abs().max())
+            if p in opt.state and len(opt.state[p]):
+                assert int(opt.state[p]["step"]) == it + 1
+                for k in ("exp_avg", "exp_avg_sq"):              # m + (g - m)(1 - b1) cancels: error relative to the largest
+                    a, b = opt.state[p][k], ref.state[q][k]
+                    assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max()), k
+        refreshed = [m for m in eng._fused.plan.mods if m is not None]
+        assert len(refreshed) >= 40
+        for m in refreshed:                                      # straight after the step, before any forward
+            thr = m._threshold_on(m.weight_mask.device)
+            assert m._wm is not None and m._wm_key == m._wm_key_now(thr)
+            assert torch.equal(m._wm.float(), m._weight_bf16().float() * m.get_masks()[0])
+    # the state is torch's own: a plain optimizer.step() carries on from it
+    loss = eng(*batch)
+    eng.backward(loss)
+    opt.step()
+    assert all(int(st["step"]) == 6 for st in opt.state.values() if len(st))
+    sd = opt.state_dict()
+    assert len(sd["state"]) >= 40

@@ -339,3 +339,37 @@ def test_momentum_update_drops_the_twins_operand_caches(gold, oracle_backend):
     model._momentum_update()
     assert twin._w16 is None and twin._wm is None and online._w16 is not None
     assert torch.allclose(twin.weight_mask, before * 0.995 + online.weight_mask * 0.005)
+
+
+def test_batch_first_vit_attention_equals_the_sequence_first_module(monkeypatch):
+    """The ViT tower runs batch-major by default (heads as strided views of the packed projection,
+    ResidualAttentionBlock._self_attention_batch_first); with CRVQA_MPLUG_FUSED=0 it goes through nn.MultiheadAttention
+    on [tokens, batch, width] as the reference does (mPLUG/models/clip/model.py:157-249).  Same function: outputs and
+    every parameter gradient agree to fp32 rounding; the module tree / state_dict is untouched."""
+    from mPLUG.models.clip.model import VisualTransformer
+    torch.manual_seed(3)
+    vit = VisualTransformer(input_resolution=32, patch_size=8, width=64, layers=3, heads=4, output_dim=32).eval()
+    img = torch.randn(3, 3, 32, 32)
+    params = [p for p in vit.parameters()]
+
+    def run():
+        out = vit(img, skip_last_layer=True)
+        grads = torch.autograd.grad((out * torch.linspace(-1, 1, out.numel()).view_as(out)).sum(), params,
+                                    allow_unused=True)
+        return out.detach(), grads
+
+    assert vit.transformer.batch_first_ok()
+    out_fast, g_fast = run()
+    monkeypatch.setenv("CRVQA_MPLUG_FUSED", "0")
+    assert not vit.transformer.batch_first_ok()
+    out_ref, g_ref = run()
+    assert out_fast.shape == out_ref.shape == (3, 17, 64)
+    assert torch.allclose(out_fast, out_ref, rtol=1e-5, atol=1e-5)
+    for p, a, b in zip(params, g_fast, g_ref):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-7
+    # a tower with an attention mask keeps the sequence-first module
+    monkeypatch.setenv("CRVQA_MPLUG_FUSED", "1")
+    assert not vit.transformer.batch_first_ok(text_mask=torch.zeros(17, 17))
+    assert "transformer.resblocks.0.attn.in_proj_weight" in vit.state_dict()
