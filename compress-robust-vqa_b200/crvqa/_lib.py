@@ -71,6 +71,9 @@ _PROTOS = {
     "crv_gelu_fwd": (c_int, [_P, _P, c_int64, _P]),
     "crv_gelu_bwd": (c_int, [_P, _P, _P, c_int64, _P]),
     "crv_momentum_update": (c_int, [_P, _P, _P, c_int, c_float, c_float, _P]),
+    "crv_fq_attention_fwd": (c_int, [_P, _P, _P, _P, c_longlong, c_longlong, _P, _P, c_int, c_int, c_int, c_int, c_float,
+                                     c_float, _P, c_int, _P]),
+    "crv_fq_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
     "crv_sumsq_multi": (c_int, [_P, _P, c_int, _P, _P, _P]),
     "crv_adamw_multi": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_double, c_int, c_double, c_double, c_double,
                                 c_double, _P, c_float, _P]),

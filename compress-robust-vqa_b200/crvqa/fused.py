@@ -12,6 +12,7 @@ the same; every GEMM operand is bf16 as before; the residual stream stays fp32. 
 (plain drop-in use) keep the generic per-module path of masking._core.MaskedLinear1.
 """
 import ctypes
+import math
 import os
 
 import torch
@@ -381,6 +382,65 @@ def layernorm_bf16_usable(x, ln):
 def layernorm_bf16(x, ln):
     """bf16 LayerNorm(x) of a frozen nn.LayerNorm on a bf16 activation (check layernorm_bf16_usable first)."""
     return LayerNormBf16Fn.apply(x, ln.weight, ln.bias, ln.eps)
+
+
+# ----------------------------------------------------------------------------- few-query attention (mPLUG text side)
+class FewQueryAttentionFn(torch.autograd.Function):
+    """ctx = dropout(softmax(Q K^T / 8 + mask)) V on [B, L, heads * 64] bf16 projections (crv_fq_attention_fwd / _bwd):
+    Lq <= 16 queries, Lk <= 1024 keys.  The forward saves the probabilities with the dropout decision in their sign."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, heads, p, site, rng):
+        B, Lq, D = q.shape
+        Lk = k.shape[1]
+        out = torch.empty((B, Lq, D), dtype=torch.bfloat16, device=q.device)
+        probs = torch.empty((B, heads, Lq, Lk), dtype=torch.bfloat16, device=q.device)
+        state = rng.state if (rng is not None and p > 0) else None
+        p = float(p) if state is not None else 0.0
+        sb = sq = 0
+        if mask is not None:
+            sb = mask.stride(0) if mask.shape[0] > 1 else 0
+            sq = mask.stride(2) if mask.shape[2] > 1 else 0
+        scale = 1.0 / math.sqrt(D // heads)
+        check(lib.crv_fq_attention_fwd(_p(q), _p(k), _p(v), _p(mask), sb, sq, _p(out), _p(probs), B, heads, Lq, Lk,
+                                       scale, p, _p(state), int(site), _stream()), "crv_fq_attention_fwd")
+        ctx.save_for_backward(q, k, v, probs)
+        ctx.heads, ctx.p, ctx.scale = heads, p, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, probs = ctx.saved_tensors
+        B, Lq, D = q.shape
+        Lk = k.shape[1]
+        d = dout if (dout.dtype == torch.bfloat16 and dout.is_contiguous()) else dout.to(torch.bfloat16).contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        check(lib.crv_fq_attention_bwd(_p(d), _p(q), _p(k), _p(v), _p(probs), _p(dq), _p(dk), _p(dv), B, ctx.heads, Lq,
+                                       Lk, ctx.scale, ctx.p, _stream()), "crv_fq_attention_bwd")
+        return dq, dk, dv, None, None, None, None, None
+
+
+def few_query_attention_usable(q, k, v, mask, heads):
+    """q / k / v: the projections' outputs [B, L, heads * 64]; mask: None or additive [B | 1, 1, Lq | 1, Lk]."""
+    if not (q.is_cuda and q.dtype == k.dtype == v.dtype == torch.bfloat16 and q.dim() == 3 and k.shape == v.shape
+            and q.shape[0] == k.shape[0] and q.shape[2] == k.shape[2] == heads * 64
+            and 0 < q.shape[1] <= 16 and 0 < k.shape[1] <= 1024
+            and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
+        return False
+    if mask is not None:
+        if not (mask.dim() == 4 and mask.shape[1] == 1 and mask.shape[0] in (1, q.shape[0])
+                and mask.shape[2] in (1, q.shape[1]) and mask.shape[3] == k.shape[1] and not mask.requires_grad):
+            return False
+    return True
+
+
+def few_query_attention(q, k, v, mask, heads, p, site, training):
+    """Attention context [B, Lq, heads * 64] (bf16) of BertSelfAttention; check few_query_attention_usable first."""
+    if mask is not None and (mask.dtype != torch.float32 or mask.stride(3) != 1):
+        mask = mask.float().contiguous()
+    p = float(p) if training else 0.0
+    rng = RngState.get(q.device) if p > 0 else None
+    return FewQueryAttentionFn.apply(q, k, v, mask, heads, p, site, rng)
 
 
 class LnAvgDropFn(torch.autograd.Function):

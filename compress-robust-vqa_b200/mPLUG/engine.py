@@ -19,6 +19,7 @@ instead of re-deriving the mask inside every GEMM call.  Code that edits scores 
 ``invalidate_masks()``.
 """
 import os
+import sys
 import types
 
 import torch
@@ -63,6 +64,13 @@ class MaskTrainEngine:
     # -- the engine face ------------------------------------------------------------------------
     def backward(self, loss):
         loss.backward()
+        # the fused layer kernels (dropout + residual + LayerNorm, few-query attention) hash their dropout masks from a
+        # device-side (seed, counter): forward and backward of this step have both been queued, so move the counter on
+        # -- without this every step would draw the SAME masks
+        fused = sys.modules.get("crvqa.fused")
+        if fused is not None:
+            for state in fused.RngState._per_device.values():
+                state.advance()
 
     def _trainable_grads(self):
         return [p.grad for p in self.module.parameters() if p.requires_grad and p.grad is not None]

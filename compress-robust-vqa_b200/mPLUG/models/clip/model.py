@@ -16,6 +16,16 @@ from torch import nn
 BF16_ATTENTION = os.environ.get("CRVQA_MPLUG_BF16_ATTENTION", "1") != "0"
 
 
+# CRVQA_MPLUG_VIT_ATTENTION=flash_attn: the tower's attention core through flash_attn's packed-QKV kernel (a library, as
+# torch's own scaled_dot_product_attention backends are) instead of torch's SDPA dispatch; anything else: SDPA
+_PACKED_ATTENTION = None
+if os.environ.get("CRVQA_MPLUG_VIT_ATTENTION", "sdpa") == "flash_attn":
+    try:
+        from flash_attn import flash_attn_qkvpacked_func as _PACKED_ATTENTION
+    except ImportError:
+        _PACKED_ATTENTION = None
+
+
 class LayerNorm(nn.LayerNorm):
     """LayerNorm that returns its input's dtype (half-precision inputs are normalised by torch in fp32 anyway)."""
 
@@ -69,9 +79,14 @@ class ResidualAttentionBlock(nn.Module):
         B, L, D = x.shape
         H = a.num_heads
         qkv = F.linear(x, a.in_proj_weight, a.in_proj_bias).view(B, L, 3, H, D // H)
-        q, k, v = (t.transpose(1, 2) for t in qkv.unbind(2))         # [B, H, L, d] views; unbind's backward is one stack
-        ctx = F.scaled_dot_product_attention(q, k, v, dropout_p=a.dropout if a.training else 0.0)
-        return F.linear(ctx.transpose(1, 2).reshape(B, L, D), a.out_proj.weight, a.out_proj.bias)
+        p_drop = a.dropout if a.training else 0.0
+        if _PACKED_ATTENTION is not None and qkv.is_cuda and qkv.dtype in (torch.bfloat16, torch.float16):
+            # library kernel on the packed projection itself: its backward writes d(qkv) in place of three tensors + a stack
+            ctx = _PACKED_ATTENTION(qkv, dropout_p=p_drop).reshape(B, L, D)
+        else:
+            q, k, v = (t.transpose(1, 2) for t in qkv.unbind(2))     # [B, H, L, d] views; unbind's backward is one stack
+            ctx = F.scaled_dot_product_attention(q, k, v, dropout_p=p_drop).transpose(1, 2).reshape(B, L, D)
+        return F.linear(ctx, a.out_proj.weight, a.out_proj.bias)
 
     def batch_first_ok(self, text_mask=None):
         a = self.attn

@@ -110,8 +110,18 @@ class BertSelfAttention(nn.Module):
     def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None):
         src = hidden_states if encoder_hidden_states is None else encoder_hidden_states
         mask = attention_mask if encoder_hidden_states is None else encoder_attention_mask
-        q, k, v = self._heads(self.query(hidden_states)), self._heads(self.key(src)), self._heads(self.value(src))
+        q, k, v = self.query(hidden_states), self.key(src), self.value(src)
         out_dtype = q.dtype
+        if q.is_cuda and q.dtype == torch.bfloat16 and os.environ.get("CRVQA_MPLUG_FUSED", "1") != "0":
+            # a handful of queries (16 question / 6 answer tokens) against up to ~600 keys: one CTA per (batch, head)
+            # reading the projections in place (crv_fq_attention_fwd / _bwd) instead of a 128-query flash tile
+            from crvqa import fused
+            if fused.few_query_attention_usable(q, k, v, mask, self.num_attention_heads):
+                if not hasattr(self, "_site"):
+                    self._site = fused.RngState.new_site()
+                return fused.few_query_attention(q, k, v, mask, self.num_attention_heads, self.dropout.p, self._site,
+                                                 self.training)
+        q, k, v = self._heads(q), self._heads(k), self._heads(v)
         if BF16_ATTENTION and q.is_cuda and q.dtype == torch.float32:
             q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
         if mask is not None:

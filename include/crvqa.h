@@ -309,6 +309,21 @@ int crv_adamw_multi(float* const* p_dev, const float* const* g_dev, float* const
                     const uint16_t* const* w16_dev, uint16_t* const* wm_dev, const float* const* thr_dev,
                     const int* rows_dev, int nrows, double lr, int step, double beta1, double beta2, double eps,
                     double weight_decay, const float* total_sumsq, float max_norm, void* stream);
+/* Few-query attention (mPLUG text side: BertSelfAttention of the text / fusion / decoder stacks,
+ * mPLUG/models/modeling_mplug.py:205-300): out = dropout(softmax(Q K^T * scale + mask)) V for Lq <= 16 queries against
+ * Lk <= 1024 keys per (batch, head), head dim 64.  q / out / dq: [B, Lq, heads * 64] bf16 contiguous; k, v, dk, dv:
+ * [B, Lk, heads * 64].  mask: additive fp32, element (b, i, j) at mask[b * mask_batch_stride + i * mask_query_stride +
+ * j] (strides 0 broadcast), or NULL.  probs: [B, heads, Lq, Lk] bf16, written by the forward: the softmax probability
+ * with the dropout decision in its sign (+P kept, -P dropped; dropout hashed from rng_state / site as crv_ln_fwd does;
+ * rng_state NULL or p_drop 0: none) -- the backward reads it instead of recomputing scores, softmax and hash, and
+ * must be given the same p_drop. */
+int crv_fq_attention_fwd(const uint16_t* q, const uint16_t* k, const uint16_t* v, const float* mask,
+                         long long mask_batch_stride, long long mask_query_stride, uint16_t* out, uint16_t* probs,
+                         int B, int heads, int Lq, int Lk, float scale, float p_drop,
+                         const unsigned long long* rng_state, int site, void* stream);
+int crv_fq_attention_bwd(const uint16_t* dout, const uint16_t* q, const uint16_t* k, const uint16_t* v,
+                         const uint16_t* probs, uint16_t* dq, uint16_t* dk, uint16_t* dv, int B, int heads, int Lq,
+                         int Lk, float scale, float p_drop, void* stream);
 /* rng_state[1] += 1 on the device (once per training step, inside the captured graph). */
 int crv_rng_advance(unsigned long long* rng_state, void* stream);
 

@@ -431,3 +431,108 @@ def test_layernorm_bf16_matches_torch():
     assert gerr <= 2 ** -7, gerr
     assert not fused.layernorm_bf16_usable(x.float(), ln)
     assert not fused.layernorm_bf16_usable(x[:, :700], torch.nn.LayerNorm(700).cuda().requires_grad_(False))
+
+
+def _fq_reference(q, k, v, mask, H, keep, p):
+    B, Lq, D = q.shape
+    Lk = k.shape[1]
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("bihd,bjhd->bhij", qf.view(B, Lq, H, 64), kf.view(B, Lk, H, 64)) / 8.0
+    if mask is not None:
+        s = s + mask.float()
+    P = torch.softmax(s, dim=-1)
+    out = torch.einsum("bhij,bjhd->bihd", P * keep / (1.0 - p), vf.view(B, Lk, H, 64)).reshape(B, Lq, D)
+    return out, P, (qf, kf, vf)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,mask_kind,p", [
+    (3, 12, 6, 593, "row", 0.0), (3, 12, 6, 593, "row", 0.1), (2, 12, 16, 577, "row", 0.1), (4, 12, 6, 6, "causal", 0.1),
+    (2, 12, 16, 16, "row", 0.0), (2, 4, 1, 37, None, 0.0), (2, 12, 9, 130, "full", 0.25), (1, 2, 16, 1024, "row1", 0.1)])
+def test_few_query_attention_matches_reference_math(B, H, Lq, Lk, mask_kind, p):
+    """crv_fq_attention_fwd / _bwd (mPLUG's text-side attention cores, mPLUG/models/modeling_mplug.py:205-300) against
+    softmax(Q K^T / 8 + mask) V in fp32 on the same bf16 projections, with the dropout decisions the kernel took (the
+    sign of its saved probabilities): saved |P| and the output differ by bf16 rounding, dQ / dK / dV by the bf16
+    rounding of P and of the results (2^-6 of the largest entry); about p of the probabilities are dropped."""
+    from crvqa import fused
+    g = torch.Generator(device="cuda").manual_seed(100 + Lq + Lk)
+    D = H * 64
+    q = torch.randn(B, Lq, D, device="cuda", generator=g).bfloat16().requires_grad_(True)
+    k = torch.randn(B, Lk, D, device="cuda", generator=g).bfloat16().requires_grad_(True)
+    v = torch.randn(B, Lk, D, device="cuda", generator=g).bfloat16().requires_grad_(True)
+    mask = None
+    if mask_kind == "row":
+        mask = torch.zeros(B, 1, 1, Lk, device="cuda")
+        mask[B - 1, :, :, Lk - max(1, Lk // 5):] = -10000.0
+    elif mask_kind == "row1":
+        mask = torch.zeros(1, 1, 1, Lk, device="cuda")
+        mask[..., ::7] = -10000.0
+    elif mask_kind == "causal":
+        mask = torch.zeros(B, 1, Lq, Lk, device="cuda").masked_fill_(
+            torch.ones(Lq, Lk, device="cuda").triu(1).bool(), -10000.0)
+    elif mask_kind == "full":
+        mask = (torch.rand(B, 1, Lq, Lk, device="cuda", generator=g) < 0.2).float() * -10000.0
+        mask[..., 0] = 0.0
+    assert fused.few_query_attention_usable(q, k, v, mask, H)
+    site = fused.RngState.new_site()
+    out = fused.few_query_attention(q, k, v, mask, H, p, site, training=True)
+    assert out.shape == (B, Lq, D) and out.dtype == torch.bfloat16
+    probs = out.grad_fn.saved_tensors[3]
+    assert probs.shape == (B, H, Lq, Lk)
+    keep = (probs.view(torch.int16) >= 0).float()
+    ref, P, leaves = _fq_reference(q, k, v, mask, H, keep, p)
+    assert float((probs.float().abs() - P).abs().max()) <= 2 ** -8 * float(P.max()) + 1e-6
+    if p == 0.0:
+        assert bool(keep.all())
+    elif keep.numel() > 20000:
+        assert abs(1.0 - float(keep.mean()) - p) < 0.02
+        again = fused.few_query_attention(q, k, v, mask, H, p, site, training=True)      # same counter: same masks
+        assert torch.equal(again.grad_fn.saved_tensors[3], probs)
+        fused.RngState.get(q.device).advance()
+        other = fused.few_query_attention(q, k, v, mask, H, p, site, training=True)
+        assert not torch.equal(other.grad_fn.saved_tensors[3], probs)
+    assert float((out.float() - ref).abs().max()) <= 2 ** -6 * float(ref.abs().max())
+    dout = torch.randn(B, Lq, D, device="cuda", generator=g).bfloat16()
+    out.backward(dout)
+    ref.backward(dout.float())
+    for name, got, want in zip("qkv", (q.grad, k.grad, v.grad), (t.grad for t in leaves)):
+        err = float((got.float() - want).abs().max()) / float(want.abs().max())
+        assert err <= 2 ** -6, (name, err)
+    # evaluation mode: no dropout whatever p says
+    ev = fused.few_query_attention(q, k, v, mask, H, p, site, training=False)
+    assert bool((ev.grad_fn.saved_tensors[3].view(torch.int16) >= 0).all())
+    assert not fused.few_query_attention_usable(q[:, :, :64], k, v, mask, H)
+    assert not fused.few_query_attention_usable(q.float(), k, v, mask, H)
+
+
+def test_bert_self_attention_takes_the_few_query_kernel(monkeypatch):
+    """mPLUG's BertSelfAttention on bf16 projections (the engine's bf16-activation mode): the cross attention of 6 answer
+    tokens to 593 image / question tokens through crv_fq_attention equals the scaled_dot_product_attention path
+    (CRVQA_MPLUG_FUSED=0) within bf16 rounding, output and input gradients; 593 queries keep the library path."""
+    from types import SimpleNamespace
+    from mPLUG.models.modeling_mplug import BertSelfAttention
+    torch.manual_seed(2)
+    cfg = SimpleNamespace(hidden_size=768, num_attention_heads=12, encoder_width=768, attention_probs_dropout_prob=0.1)
+    att = BertSelfAttention(cfg, is_cross_attention=True).cuda().eval()
+    hid = torch.randn(4, 6, 768, device="cuda", requires_grad=True)
+    enc = torch.randn(4, 593, 768, device="cuda", requires_grad=True)
+    mask = torch.zeros(4, 1, 1, 593, device="cuda")
+    mask[2, ..., 580:] = -10000.0
+    dy = torch.randn(4, 6, 768, device="cuda")
+
+    def run(h, e):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = att(h, None, e, mask)
+        gh, ge = torch.autograd.grad(y, (h, e), dy.to(y.dtype))
+        return y, gh, ge
+
+    y1, gh1, ge1 = run(hid, enc)
+    assert "FewQueryAttention" in type(y1.grad_fn).__name__
+    monkeypatch.setenv("CRVQA_MPLUG_FUSED", "0")
+    y0, gh0, ge0 = run(hid, enc)
+    assert "FewQueryAttention" not in type(y0.grad_fn).__name__
+    for a, b in ((y1, y0), (gh1, gh0), (ge1, ge0)):
+        assert float((a.float() - b.float()).abs().max()) <= 2 ** -5 * float(b.float().abs().max())
+    monkeypatch.setenv("CRVQA_MPLUG_FUSED", "1")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        big = att(enc, mask, None, None)
+    assert "FewQueryAttention" not in type(big.grad_fn).__name__ and big.shape == (4, 593, 768)

@@ -41,8 +41,11 @@ def test_mplug_bf16_activation_mode():
     assert mod(torch.randn(2, 7, mod.weight.shape[1], device="cuda")).dtype == torch.float32
 
 
-def test_mplug_training_trajectory_follows_reference():
-    """The drop-in masker + torch AdamW on the GPU against the reference's six-step trajectory (golden 'T'): losses
+@pytest.mark.parametrize("through_engine", [False, True])
+def test_mplug_training_trajectory_follows_reference(through_engine):
+    """through_engine: the same steps driven by MaskTrainEngine (fp32 score comparison as in the golden run), i.e. the
+    multi-tensor clip + AdamW launches with the masked operands refreshed by the optimiser pass.
+    The drop-in masker + torch AdamW on the GPU against the reference's six-step trajectory (golden 'T'): losses
     within 2e-2, thresholds within one bf16 step, kept counts within 2 % (bf16 MMA operands perturb the scores that
     the order statistics are taken from, so exact equality is not expected after optimiser steps; measured on B200:
     worst module 34 of 2846 kept entries = 1.2 %)."""
@@ -58,12 +61,23 @@ def test_mplug_training_trajectory_follows_reference():
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=T["lr"], weight_decay=0.0)
     data = [t.cuda() for t in sk.batch()]
     model.train()
+    eng = None
+    if through_engine:
+        from mPLUG.engine import MaskTrainEngine
+        eng = MaskTrainEngine(model, opt, gradient_clipping=1.0, bf16=False)
     for step, want in enumerate(T["steps"]):
-        loss = model(*data)
-        opt.zero_grad()
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad and p.grad is not None], 1.0)
-        opt.step()
+        if eng is not None:
+            loss = eng(*data)
+            eng.backward(loss)
+            eng.step()
+            assert eng._fused and eng._fused.plan is not None and eng._fused.plan.uniform_steps
+        else:
+            loss = model(*data)
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad and p.grad is not None],
+                                           1.0)
+            opt.step()
         assert float(loss.detach()) == pytest.approx(want["loss"], rel=2e-2), step
         if "target" in want:
             _, target, _ = masker.masker_scheduler.step(cur_epoch=(step + 1) // 2)
