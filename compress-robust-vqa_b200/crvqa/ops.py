@@ -35,12 +35,28 @@ class _Timed:
             PROFILE.append(self.rec)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def _launch(kind, M, N, K, name, fn, *args):
+    """One library GEMM call; the CUDA-event bracket only when bench.py asked for per-launch timings."""
+    if PROFILE is None:
+        check(fn(*args), name)
+    else:
+        with _Timed(kind, M, N, K):
+            check(fn(*args), name)
+
+
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """torch's current CUDA stream as an integer handle (every entry point declares void* argtypes, so ctypes takes
+    plain ints / None: no c_void_p objects on the per-launch path -- an eager mPLUG step makes ~1 100 library calls)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
+    return torch.cuda.current_stream().cuda_stream
 
 
 def _p(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    return t.data_ptr() if t is not None else None
 
 
 def _need_cuda(*ts):
@@ -135,10 +151,8 @@ def masked_linear_fwd(x_bf16, w_bf16, scores, thr, bias, out_dtype=torch.float32
     thr_t = as_thr(thr, x_bf16.device) if scores is not None else None
     if RECORD is not None:
         RECORD.append(("fwd", M, N, K, lambda: masked_linear_fwd(x_bf16, w_bf16, scores, thr, bias, out_dtype)))
-    with _Timed("fwd", M, N, K):
-        check(lib.crv_masked_linear_fwd(_p(x_bf16), _p(w_bf16), _p(scores), _p(thr_t), _p(bias), _p(y),
-                                        DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _stream()),
-              "crv_masked_linear_fwd")
+    _launch("fwd", M, N, K, "crv_masked_linear_fwd", lib.crv_masked_linear_fwd, _p(x_bf16), _p(w_bf16), _p(scores),
+            _p(thr_t), _p(bias), _p(y), DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _stream())
     return y
 
 
@@ -150,10 +164,8 @@ def masked_linear_bwd_dx(dy_bf16, w_bf16, scores, thr, out_dtype=torch.float32):
     thr_t = as_thr(thr, dy_bf16.device) if scores is not None else None
     if RECORD is not None:
         RECORD.append(("dx", M, N, K, lambda: masked_linear_bwd_dx(dy_bf16, w_bf16, scores, thr, out_dtype)))
-    with _Timed("dx", M, N, K):
-        check(lib.crv_masked_linear_bwd_dx(_p(dy_bf16), _p(w_bf16), _p(scores), _p(thr_t), _p(dx),
-                                           DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _stream()),
-              "crv_masked_linear_bwd_dx")
+    _launch("dx", M, N, K, "crv_masked_linear_bwd_dx", lib.crv_masked_linear_bwd_dx, _p(dy_bf16), _p(w_bf16),
+            _p(scores), _p(thr_t), _p(dx), DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _stream())
     return dx
 
 
@@ -171,9 +183,8 @@ def masked_linear_bwd_ds(dy_bf16, x_bf16, w_f32, out=None, accumulate=False):
         scratch = torch.empty_like(out)
         RECORD.append(("ds", M, N, K, lambda: masked_linear_bwd_ds(dy_bf16, x_bf16, w_f32, out=scratch,
                                                                      accumulate=accumulate)))
-    with _Timed("ds", M, N, K):
-        check(lib.crv_masked_linear_bwd_ds(_p(dy_bf16), _p(x_bf16), _p(w_f32), _p(out), int(accumulate),
-                                           M, N, K, _stream()), "crv_masked_linear_bwd_ds")
+    _launch("ds", M, N, K, "crv_masked_linear_bwd_ds", lib.crv_masked_linear_bwd_ds, _p(dy_bf16), _p(x_bf16),
+            _p(w_f32), _p(out), int(accumulate), M, N, K, _stream())
     return out
 
 
@@ -385,7 +396,8 @@ class MaskedLinearFn(torch.autograd.Function):
         thr_t = as_thr(thr, x.device)
         if w_f32 is None:
             w_f32 = w_bf16.float()
-        w_f32 = w_f32.detach()
+        if w_f32.requires_grad:
+            w_f32 = w_f32.detach()
         ctx.split = operand_mode() == "split" and x.dtype == torch.float32
         if ctx.split:
             return MaskedLinearFn._forward_split(ctx, x, scores, w_bf16, thr_t, bias, sink, wm_bf16, w_f32)

@@ -90,51 +90,81 @@ __device__ __forceinline__ void dot_rows(const float* __restrict__ A, const uint
   }
 }
 
-// out[i][col..col+1] = sum_j C[i][j] * M[j][col..col+1] for the queries i = warp, warp + 4, ... of this warp; M is a
-// [Lk, H*64] bf16 matrix in global memory read once per warp (lanes cover the 64 columns, two each)
+// dst[i][0..63] = sum_j C[i][j] * M[j][0..63] for all queries i < Lq; M is a [Lk, H*64] bf16 matrix in global memory.
+// The keys are dealt to the four warps (j = warp, warp + 4, ...), eight 128-byte rows in flight per warp (the lanes
+// cover the 64 columns, two each); the warps' partial sums meet in `red` ([2][LQ][64] floats of shared memory).
+// Every thread of the CTA must call this (it synchronises).
 template <int LQ>
 __device__ __forceinline__ void rows_times_matrix(const float* __restrict__ C, int lkp, const uint16_t* __restrict__ M,
                                                   long long row_stride, int Lk, int warp, int lane,
-                                                  float (&o)[LQ / 4][2]) {
+                                                  float* __restrict__ red, uint16_t* __restrict__ dst,
+                                                  long long dst_stride, int Lq) {
+  float acc[LQ][2];
 #pragma unroll
-  for (int a = 0; a < LQ / 4; ++a) o[a][0] = o[a][1] = 0.f;
+  for (int i = 0; i < LQ; ++i) acc[i][0] = acc[i][1] = 0.f;
   const uint32_t* col = reinterpret_cast<const uint32_t*>(M) + lane;
   const long long rs = row_stride / 2;      // in 32-bit words
-  int j = 0;
-  for (; j + 4 <= Lk; j += 4) {
-    uint32_t w[4];
+  int j = warp;
+  for (; j + 28 < Lk; j += 32) {
+    uint32_t w[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) w[u] = __ldg(col + (j + u) * rs);
+    for (int u = 0; u < 8; ++u) w[u] = __ldg(col + (j + 4 * u) * rs);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const float lo = bf_lo(w[u]), hi = bf_hi(w[u]);
 #pragma unroll
-      for (int a = 0; a < LQ / 4; ++a) {
-        const float c = C[(warp + 4 * a) * lkp + j + u];
-        o[a][0] += c * lo;
-        o[a][1] += c * hi;
+      for (int i = 0; i < LQ; ++i) {
+        const float c = C[i * lkp + j + 4 * u];
+        acc[i][0] += c * lo;
+        acc[i][1] += c * hi;
       }
     }
   }
-  for (; j < Lk; ++j) {
+  for (; j < Lk; j += 4) {
     const uint32_t w = __ldg(col + j * rs);
     const float lo = bf_lo(w), hi = bf_hi(w);
 #pragma unroll
-    for (int a = 0; a < LQ / 4; ++a) {
-      const float c = C[(warp + 4 * a) * lkp + j];
-      o[a][0] += c * lo;
-      o[a][1] += c * hi;
+    for (int i = 0; i < LQ; ++i) {
+      const float c = C[i * lkp + j];
+      acc[i][0] += c * lo;
+      acc[i][1] += c * hi;
     }
+  }
+  // 4 -> 2 -> 1 over the warps
+  float2* r2 = reinterpret_cast<float2*>(red);
+  if (warp >= 2) {
+#pragma unroll
+    for (int i = 0; i < LQ; ++i) r2[((warp - 2) * LQ + i) * 32 + lane] = make_float2(acc[i][0], acc[i][1]);
+  }
+  __syncthreads();
+  if (warp < 2) {
+#pragma unroll
+    for (int i = 0; i < LQ; ++i) {
+      const float2 t = r2[(warp * LQ + i) * 32 + lane];
+      acc[i][0] += t.x;
+      acc[i][1] += t.y;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+#pragma unroll
+    for (int i = 0; i < LQ; ++i) r2[i * 32 + lane] = make_float2(acc[i][0], acc[i][1]);
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < LQ; ++i)
+      if (i < Lq) {
+        const float2 t = r2[i * 32 + lane];
+        reinterpret_cast<uint32_t*>(dst + i * dst_stride)[lane] = pack2(acc[i][0] + t.x, acc[i][1] + t.y);
+      }
   }
 }
 
-// one key's gradient row: dst[0..63] = sum_i coef[i * pitch] * A[i][0..63]  (A: [LQ][64] fp32 in shared memory)
+// one key's gradient row: dst[0..63] = sum_i c[i] * A[i][0..63]  (A: [LQ][64] fp32 in shared memory)
 template <int LQ>
-__device__ __forceinline__ void key_row_gradient(const float* __restrict__ coef, int pitch, const float* __restrict__ A,
+__device__ __forceinline__ void key_row_gradient(const float (&c)[LQ], const float* __restrict__ A,
                                                  uint4* __restrict__ dst) {
-  float c[LQ];
-#pragma unroll
-  for (int i = 0; i < LQ; ++i) c[i] = coef[i * pitch];
 #pragma unroll 1
   for (int ch = 0; ch < 8; ++ch) {
     float a[8];
@@ -154,8 +184,9 @@ __device__ __forceinline__ void key_row_gradient(const float* __restrict__ coef,
 template <int LQ>
 __global__ void __launch_bounds__(kFqThreads) fq_attention_fwd_kernel(FqParams p) {
   extern __shared__ __align__(16) float fq_smem[];
-  float* Qs = fq_smem;                 // [LQ][64], scaled; rows >= Lq are zero
-  float* S = fq_smem + LQ * kFqD;      // [LQ][lkp]; rows >= Lq are zero
+  float* Qs = fq_smem;                 // [2][LQ][64]: first half Q (scaled; rows >= Lq zero), all of it the reduction
+                                       // scratch of step (3)
+  float* S = fq_smem + 2 * LQ * kFqD;  // [LQ][lkp]; rows >= Lq are zero
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const long long ld = static_cast<long long>(p.H) * kFqD;
@@ -216,15 +247,9 @@ __global__ void __launch_bounds__(kFqThreads) fq_attention_fwd_kernel(FqParams p
     }
   }
   __syncthreads();
-  // (3) O = P~ V
-  float o[LQ / 4][2];
-  rows_times_matrix<LQ>(S, p.lkp, v, ld, p.Lk, warp, lane, o);
-  uint16_t* out = p.out + (static_cast<long long>(b) * p.Lq) * ld + h * kFqD;
-#pragma unroll
-  for (int a = 0; a < LQ / 4; ++a) {
-    const int i = warp + 4 * a;
-    if (i < p.Lq) reinterpret_cast<uint32_t*>(out + i * ld)[lane] = pack2(o[a][0], o[a][1]);
-  }
+  // (3) O = P~ V  (Q is no longer needed: its shared memory is the reduction scratch)
+  rows_times_matrix<LQ>(S, p.lkp, v, ld, p.Lk, warp, lane, Qs,
+                        p.out + (static_cast<long long>(b) * p.Lq) * ld + h * kFqD, ld, p.Lq);
 }
 
 template <int LQ>
@@ -232,8 +257,8 @@ __global__ void __launch_bounds__(kFqThreads) fq_attention_bwd_kernel(FqParams p
   extern __shared__ __align__(16) float fq_smem[];
   float* dOs = fq_smem;                          // [LQ][64]; rows >= Lq are zero
   float* Qs = dOs + LQ * kFqD;                   // [LQ][64] (unscaled); rows >= Lq are zero
-  float* Ps = Qs + LQ * kFqD;                    // [LQ][lkp] signed probabilities, later P~ (after dropout)
-  float* dS = Ps + LQ * p.lkp;                   // [LQ][lkp] dP, later dS / sqrt(d)
+  float* dS = Qs + LQ * kFqD;                    // [LQ][lkp] dP, later dS / sqrt(d); rows >= Lq are zero
+  uint16_t* Ps = reinterpret_cast<uint16_t*>(dS + LQ * p.lkp);   // [LQ][lkp] the saved signed probabilities (bf16 bits)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const long long ld = static_cast<long long>(p.H) * kFqD;
@@ -249,7 +274,10 @@ __global__ void __launch_bounds__(kFqThreads) fq_attention_bwd_kernel(FqParams p
     dOs[idx] = i < p.Lq ? bf_to_f(dout[i * ld + d]) : 0.f;
     Qs[idx] = i < p.Lq ? bf_to_f(q[i * ld + d]) : 0.f;
   }
-  for (int idx = tid; idx < 2 * LQ * p.lkp; idx += kFqThreads) Ps[idx] = 0.f;     // Ps and dS are adjacent
+  for (int idx = tid; idx < LQ * p.lkp; idx += kFqThreads) {
+    dS[idx] = 0.f;
+    Ps[idx] = 0;
+  }
   __syncthreads();
   // (1) dP~ = dO V^T per key; dP = dP~ / (1 - p) where kept, 0 where dropped
   const uint16_t* probs = p.probs + (static_cast<long long>(b) * p.H + h) * p.Lq * p.Lk;
@@ -261,42 +289,38 @@ __global__ void __launch_bounds__(kFqThreads) fq_attention_bwd_kernel(FqParams p
     for (int i = 0; i < LQ; ++i)
       if (i < p.Lq) {
         const uint16_t sp = probs[i * p.Lk + j];
-        const bool keep = (sp & 0x8000u) == 0;
-        Ps[i * p.lkp + j] = bf_to_f(sp);                    // signed
-        dS[i * p.lkp + j] = keep ? acc[i] * keep_scale : 0.f;
+        Ps[i * p.lkp + j] = sp;
+        dS[i * p.lkp + j] = (sp & 0x8000u) ? 0.f : acc[i] * keep_scale;
       }
   }
   __syncthreads();
-  // (2) D_i = sum_j P dP; dS = P (dP - D_i) / sqrt(d); Ps becomes P~
+  // (2) D_i = sum_j P dP; dS = P (dP - D_i) / sqrt(d)
   for (int i = warp; i < p.Lq; i += 4) {
-    float* pr = Ps + i * p.lkp;
+    const uint16_t* pr = Ps + i * p.lkp;
     float* dr = dS + i * p.lkp;
     float dsum = 0.f;
-    for (int j = lane; j < p.Lk; j += 32) dsum += fabsf(pr[j]) * dr[j];
+    for (int j = lane; j < p.Lk; j += 32) dsum += bf_to_f(pr[j] & 0x7FFFu) * dr[j];
     dsum = warp_add(dsum);
-    for (int j = lane; j < p.Lk; j += 32) {
-      const float sp = pr[j];
-      const float P = fabsf(sp);
-      dr[j] = P * (dr[j] - dsum) * p.scale;
-      pr[j] = (__float_as_uint(sp) & 0x80000000u) ? 0.f : P * keep_scale;
-    }
+    for (int j = lane; j < p.Lk; j += 32) dr[j] = bf_to_f(pr[j] & 0x7FFFu) * (dr[j] - dsum) * p.scale;
   }
   __syncthreads();
   // (3) per key: dV_j = sum_i P~_ij dO_i, dK_j = sum_i dS_ij Q_i  (a thread owns a key, eight columns at a time)
 #pragma unroll 1
   for (int j = tid; j < p.Lk; j += kFqThreads) {
-    key_row_gradient<LQ>(Ps + j, p.lkp, dOs, reinterpret_cast<uint4*>(p.dv + koff + j * ld));
-    key_row_gradient<LQ>(dS + j, p.lkp, Qs, reinterpret_cast<uint4*>(p.dk + koff + j * ld));
-  }
-  // (4) dQ = dS K (dS already carries 1 / sqrt(d))
-  float o[LQ / 4][2];
-  rows_times_matrix<LQ>(dS, p.lkp, k, ld, p.Lk, warp, lane, o);
-  uint16_t* dq = p.dq + qoff;
+    float c[LQ];
 #pragma unroll
-  for (int a = 0; a < LQ / 4; ++a) {
-    const int i = warp + 4 * a;
-    if (i < p.Lq) reinterpret_cast<uint32_t*>(dq + i * ld)[lane] = pack2(o[a][0], o[a][1]);
+    for (int i = 0; i < LQ; ++i) {
+      const uint16_t sp = Ps[i * p.lkp + j];
+      c[i] = (sp & 0x8000u) ? 0.f : bf_to_f(sp) * keep_scale;
+    }
+    key_row_gradient<LQ>(c, dOs, reinterpret_cast<uint4*>(p.dv + koff + j * ld));
+#pragma unroll
+    for (int i = 0; i < LQ; ++i) c[i] = dS[i * p.lkp + j];
+    key_row_gradient<LQ>(c, Qs, reinterpret_cast<uint4*>(p.dk + koff + j * ld));
   }
+  __syncthreads();      // dO / Q in shared memory are done with: their space is the reduction scratch of step (4)
+  // (4) dQ = dS K (dS already carries 1 / sqrt(d))
+  rows_times_matrix<LQ>(dS, p.lkp, k, ld, p.Lk, warp, lane, dOs, p.dq + qoff, ld, p.Lq);
 }
 
 int fq_check(const FqParams& p) {
@@ -328,12 +352,12 @@ extern "C" int crv_fq_attention_fwd(const uint16_t* q, const uint16_t* k, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(B * heads), block(crv::kFqThreads);
   if (Lq <= 8) {
-    const size_t smem = (8 * crv::kFqD + 8 * static_cast<size_t>(p.lkp)) * sizeof(float);
+    const size_t smem = (2 * 8 * crv::kFqD + 8 * static_cast<size_t>(p.lkp)) * sizeof(float);
     crv::fq_attention_fwd_kernel<8><<<grid, block, smem, st>>>(p);
   } else {
-    const size_t smem = (16 * crv::kFqD + 16 * static_cast<size_t>(p.lkp)) * sizeof(float);
+    const size_t smem = (2 * 16 * crv::kFqD + 16 * static_cast<size_t>(p.lkp)) * sizeof(float);
     CRV_CUDA(cudaFuncSetAttribute(crv::fq_attention_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>((16 * crv::kFqD + 16 * 1024) * sizeof(float))));
+                                  static_cast<int>((2 * 16 * crv::kFqD + 16 * 1024) * sizeof(float))));
     crv::fq_attention_fwd_kernel<16><<<grid, block, smem, st>>>(p);
   }
   return crv::launch_status();
@@ -352,14 +376,14 @@ extern "C" int crv_fq_attention_bwd(const uint16_t* dout, const uint16_t* q, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(B * heads), block(crv::kFqThreads);
   if (Lq <= 8) {
-    const size_t smem = (2 * 8 * crv::kFqD + 2 * 8 * static_cast<size_t>(p.lkp)) * sizeof(float);
+    const size_t smem = 2 * 8 * crv::kFqD * sizeof(float) + 8 * static_cast<size_t>(p.lkp) * 6;   // fp32 dS + bf16 P
     CRV_CUDA(cudaFuncSetAttribute(crv::fq_attention_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>((2 * 8 * crv::kFqD + 2 * 8 * 1024) * sizeof(float))));
+                                  static_cast<int>(2 * 8 * crv::kFqD * sizeof(float) + 8 * 1024 * 6)));
     crv::fq_attention_bwd_kernel<8><<<grid, block, smem, st>>>(p);
   } else {
-    const size_t smem = (2 * 16 * crv::kFqD + 2 * 16 * static_cast<size_t>(p.lkp)) * sizeof(float);
+    const size_t smem = 2 * 16 * crv::kFqD * sizeof(float) + 16 * static_cast<size_t>(p.lkp) * 6;
     CRV_CUDA(cudaFuncSetAttribute(crv::fq_attention_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>((2 * 16 * crv::kFqD + 2 * 16 * 1024) * sizeof(float))));
+                                  static_cast<int>(2 * 16 * crv::kFqD * sizeof(float) + 16 * 1024 * 6)));
     crv::fq_attention_bwd_kernel<16><<<grid, block, smem, st>>>(p);
   }
   return crv::launch_status();
