@@ -57,6 +57,12 @@ class RngState:
     def advance(self):
         check(lib.crv_rng_advance(_p(self.state), _stream()), "crv_rng_advance")
 
+    @classmethod
+    def advance_all(cls):
+        """Move the counter of every device that has drawn masks (once per training step, after its backward)."""
+        for st in cls._per_device.values():
+            st.advance()
+
 
 # ----------------------------------------------------------------------------- grouped masked linear
 class ProjectionGroup:

@@ -67,10 +67,9 @@ class MaskTrainEngine:
         # the fused layer kernels (dropout + residual + LayerNorm, few-query attention) hash their dropout masks from a
         # device-side (seed, counter): forward and backward of this step have both been queued, so move the counter on
         # -- without this every step would draw the SAME masks
-        fused = sys.modules.get("crvqa.fused")
+        fused = sys.modules.get("crvqa.fused")       # loaded only if one of those kernels ran
         if fused is not None:
-            for state in fused.RngState._per_device.values():
-                state.advance()
+            fused.RngState.advance_all()
 
     def _trainable_grads(self):
         return [p.grad for p in self.module.parameters() if p.requires_grad and p.grad is not None]
@@ -221,7 +220,9 @@ class _FusedAdamW:
                      if m is not None else None for m in mods],
             moments=[(st["exp_avg"], st["exp_avg_sq"]) for st in states],
             group_sizes=[len(ps) for _, ps in groups], grad_ptrs=None)
-        ptr = lambda t: t.data_ptr() if t is not None else 0
+        def ptr(t):
+            return t.data_ptr() if t is not None else 0
+
         fixed = [[ptr(p) for p in params], [ptr(st["exp_avg"]) for st in states],
                  [ptr(st["exp_avg_sq"]) for st in states], [ptr(t) for t in w16], [ptr(t) for t in wm],
                  [ptr(t) for t in thr]]

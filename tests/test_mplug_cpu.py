@@ -366,6 +366,27 @@ def test_load_mask_and_prune_reparametrises_the_named_modules(gold, oracle_backe
     assert "text_encoder.encoder.layer.0.intermediate.dense.weight_orig" in dict(model.named_parameters())
 
 
+def test_engine_backward_advances_the_dropout_counter_of_the_fused_kernels(monkeypatch):
+    """The fused layer kernels hash their dropout masks from a device-side (seed, counter); MaskTrainEngine.backward()
+    moves the counter of every device that drew masks, once per call, after the backward has been queued."""
+    from crvqa import fused
+    from mPLUG.engine import MaskTrainEngine
+    events = []
+
+    class Counter:
+        def advance(self):
+            events.append("advance")
+
+    monkeypatch.setattr(fused.RngState, "_per_device", {("cuda", 0): Counter(), ("cuda", 1): Counter()})
+    net = torch.nn.Linear(4, 2)
+    net.weight.register_hook(lambda g: events.append("backward"))
+    eng = MaskTrainEngine(net, torch.optim.SGD(net.parameters(), lr=0.1))
+    eng.backward(eng(torch.randn(3, 4)).sum())
+    assert events == ["backward", "advance", "advance"]
+    eng.backward(eng(torch.randn(3, 4)).sum())
+    assert events.count("advance") == 4
+
+
 def test_engine_step_protocol_on_cpu():
     """The DeepSpeed-engine stand-in: backward / clip / optimiser step / counters, on a plain module."""
     from mPLUG.engine import MaskTrainEngine
