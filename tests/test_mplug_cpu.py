@@ -458,6 +458,68 @@ def test_engine_allreduces_trainable_gradients_world2_gloo():
     assert sorted(q.get(timeout=5) for _ in range(2)) == [0, 1]
 
 
+def _fused_engine_worker(rank, world, port, q):
+    """Two data-parallel ranks through the engine's multi-tensor step (kernels emulated, gloo): gradients averaged,
+    one clip coefficient, identical parameters on both ranks == one process on the union batch with torch's AdamW."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (os.path.join(root, "compress-robust-vqa_b200"), root, os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from crvqa import ops
+    from mPLUG import engine as eng_mod
+    calls = _emulated_multi_kernels(None, ops)
+    eng_mod._FusedAdamW.device_types = ("cpu", "cuda")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    net[0].bias.requires_grad = False
+    groups = [{"params": [net[0].weight, net[2].weight], "weight_decay": 0.05},
+              {"params": [net[2].bias], "weight_decay": 0.0}]
+    opt = torch.optim.AdamW(groups, lr=0.02)
+    eng = eng_mod.MaskTrainEngine(net, opt, gradient_clipping=0.05)
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    ref.load_state_dict(net.state_dict())
+    ref[0].bias.requires_grad = False
+    ropt = torch.optim.AdamW([{"params": [ref[0].weight, ref[2].weight], "weight_decay": 0.05},
+                              {"params": [ref[2].bias], "weight_decay": 0.0}], lr=0.02)
+    g = torch.Generator().manual_seed(100)
+    xs = [torch.randn(4, 6, generator=g) for _ in range(world)]
+    for step in range(3):
+        loss = eng(xs[rank]).pow(2).mean()
+        eng.backward(loss)
+        eng.step()
+        ropt.zero_grad()
+        torch.stack([ref(x).pow(2).mean() for x in xs]).mean().backward()
+        norm = torch.nn.utils.clip_grad_norm_([p for p in ref.parameters() if p.requires_grad], 0.05)
+        ropt.step()
+        assert float(norm) > 0.05 and float(eng.last_grad_norm) == pytest.approx(float(norm), rel=1e-5)
+        for (n, p), (_, pr) in zip(net.named_parameters(), ref.named_parameters()):
+            assert torch.allclose(p, pr, rtol=1e-5, atol=1e-7), (rank, step, n)
+    assert calls["sumsq"] == 3 and calls["adamw"] == 6 and eng.global_steps == 3
+    gathered = [torch.zeros_like(net[2].weight) for _ in range(world)]
+    dist.all_gather(gathered, net[2].weight.detach())
+    assert torch.equal(gathered[0], gathered[1])                 # bit-identical replicas
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put(rank)
+
+
+def test_fused_engine_step_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_fused_engine_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5) for _ in range(2)) == [0, 1]
+
+
 def test_held_masked_operand_is_rebuilt_exactly_when_it_must(gold, oracle_backend, monkeypatch):
     """The engine-managed operand cache of the masked modules: built once, reused while nothing changes, rebuilt after
     the engine's step (drop), after a threshold refresh (new threshold object) and after a score-dtype switch."""
@@ -547,9 +609,10 @@ def _emulated_multi_kernels(monkeypatch, ops):
                 W = _at(int(w16[t]) + off * 2, n, ctypes.c_uint16, np.uint16)
                 _at(int(wm[t]) + off * 2, n, ctypes.c_uint16, np.uint16)[:] = np.where(P > T, W, np.uint16(0))
 
-    monkeypatch.setattr(ops, "upload", upload)
-    monkeypatch.setattr(ops, "sumsq_multi", sumsq_multi)
-    monkeypatch.setattr(ops, "adamw_multi", adamw_multi)
+    put = monkeypatch.setattr if monkeypatch is not None else setattr     # a spawned worker has no monkeypatch fixture
+    put(ops, "upload", upload)
+    put(ops, "sumsq_multi", sumsq_multi)
+    put(ops, "adamw_multi", adamw_multi)
     return calls
 
 
