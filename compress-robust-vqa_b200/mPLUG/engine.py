@@ -131,7 +131,7 @@ class _FusedAdamW:
     in; the masked bf16 operand W (.) (S_new > T) of every held module is rewritten from the new scores in registers).
     step() returns False -- nothing done, the caller runs the PyTorch path -- whenever something is outside that
     contract (another optimiser class, amsgrad / maximize / capturable, CPU, non-fp32 or strided tensors, sparse
-    gradients, unequal step counts inside a group)."""
+    gradients).  Parameters of one group whose step counts differ are stepped by separate launches."""
 
     device_types = ("cuda",)          # the kernels have no CPU implementation (tests/test_mplug_cpu.py swaps in an emulation)
 
@@ -147,14 +147,12 @@ class _FusedAdamW:
         self.plan = None
         self.grad_norm = None
         self.not_refreshed = self.masked
+        # a plain optimizer.step() (ours never calls it) may advance the step counters of SOME tensors: re-plan after it
+        self._stepped_outside = False
+        optimizer.register_step_post_hook(self._note_outside_step)
 
-    @staticmethod
-    def _group_spans(sizes):
-        spans, a = [], 0
-        for n in sizes:
-            spans.append((a, a + n))
-            a += n
-        return spans
+    def _note_outside_step(self, *_):
+        self._stepped_outside = True
 
     @staticmethod
     def wanted(optimizer):
@@ -194,7 +192,18 @@ class _FusedAdamW:
 
     def _build(self, groups):
         from crvqa import ops
-        params = [p for _, ps in groups for p in ps]
+        # torch keeps one step counter per parameter (a tensor that starts receiving gradients later is behind the
+        # others), the kernel takes one step number per launch: inside each group the parameters are ordered by their
+        # count and every run of equal counts becomes one launch -- normally one run per group
+        self._stepped_outside = False
+        params, spans = [], []
+        for gi, (_, ps) in enumerate(groups):
+            for p in sorted(ps, key=lambda p: int(self._state_of(p)["step"])):
+                t = int(self.optimizer.state[p]["step"])
+                if not spans or spans[-1][0] != gi or spans[-1][3] != t:
+                    spans.append([gi, len(params), len(params), t])
+                params.append(p)
+                spans[-1][2] = len(params)
         dev = params[0].device
         states = [self._state_of(p) for p in params]
         for st in states:
@@ -219,7 +228,7 @@ class _FusedAdamW:
             thr_src=[(m.threshold, m.threshold._version if torch.is_tensor(m.threshold) else None, m.score_dtype)
                      if m is not None else None for m in mods],
             moments=[(st["exp_avg"], st["exp_avg_sq"]) for st in states],
-            group_sizes=[len(ps) for _, ps in groups], grad_ptrs=None)
+            group_ids=[tuple(id(p) for p in ps) for _, ps in groups], grad_ptrs=None)
         def ptr(t):
             return t.data_ptr() if t is not None else 0
 
@@ -228,47 +237,41 @@ class _FusedAdamW:
                  [ptr(t) for t in thr]]
         if any(a % 16 for row in fixed[:5] for a in row):          # the threshold scalars need no vector alignment
             return None
-        plan.uniform_steps = all(len({int(plan.states[j]["step"]) for j in range(a, b)}) <= 1
-                                 for a, b in self._group_spans(plan.group_sizes))
+        plan.uniform_steps = len(spans) == sum(1 for _, ps in groups if ps)      # one launch per group
         plan.fixed_key = tuple(fixed[0])
         plan.tables = ops.upload(fixed, torch.int64, dev)          # [6, n]: p, m, v, w16, wm, thr
         plan.g_table = torch.empty(len(params), dtype=torch.int64, device=dev)
         rows = ops.multi_rows([p.numel() for p in params], [1 if m is not None else 0 for m in mods])
         plan.rows = ops.upload(rows, torch.int32, dev).contiguous()
-        bounds, first, r0 = [], 0, 0
         counts = [0] * len(params)
         for r in rows:
             counts[r[0]] += 1
-        for n in plan.group_sizes:
-            nrows = sum(counts[first:first + n])
-            bounds.append((r0, r0 + nrows))
-            first, r0 = first + n, r0 + nrows
-        plan.group_rows = bounds
+        first_row = [0]
+        for c in counts:
+            first_row.append(first_row[-1] + c)
+        plan.spans = [(gi, a, b, first_row[a], first_row[b]) for gi, a, b, _ in spans]   # group, params [a, b), rows
         plan.total = torch.zeros(1, dtype=torch.float32, device=dev)
         refreshed = {id(m) for m in mods if m is not None}
         self.not_refreshed = [m for m in self.masked if id(m) not in refreshed]
         return plan
 
     def _plan_is_current(self, plan, groups):
-        if plan is None or plan.group_sizes != [len(ps) for _, ps in groups]:
-            return False
-        i = 0
-        for _, ps in groups:
-            for p in ps:
-                if plan.params[i] is not p or plan.fixed_key[i] != p.data_ptr():
+        if plan is None or self._stepped_outside or plan.group_ids != [tuple(id(p) for p in ps) for _, ps in groups]:
+            return False              # (the plan keeps its parameters alive, so an id cannot have been reused)
+        for i, p in enumerate(plan.params):
+            if plan.fixed_key[i] != p.data_ptr():
+                return False
+            st = self.optimizer.state[p]              # load_state_dict() swaps in new dicts and tensors
+            if st is not plan.states[i] or st.get("exp_avg") is not plan.moments[i][0] or \
+                    st.get("exp_avg_sq") is not plan.moments[i][1]:
+                return False
+            m = plan.mods[i]
+            if m is not None:
+                t, ver, sd = plan.thr_src[i]
+                cur = m.threshold
+                if cur is not t or (ver is not None and cur._version != ver) or m.score_dtype is not sd \
+                        or not m.holds_masked_operand() or m._w16 is not plan.w16[i]:
                     return False
-                st = self.optimizer.state[p]          # load_state_dict() swaps in new dicts and tensors
-                if st is not plan.states[i] or st.get("exp_avg") is not plan.moments[i][0] or \
-                        st.get("exp_avg_sq") is not plan.moments[i][1]:
-                    return False
-                m = plan.mods[i]
-                if m is not None:
-                    t, ver, sd = plan.thr_src[i]
-                    cur = m.threshold
-                    if cur is not t or (ver is not None and cur._version != ver) or m.score_dtype is not sd \
-                            or not m.holds_masked_operand() or m._w16 is not plan.w16[i]:
-                        return False
-                i += 1
         return True
 
     def step(self, max_norm):
@@ -281,9 +284,6 @@ class _FusedAdamW:
             if self.plan is None:
                 return False
         plan = self.plan
-        if not plan.uniform_steps:                              # torch keeps one step counter per parameter
-            return False
-        steps = [int(plan.states[a]["step"]) + 1 if b > a else 1 for a, b in self._group_spans(plan.group_sizes)]
         grad_ptrs = [p.grad.data_ptr() for p in plan.params]
         if grad_ptrs != plan.grad_ptrs:                         # fresh gradient tensors usually land where the last were
             if any(a % 16 for a in grad_ptrs):
@@ -297,12 +297,12 @@ class _FusedAdamW:
             ops.sumsq_multi(plan.g_table, plan.rows, plan.total)
             total = plan.total
             self.grad_norm = plan.total.sqrt().reshape(())
-        for (group, ps), (r0, r1), t in zip(groups, plan.group_rows, steps):
-            if not ps:
-                continue
+        for gi, a, _, r0, r1 in plan.spans:
+            group = groups[gi][0]
             b1, b2 = group["betas"]
-            ops.adamw_multi(tp, plan.g_table, tm, tv, tw, twm, tthr, plan.rows[r0:r1], group["lr"], t, b1, b2,
-                            group["eps"], group["weight_decay"], total, max_norm or 1.0)
+            ops.adamw_multi(tp, plan.g_table, tm, tv, tw, twm, tthr, plan.rows[r0:r1], group["lr"],
+                            int(plan.states[a]["step"]) + 1, b1, b2, group["eps"], group["weight_decay"], total,
+                            max_norm or 1.0)
         torch._foreach_add_([st["step"] for st in plan.states], 1)
         for m, wm, thr in zip(plan.mods, plan.wm, plan.thr):
             if m is not None and m._wm is not wm:

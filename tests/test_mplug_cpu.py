@@ -667,10 +667,11 @@ def test_fused_engine_step_host_logic_follows_clip_plus_torch_adamw(gold, oracle
         before = dict(calls)
         eng.step()
         plans.append(eng._fused.plan)
-        if it == 2:
-            # two scores join with step counters behind the others' in their group: the kernels take one step number
-            # per launch, so this step (and every later one) must go through the PyTorch path -- still correct
-            assert not eng._fused.plan.uniform_steps and calls["adamw"] == before["adamw"]
+        if it >= 2:
+            # two scores joined with step counters behind the others' in their group: the kernels take one step number
+            # per launch, so that group is stepped by two launches from now on
+            assert not eng._fused.plan.uniform_steps and calls["adamw"] == before["adamw"] + 3
+            assert calls["sumsq"] == before["sumsq"] + 1
         want_norm = torch.nn.utils.clip_grad_norm_([q for q in flat_twin if q.grad is not None], 0.05)
         ref.step()
         assert float(eng.last_grad_norm) == pytest.approx(float(want_norm), rel=1e-5) and float(want_norm) > 0.05
@@ -691,9 +692,24 @@ def test_fused_engine_step_host_logic_follows_clip_plus_torch_adamw(gold, oracle
                 assert m._held_masked_weight(thr) is m._wm            # no rebuild on the next forward
             assert len(applied) == n_applied
             assert held[0]._wm is None                                # outside the pass: dropped, rebuilt on demand
-    assert plans[0] is plans[1] and plans[1] is not plans[2]
+    assert plans[0] is plans[1] and plans[1] is not plans[2] and plans[2] is not plans[3] and plans[3] is plans[4]
+    # a plain optimizer.step() on SOME of the tensors splits a run of equal step counts: the plan is rebuilt around it
+    for p in trainable:
+        p.grad = None
+    lone = held[5].weight_mask
+    lone.grad = torch.zeros_like(lone)
+    opt.step()
+    for p, q in zip(trainable, flat_twin):
+        p.grad = torch.randn(p.shape, generator=gen) * 0.01
+        q.grad = p.grad.clone()
+    flat_twin[[id(p) for p in trainable].index(id(lone))].grad = None     # the twin takes the lone step now ...
+    before = dict(calls)
+    eng.step()
+    assert eng._fused.plan is not plans[4] and calls["adamw"] == before["adamw"] + 4
     sd = opt.state_dict()
     assert len(sd["state"]) == len(trainable)
+    steps = {int(st["step"]) for st in opt.state.values()}
+    assert steps == {4, 6, 7}                  # late joiners, everyone else, the one tensor stepped on its own as well
 
 
 def test_fused_engine_step_uniform_run_rebuilds_plan_on_new_thresholds(gold, oracle_backend, monkeypatch):
